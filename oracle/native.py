@@ -1,0 +1,85 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+
+ctypes binding of oracle/pointops_ref.c, exposed with the exact names and signatures of the
+reference's pybind module ``pointops_cuda`` (cpp_wrappers/pointops/src/pointops_api.cpp:13-14)
+so the unmodified reference Python (cpp_wrappers/pointops/functions/pointops.py:23,42) can run on
+CPU tensors with this object injected as ``sys.modules['pointops_cuda']``.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libpointops_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "pointops_ref.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        P, I = ctypes.c_void_p, ctypes.c_int
+        L.oracle_knnquery.argtypes = [I, I, P, P, P, P, P, P]
+        L.oracle_knnquery.restype = I
+        L.oracle_furthestsampling.argtypes = [I, I, P, P, P, P, P]
+        L.oracle_furthestsampling.restype = I
+        L.oracle_fps_block_size.argtypes = [I]
+        L.oracle_fps_block_size.restype = I
+        _lib = L
+    return _lib
+
+
+def _chk(t, dtype):
+    assert t.device.type == "cpu" and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):
+    """Same contract as knnquery_cuda (knnquery_cuda_kernel.h:7): caller allocates idx/dist2."""
+    rc = lib().oracle_knnquery(int(m), int(nsample), _chk(xyz, torch.float32), _chk(new_xyz, torch.float32),
+                               _chk(offset, torch.int32), _chk(new_offset, torch.int32),
+                               _chk(idx, torch.int32), _chk(dist2, torch.float32))
+    if rc:
+        raise RuntimeError("oracle_knnquery failed rc=%d" % rc)
+
+
+def furthestsampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
+    """Same contract as furthestsampling_cuda (sampling_cuda_kernel.h:7); n is the max segment length."""
+    rc = lib().oracle_furthestsampling(int(b), int(n), _chk(xyz, torch.float32), _chk(offset, torch.int32),
+                                       _chk(new_offset, torch.int32), _chk(tmp, torch.float32),
+                                       _chk(idx, torch.int32))
+    if rc:
+        raise RuntimeError("oracle_furthestsampling failed rc=%d" % rc)
+
+
+def fps_block_size(n_max: int) -> int:
+    return lib().oracle_fps_block_size(int(n_max))
+
+
+# ---- convenience wrappers (allocate like pointops.py:18-23,39-43) ----
+def knn(nsample, xyz, new_xyz, offset, new_offset):
+    m = new_xyz.shape[0]
+    idx = torch.zeros(m, nsample, dtype=torch.int32)
+    d2 = torch.zeros(m, nsample, dtype=torch.float32)
+    knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, d2)
+    return idx, d2
+
+
+def fps(xyz, offset, new_offset):
+    b = offset.shape[0]
+    ends = offset.tolist()
+    n_max = max(e - s for s, e in zip([0] + ends[:-1], ends))
+    idx = torch.zeros(int(new_offset[-1]), dtype=torch.int32)
+    tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32)
+    furthestsampling_cuda(b, n_max, xyz, offset, new_offset, tmp, idx)
+    return idx
