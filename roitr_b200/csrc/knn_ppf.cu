@@ -1,0 +1,288 @@
+// Exact kNN fused with point-pair-feature construction (sm_100a).
+//
+// Replaces knnquery_cuda_kernel (cpp_wrappers/pointops/src/knnquery/knnquery_cuda_kernel.cu:65-108) and the ~17
+// eager ops of queryandgroup(return_idx) + gathers + calc_ppf_gpu (pointops.py:87-92, model/model.py:36-41,
+// lib/utils.py:358-389) with one kernel.
+//
+// Design (B200): the reference runs one thread per query with a 100-slot heap in local memory (800 B stack) and a
+// full scan from global memory; 79 CTAs for 20k queries. Here a WARP owns QW queries. Reference points are streamed
+// through shared memory in 2048-point tiles by the TMA engine (1-D cp.async.bulk + mbarrier, double buffered; xyz
+// rows are 12 B so tiles are flat byte ranges starting at multiples of 4 points = 48 B, 16-B aligned). Each lane
+// evaluates one reference point per step for all QW queries (stride-3-word LDS is bank-conflict free). The running
+// top-k of a query is a sorted list DISTRIBUTED OVER THE LANES (lane l holds the l-th best), so admission is one
+// compare + ballot per 32 points and an insertion is a ballot/popc + one shuffle — no local memory, no divergence.
+// Points are consumed in ascending index order and admission is strict '<', so among exactly equal distances the
+// lower index wins (reference: knnquery_cuda_kernel.cu:97 strict '<' while scanning i ascending).
+// The epilogue drops the self column and computes the PPF tuple per (query, neighbour) lane, writing coalesced
+// idx and float4 PPF.
+#include <math_constants.h>
+
+#include "../../include/roitr_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_WARPS = KNN_THREADS / 32;
+constexpr int TILE_PTS = 2048;
+constexpr int TILE_BYTES = TILE_PTS * 12;  // 24 KB, multiple of 16
+
+struct KnnParams {
+    const float* xyz;
+    const float* nrm;
+    const float* qxyz;
+    const float* qnrm;
+    const int* offset;
+    const int* new_offset;
+    int b, m, nslots, drop;
+    int* idx;
+    float* dist;
+    float* ppf;
+    int dist_squared;
+    int n_total;
+    int use_tma;
+};
+
+__device__ __forceinline__ int find_segment(int q, const int* __restrict__ ends, int b) {
+    int lo = 0, hi = b - 1;  // first s with q < ends[s]
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (q < __ldg(ends + mid)) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// angle(a, b) / pi  =  atan2(|a x b|, a.b) / pi   (lib/utils.py:372-387). Products and sums are rounded separately
+// (no FMA contraction) like the eager elementwise reference.
+__device__ __forceinline__ float angle_over_pi(float ax, float ay, float az, float bx, float by, float bz) {
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+    float cx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+    float cy = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+    float cz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+    float cn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+    return __fdiv_rn(atan2f(cn, dot), 3.14159265358979323846f);
+}
+
+template <int QW>
+__global__ void __launch_bounds__(KNN_THREADS) knn_ppf_kernel(const KnnParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tile0 = reinterpret_cast<float*>(smem_raw);
+    float* tile1 = reinterpret_cast<float*>(smem_raw + TILE_BYTES);
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ int s_cta[3];  // lo, hi, mixed
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = P.nslots;
+    const unsigned kmask = (K >= 32) ? FULL_MASK : ((1u << K) - 1u);
+    const int q_cta0 = blockIdx.x * (KNN_WARPS * QW);
+
+    if (tid == 0) {
+        int q_last = min(q_cta0 + KNN_WARPS * QW, P.m) - 1;
+        int s0 = find_segment(q_cta0, P.new_offset, P.b);
+        int s1 = find_segment(q_last, P.new_offset, P.b);
+        s_cta[0] = s0 == 0 ? 0 : __ldg(P.offset + s0 - 1);
+        s_cta[1] = __ldg(P.offset + s1);
+        s_cta[2] = (s0 != s1);
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        mbar_fence_init();
+    }
+
+    // ---- per-query state (replicated across the warp except the distributed list) ----
+    float qx[QW], qy[QW], qz[QW], ld[QW], tau[QW];
+    int qs[QW], qe[QW], li[QW];
+#pragma unroll
+    for (int j = 0; j < QW; ++j) {
+        int q = q_cta0 + warp * QW + j;
+        if (q < P.m) {
+            int s = find_segment(q, P.new_offset, P.b);
+            qs[j] = s == 0 ? 0 : __ldg(P.offset + s - 1);
+            qe[j] = __ldg(P.offset + s);
+            qx[j] = __ldg(P.qxyz + 3 * (size_t)q);
+            qy[j] = __ldg(P.qxyz + 3 * (size_t)q + 1);
+            qz[j] = __ldg(P.qxyz + 3 * (size_t)q + 2);
+            ld[j] = 1e10f;  // knnquery_cuda_kernel.cu:88-91
+            li[j] = qs[j];
+            tau[j] = 1e10f;
+        } else {
+            qs[j] = qe[j] = 0;
+            qx[j] = qy[j] = qz[j] = 0.f;
+            ld[j] = -1.f;
+            li[j] = 0;
+            tau[j] = -1.f;  // nothing is ever admitted
+        }
+    }
+    __syncthreads();
+    const int lo = s_cta[0], hi = s_cta[1];
+    const bool mixed = s_cta[2] != 0;
+    const int base0 = lo & ~3;
+    const int ntiles = (hi > base0) ? (hi - base0 + TILE_PTS - 1) / TILE_PTS : 0;
+
+    auto tile_is_tma = [&](int t) { return P.use_tma && (base0 + (t + 1) * TILE_PTS <= P.n_total); };
+    auto issue_tma = [&](int t) {
+        int buf = t & 1;
+        mbar_expect_tx(&full_bar[buf], TILE_BYTES);
+        tma_load_1d(buf ? tile1 : tile0, P.xyz + 3 * (size_t)(base0 + t * TILE_PTS), TILE_BYTES, &full_bar[buf]);
+    };
+
+    if (tid == 0 && ntiles > 0 && tile_is_tma(0)) issue_tma(0);
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const float* tile = buf ? tile1 : tile0;
+        const int base = base0 + t * TILE_PTS;
+        if (tile_is_tma(t)) {
+            // prefetch the next tile into the other buffer (its readers finished at the barrier ending iteration t-1)
+            if (tid == 0 && t + 1 < ntiles && tile_is_tma(t + 1)) issue_tma(t + 1);
+            mbar_wait(&full_bar[buf], (t >> 1) & 1);
+        } else {
+            if (tid == 0 && t + 1 < ntiles && tile_is_tma(t + 1)) issue_tma(t + 1);
+            const int npts = min(TILE_PTS, P.n_total - base);
+            float* wt = buf ? tile1 : tile0;
+            const float* src = P.xyz + 3 * (size_t)base;
+            for (int i = tid; i < npts * 3; i += KNN_THREADS) wt[i] = __ldg(src + i);
+            __syncthreads();
+        }
+
+        const int t_lo = max(base, lo) - base;
+        const int t_hi = min(base + TILE_PTS, hi) - base;
+        for (int s = t_lo & ~31; s < t_hi; s += 32) {
+            const int pos = s + lane;
+            const bool inb = (pos >= t_lo) && (pos < t_hi);
+            const float x = tile[3 * pos], y = tile[3 * pos + 1], z = tile[3 * pos + 2];
+            const int gi = base + pos;
+#pragma unroll
+            for (int j = 0; j < QW; ++j) {
+                const float d = sqdist_ref(qx[j] - x, qy[j] - y, qz[j] - z);
+                bool ok = inb;
+                if (mixed) ok = ok && (gi >= qs[j]) && (gi < qe[j]);
+                unsigned mask = __ballot_sync(FULL_MASK, ok && (d < tau[j]));
+                while (mask) {
+                    const int l = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float cd = __shfl_sync(FULL_MASK, d, l);
+                    if (cd < tau[j]) {
+                        const int ci = base + s + l;
+                        const int ins = __popc(__ballot_sync(FULL_MASK, ld[j] <= cd) & kmask);
+                        const float up_d = __shfl_up_sync(FULL_MASK, ld[j], 1);
+                        const int up_i = __shfl_up_sync(FULL_MASK, li[j], 1);
+                        if (lane > ins) { ld[j] = up_d; li[j] = up_i; }
+                        else if (lane == ins) { ld[j] = cd; li[j] = ci; }
+                        tau[j] = __shfl_sync(FULL_MASK, ld[j], K - 1);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with `buf` before it is refilled
+    }
+
+    // ---- epilogue: drop leading columns, PPF per (query, neighbour) lane ----
+    const int kout = K - P.drop;
+#pragma unroll
+    for (int j = 0; j < QW; ++j) {
+        const int q = q_cta0 + warp * QW + j;
+        if (q >= P.m) continue;
+        const int slot = lane - P.drop;
+        if (slot < 0 || lane >= K) continue;
+        const size_t o = (size_t)q * kout + slot;
+        const int nb = li[j];
+        P.idx[o] = nb;
+        if (P.dist) P.dist[o] = P.dist_squared ? ld[j] : __fsqrt_rn(ld[j]);
+        if (P.ppf) {
+            const float n1x = __ldg(P.qnrm + 3 * (size_t)q), n1y = __ldg(P.qnrm + 3 * (size_t)q + 1),
+                        n1z = __ldg(P.qnrm + 3 * (size_t)q + 2);
+            const float px = __ldg(P.xyz + 3 * (size_t)nb), py = __ldg(P.xyz + 3 * (size_t)nb + 1),
+                        pz = __ldg(P.xyz + 3 * (size_t)nb + 2);
+            const float n2x = __ldg(P.nrm + 3 * (size_t)nb), n2y = __ldg(P.nrm + 3 * (size_t)nb + 1),
+                        n2z = __ldg(P.nrm + 3 * (size_t)nb + 2);
+            const float dx = __fsub_rn(px, qx[j]), dy = __fsub_rn(py, qy[j]), dz = __fsub_rn(pz, qz[j]);
+            float4 f;
+            f.x = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            f.y = angle_over_pi(n1x, n1y, n1z, dx, dy, dz);
+            f.z = angle_over_pi(n2x, n2y, n2z, dx, dy, dz);
+            f.w = angle_over_pi(n1x, n1y, n1z, n2x, n2y, n2z);
+            reinterpret_cast<float4*>(P.ppf)[o] = f;
+        }
+    }
+}
+
+int launch_knn(const KnnParams& P, cudaStream_t st) {
+    if (P.m == 0) return ROITR_OK;
+    const int smem = 2 * TILE_BYTES;
+    // many queries: 4 per warp (amortises the shared-memory reads); few queries: 1 per warp (more CTAs in flight)
+    const bool wide = P.m >= 4 * KNN_WARPS * 148 * 2;
+    if (wide) {
+        static bool attr4 = false;
+        if (!attr4) {
+            ROITR_CUDA(cudaFuncSetAttribute(knn_ppf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr4 = true;
+        }
+        knn_ppf_kernel<4><<<ceil_div(P.m, KNN_WARPS * 4), KNN_THREADS, smem, st>>>(P);
+    } else {
+        static bool attr1 = false;
+        if (!attr1) {
+            ROITR_CUDA(cudaFuncSetAttribute(knn_ppf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr1 = true;
+        }
+        knn_ppf_kernel<1><<<ceil_div(P.m, KNN_WARPS), KNN_THREADS, smem, st>>>(P);
+    }
+    ROITR_CHECK_LAUNCH("knn_ppf_kernel");
+    return ROITR_OK;
+}
+
+}  // namespace
+
+// n_total (rows of xyz) is needed on the host to clip the TMA tiles. The reference ABI does not carry it
+// (knnquery_cuda_kernel.h:13): the *_n entry points take it from the caller (no host sync; what the engine uses), the
+// reference-shaped ones read offset[b-1] back (one 4-byte D2H + stream sync, like the reference's own .item() calls).
+static int knn_common(int b, int m, int nslots, int drop, const float* xyz, const float* nrm, const float* qxyz,
+                      const float* qnrm, const int* offset, const int* new_offset, int* idx, float* dist, float* ppf,
+                      int dist_squared, int n_total, void* stream) {
+    ROITR_CHECK_ARG(b >= 1 && m >= 0, "knn: bad b=%d m=%d", b, m);
+    ROITR_CHECK_ARG(nslots >= 1 && nslots <= 32, "knn: nsample(+drop) must be in [1,32], got %d", nslots);
+    ROITR_CHECK_ARG(drop >= 0 && drop < nslots, "knn: bad drop_first=%d", drop);
+    ROITR_CHECK_ARG(xyz && qxyz && offset && new_offset && idx, "knn: null pointer");
+    ROITR_CHECK_ARG(!ppf || (nrm && qnrm), "knn: ppf output needs normals");
+    ROITR_CHECK_ARG(!ppf || ((uintptr_t)ppf % 16 == 0), "knn: ppf must be 16-byte aligned");
+    KnnParams P;
+    P.xyz = xyz; P.nrm = nrm; P.qxyz = qxyz; P.qnrm = qnrm; P.offset = offset; P.new_offset = new_offset;
+    P.b = b; P.m = m; P.nslots = nslots; P.drop = drop; P.idx = idx; P.dist = dist; P.ppf = ppf;
+    P.dist_squared = dist_squared;
+    P.use_tma = (n_total > 0) && ((uintptr_t)xyz % 16 == 0);
+    P.n_total = n_total > 0 ? n_total : 0x7fffffff;
+    return launch_knn(P, (cudaStream_t)stream);
+}
+
+extern "C" int roitr_knnquery_n(int b, int m, int nsample, int n_total, const float* xyz, const float* new_xyz,
+                                const int* offset, const int* new_offset, int* idx, float* dist2, void* stream) {
+    return knn_common(b, m, nsample, 0, xyz, nullptr, new_xyz, nullptr, offset, new_offset, idx, dist2, nullptr, 1,
+                      n_total, stream);
+}
+
+extern "C" int roitr_knnquery(int b, int m, int nsample, const float* xyz, const float* new_xyz, const int* offset,
+                              const int* new_offset, int* idx, float* dist2, void* stream) {
+    // reference ABI: the row count of xyz is not passed. Read it from offset[b-1] (one 4-byte D2H on `stream`).
+    int n_total = 0;
+    ROITR_CHECK_ARG(offset != nullptr && b >= 1, "knnquery: bad offset/b");
+    ROITR_CUDA(cudaMemcpyAsync(&n_total, offset + (b - 1), sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ROITR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return roitr_knnquery_n(b, m, nsample, n_total, xyz, new_xyz, offset, new_offset, idx, dist2, stream);
+}
+
+extern "C" int roitr_knn_ppf_n(int b, int m, int k_out, int drop_first, int n_total, const float* xyz,
+                               const float* normals, const float* new_xyz, const float* new_normals, const int* offset,
+                               const int* new_offset, int* idx, float* dist, float* ppf, void* stream) {
+    return knn_common(b, m, k_out + drop_first, drop_first, xyz, normals, new_xyz, new_normals, offset, new_offset, idx,
+                      dist, ppf, 0, n_total, stream);
+}
+
+extern "C" int roitr_knn_ppf(int b, int m, int k_out, int drop_first, const float* xyz, const float* normals,
+                             const float* new_xyz, const float* new_normals, const int* offset, const int* new_offset,
+                             int* idx, float* dist, float* ppf, void* stream) {
+    int n_total = 0;
+    ROITR_CHECK_ARG(offset != nullptr && b >= 1, "knn_ppf: bad offset/b");
+    ROITR_CUDA(cudaMemcpyAsync(&n_total, offset + (b - 1), sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ROITR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return roitr_knn_ppf_n(b, m, k_out, drop_first, n_total, xyz, normals, new_xyz, new_normals, offset, new_offset, idx,
+                           dist, ppf, stream);
+}

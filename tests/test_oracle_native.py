@@ -65,3 +65,9 @@ def test_native_reproduces_golden_traces():
     assert np.array_equal(torch.sqrt(d2).numpy(), z["knn_0_dist"])
     f = native.fps(pair["src_raw_pcd"], o, torch.tensor([256], dtype=torch.int32))
     assert np.array_equal(f.numpy(), z["fps_0"])
+
+
+def test_reference_block_size_rule_is_integer_log2():
+    # the CUDA FPS kernel derives the reference's block size (src/cuda_utils.h:11-14) with integer arithmetic
+    for n in list(range(1, 5000)) + [2 ** p + d for p in range(12, 17) for d in (-1, 0, 1)]:
+        assert native.fps_block_size(n) == min(1 << (n.bit_length() - 1), 1024), n
