@@ -96,6 +96,116 @@ int roitr_interpolate(int n, int c, int k, const int* idx, const float* dist, co
 int roitr_gather_rows(long long rows, int c, const void* index, int index_is_i64, const float* src, float* out,
                       long long pad_row, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense layers and row epilogues (nn.Linear / nn.LayerNorm / F.relu / F.normalize chains of model/model.py:90-117,
+ * 131-142, model/transformer/attention.py:166-170,317-319, geoattention.py:177-192, model/RIGA_v2.py:64-68).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* C[M,N] = (A [+ a_add])[rows,:K] W[:N,:K]^T + bias (+ReLU). Row-major; lda/ldw/ldc leading dimensions so operands may be
+ * column slices of wider buffers; a_index (int32, M entries) gathers rows of A / a_add; bias, a_add, a_index may be NULL.
+ * fp32 FFMA arithmetic. */
+int roitr_linear(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index, const float* W,
+                 int ldw, const float* bias, float* C, int ldc, int relu, void* stream);
+
+/* out = [L2norm] [ReLU] ( [LayerNorm_{gamma,beta,eps=1e-5}] (x + res_pre[res_pre_index]) + res_post ), one row of C<=1024
+ * floats per warp. mode bits: 1 LayerNorm, 2 ReLU, 4 x / max(|x|_2, 1e-12). Any of the residuals may be NULL. */
+int roitr_row_epilogue(int M, int C, const float* x, const float* res_pre, const int* res_pre_index, const float* gamma,
+                       const float* beta, const float* res_post, float* out, int mode, void* stream);
+
+/* TransitionUp head (model/model.py:101-112): per-segment column mean, and cat(x, repeat(g[segment])) -> (M, 2C). */
+int roitr_segment_mean(int b, int C, const float* x, const int* offset, float* out, void* stream);
+int roitr_concat_segment(int M, int C, int b, const float* x, const float* g, const int* offset, float* out,
+                         void* stream);
+
+/*
+ * Fused local PPF attention: LocalRPEMultiHeadAttention.forward (model/transformer/attention.py:166-200) between the
+ * q/k/v projections and the output linear, with the positional projections folded into (C,4)+(C) maps:
+ *   Ap = W_p W_e, cp = W_p b_e + b_p, Avp = W_vp W_e, cvp = W_vp b_e + b_vp  (W_e,b_e = PPFStructualEmbedding.proj).
+ * q/k/v: (n,C) row-major with leading dims ldq/ldk/ldv (may alias one (n,3C) buffer); node_idx (m) int32 or NULL;
+ * group_idx (m,knb) int32; ppf (m,knb,4); out (m,C). heads = 4, C in {64,128,256,512}, knb in {8,16}.
+ */
+int roitr_local_attention(int m, int C, int heads, int knb, const float* q, int ldq, const float* k, int ldk,
+                          const float* v, int ldv, const int* node_idx, const int* group_idx, const float* ppf,
+                          const float* Ap, const float* cp, const float* Avp, const float* cvp, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Global geometric transformer (model/transformer/positional_encoding.py:94-154, geoattention.py:43-136).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* k nearest superpoints of every superpoint on dist = sqrt(clamp(x2 - 2xy + y2, 0)) (topk(k+1)[1:], :120-124). k = 3. */
+int roitr_geo_knn(int N, int k, const float* pts, int* nn, void* stream);
+
+/* E (N,N,C) = proj_d(sinusoid(dist/sigma_d)) + max_{r<3} proj_a(sinusoid(angle_r * 180/(sigma_a*pi)))
+ * (GeometricStructureEmbedding.forward, :139-154); sinusoids are generated in-kernel. C multiple of 128. */
+int roitr_geo_embedding(int N, int C, const float* pts, const int* nn3, const float* Wd, const float* bd,
+                        const float* Wa, const float* ba, const float* div_term, float sigma_d, float sigma_a, float* E,
+                        void* stream);
+
+/* Attention core. E == NULL: MultiHeadAttention (geoattention.py:50-64) hidden = softmax(q k^T / sqrt(c)) v.
+ * E != NULL (N == M): RPEMultiHeadAttention (geoattention.py:107-134) with gq (N,4,C) = folded positional queries
+ * (gq[n,h,:] = W_p[h*c:(h+1)*c,:]^T q[n,h*c:(h+1)*c]) and bp = proj_p.bias; also G (N,4,C) = sum_m A-_nm E_nm where A- is
+ * the softmax with the diagonal removed (the caller maps G through proj_vp per head). heads = 4, C in {256,512}. */
+int roitr_geo_attention(int N, int M, int C, int heads, const float* q, int ldq, const float* k, int ldk, const float* v,
+                        int ldv, const float* E, const float* gq, const float* bp, float* hidden, float* G, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Matching head (lib/utils.py:428-471, model/modules.py:10-72,135-178,216-324, model/RIGA_v2.py:150-173).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* point_to_node_partition (lib/utils.py:448-463): owner (N) int32 = nearest node (matmul-form distance, clamp 1e-12),
+ * per node the `limit` nearest of its own points ascending (ties: lower index); unfilled slots = N (pad row) with mask 0.
+ * dmin (N) f32 and count (M) int32 are scratch outputs. Masks are bytes (0/1). */
+int roitr_point_to_node(int N, int M, int limit, const float* pts, const float* nodes, int* owner, float* dmin,
+                        int* count, int* knn_idx, unsigned char* knn_mask, unsigned char* node_mask, void* stream);
+
+/* torch.nonzero replacement: ascending flat indices of the non-zero bytes, at most `capacity` written, the true total in
+ * *count (device). chunk_scratch needs roitr_compact_scratch_ints(n) ints. */
+int roitr_compact_flags(long long n, const unsigned char* flags, int* chunk_scratch, int* out, int capacity, int* count,
+                        void* stream);
+long long roitr_compact_scratch_ints(long long n);
+
+/* CoarseMatching.forward (model/modules.py:141-178) on (Mr,C) x (Ms,C) L2-normalised descriptors with validity masks:
+ * exp(-sqdist), dual normalisation, flat top-k (sorted descending). xy = ref @ src^T (Mr,Ms) is supplied by the caller
+ * (roitr_linear). work: Mr*Ms + 2*(Mr+Ms) floats. Outputs padded to k; *out_count = min(k, #valid pairs). k <= 1024. */
+int roitr_coarse_matching(int Mr, int Ms, int C, int k, int dual, const float* ref_feats, const float* src_feats,
+                          const unsigned char* ref_mask, const unsigned char* src_mask, const float* xy, float* work,
+                          int* out_ref, int* out_src, float* out_score, int* out_count, void* stream);
+
+/* One CTA per superpoint correspondence p < *corr_count: gather the two 64-point patches' descriptors, scores =
+ * Ft Fs^T / sqrt(C) (RIGA_v2.py:150-152), LearnableLogOptimalTransport (modules.py:28-68, num_iter Sinkhorn iterations
+ * in shared memory) -> scores (Pmax,65,65); then FineMatching.compute_correspondence_matrix (modules.py:242-274) ->
+ * flags (Pmax,64,64) bytes. */
+int roitr_fine_matching(int Pmax, int Nt, int Ns, int C, const float* tgt_feat, const float* src_feat, const int* tgt_knn,
+                        const int* src_knn, const unsigned char* tgt_kmask, const unsigned char* src_kmask,
+                        const int* corr_t, const int* corr_s, const int* corr_count, const float* alpha, int num_iter,
+                        int topk, int mutual, float threshold, float* scores, unsigned char* flags, void* stream);
+
+/* FineMatching.extract_correspondences (modules.py:276-283) from the compacted flat (p,row,col) indices. */
+int roitr_fine_gather(int capacity, const int* flat, const int* count, const float* scores, const int* corr_t,
+                      const int* corr_s, const int* tgt_knn, const int* src_knn, const float* tgt_pts,
+                      const float* src_pts, float* out_t, float* out_s, float* out_score, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Ground-truth bookkeeping that RIGA_v2.forward runs in test mode too (lib/utils.py:474-614).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* out (N+1,3): [pts ; zero row] (RIGA_v2.py:86-87), optionally mapped through p R^T + t (lib/utils.py:505). */
+int roitr_pad_transform(int N, const float* pts, const float* rot, const float* trans, float* out, void* stream);
+
+/* get_node_occlusion_score tail (lib/utils.py:511-526) given the 1-NN distances of the padded clouds. */
+int roitr_node_occlusion(int M, int K, const int* knn, const unsigned char* kmask, const unsigned char* nmask,
+                         const float* nn_dist, float thr, float* occ, void* stream);
+
+/* get_node_correspondences (lib/utils.py:562-606): dense (Mr,Ms) overlap ratios and >0 flags (compact them with
+ * roitr_compact_flags, then roitr_corr_gather). work: 4*(Mr+Ms) floats. K = 64. */
+int roitr_node_overlaps(int Mr, int Ms, int K, int Nr, int Nsrc, const float* ref_nodes, const float* src_nodes,
+                        const int* ref_knn, const int* src_knn, const unsigned char* ref_kmask,
+                        const unsigned char* src_kmask, const unsigned char* ref_mask, const unsigned char* src_mask,
+                        const float* ref_pts, const float* src_pts, const float* rot, const float* trans, float radius,
+                        float* work, float* overlap, unsigned char* flag, void* stream);
+int roitr_corr_gather(int capacity, int Ms, const int* flat, const int* count, const float* overlap, long long* out_idx,
+                      float* out_ov, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

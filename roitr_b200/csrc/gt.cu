@@ -1,0 +1,222 @@
+// Ground-truth bookkeeping that RIGA_v2.forward also runs in test mode (sm_100a): superpoint occlusion scores and
+// ground-truth superpoint correspondences from (rot, trans). Observable outputs of the forward
+// (gt_node_corr_indices, gt_node_corr_overlaps, gt_{tgt,src}_node_occ; lib/tester.py:64-65 saves the latter).
+//
+// Replaces get_node_occlusion_score (lib/utils.py:474-527) and get_node_correspondences (lib/utils.py:530-614).
+#include <math_constants.h>
+
+#include "../../include/roitr_b200.h"
+#include "common.cuh"
+
+namespace {
+
+struct Rt { float r[9]; float t[3]; };
+
+// torch.matmul(p, rot.T) + trans.T for one point: fma chain over k like the matmul, then the add
+__device__ __forceinline__ void apply_rt(const float* R, const float* t, float x, float y, float z, float* o) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        o[i] = __fadd_rn(fmaf(z, R[3 * i + 2], fmaf(y, R[3 * i + 1], __fmul_rn(x, R[3 * i]))), t[i]);
+}
+
+// out (N+1,3): rows < N = (transformed) points, row N = the zero pad row of RIGA_v2.py:86-87 (transformed too, since the
+// reference transforms the padded array, lib/utils.py:505).
+__global__ void pad_transform_kernel(int N, const float* __restrict__ pts, const float* __restrict__ rot,
+                                     const float* __restrict__ trans, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > N) return;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (i < N) { x = __ldg(pts + 3 * i); y = __ldg(pts + 3 * i + 1); z = __ldg(pts + 3 * i + 2); }
+    float o[3] = {x, y, z};
+    if (rot) {
+        float R[9], t[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = __ldg(rot + k);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = __ldg(trans + k);
+        apply_rt(R, t, x, y, z, o);
+    }
+    out[3 * (size_t)i] = o[0]; out[3 * (size_t)i + 1] = o[1]; out[3 * (size_t)i + 2] = o[2];
+}
+
+// occ[node] = node_mask * sum_j (nn_dist[knn[node,j]] < thr) * kmask / (sum_j kmask + 1e-10)     (lib/utils.py:511-526)
+__global__ void node_occ_kernel(int M, int K, const int* __restrict__ knn, const unsigned char* __restrict__ kmask,
+                                const unsigned char* __restrict__ nmask, const float* __restrict__ nn_dist, float thr,
+                                float* __restrict__ occ) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (node >= M) return;
+    float hit = 0.f, cnt = 0.f;
+    for (int j = lane; j < K; j += 32) {
+        const float mk = kmask[(size_t)node * K + j] ? 1.f : 0.f;
+        const float ov = (__ldg(nn_dist + __ldg(knn + (size_t)node * K + j)) < thr) ? 1.f : 0.f;
+        hit += ov * mk;
+        cnt += mk;
+    }
+    hit = warp_sum(hit); cnt = warp_sum(cnt);
+    if (lane == 0) occ[node] = (hit / (cnt + 1e-10f)) * (nmask[node] ? 1.f : 0.f);
+}
+
+// per node: (optionally transformed) node centre and the radius of its patch: max_j kmask * |p_j - node|  (:573-578)
+__global__ void node_radius_kernel(int M, int K, int N, const float* __restrict__ nodes, const int* __restrict__ knn,
+                                   const unsigned char* __restrict__ kmask, const float* __restrict__ pts,
+                                   const float* __restrict__ rot, const float* __restrict__ trans,
+                                   float* __restrict__ nodes_out, float* __restrict__ radius) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (node >= M) return;
+    float R[9], t[3];
+    if (rot) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = __ldg(rot + k);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = __ldg(trans + k);
+    }
+    float c[3] = {__ldg(nodes + 3 * node), __ldg(nodes + 3 * node + 1), __ldg(nodes + 3 * node + 2)};
+    if (rot) { float o[3]; apply_rt(R, t, c[0], c[1], c[2], o); c[0] = o[0]; c[1] = o[1]; c[2] = o[2]; }
+    float mx = 0.f;
+    for (int j = lane; j < K; j += 32) {
+        if (!kmask[(size_t)node * K + j]) continue;
+        const int pi = __ldg(knn + (size_t)node * K + j);
+        float p[3] = {0.f, 0.f, 0.f};
+        if (pi < N) { p[0] = __ldg(pts + 3 * (size_t)pi); p[1] = __ldg(pts + 3 * (size_t)pi + 1); p[2] = __ldg(pts + 3 * (size_t)pi + 2); }
+        if (rot) { float o[3]; apply_rt(R, t, p[0], p[1], p[2], o); p[0] = o[0]; p[1] = o[1]; p[2] = o[2]; }
+        const float dx = __fsub_rn(p[0], c[0]), dy = __fsub_rn(p[1], c[1]), dz = __fsub_rn(p[2], c[2]);
+        mx = fmaxf(mx, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+    }
+    mx = warp_max(mx);
+    if (lane == 0) {
+        radius[node] = mx;
+        nodes_out[3 * node] = c[0]; nodes_out[3 * node + 1] = c[1]; nodes_out[3 * node + 2] = c[2];
+    }
+}
+
+__device__ __forceinline__ float sqd_mm(const float* a, const float* b) {  // square_distance, lib/utils.py:139-156
+    const float xy = fmaf(a[2], b[2], fmaf(a[1], b[1], __fmul_rn(a[0], b[0])));
+    const float a2 = __fadd_rn(__fadd_rn(__fmul_rn(a[0], a[0]), __fmul_rn(a[1], a[1])), __fmul_rn(a[2], a[2]));
+    const float b2 = __fadd_rn(__fadd_rn(__fmul_rn(b[0], b[0]), __fmul_rn(b[1], b[1])), __fmul_rn(b[2], b[2]));
+    return fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(-2.0f, xy), a2), b2), 1e-12f);
+}
+
+// one CTA (64 threads) per (ref node i, src node j): enclosing-sphere prefilter, then the 64x64 point test (:580-606)
+__global__ void __launch_bounds__(64) node_overlap_kernel(int Mr, int Ms, int K, int Nr, int Nsrc,
+                                                          const float* __restrict__ rnodes, const float* __restrict__ snodes_t,
+                                                          const float* __restrict__ rrad, const float* __restrict__ srad,
+                                                          const unsigned char* __restrict__ rmask, const unsigned char* __restrict__ smask,
+                                                          const int* __restrict__ rknn, const int* __restrict__ sknn,
+                                                          const unsigned char* __restrict__ rkmask, const unsigned char* __restrict__ skmask,
+                                                          const float* __restrict__ rpts, const float* __restrict__ spts,
+                                                          const float* __restrict__ rot, const float* __restrict__ trans,
+                                                          float radius, float radius2, float* __restrict__ overlap,
+                                                          unsigned char* __restrict__ flag) {
+    const int i = blockIdx.y, j = blockIdx.x, tid = threadIdx.x;
+    const size_t e = (size_t)i * Ms + j;
+    bool go = rmask[i] && smask[j];
+    if (go) {
+        float a[3] = {__ldg(rnodes + 3 * i), __ldg(rnodes + 3 * i + 1), __ldg(rnodes + 3 * i + 2)};
+        float b[3] = {__ldg(snodes_t + 3 * j), __ldg(snodes_t + 3 * j + 1), __ldg(snodes_t + 3 * j + 2)};
+        const float d = __fsqrt_rn(sqd_mm(a, b));
+        go = __fsub_rn(__fadd_rn(__fadd_rn(__ldg(rrad + i), __ldg(srad + j)), radius), d) > 0.f;
+    }
+    if (!go) { if (tid == 0) { overlap[e] = 0.f; flag[e] = 0; } return; }
+    __shared__ float sp[64][3];
+    __shared__ unsigned char sok[64], colhit[64], rowhit[64];
+    {
+        float R[9], t[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = __ldg(rot + k);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = __ldg(trans + k);
+        const int pi = __ldg(sknn + (size_t)j * K + tid);
+        float p[3] = {0.f, 0.f, 0.f};
+        if (pi < Nsrc) { p[0] = __ldg(spts + 3 * (size_t)pi); p[1] = __ldg(spts + 3 * (size_t)pi + 1); p[2] = __ldg(spts + 3 * (size_t)pi + 2); }
+        float o[3];
+        apply_rt(R, t, p[0], p[1], p[2], o);
+        sp[tid][0] = o[0]; sp[tid][1] = o[1]; sp[tid][2] = o[2];
+        sok[tid] = skmask[(size_t)j * K + tid];
+        colhit[tid] = 0;
+    }
+    __syncthreads();
+    const bool rok = rkmask[(size_t)i * K + tid];
+    const int ri = __ldg(rknn + (size_t)i * K + tid);
+    float a[3] = {0.f, 0.f, 0.f};
+    if (ri < Nr) { a[0] = __ldg(rpts + 3 * (size_t)ri); a[1] = __ldg(rpts + 3 * (size_t)ri + 1); a[2] = __ldg(rpts + 3 * (size_t)ri + 2); }
+    bool any = false;
+    if (rok)
+        for (int c = 0; c < 64; ++c) {
+            if (!sok[c]) continue;
+            if (sqd_mm(a, sp[c]) < radius2) { any = true; colhit[c] = 1; }
+        }
+    rowhit[tid] = any;
+    __syncthreads();
+    if (tid == 0) {
+        int rc = 0, sc = 0, rn = 0, sn = 0;
+        for (int c = 0; c < 64; ++c) { rc += rowhit[c]; sc += colhit[c]; sn += sok[c]; rn += rkmask[(size_t)i * K + c]; }
+        const float ov = __fdiv_rn(__fadd_rn(__fdiv_rn((float)rc, (float)rn), __fdiv_rn((float)sc, (float)sn)), 2.0f);
+        overlap[e] = ov;
+        flag[e] = ov > 0.f;
+    }
+}
+
+__global__ void corr_gather_kernel(const int* __restrict__ flat, const int* __restrict__ count, int capacity, int Ms,
+                                   const float* __restrict__ overlap, long long* __restrict__ out_idx,
+                                   float* __restrict__ out_ov) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(__ldg(count), capacity)) return;
+    const int f = __ldg(flat + i);
+    out_idx[2 * (size_t)i] = f / Ms;
+    out_idx[2 * (size_t)i + 1] = f % Ms;
+    out_ov[i] = __ldg(overlap + f);
+}
+
+}  // namespace
+
+extern "C" int roitr_pad_transform(int N, const float* pts, const float* rot, const float* trans, float* out,
+                                   void* stream) {
+    ROITR_CHECK_ARG(N >= 0 && pts && out && (!rot || trans), "pad_transform: bad arguments");
+    pad_transform_kernel<<<ceil_div(N + 1, 256), 256, 0, (cudaStream_t)stream>>>(N, pts, rot, trans, out);
+    ROITR_CHECK_LAUNCH("pad_transform_kernel");
+    return ROITR_OK;
+}
+
+extern "C" int roitr_node_occlusion(int M, int K, const int* knn, const unsigned char* kmask, const unsigned char* nmask,
+                                    const float* nn_dist, float thr, float* occ, void* stream) {
+    ROITR_CHECK_ARG(M >= 1 && K >= 1 && knn && kmask && nmask && nn_dist && occ, "node_occlusion: bad arguments");
+    node_occ_kernel<<<ceil_div(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(M, K, knn, kmask, nmask, nn_dist, thr, occ);
+    ROITR_CHECK_LAUNCH("node_occ_kernel");
+    return ROITR_OK;
+}
+
+extern "C" int roitr_node_overlaps(int Mr, int Ms, int K, int Nr, int Nsrc, const float* ref_nodes,
+                                   const float* src_nodes, const int* ref_knn, const int* src_knn,
+                                   const unsigned char* ref_kmask, const unsigned char* src_kmask,
+                                   const unsigned char* ref_mask, const unsigned char* src_mask, const float* ref_pts,
+                                   const float* src_pts, const float* rot, const float* trans, float radius,
+                                   float* work, float* overlap, unsigned char* flag, void* stream) {
+    // work: 4*Ms + Mr + 3*Mr floats
+    ROITR_CHECK_ARG(K == 64, "node_overlaps: point_per_patch must be 64, got %d", K);
+    ROITR_CHECK_ARG(ref_nodes && src_nodes && ref_knn && src_knn && rot && trans && work && overlap && flag, "node_overlaps: null");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* snodes_t = work;
+    float* srad = snodes_t + 3 * (size_t)Ms;
+    float* rnodes_c = srad + Ms;
+    float* rrad = rnodes_c + 3 * (size_t)Mr;
+    node_radius_kernel<<<ceil_div(Mr * 32, 256), 256, 0, st>>>(Mr, K, Nr, ref_nodes, ref_knn, ref_kmask, ref_pts, nullptr,
+                                                              nullptr, rnodes_c, rrad);
+    node_radius_kernel<<<ceil_div(Ms * 32, 256), 256, 0, st>>>(Ms, K, Nsrc, src_nodes, src_knn, src_kmask, src_pts, rot,
+                                                              trans, snodes_t, srad);
+    const double r2 = (double)radius * (double)radius;  // pos_radius ** 2 in double, then cast (lib/utils.py:597)
+    dim3 grid(Ms, Mr);
+    node_overlap_kernel<<<grid, 64, 0, st>>>(Mr, Ms, K, Nr, Nsrc, rnodes_c, snodes_t, rrad, srad, ref_mask, src_mask,
+                                             ref_knn, src_knn, ref_kmask, src_kmask, ref_pts, src_pts, rot, trans,
+                                             radius, (float)r2, overlap, flag);
+    ROITR_CHECK_LAUNCH("node_overlap_kernel");
+    return ROITR_OK;
+}
+
+extern "C" int roitr_corr_gather(int capacity, int Ms, const int* flat, const int* count, const float* overlap,
+                                 long long* out_idx, float* out_ov, void* stream) {
+    if (capacity == 0) return ROITR_OK;
+    corr_gather_kernel<<<ceil_div(capacity, 256), 256, 0, (cudaStream_t)stream>>>(flat, count, capacity, Ms, overlap,
+                                                                                  out_idx, out_ov);
+    ROITR_CHECK_LAUNCH("corr_gather_kernel");
+    return ROITR_OK;
+}

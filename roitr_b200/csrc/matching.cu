@@ -1,0 +1,651 @@
+// Coarse-to-fine matching head (sm_100a): point-to-node partition, coarse superpoint matching, fused fine scoring +
+// log-domain Sinkhorn optimal transport + mutual top-k, and the ordered compaction that replaces torch.nonzero.
+//
+// Replaces point_to_node_partition (lib/utils.py:428-471), CoarseMatching.forward (model/modules.py:141-178),
+// the einsum + LearnableLogOptimalTransport.forward (model/RIGA_v2.py:150-153, modules.py:21-68) and
+// FineMatching.forward (modules.py:242-324).
+#include <math_constants.h>
+
+#include "../../include/roitr_b200.h"
+#include "common.cuh"
+
+namespace {
+
+// square_distance(a, b) of lib/utils.py:139-156 for one pair given the matmul term xy: clamp((-2 xy + |a|^2) + |b|^2, 1e-12)
+__device__ __forceinline__ float sqdist_matmul_form(float xy, float a2, float b2) {
+    return fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(-2.0f, xy), a2), b2), 1e-12f);
+}
+__device__ __forceinline__ float sumsq3(float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// ------------------------------------------------------------------------------------------------ partition
+// owner[p] = argmin_nodes d(node, p) (first minimum), dmin[p] = that distance, count[node]++.
+__global__ void point_owner_kernel(int N, int M, const float* __restrict__ pts, const float* __restrict__ nodes,
+                                   int* __restrict__ owner, float* __restrict__ dmin, int* __restrict__ count) {
+    extern __shared__ float sn[];  // M x 4: x, y, z, |n|^2
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const float x = __ldg(nodes + 3 * i), y = __ldg(nodes + 3 * i + 1), z = __ldg(nodes + 3 * i + 2);
+        sn[4 * i] = x; sn[4 * i + 1] = y; sn[4 * i + 2] = z; sn[4 * i + 3] = sumsq3(x, y, z);
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const float px = __ldg(pts + 3 * p), py = __ldg(pts + 3 * p + 1), pz = __ldg(pts + 3 * p + 2);
+    const float p2 = sumsq3(px, py, pz);
+    float best = CUDART_INF_F;
+    int bi = 0;
+    for (int i = 0; i < M; ++i) {
+        const float4 nd = *reinterpret_cast<const float4*>(sn + 4 * i);
+        const float xy = fmaf(nd.z, pz, fmaf(nd.y, py, __fmul_rn(nd.x, px)));
+        const float d = sqdist_matmul_form(xy, nd.w, p2);
+        if (d < best) { best = d; bi = i; }
+    }
+    owner[p] = bi;
+    dmin[p] = best;
+    atomicAdd(count + bi, 1);
+}
+
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* a, int n, int tid, int nthreads) {
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n; i += nthreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = a[i], y = a[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// per node: its own points sorted by (distance, index), first `limit` kept (topk(k=limit, largest=False), :459);
+// remaining slots = N (the pad row) with mask false.
+constexpr int PART_CAP = 4096;
+__global__ void __launch_bounds__(256) node_knn_kernel(int N, int M, int limit, const int* __restrict__ owner,
+                                                       const float* __restrict__ dmin, const int* __restrict__ count,
+                                                       int* __restrict__ knn_idx, unsigned char* __restrict__ knn_mask,
+                                                       unsigned char* __restrict__ node_mask) {
+    __shared__ unsigned long long keys[PART_CAP];
+    __shared__ int s_n;
+    const int node = blockIdx.x, tid = threadIdx.x;
+    const int cnt = __ldg(count + node);
+    if (tid == 0) { s_n = 0; node_mask[node] = cnt > 0; }
+    __syncthreads();
+    if (cnt <= PART_CAP) {
+        for (int p = tid; p < N; p += blockDim.x)
+            if (__ldg(owner + p) == node) {
+                const int slot = atomicAdd(&s_n, 1);
+                keys[slot] = ((unsigned long long)__float_as_uint(__ldg(dmin + p)) << 32) | (unsigned)p;
+            }
+        __syncthreads();
+        int n2 = 64;
+        while (n2 < cnt) n2 <<= 1;
+        for (int i = cnt + tid; i < n2; i += blockDim.x) keys[i] = ~0ull;
+        __syncthreads();
+        bitonic_sort_u64(keys, n2, tid, blockDim.x);
+        for (int j = tid; j < limit; j += blockDim.x) {
+            const bool ok = j < cnt;
+            knn_idx[(size_t)node * limit + j] = ok ? (int)(keys[j] & 0xffffffffu) : N;
+            knn_mask[(size_t)node * limit + j] = ok;
+        }
+    } else {
+        // pathological node owning more than PART_CAP points: `limit` rounds of "smallest key greater than the last"
+        __shared__ unsigned long long red[256];
+        unsigned long long last = 0ull;
+        bool first = true;
+        for (int j = 0; j < limit; ++j) {
+            unsigned long long best = ~0ull;
+            for (int p = tid; p < N; p += blockDim.x)
+                if (__ldg(owner + p) == node) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(__ldg(dmin + p)) << 32) | (unsigned)p;
+                    if ((first || key > last) && key < best) best = key;
+                }
+            red[tid] = best;
+            __syncthreads();
+            for (int s = 128; s > 0; s >>= 1) {
+                if (tid < s && red[tid + s] < red[tid]) red[tid] = red[tid + s];
+                __syncthreads();
+            }
+            last = red[0];
+            first = false;
+            __syncthreads();
+            if (tid == 0) {
+                knn_idx[(size_t)node * limit + j] = (int)(last & 0xffffffffu);
+                knn_mask[(size_t)node * limit + j] = 1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ ordered compaction
+// out = flat indices of the non-zero flags in ascending order (torch.nonzero order). Three passes.
+constexpr int CMP_CHUNK = 2048;
+__global__ void compact_count_kernel(long long n, const unsigned char* __restrict__ flags, int* __restrict__ chunk_count) {
+    const long long base = (long long)blockIdx.x * CMP_CHUNK;
+    int c = 0;
+    for (int i = threadIdx.x; i < CMP_CHUNK; i += blockDim.x)
+        if (base + i < n && flags[base + i]) ++c;
+    c = __reduce_add_sync(FULL_MASK, c);
+    __shared__ int ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += ws[w];
+        chunk_count[blockIdx.x] = t;
+    }
+}
+__global__ void compact_scan_kernel(int nchunks, int* __restrict__ chunk_count, int* __restrict__ total) {
+    // single CTA exclusive scan (nchunks is small: n / 2048)
+    __shared__ int carry;
+    __shared__ int buf[1024];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nchunks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nchunks ? chunk_count[i] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nchunks) chunk_count[i] = carry + buf[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += buf[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void compact_write_kernel(long long n, const unsigned char* __restrict__ flags,
+                                     const int* __restrict__ chunk_offset, int* __restrict__ out, int capacity) {
+    // 256 threads, each owns 8 consecutive flags of the chunk -> order preserved
+    const long long base = (long long)blockIdx.x * CMP_CHUNK + threadIdx.x * 8;
+    int c = 0;
+    unsigned bits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (base + i < n && flags[base + i]) { bits |= 1u << i; ++c; }
+    __shared__ int sc[256];
+    sc[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int t = threadIdx.x >= o ? sc[threadIdx.x - o] : 0;
+        __syncthreads();
+        sc[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int pos = chunk_offset[blockIdx.x] + sc[threadIdx.x] - c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (bits & (1u << i)) {
+            if (pos < capacity) out[pos] = (int)(base + i);
+            ++pos;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ coarse matching
+__global__ void row_sqnorm_kernel(int M, int C, const float* __restrict__ f, float* __restrict__ out) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = __ldg(f + (size_t)row * C + c); s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+}
+// s_ij = exp(-sqdist) on valid (i,j), else 0; one CTA per row, also the row sum (modules.py:163)
+__global__ void coarse_exp_kernel(int Mr, int Ms, const float* __restrict__ xy, const float* __restrict__ r2,
+                                  const float* __restrict__ s2, const unsigned char* __restrict__ rmask,
+                                  const unsigned char* __restrict__ smask, float* __restrict__ S,
+                                  float* __restrict__ rowsum) {
+    const int i = blockIdx.x;
+    __shared__ float red[8];
+    float acc = 0.f;
+    const bool rv = rmask[i];
+    for (int j = threadIdx.x; j < Ms; j += blockDim.x) {
+        float v = 0.f;
+        if (rv && smask[j]) v = expf(-sqdist_matmul_form(__ldg(xy + (size_t)i * Ms + j), __ldg(r2 + i), __ldg(s2 + j)));
+        S[(size_t)i * Ms + j] = v;
+        acc += v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        rowsum[i] = t;
+    }
+}
+__global__ void col_sum_kernel(int Mr, int Ms, const float* __restrict__ S, float* __restrict__ colsum) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Ms) return;
+    float t = 0.f;
+    for (int i = 0; i < Mr; ++i) t += __ldg(S + (size_t)i * Ms + j);
+    colsum[j] = t;
+}
+// dual normalisation (modules.py:166-169); invalid entries get -1 so they are never selected
+__global__ void coarse_dualnorm_kernel(int Mr, int Ms, float* __restrict__ S, const float* __restrict__ rowsum,
+                                       const float* __restrict__ colsum, const unsigned char* __restrict__ rmask,
+                                       const unsigned char* __restrict__ smask, int dual) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)Mr * Ms) return;
+    const int i = (int)(e / Ms), j = (int)(e % Ms);
+    if (!(rmask[i] && smask[j])) { S[e] = -1.f; return; }
+    const float s = S[e];
+    if (dual) S[e] = __fmul_rn(__fdiv_rn(s, __fadd_rn(rowsum[i], 1e-8f)), __fdiv_rn(s, __fadd_rn(colsum[j], 1e-8f)));
+}
+
+// Flat top-k (largest, sorted descending; ties by ascending flat index) of n floats >= 0 (entries < 0 are excluded),
+// single CTA of 1024 threads: 4 x 8-bit radix-select passes for the k-th value, collect, bitonic sort.
+constexpr int TOPK_MAX = 1024;
+__global__ void __launch_bounds__(1024) flat_topk_kernel(int n, int k, const float* __restrict__ v, int row_len,
+                                                         int* __restrict__ out_row, int* __restrict__ out_col,
+                                                         float* __restrict__ out_val, int* __restrict__ out_count) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_remaining;
+    __shared__ int s_valid, s_cnt;
+    __shared__ unsigned long long keys[TOPK_MAX];
+    const int tid = threadIdx.x;
+    // number of candidates
+    if (tid == 0) { s_valid = 0; s_cnt = 0; }
+    __syncthreads();
+    int c = 0;
+    for (int i = tid; i < n; i += blockDim.x) c += (__ldg(v + i) >= 0.f);
+    atomicAdd(&s_valid, c);
+    __syncthreads();
+    const int kk = min(k, s_valid);
+    if (kk == 0) { if (tid == 0) *out_count = 0; return; }
+    // radix select the kk-th largest bit pattern
+    if (tid == 0) { s_prefix = 0; s_remaining = (unsigned)kk; }
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        const unsigned himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < n; i += blockDim.x) {
+            const float f = __ldg(v + i);
+            if (f < 0.f) continue;
+            const unsigned b = __float_as_uint(f);
+            if ((b & himask) == (prefix & himask)) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned rem = s_remaining;
+            int d = 255;
+            for (; d > 0; --d) {
+                if (hist[d] >= rem) break;
+                rem -= hist[d];
+            }
+            s_prefix = prefix | ((unsigned)d << shift);
+            s_remaining = rem;
+        }
+        __syncthreads();
+    }
+    const unsigned pivot = s_prefix;      // bit pattern of the kk-th largest value
+    const unsigned need_eq = s_remaining; // how many entries equal to the pivot are taken (lowest flat index first)
+    // entries strictly greater than the pivot
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float f = __ldg(v + i);
+        if (f >= 0.f && __float_as_uint(f) > pivot) {
+            const int s = atomicAdd(&s_cnt, 1);
+            keys[s] = ((unsigned long long)(~__float_as_uint(f)) << 32) | (unsigned)i;  // ascending sort == descending value
+        }
+    }
+    __syncthreads();
+    // entries equal to the pivot: lowest flat indices first. Collect them in parallel (ties are rare), sort by index.
+    __shared__ unsigned eq_idx[TOPK_MAX];
+    __shared__ int s_eq;
+    if (tid == 0) s_eq = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float f = __ldg(v + i);
+        if (f >= 0.f && __float_as_uint(f) == pivot) {
+            const int s = atomicAdd(&s_eq, 1);
+            if (s < TOPK_MAX) eq_idx[s] = (unsigned)i;
+        }
+    }
+    __syncthreads();
+    const int base_cnt = s_cnt;
+    if (s_eq <= TOPK_MAX) {
+        // small odd-even transposition sort by index (s_eq is almost always 1)
+        const int ne = s_eq;
+        for (int round = 0; round < ne; ++round) {
+            for (int i = 2 * tid + (round & 1); i + 1 < ne; i += 2 * blockDim.x)
+                if (eq_idx[i] > eq_idx[i + 1]) { const unsigned t = eq_idx[i]; eq_idx[i] = eq_idx[i + 1]; eq_idx[i + 1] = t; }
+            __syncthreads();
+        }
+        for (int t = tid; t < (int)need_eq; t += blockDim.x)
+            keys[base_cnt + t] = ((unsigned long long)(~pivot) << 32) | eq_idx[t];
+    } else if (tid == 0) {  // massive ties (e.g. constant scores): sequential walk in index order
+        unsigned taken = 0;
+        for (int i = 0; i < n && taken < need_eq; ++i)
+            if (__ldg(v + i) >= 0.f && __float_as_uint(__ldg(v + i)) == pivot) {
+                keys[base_cnt + taken] = ((unsigned long long)(~pivot) << 32) | (unsigned)i;
+                ++taken;
+            }
+    }
+    __syncthreads();
+    int n2 = 2;
+    while (n2 < kk) n2 <<= 1;
+    for (int i = kk + tid; i < n2; i += blockDim.x) keys[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(keys, n2, tid, blockDim.x);
+    for (int j = tid; j < kk; j += blockDim.x) {
+        const int flat = (int)(keys[j] & 0xffffffffu);
+        out_row[j] = flat / row_len;
+        out_col[j] = flat % row_len;
+        out_val[j] = __uint_as_float(~(unsigned)(keys[j] >> 32));
+    }
+    if (tid == 0) *out_count = kk;
+}
+
+// ------------------------------------------------------------------------------------------------ fine matching
+// One CTA per superpoint correspondence p: gather the two 64-point patches' descriptors, S = Ft Fs^T / sqrt(C),
+// 100 log-Sinkhorn iterations with the 65x65 matrix resident in shared memory, write the (65,65) log-assignment,
+// then exp / mutual top-k / threshold / validity -> match flags.
+struct FineParams {
+    const float* tgt_feat; const float* src_feat;      // (Nt, C), (Ns, C) fine descriptors
+    int Nt, Ns, C;
+    const int* tgt_knn; const int* src_knn;            // (Mt, 64), (Ms, 64) int32, pad = Nt / Ns
+    const unsigned char* tgt_kmask; const unsigned char* src_kmask;
+    const int* corr_t; const int* corr_s; const int* corr_count;   // (Pmax) node pairs, device count
+    const float* alpha;
+    float* scores;               // (Pmax, 65, 65)
+    unsigned char* flags;        // (Pmax, 64, 64)
+    int num_iter, topk, mutual;
+    float threshold, sqrt_c;
+};
+
+constexpr int FP = 64, FP1 = 65;
+
+__device__ __forceinline__ float warp_lse3(float x0, float x1, float x2) {
+    // logsumexp over the values spread across the warp (x* = -inf for absent slots), torch.logsumexp semantics
+    float mx = warp_max(fmaxf(fmaxf(x0, x1), x2));
+    const float m0 = (mx == CUDART_INF_F || mx == -CUDART_INF_F) ? 0.f : mx;
+    float s = expf(x0 - m0) + expf(x1 - m0) + expf(x2 - m0);
+    s = warp_sum(s);
+    return logf(s) + m0;
+}
+
+__global__ void __launch_bounds__(256) fine_patch_kernel(const FineParams P) {
+    __shared__ float Z[FP1 * FP1];
+    __shared__ __align__(16) float At[32][FP + 4];
+    __shared__ __align__(16) float Bs[32][FP + 4];
+    __shared__ float u[FP1], v[FP1], log_mu[FP1], log_nu[FP1];
+    __shared__ int t_idx[FP], s_idx[FP];
+    __shared__ unsigned char t_ok[FP], s_ok[FP];
+    __shared__ unsigned char rowf[FP * FP];
+    __shared__ float s_norm;
+
+    const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (p >= __ldg(P.corr_count)) return;
+    const int nt = __ldg(P.corr_t + p), ns = __ldg(P.corr_s + p);
+    if (tid < FP) {
+        t_idx[tid] = __ldg(P.tgt_knn + (size_t)nt * FP + tid);
+        t_ok[tid] = P.tgt_kmask[(size_t)nt * FP + tid];
+    } else if (tid < 2 * FP) {
+        s_idx[tid - FP] = __ldg(P.src_knn + (size_t)ns * FP + tid - FP);
+        s_ok[tid - FP] = P.src_kmask[(size_t)ns * FP + tid - FP];
+    }
+    __syncthreads();
+
+    // ---- 64 x 64 x C scores (rows = tgt patch points, cols = src patch points) ----
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lrow = tid >> 2, lk = (tid & 3) * 8;
+    const int ti = t_idx[lrow], si = s_idx[lrow];
+    for (int k0 = 0; k0 < P.C; k0 += 32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (ti < P.Nt) a = __ldg(reinterpret_cast<const float4*>(P.tgt_feat + (size_t)ti * P.C + k0 + lk) + h);
+            if (si < P.Ns) b = __ldg(reinterpret_cast<const float4*>(P.src_feat + (size_t)si * P.C + k0 + lk) + h);
+            At[lk + 4 * h][lrow] = a.x; At[lk + 4 * h + 1][lrow] = a.y; At[lk + 4 * h + 2][lrow] = a.z; At[lk + 4 * h + 3][lrow] = a.w;
+            Bs[lk + 4 * h][lrow] = b.x; Bs[lk + 4 * h + 1][lrow] = b.y; Bs[lk + 4 * h + 2][lrow] = b.z; Bs[lk + 4 * h + 3][lrow] = b.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&At[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    // ---- padded, masked score matrix (modules.py:36-46) and marginals (:48-60) ----
+    const float alpha = __ldg(P.alpha);
+    const float NEG = -1e6f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = ty * 4 + i, c = tx * 4 + j;
+            Z[r * FP1 + c] = (t_ok[r] && s_ok[c]) ? __fdiv_rn(acc[i][j], P.sqrt_c) : NEG;
+        }
+    if (tid < FP) {
+        Z[tid * FP1 + FP] = t_ok[tid] ? alpha : NEG;   // dustbin column
+        Z[FP * FP1 + tid] = s_ok[tid] ? alpha : NEG;   // dustbin row
+    }
+    if (tid == 0) {
+        Z[FP * FP1 + FP] = alpha;
+        int nr = 0, nc = 0;
+        for (int i = 0; i < FP; ++i) { nr += t_ok[i]; nc += s_ok[i]; }
+        const float norm = -logf((float)nr + (float)nc);
+        s_norm = norm;
+        log_mu[FP] = logf((float)nc) + norm;
+        log_nu[FP] = logf((float)nr) + norm;
+    }
+    __syncthreads();
+    if (tid < FP) {
+        log_mu[tid] = t_ok[tid] ? s_norm : NEG;
+        log_nu[tid] = s_ok[tid] ? s_norm : NEG;
+    }
+    if (tid < FP1) { u[tid] = 0.f; v[tid] = 0.f; }
+    __syncthreads();
+    // ---- log-domain Sinkhorn (modules.py:21-26) ----
+    for (int it = 0; it < P.num_iter; ++it) {
+        for (int i = warp; i < FP1; i += 8) {   // u = log_mu - LSE_j(Z + v)
+            const float x0 = Z[i * FP1 + lane] + v[lane];
+            const float x1 = Z[i * FP1 + lane + 32] + v[lane + 32];
+            const float x2 = (lane == 0) ? Z[i * FP1 + 64] + v[64] : -CUDART_INF_F;
+            const float l = warp_lse3(x0, x1, x2);
+            if (lane == 0) u[i] = log_mu[i] - l;
+        }
+        __syncthreads();
+        for (int j = warp; j < FP1; j += 8) {   // v = log_nu - LSE_i(Z + u)
+            const float x0 = Z[lane * FP1 + j] + u[lane];
+            const float x1 = Z[(lane + 32) * FP1 + j] + u[lane + 32];
+            const float x2 = (lane == 0) ? Z[64 * FP1 + j] + u[64] : -CUDART_INF_F;
+            const float l = warp_lse3(x0, x1, x2);
+            if (lane == 0) v[j] = log_nu[j] - l;
+        }
+        __syncthreads();
+    }
+    // ---- output (P,65,65) log-assignment; keep it in Z for the matching step ----
+    float* out = P.scores + (size_t)p * FP1 * FP1;
+    for (int e = tid; e < FP1 * FP1; e += 256) {
+        const int r = e / FP1, c = e % FP1;
+        const float val = Z[e] + u[r] + v[c] - s_norm;
+        Z[e] = val;
+        out[e] = val;
+    }
+    __syncthreads();
+    // ---- FineMatching (modules.py:242-274): exp, top-k along rows and columns, threshold, mutual, validity ----
+    for (int e = tid; e < FP * FP; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        Z[r * FP1 + c] = expf(Z[r * FP1 + c]);
+        rowf[e] = 0;
+    }
+    __syncthreads();
+    // row-wise top-k: warp per row, each lane holds columns lane and lane+32; ties -> lower index
+    for (int r = warp; r < FP; r += 8) {
+        float a0 = Z[r * FP1 + lane], a1 = Z[r * FP1 + lane + 32];
+        for (int t = 0; t < P.topk; ++t) {
+            float bv = a0 >= a1 ? a0 : a1;
+            int bi = a0 >= a1 ? lane : lane + 32;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL_MASK, bv, o);
+                const int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (bi == lane) a0 = -CUDART_INF_F;
+            if (bi == lane + 32) a1 = -CUDART_INF_F;
+            if (lane == 0 && bv > P.threshold) rowf[r * FP + bi] = 1;
+        }
+    }
+    __syncthreads();
+    unsigned char* fl = P.flags + (size_t)p * FP * FP;
+    for (int c = warp; c < FP; c += 8) {
+        float a0 = Z[lane * FP1 + c], a1 = Z[(lane + 32) * FP1 + c];
+        unsigned colsel0 = 0, colsel1 = 0;  // whether my rows were selected by the column top-k
+        for (int t = 0; t < P.topk; ++t) {
+            float bv = a0 >= a1 ? a0 : a1;
+            int bi = a0 >= a1 ? lane : lane + 32;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL_MASK, bv, o);
+                const int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (bi == lane) { a0 = -CUDART_INF_F; colsel0 = bv > P.threshold; }
+            if (bi == lane + 32) { a1 = -CUDART_INF_F; colsel1 = bv > P.threshold; }
+        }
+        const bool r0 = rowf[lane * FP + c], r1 = rowf[(lane + 32) * FP + c];
+        const bool m0 = (P.mutual ? (r0 && colsel0) : (r0 || colsel0)) && t_ok[lane] && s_ok[c];
+        const bool m1 = (P.mutual ? (r1 && colsel1) : (r1 || colsel1)) && t_ok[lane + 32] && s_ok[c];
+        fl[lane * FP + c] = m0;
+        fl[(lane + 32) * FP + c] = m1;
+    }
+}
+
+// gather the final correspondences from the compacted flat indices (modules.py:276-283)
+__global__ void fine_gather_kernel(const int* __restrict__ flat, const int* __restrict__ count, int capacity,
+                                   const float* __restrict__ scores, const int* __restrict__ corr_t,
+                                   const int* __restrict__ corr_s, const int* __restrict__ tgt_knn,
+                                   const int* __restrict__ src_knn, const float* __restrict__ tgt_pts,
+                                   const float* __restrict__ src_pts, float* __restrict__ out_t,
+                                   float* __restrict__ out_s, float* __restrict__ out_score) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(__ldg(count), capacity);
+    if (i >= n) return;
+    const int f = __ldg(flat + i);
+    const int p = f >> 12, r = (f >> 6) & 63, c = f & 63;
+    const int pt = __ldg(tgt_knn + (size_t)__ldg(corr_t + p) * FP + r);
+    const int ps = __ldg(src_knn + (size_t)__ldg(corr_s + p) * FP + c);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        out_t[3 * (size_t)i + d] = __ldg(tgt_pts + 3 * (size_t)pt + d);
+        out_s[3 * (size_t)i + d] = __ldg(src_pts + 3 * (size_t)ps + d);
+    }
+    out_score[i] = expf(__ldg(scores + (size_t)p * FP1 * FP1 + r * FP1 + c));
+}
+
+}  // namespace
+
+extern "C" int roitr_point_to_node(int N, int M, int limit, const float* pts, const float* nodes, int* owner,
+                                   float* dmin, int* count, int* knn_idx, unsigned char* knn_mask,
+                                   unsigned char* node_mask, void* stream) {
+    ROITR_CHECK_ARG(N >= 1 && M >= 1 && limit >= 1 && limit <= PART_CAP, "point_to_node: bad sizes");
+    ROITR_CHECK_ARG(pts && nodes && owner && dmin && count && knn_idx && knn_mask && node_mask, "point_to_node: null");
+    ROITR_CHECK_ARG((size_t)M * 16 <= 200 * 1024, "point_to_node: too many nodes (%d)", M);
+    cudaStream_t st = (cudaStream_t)stream;
+    ROITR_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * M, st));
+    const size_t smem = (size_t)M * 16;
+    if (smem > 48 * 1024)
+        ROITR_CUDA(cudaFuncSetAttribute(point_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    point_owner_kernel<<<ceil_div(N, 256), 256, smem, st>>>(N, M, pts, nodes, owner, dmin, count);
+    ROITR_CHECK_LAUNCH("point_owner_kernel");
+    node_knn_kernel<<<M, 256, 0, st>>>(N, M, limit, owner, dmin, count, knn_idx, knn_mask, node_mask);
+    ROITR_CHECK_LAUNCH("node_knn_kernel");
+    return ROITR_OK;
+}
+
+extern "C" int roitr_compact_flags(long long n, const unsigned char* flags, int* chunk_scratch, int* out, int capacity,
+                                   int* count, void* stream) {
+    ROITR_CHECK_ARG(n >= 0 && flags && chunk_scratch && out && count, "compact_flags: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nchunks = (int)ceil_div_ll(n, CMP_CHUNK);
+    if (nchunks == 0) { ROITR_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st)); return ROITR_OK; }
+    compact_count_kernel<<<nchunks, 256, 0, st>>>(n, flags, chunk_scratch);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(nchunks, chunk_scratch, count);
+    compact_write_kernel<<<nchunks, 256, 0, st>>>(n, flags, chunk_scratch, out, capacity);
+    ROITR_CHECK_LAUNCH("compact_flags");
+    return ROITR_OK;
+}
+
+extern "C" long long roitr_compact_scratch_ints(long long n) { return ceil_div_ll(n, CMP_CHUNK) + 1; }
+
+extern "C" int roitr_coarse_matching(int Mr, int Ms, int C, int k, int dual, const float* ref_feats,
+                                     const float* src_feats, const unsigned char* ref_mask,
+                                     const unsigned char* src_mask, const float* xy, float* work, int* out_ref,
+                                     int* out_src, float* out_score, int* out_count, void* stream) {
+    // xy = ref_feats @ src_feats^T (Mr x Ms) computed by the caller with roitr_linear; work: Mr*Ms + 2*(Mr+Ms) floats
+    ROITR_CHECK_ARG(Mr >= 1 && Ms >= 1 && k >= 1 && k <= TOPK_MAX, "coarse_matching: bad sizes (k <= %d)", TOPK_MAX);
+    ROITR_CHECK_ARG(ref_feats && src_feats && ref_mask && src_mask && xy && work && out_ref && out_src && out_score && out_count,
+                    "coarse_matching: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* S = work;
+    float* r2 = S + (size_t)Mr * Ms;
+    float* s2 = r2 + Mr;
+    float* rowsum = s2 + Ms;
+    float* colsum = rowsum + Mr;
+    row_sqnorm_kernel<<<ceil_div(Mr * 32, 256), 256, 0, st>>>(Mr, C, ref_feats, r2);
+    row_sqnorm_kernel<<<ceil_div(Ms * 32, 256), 256, 0, st>>>(Ms, C, src_feats, s2);
+    coarse_exp_kernel<<<Mr, 256, 0, st>>>(Mr, Ms, xy, r2, s2, ref_mask, src_mask, S, rowsum);
+    col_sum_kernel<<<ceil_div(Ms, 128), 128, 0, st>>>(Mr, Ms, S, colsum);
+    coarse_dualnorm_kernel<<<(unsigned)ceil_div_ll((long long)Mr * Ms, 256), 256, 0, st>>>(Mr, Ms, S, rowsum, colsum,
+                                                                                           ref_mask, src_mask, dual);
+    flat_topk_kernel<<<1, 1024, 0, st>>>(Mr * Ms, k, S, Ms, out_ref, out_src, out_score, out_count);
+    ROITR_CHECK_LAUNCH("coarse_matching");
+    return ROITR_OK;
+}
+
+extern "C" int roitr_fine_matching(int Pmax, int Nt, int Ns, int C, const float* tgt_feat, const float* src_feat,
+                                   const int* tgt_knn, const int* src_knn, const unsigned char* tgt_kmask,
+                                   const unsigned char* src_kmask, const int* corr_t, const int* corr_s,
+                                   const int* corr_count, const float* alpha, int num_iter, int topk, int mutual,
+                                   float threshold, float* scores, unsigned char* flags, void* stream) {
+    ROITR_CHECK_ARG(Pmax >= 1 && C % 32 == 0 && topk >= 1 && topk <= 32, "fine_matching: bad sizes");
+    ROITR_CHECK_ARG(tgt_feat && src_feat && tgt_knn && src_knn && tgt_kmask && src_kmask && corr_t && corr_s &&
+                    corr_count && alpha && scores && flags, "fine_matching: null pointer");
+    ROITR_CHECK_ARG(((uintptr_t)tgt_feat | (uintptr_t)src_feat) % 16 == 0, "fine_matching: alignment");
+    FineParams P;
+    P.tgt_feat = tgt_feat; P.src_feat = src_feat; P.Nt = Nt; P.Ns = Ns; P.C = C; P.tgt_knn = tgt_knn; P.src_knn = src_knn;
+    P.tgt_kmask = tgt_kmask; P.src_kmask = src_kmask; P.corr_t = corr_t; P.corr_s = corr_s; P.corr_count = corr_count;
+    P.alpha = alpha; P.scores = scores; P.flags = flags; P.num_iter = num_iter; P.topk = topk; P.mutual = mutual;
+    P.threshold = threshold; P.sqrt_c = sqrtf((float)C);
+    cudaStream_t st = (cudaStream_t)stream;
+    ROITR_CUDA(cudaMemsetAsync(flags, 0, (size_t)Pmax * FP * FP, st));
+    fine_patch_kernel<<<Pmax, 256, 0, st>>>(P);
+    ROITR_CHECK_LAUNCH("fine_patch_kernel");
+    return ROITR_OK;
+}
+
+extern "C" int roitr_fine_gather(int capacity, const int* flat, const int* count, const float* scores,
+                                 const int* corr_t, const int* corr_s, const int* tgt_knn, const int* src_knn,
+                                 const float* tgt_pts_padded, const float* src_pts_padded, float* out_t, float* out_s,
+                                 float* out_score, void* stream) {
+    ROITR_CHECK_ARG(capacity >= 0 && flat && count && scores && out_t && out_s && out_score, "fine_gather: bad arguments");
+    if (capacity == 0) return ROITR_OK;
+    fine_gather_kernel<<<ceil_div(capacity, 256), 256, 0, (cudaStream_t)stream>>>(
+        flat, count, capacity, scores, corr_t, corr_s, tgt_knn, src_knn, tgt_pts_padded, src_pts_padded, out_t, out_s,
+        out_score);
+    ROITR_CHECK_LAUNCH("fine_gather_kernel");
+    return ROITR_OK;
+}

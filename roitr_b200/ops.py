@@ -1,0 +1,248 @@
+"""Thin typed wrappers over the C ABI (include/roitr_b200.h). torch only allocates the output tensors and names the
+stream; every computation happens in libroitr_b200. No fallbacks: errors raise RoitrError."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import c_float, c_int, f32, i32, ptr, stream_ptr
+
+c_ll = ctypes.c_longlong
+MODE_LN, MODE_RELU, MODE_L2NORM = 1, 2, 4
+
+
+def _u8(t):
+    return ptr(t, torch.uint8)
+
+
+def empty(*shape, dtype=torch.float32, like=None, device=None):
+    return torch.empty(*shape, dtype=dtype, device=like.device if like is not None else device)
+
+
+def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=None, K=None, lda=None, ldw=None,
+           ldc=None):
+    """out[M,N] = (a [+ a_add])[rows, :K] @ w[:N, :K]^T + bias. ``a``/``out`` may be column slices of wider buffers
+    (pass lda/ldc); ``a_index`` gathers rows of ``a``."""
+    N = w.shape[0]
+    K = w.shape[1] if K is None else K
+    if M is None:
+        M = a_index.shape[0] if a_index is not None else a.shape[0]
+    lda = a.stride(0) if lda is None else lda
+    ldw = w.stride(0) if ldw is None else ldw
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    ldc = out.stride(0) if ldc is None else ldc
+    _lib.call("roitr_linear", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
+              c_void(w), c_int(ldw), c_void(bias), c_void(out), c_int(ldc), c_int(1 if relu else 0), stream_ptr())
+    return out
+
+
+def c_void(t):
+    """Device pointer of a (possibly strided-view) f32 tensor: views into wider buffers are allowed here because the
+    leading dimension is passed explicitly."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    assert t.is_cuda and t.dtype == torch.float32
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def row_epilogue(x, res_pre=None, res_pre_index=None, gamma=None, beta=None, res_post=None, mode=0, out=None):
+    M, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("roitr_row_epilogue", c_int(M), c_int(C), f32(x), f32(res_pre), i32(res_pre_index), f32(gamma), f32(beta),
+              f32(res_post), f32(out), c_int(mode), stream_ptr())
+    return out
+
+
+def segment_mean(x, offset):
+    b, C = offset.shape[0], x.shape[1]
+    out = torch.empty(b, C, dtype=torch.float32, device=x.device)
+    _lib.call("roitr_segment_mean", c_int(b), c_int(C), f32(x), i32(offset), f32(out), stream_ptr())
+    return out
+
+
+def concat_segment(x, g, offset):
+    M, C = x.shape
+    out = torch.empty(M, 2 * C, dtype=torch.float32, device=x.device)
+    _lib.call("roitr_concat_segment", c_int(M), c_int(C), c_int(offset.shape[0]), f32(x), f32(g), i32(offset), f32(out),
+              stream_ptr())
+    return out
+
+
+def knn_ppf(k, xyz, nrm, new_xyz, new_nrm, offset, new_offset, drop_first=1, want_ppf=True, want_dist=False):
+    m = new_xyz.shape[0]
+    idx = torch.empty(m, k, dtype=torch.int32, device=xyz.device)
+    ppf = torch.empty(m, k, 4, dtype=torch.float32, device=xyz.device) if want_ppf else None
+    dist = torch.empty(m, k, dtype=torch.float32, device=xyz.device) if want_dist else None
+    _lib.call("roitr_knn_ppf_n", c_int(offset.shape[0]), c_int(m), c_int(k), c_int(drop_first), c_int(xyz.shape[0]),
+              f32(xyz), f32(nrm) if want_ppf else None, f32(new_xyz), f32(new_nrm) if want_ppf else None, i32(offset),
+              i32(new_offset), i32(idx), f32(dist), f32(ppf), stream_ptr())
+    return idx, ppf, dist
+
+
+def fps(xyz, offset, new_offset, n_seg_max, m_total, per_segment_rule=True, cluster=0):
+    idx = torch.empty(m_total, dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty(m_total, 3, dtype=torch.float32, device=xyz.device)
+    _lib.call("roitr_furthestsampling_cfg", c_int(offset.shape[0]), c_int(0 if per_segment_rule else n_seg_max),
+              c_int(n_seg_max), f32(xyz), i32(offset), i32(new_offset), i32(idx), f32(new_xyz), c_int(cluster),
+              stream_ptr())
+    return idx, new_xyz
+
+
+def gather_rows(src, index, pad_row=-1):
+    c = src.shape[1]
+    out = torch.empty(*index.shape, c, dtype=torch.float32, device=src.device)
+    _lib.call("roitr_gather_rows", c_ll(index.numel()), c_int(c), ptr(index), c_int(1 if index.dtype == torch.int64 else 0),
+              f32(src), f32(out), c_ll(pad_row), stream_ptr())
+    return out
+
+
+def interpolate(idx, dist, feat, base=None):
+    n, k = idx.shape
+    c = feat.shape[1]
+    out = torch.empty(n, c, dtype=torch.float32, device=feat.device)
+    _lib.call("roitr_interpolate", c_int(n), c_int(c), c_int(k), i32(idx), f32(dist), f32(feat), f32(base), f32(out),
+              stream_ptr())
+    return out
+
+
+def local_attention(qkv, C, node_idx, group_idx, ppf, Ap, cp, Avp, cvp):
+    m, knb = group_idx.shape
+    out = torch.empty(m, C, dtype=torch.float32, device=qkv.device)
+    ld = qkv.stride(0)
+    base = qkv.data_ptr()
+    P = ctypes.c_void_p
+    _lib.call("roitr_local_attention", c_int(m), c_int(C), c_int(4), c_int(knb), P(base), c_int(ld), P(base + 4 * C),
+              c_int(ld), P(base + 8 * C), c_int(ld), i32(node_idx), i32(group_idx), f32(ppf), f32(Ap), f32(cp), f32(Avp),
+              f32(cvp), f32(out), stream_ptr())
+    return out
+
+
+def geo_knn(pts, k=3):
+    N = pts.shape[0]
+    nn = torch.empty(N, k, dtype=torch.int32, device=pts.device)
+    _lib.call("roitr_geo_knn", c_int(N), c_int(k), f32(pts), i32(nn), stream_ptr())
+    return nn
+
+
+def geo_embedding(pts, nn3, Wd, bd, Wa, ba, div_term, sigma_d, sigma_a):
+    N, C = pts.shape[0], Wd.shape[0]
+    E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device)
+    _lib.call("roitr_geo_embedding", c_int(N), c_int(C), f32(pts), i32(nn3), f32(Wd), f32(bd), f32(Wa), f32(ba),
+              f32(div_term), c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
+    return E
+
+
+def geo_attention(q, k, v, C, E=None, gq=None, bp=None):
+    """q (N, >=C view), k, v (M, >=C views) with explicit strides. Returns hidden (N,C) [, G (N,4,C)]."""
+    N, M = q.shape[0], k.shape[0]
+    hidden = torch.empty(N, C, dtype=torch.float32, device=q.device)
+    G = torch.empty(N, 4, C, dtype=torch.float32, device=q.device) if E is not None else None
+    _lib.call("roitr_geo_attention", c_int(N), c_int(M), c_int(C), c_int(4), c_void(q), c_int(q.stride(0)), c_void(k),
+              c_int(k.stride(0)), c_void(v), c_int(v.stride(0)), f32(E), f32(gq), f32(bp), f32(hidden), f32(G),
+              stream_ptr())
+    return (hidden, G) if E is not None else hidden
+
+
+def point_to_node(pts, nodes, limit):
+    N, M = pts.shape[0], nodes.shape[0]
+    dev = pts.device
+    owner = torch.empty(N, dtype=torch.int32, device=dev)
+    dmin = torch.empty(N, dtype=torch.float32, device=dev)
+    count = torch.empty(M, dtype=torch.int32, device=dev)
+    knn_idx = torch.empty(M, limit, dtype=torch.int32, device=dev)
+    knn_mask = torch.empty(M, limit, dtype=torch.uint8, device=dev)
+    node_mask = torch.empty(M, dtype=torch.uint8, device=dev)
+    _lib.call("roitr_point_to_node", c_int(N), c_int(M), c_int(limit), f32(pts), f32(nodes), i32(owner), f32(dmin),
+              i32(count), i32(knn_idx), _u8(knn_mask), _u8(node_mask), stream_ptr())
+    return owner, node_mask, knn_idx, knn_mask
+
+
+def compact_flags(flags, capacity):
+    """Ascending flat indices of the non-zero bytes (torch.nonzero order), padded to ``capacity``; device count."""
+    n = flags.numel()
+    fn = _lib.lib().roitr_compact_scratch_ints
+    fn.restype = c_ll
+    scratch = torch.empty(int(fn(c_ll(n))), dtype=torch.int32, device=flags.device)
+    out = torch.empty(max(capacity, 1), dtype=torch.int32, device=flags.device)
+    count = torch.empty(1, dtype=torch.int32, device=flags.device)
+    _lib.call("roitr_compact_flags", c_ll(n), _u8(flags), i32(scratch), i32(out), c_int(capacity), i32(count),
+              stream_ptr())
+    return out, count
+
+
+def coarse_matching(ref_feats, src_feats, ref_mask, src_mask, k, dual=True):
+    Mr, Ms, C = ref_feats.shape[0], src_feats.shape[0], ref_feats.shape[1]
+    dev = ref_feats.device
+    xy = linear(ref_feats, src_feats)                       # (Mr, Ms) = ref @ src^T
+    work = torch.empty(Mr * Ms + 2 * (Mr + Ms), dtype=torch.float32, device=dev)
+    out_ref = torch.zeros(k, dtype=torch.int32, device=dev)
+    out_src = torch.zeros(k, dtype=torch.int32, device=dev)
+    out_score = torch.zeros(k, dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.call("roitr_coarse_matching", c_int(Mr), c_int(Ms), c_int(C), c_int(k), c_int(1 if dual else 0), f32(ref_feats),
+              f32(src_feats), _u8(ref_mask), _u8(src_mask), f32(xy), f32(work), i32(out_ref), i32(out_src),
+              f32(out_score), i32(count), stream_ptr())
+    return out_ref, out_src, out_score, count
+
+
+def fine_matching(tgt_feat, src_feat, tgt_knn, src_knn, tgt_kmask, src_kmask, corr_t, corr_s, corr_count, alpha,
+                  num_iter, topk, mutual, threshold):
+    Pmax = corr_t.shape[0]
+    dev = tgt_feat.device
+    scores = torch.zeros(Pmax, 65, 65, dtype=torch.float32, device=dev)
+    flags = torch.empty(Pmax, 64, 64, dtype=torch.uint8, device=dev)
+    _lib.call("roitr_fine_matching", c_int(Pmax), c_int(tgt_feat.shape[0]), c_int(src_feat.shape[0]),
+              c_int(tgt_feat.shape[1]), f32(tgt_feat), f32(src_feat), i32(tgt_knn), i32(src_knn), _u8(tgt_kmask),
+              _u8(src_kmask), i32(corr_t), i32(corr_s), i32(corr_count), f32(alpha), c_int(num_iter), c_int(topk),
+              c_int(1 if mutual else 0), c_float(threshold), f32(scores), _u8(flags), stream_ptr())
+    return scores, flags
+
+
+def fine_gather(capacity, flat, count, scores, corr_t, corr_s, tgt_knn, src_knn, tgt_pts, src_pts):
+    dev = scores.device
+    out_t = torch.empty(capacity, 3, dtype=torch.float32, device=dev)
+    out_s = torch.empty(capacity, 3, dtype=torch.float32, device=dev)
+    out_sc = torch.empty(capacity, dtype=torch.float32, device=dev)
+    _lib.call("roitr_fine_gather", c_int(capacity), i32(flat), i32(count), f32(scores), i32(corr_t), i32(corr_s),
+              i32(tgt_knn), i32(src_knn), f32(tgt_pts), f32(src_pts), f32(out_t), f32(out_s), f32(out_sc), stream_ptr())
+    return out_t, out_s, out_sc
+
+
+def pad_transform(pts, rot=None, trans=None):
+    N = pts.shape[0]
+    out = torch.empty(N + 1, 3, dtype=torch.float32, device=pts.device)
+    _lib.call("roitr_pad_transform", c_int(N), f32(pts), f32(rot), f32(trans), f32(out), stream_ptr())
+    return out
+
+
+def node_occlusion(knn, kmask, nmask, nn_dist, thr=0.0375):
+    M, K = knn.shape
+    occ = torch.empty(M, dtype=torch.float32, device=knn.device)
+    _lib.call("roitr_node_occlusion", c_int(M), c_int(K), i32(knn), _u8(kmask), _u8(nmask), f32(nn_dist), c_float(thr),
+              f32(occ), stream_ptr())
+    return occ
+
+
+def node_overlaps(ref_nodes, src_nodes, ref_knn, src_knn, ref_kmask, src_kmask, ref_mask, src_mask, ref_pts, src_pts,
+                  rot, trans, radius):
+    Mr, Ms, K = ref_nodes.shape[0], src_nodes.shape[0], ref_knn.shape[1]
+    dev = ref_nodes.device
+    work = torch.empty(4 * Ms + 4 * Mr, dtype=torch.float32, device=dev)
+    overlap = torch.empty(Mr, Ms, dtype=torch.float32, device=dev)
+    flag = torch.empty(Mr, Ms, dtype=torch.uint8, device=dev)
+    _lib.call("roitr_node_overlaps", c_int(Mr), c_int(Ms), c_int(K), c_int(ref_pts.shape[0]), c_int(src_pts.shape[0]),
+              f32(ref_nodes), f32(src_nodes), i32(ref_knn), i32(src_knn), _u8(ref_kmask), _u8(src_kmask), _u8(ref_mask),
+              _u8(src_mask), f32(ref_pts), f32(src_pts), f32(rot), f32(trans), c_float(radius), f32(work), f32(overlap),
+              _u8(flag), stream_ptr())
+    return overlap, flag
+
+
+def corr_gather(capacity, Ms, flat, count, overlap):
+    dev = overlap.device
+    out_idx = torch.empty(capacity, 2, dtype=torch.int64, device=dev)
+    out_ov = torch.empty(capacity, dtype=torch.float32, device=dev)
+    _lib.call("roitr_corr_gather", c_int(capacity), c_int(Ms), i32(flat), i32(count), f32(overlap), ptr(out_idx),
+              f32(out_ov), stream_ptr())
+    return out_idx, out_ov

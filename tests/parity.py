@@ -1,0 +1,142 @@
+"""Stage-by-stage parity of the CUDA forward (roitr_b200) against the oracle (oracle/forward_ref.py) on the same seeded
+inputs and weights. Used by tests/test_forward_gpu.py (with thresholds) and scripts/parity_report.py (prints the table).
+
+Discrete stages are compared exactly (FPS / kNN indices, partition) or as keyed sets with a flip budget (coarse
+selection, final correspondences: random-weight descriptors are nearly flat, so ~1e-6 score differences can swap
+entries at the selection boundary); float stages by max abs error.
+"""
+import numpy as np
+import torch
+
+from oracle import forward_ref as fr
+from roitr_b200 import model
+from roitr_b200.synthetic import forward_args
+
+
+def _maxabs(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    if a.shape != b.shape:
+        return float("inf")
+    return float((a - b).abs().max()) if a.numel() else 0.0
+
+
+def run(pair, cfg, sd, device="cuda:0"):
+    """-> (rows, out_gpu, out_ref): rows = list of (stage, metric_name, value, kind)."""
+    m = model.create_model(cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(device).eval()
+    aux = {}
+    out = m(*forward_args(pair, device), _aux=aux)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = fr.riga_forward(sd, cfg, *forward_args(pair), with_aux=True)
+    raux = ref["_aux"]
+    rows = []
+    add = lambda *r: rows.append(r)
+    for side in ("src", "tgt"):
+        G, R = aux[side + "_levels"], raux[side + "_levels"]
+        for li in range(4):
+            if li > 0:
+                add("%s L%d fps idx" % (side, li + 1), "mismatches", int((G[li]["down_idx"].cpu().long() != R[li]["down_idx"]).sum()), "exact")
+            same = G[li]["idx"].cpu().long() == R[li]["idx"]
+            add("%s L%d knn idx" % (side, li + 1), "mismatch frac", float(1 - same.float().mean()), "ties")
+            add("%s L%d ppf" % (side, li + 1), "maxabs (agreeing idx)", float((G[li]["ppf"].cpu() - R[li]["ppf"])[same].abs().max()), "f1e-5")
+            add("%s L%d enc feats" % (side, li + 1), "maxabs", _maxabs(G[li]["x"], R[li]["x"]), "feat")
+        for li in range(4):
+            add("%s L%d dec feats" % (side, li + 1), "maxabs", _maxabs(aux[side + "_dec"][li], raux[side + "_dec"][li]), "feat")
+    add("geo embedding src", "maxabs", _maxabs(aux["emb0"], raux["emb0"][0]), "feat")
+    add("geo embedding tgt", "maxabs", _maxabs(aux["emb1"], raux["emb1"][0]), "feat")
+    for k in ("src_nodes", "tgt_nodes"):
+        add(k, "maxabs", _maxabs(out[k], ref[k]), "exactf")
+    for k in ("src_node_feats", "tgt_node_feats", "src_point_feats", "tgt_point_feats"):
+        add(k, "maxabs", _maxabs(out[k], ref[k]), "feat")
+    for side in ("src", "tgt"):
+        gi, ri = aux[side + "_node_knn_indices"].cpu().long(), raux[side + "_node_knn_indices"]
+        add(side + " partition knn idx", "mismatch frac", float((gi != ri).float().mean()), "ties")
+        add(side + " partition masks", "mismatches", int((aux[side + "_node_knn_masks"].cpu() != raux[side + "_node_knn_masks"]).sum())
+            + int((aux[side + "_node_masks"].cpu() != raux[side + "_node_masks"]).sum()), "exact")
+    add("gt occ tgt", "maxabs", _maxabs(out["gt_tgt_node_occ"], ref["gt_tgt_node_occ"]), "f1e-5")
+    add("gt occ src", "maxabs", _maxabs(out["gt_src_node_occ"], ref["gt_src_node_occ"]), "f1e-5")
+    g_gt = {tuple(r): float(v) for r, v in zip(out["gt_node_corr_indices"].cpu().tolist(), out["gt_node_corr_overlaps"].cpu().tolist())}
+    r_gt = {tuple(r): float(v) for r, v in zip(ref["gt_node_corr_indices"].tolist(), ref["gt_node_corr_overlaps"].tolist())}
+    add("gt node corr", "sym diff / ref", len(set(g_gt) ^ set(r_gt)) / max(1, len(r_gt)), "set")
+    add("gt node corr overlaps", "maxabs (common)", max([abs(g_gt[k] - r_gt[k]) for k in set(g_gt) & set(r_gt)] or [0.0]), "f1e-2")
+    add("gt node corr order", "is nonzero order", float(out["gt_node_corr_indices"].cpu().tolist() == sorted(out["gt_node_corr_indices"].cpu().tolist())), "true")
+
+    # coarse: the full score matrix is the robust comparison; the selected set may flip at the boundary
+    tm, smk = raux["tgt_node_masks"], raux["src_node_masks"]
+    ref_scores = fr.coarse_scores_3d(ref["tgt_node_feats"][tm], ref["src_node_feats"][smk])
+    gpu_scores = fr.coarse_scores_3d(out["tgt_node_feats"].cpu()[tm], out["src_node_feats"].cpu()[smk])
+    add("coarse score matrix (from gpu feats)", "max rel err", float(((ref_scores - gpu_scores).abs() / ref_scores).max()), "f1e-3")
+    g_pairs = list(zip(out["tgt_node_corr_indices"].cpu().tolist(), out["src_node_corr_indices"].cpu().tolist()))
+    r_pairs = list(zip(ref["tgt_node_corr_indices"].tolist(), ref["src_node_corr_indices"].tolist()))
+    add("coarse P", "gpu - ref", len(g_pairs) - len(r_pairs), "exact")
+    add("coarse selected pairs", "sym diff / P", len(set(g_pairs) ^ set(r_pairs)) / max(1, len(r_pairs)), "set")
+    # is the gpu selection the exact top-k of its OWN scores? (selection logic check, independent of flips)
+    ti = torch.nonzero(tm).flatten()
+    si = torch.nonzero(smk).flatten()
+    kk = min(len(g_pairs), gpu_scores.numel())
+    top = gpu_scores.flatten().topk(kk)[0]
+    mine = torch.tensor([gpu_scores[(ti == a).nonzero().item(), (si == b).nonzero().item()] for a, b in g_pairs])
+    add("coarse selection vs own scores", "max rel err of sorted values", float(((top - mine).abs() / top).max()) if kk else 0.0, "f1e-5")
+
+    common = [p for p in g_pairs if p in set(r_pairs)]
+    gpos = {p: i for i, p in enumerate(g_pairs)}
+    rpos = {p: i for i, p in enumerate(r_pairs)}
+    if common:
+        gi = torch.tensor([gpos[p] for p in common])
+        ri = torch.tensor([rpos[p] for p in common])
+        ms_g, ms_r = out["matching_scores"].cpu()[gi], ref["matching_scores"][ri]
+        live = ms_r > -1e5
+        add("matching_scores (common patches)", "maxabs (unmasked)", float((ms_g - ms_r)[live].abs().max()), "f1e-3")
+        add("matching_scores masked pattern", "mismatches", int(((ms_g > -1e5) != live).sum()), "exact")
+        add("patch knn points", "maxabs", _maxabs(out["tgt_node_corr_knn_points"].cpu()[gi], ref["tgt_node_corr_knn_points"][ri])
+            + _maxabs(out["src_node_corr_knn_points"].cpu()[gi], ref["src_node_corr_knn_points"][ri]), "exactf")
+        # final correspondences keyed by (tgt_node, src_node, row, col)
+        gflat = aux["corr_flat"].cpu().long()
+        gk = {(g_pairs[int(f) >> 12], (int(f) >> 6) & 63, int(f) & 63): float(s) for f, s in zip(gflat, out["corr_scores"].cpu())}
+        rk = {(r_pairs[int(b)], int(r), int(c)): float(s) for (b, r, c), s in zip(raux["corr_brc"].tolist(), ref["corr_scores"])}
+        cs = set(common)
+        gk = {k: v for k, v in gk.items() if k[0] in cs}
+        rk = {k: v for k, v in rk.items() if k[0] in cs}
+        add("final corr (common patches)", "count gpu / ref", "%d / %d" % (len(gk), len(rk)), "info")
+        add("final corr (common patches)", "sym diff / ref", len(set(gk) ^ set(rk)) / max(1, len(rk)), "set")
+        add("final corr scores", "maxabs (common)", max([abs(gk[k] - rk[k]) for k in set(gk) & set(rk)] or [0.0]), "f1e-4")
+        # flips must sit at a decision boundary: threshold 0.05 or a top-k rank tie
+        thr = float(cfg["fine_matching_confidence_threshold"])
+        far = [k for k in set(gk) ^ set(rk) if abs((gk.get(k) or rk.get(k)) - thr) > 1e-3]
+        add("final corr flips away from threshold", "count", len(far), "info")
+    add("corr points consistent", "maxabs", _corr_points_check(out, aux, g_pairs), "exactf")
+    return rows, out, ref
+
+
+def _corr_points_check(out, aux, g_pairs):
+    """tgt/src_corr_points must be the patch points addressed by the compacted (p,row,col)."""
+    f = aux["corr_flat"].cpu().long()
+    if f.numel() == 0:
+        return 0.0
+    p, r, c = f >> 12, (f >> 6) & 63, f & 63
+    t = out["tgt_node_corr_knn_points"].cpu()[p, r]
+    s = out["src_node_corr_knn_points"].cpu()[p, c]
+    return float(max((t - out["tgt_corr_points"].cpu()).abs().max(), (s - out["src_corr_points"].cpu()).abs().max()))
+
+
+THRESH = {"exact": 0, "exactf": 0.0, "ties": 1e-3, "f1e-5": 1e-5, "feat": 2e-4, "f1e-4": 1e-4, "f1e-3": 1e-3, "f1e-2": 1e-2,
+          "set": 0.05}
+
+
+def failures(rows):
+    bad = []
+    for stage, name, val, kind in rows:
+        if kind == "info":
+            continue
+        if kind == "true":
+            if val != 1.0:
+                bad.append((stage, name, val))
+        elif not (abs(val) <= THRESH[kind]):
+            bad.append((stage, name, val, "limit %g" % THRESH[kind]))
+    return bad
+
+
+def format_rows(rows):
+    return "\n".join("%-42s %-34s %s" % (s, n, ("%.3e" % v) if isinstance(v, float) else str(v)) for s, n, v, _ in rows)

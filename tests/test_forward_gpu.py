@@ -1,0 +1,29 @@
+"""End-to-end parity of RIGA_v2.forward on the GPU (through model.create_model -> C ABI) vs the oracle, stage by stage."""
+import pytest
+import torch
+
+from roitr_b200.synthetic import synthetic_pair
+from tests import parity
+from tests.helpers import CONFIG_3D, weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,index", [(1024, 0), (4096, 1), (20000, 0)])
+def test_forward_parity_3dmatch(n, index):
+    rows, out, ref = parity.run(synthetic_pair(index, n), CONFIG_3D, weights(1))
+    print("\n" + parity.format_rows(rows))
+    assert set(out) == {k for k in ref if k != "_aux"}
+    for k in out:
+        assert out[k].dtype == ref[k].dtype, (k, out[k].dtype, ref[k].dtype)
+        assert out[k].shape[1:] == ref[k].shape[1:], (k, out[k].shape, ref[k].shape)
+    assert not parity.failures(rows), parity.failures(rows)
+
+
+def test_forward_ragged_sizes():
+    # unequal clouds, sizes not multiples of 4/32
+    pair = synthetic_pair(5, 3000)
+    pair["tgt_pcd"], pair["tgt_normals"], pair["tgt_feats"] = pair["tgt_pcd"][:2741].contiguous(), pair["tgt_normals"][:2741].contiguous(), pair["tgt_feats"][:2741].contiguous()
+    rows, out, ref = parity.run(pair, CONFIG_3D, weights(1))
+    print("\n" + parity.format_rows(rows))
+    assert not parity.failures(rows), parity.failures(rows)

@@ -48,7 +48,7 @@ def test_reference_knn_kernel_vs_oracle_and_ours(ref, n, m, ns):
     assert torch.equal(d2_r.cpu(), d2_o)          # C oracle == reference kernel, bit for bit
     assert torch.equal(idx_r.cpu(), idx_o)        # including the heap's order among exact ties
     idx_g, dist_g = pointops.knnquery(ns, xd, qd, od, nd)
-    assert torch.equal(dist_g.cpu(), torch.sqrt(d2_o))
+    assert torch.equal(dist_g.cpu(), torch.sqrt(d2_o.to(DEV)).cpu())   # IEEE sqrt, as torch.sqrt on CUDA
     assert _boundary_ok(idx_g.cpu().numpy(), d2_o.numpy(), idx_r.cpu().numpy(), d2_o.numpy(), xyz.numpy(), q.numpy())
 
 
