@@ -56,10 +56,39 @@ def i32(t):
     return ptr(t, torch.int32)
 
 
+# kernels launched by one call of each entry point (for bench.py's gpu_launches claim; memsets not counted)
+KERNELS_PER_CALL = {
+    "roitr_knnquery_n": 2, "roitr_knn_ppf_n": 2, "roitr_furthestsampling_cfg": 1, "roitr_interpolate": 1,
+    "roitr_gather_rows": 1, "roitr_linear": 1, "roitr_row_epilogue": 1, "roitr_segment_mean": 1,
+    "roitr_concat_segment": 1, "roitr_local_attention": 1, "roitr_geo_knn": 1, "roitr_geo_embedding": 1,
+    "roitr_geo_attention": 1, "roitr_point_to_node": 2, "roitr_compact_flags": 3, "roitr_coarse_matching": 6,
+    "roitr_fine_matching": 1, "roitr_fine_gather": 1, "roitr_pad_transform": 1, "roitr_node_occlusion": 1,
+    "roitr_node_overlaps": 3, "roitr_corr_gather": 1,
+}
+STATS = {"launches": 0, "calls": {}}
+TIMED = {}        # entry-point name -> list of (start_event, end_event); filled only for names present as keys
+
+
+def reset_stats():
+    STATS["launches"] = 0
+    STATS["calls"] = {}
+    for k in TIMED:
+        TIMED[k] = []
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise with the library's message on failure."""
     fn = getattr(lib(), name)
     fn.restype = c_int
+    timed = TIMED.get(name)
+    if timed is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = fn(*args)
+    if timed is not None:
+        e1.record()
+        timed.append((e0, e1))
     if rc != 0:
         raise RoitrError("%s failed (rc=%d): %s" % (name, rc, lib().roitr_last_error().decode()))
+    STATS["launches"] += KERNELS_PER_CALL.get(name, 1)
+    STATS["calls"][name] = STATS["calls"].get(name, 0) + 1

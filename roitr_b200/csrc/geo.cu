@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(GE_THREADS) geo_embedding_kernel(const GeoEmbP
                 const float cy = __fsub_rn(__fmul_rn(rz, ax), __fmul_rn(rx, az));
                 const float cz = __fsub_rn(__fmul_rn(rx, ay), __fmul_rn(ry, ax));
                 const float sinv = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
-                const float cosv = __fadd_rn(__fadd_rn(__fmul_rn(rx, ax), __fmul_rn(ry, ay)), __fmul_rn(rz, az));
+                // torch.sum starts from +0: (+0) + (-0) = +0, so a zero dot product is +0 and atan2(0, +0) = 0 (not pi)
+                const float cosv = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(rx, ax)), __fmul_rn(ry, ay)), __fmul_rn(rz, az));
                 t_row = __fmul_rn(atan2f(sinv, cosv), P.factor_a);
             }
         }

@@ -12,7 +12,8 @@
 // top-k of a query is a sorted list DISTRIBUTED OVER THE LANES (lane l holds the l-th best), so admission is one
 // compare + ballot per 32 points and an insertion is a ballot/popc + one shuffle — no local memory, no divergence.
 // Points are consumed in ascending index order and admission is strict '<', so among exactly equal distances the
-// lower index wins (reference: knnquery_cuda_kernel.cu:97 strict '<' while scanning i ascending).
+// lower index wins; queries in which an exact-distance tie played any role (rare) are marked and replayed by
+// knn_tie_fixup_kernel with the reference's sequential max-heap, so results equal the reference bit for bit, ties included.
 // The epilogue drops the self column and computes the PPF tuple per (query, neighbour) lane, writing coalesced
 // idx and float4 PPF.
 #include <math_constants.h>
@@ -55,12 +56,36 @@ __device__ __forceinline__ int find_segment(int q, const int* __restrict__ ends,
 // angle(a, b) / pi  =  atan2(|a x b|, a.b) / pi   (lib/utils.py:372-387). Products and sums are rounded separately
 // (no FMA contraction) like the eager elementwise reference.
 __device__ __forceinline__ float angle_over_pi(float ax, float ay, float az, float bx, float by, float bz) {
-    float dot = __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+    // torch.sum starts from +0, so an all-(-0) dot product is +0 and atan2(0, +0) = 0 (not pi)
+    float dot = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(ax, bx)), __fmul_rn(ay, by)), __fmul_rn(az, bz));
     float cx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
     float cy = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
     float cz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
     float cn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
     return __fdiv_rn(atan2f(cn, dot), 3.14159265358979323846f);
+}
+
+// writes one (query, slot) result: index, distance, PPF tuple
+__device__ __forceinline__ void emit_result(const KnnParams& P, int q, int slot, int kout, int nb, float d2, float qx,
+                                            float qy, float qz) {
+    const size_t o = (size_t)q * kout + slot;
+    P.idx[o] = nb;
+    if (P.dist) P.dist[o] = P.dist_squared ? d2 : __fsqrt_rn(d2);
+    if (P.ppf) {
+        const float n1x = __ldg(P.qnrm + 3 * (size_t)q), n1y = __ldg(P.qnrm + 3 * (size_t)q + 1),
+                    n1z = __ldg(P.qnrm + 3 * (size_t)q + 2);
+        const float px = __ldg(P.xyz + 3 * (size_t)nb), py = __ldg(P.xyz + 3 * (size_t)nb + 1),
+                    pz = __ldg(P.xyz + 3 * (size_t)nb + 2);
+        const float n2x = __ldg(P.nrm + 3 * (size_t)nb), n2y = __ldg(P.nrm + 3 * (size_t)nb + 1),
+                    n2z = __ldg(P.nrm + 3 * (size_t)nb + 2);
+        const float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+        float4 f;
+        f.x = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        f.y = angle_over_pi(n1x, n1y, n1z, dx, dy, dz);
+        f.z = angle_over_pi(n2x, n2y, n2z, dx, dy, dz);
+        f.w = angle_over_pi(n1x, n1y, n1z, n2x, n2y, n2z);
+        reinterpret_cast<float4*>(P.ppf)[o] = f;
+    }
 }
 
 template <int QW>
@@ -91,8 +116,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_ppf_kernel(const KnnParams P)
     // ---- per-query state (replicated across the warp except the distributed list) ----
     float qx[QW], qy[QW], qz[QW], ld[QW], tau[QW];
     int qs[QW], qe[QW], li[QW];
+    bool tie[QW];  // an exact-distance tie influenced this query: its result is recomputed by knn_tie_fixup_kernel
 #pragma unroll
     for (int j = 0; j < QW; ++j) {
+        tie[j] = false;
         int q = q_cta0 + warp * QW + j;
         if (q < P.m) {
             int s = find_segment(q, P.new_offset, P.b);
@@ -156,19 +183,29 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_ppf_kernel(const KnnParams P)
                 const float d = sqdist_ref(qx[j] - x, qy[j] - y, qz[j] - z);
                 bool ok = inb;
                 if (mixed) ok = ok && (gi >= qs[j]) && (gi < qe[j]);
-                unsigned mask = __ballot_sync(FULL_MASK, ok && (d < tau[j]));
+                unsigned mask = __ballot_sync(FULL_MASK, ok && (d <= tau[j]));
                 while (mask) {
                     const int l = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const float cd = __shfl_sync(FULL_MASK, d, l);
                     if (cd < tau[j]) {
                         const int ci = base + s + l;
-                        const int ins = __popc(__ballot_sync(FULL_MASK, ld[j] <= cd) & kmask);
+                        const unsigned le = __ballot_sync(FULL_MASK, ld[j] <= cd) & kmask;
+                        // equal to an element already in the list: the reference's order among equal distances is its
+                        // heap's, not ours -> recompute this query exactly
+                        if (__ballot_sync(FULL_MASK, ld[j] == cd) & kmask) tie[j] = true;
+                        const int ins = __popc(le);
                         const float up_d = __shfl_up_sync(FULL_MASK, ld[j], 1);
                         const int up_i = __shfl_up_sync(FULL_MASK, li[j], 1);
                         if (lane > ins) { ld[j] = up_d; li[j] = up_i; }
                         else if (lane == ins) { ld[j] = cd; li[j] = ci; }
+                        const float tau_old = tau[j];
                         tau[j] = __shfl_sync(FULL_MASK, ld[j], K - 1);
+                        // the evicted element equals the new k-th one: which of the two the reference keeps depends on
+                        // its heap history (1e10 = the unfilled-slot filler, all identical, no ambiguity)
+                        if (tau[j] == tau_old && tau_old != 1e10f) tie[j] = true;
+                    } else if (cd == tau[j] && cd != 1e10f) {
+                        tie[j] = true;  // rejected at the boundary by strict '<' here; the heap may have kept another one
                     }
                 }
             }
@@ -184,26 +221,49 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_ppf_kernel(const KnnParams P)
         if (q >= P.m) continue;
         const int slot = lane - P.drop;
         if (slot < 0 || lane >= K) continue;
-        const size_t o = (size_t)q * kout + slot;
-        const int nb = li[j];
-        P.idx[o] = nb;
-        if (P.dist) P.dist[o] = P.dist_squared ? ld[j] : __fsqrt_rn(ld[j]);
-        if (P.ppf) {
-            const float n1x = __ldg(P.qnrm + 3 * (size_t)q), n1y = __ldg(P.qnrm + 3 * (size_t)q + 1),
-                        n1z = __ldg(P.qnrm + 3 * (size_t)q + 2);
-            const float px = __ldg(P.xyz + 3 * (size_t)nb), py = __ldg(P.xyz + 3 * (size_t)nb + 1),
-                        pz = __ldg(P.xyz + 3 * (size_t)nb + 2);
-            const float n2x = __ldg(P.nrm + 3 * (size_t)nb), n2y = __ldg(P.nrm + 3 * (size_t)nb + 1),
-                        n2z = __ldg(P.nrm + 3 * (size_t)nb + 2);
-            const float dx = __fsub_rn(px, qx[j]), dy = __fsub_rn(py, qy[j]), dz = __fsub_rn(pz, qz[j]);
-            float4 f;
-            f.x = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-            f.y = angle_over_pi(n1x, n1y, n1z, dx, dy, dz);
-            f.z = angle_over_pi(n2x, n2y, n2z, dx, dy, dz);
-            f.w = angle_over_pi(n1x, n1y, n1z, n2x, n2y, n2z);
-            reinterpret_cast<float4*>(P.ppf)[o] = f;
+        if (tie[j]) {
+            if (slot == 0) P.idx[(size_t)q * kout] = -1;  // marker consumed by knn_tie_fixup_kernel
+            continue;
         }
+        emit_result(P, q, slot, kout, li[j], ld[j], qx[j], qy[j], qz[j]);
     }
+}
+
+// Exact replay of the reference algorithm (sequential scan, max-heap with strict '<', heap sort:
+// knnquery_cuda_kernel.cu:21-48,86-107) for the queries the main kernel marked as tie-affected. Rare (about one query
+// per 20k x 20k call on random data), so one thread per marked query is fine.
+__global__ void knn_tie_fixup_kernel(const KnnParams P) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = P.nslots, kout = K - P.drop;
+    if (q >= P.m || P.idx[(size_t)q * kout] >= 0) return;
+    const int s = find_segment(q, P.new_offset, P.b);
+    const int start = s == 0 ? 0 : __ldg(P.offset + s - 1), end = __ldg(P.offset + s);
+    const float qx = __ldg(P.qxyz + 3 * (size_t)q), qy = __ldg(P.qxyz + 3 * (size_t)q + 1), qz = __ldg(P.qxyz + 3 * (size_t)q + 2);
+    float bd[32];
+    int bi[32];
+    for (int i = 0; i < K; ++i) { bd[i] = 1e10f; bi[i] = start; }
+    auto sift = [&](int k) {
+        int root = 0, child = 1;
+        while (child < k) {
+            if (child + 1 < k && bd[child + 1] > bd[child]) child++;
+            if (bd[root] > bd[child]) return;
+            const float td = bd[root]; bd[root] = bd[child]; bd[child] = td;
+            const int ti = bi[root]; bi[root] = bi[child]; bi[child] = ti;
+            root = child;
+            child = 2 * root + 1;
+        }
+    };
+    for (int i = start; i < end; ++i) {
+        const float d2 = sqdist_ref(qx - __ldg(P.xyz + 3 * (size_t)i), qy - __ldg(P.xyz + 3 * (size_t)i + 1),
+                                    qz - __ldg(P.xyz + 3 * (size_t)i + 2));
+        if (d2 < bd[0]) { bd[0] = d2; bi[0] = i; sift(K); }
+    }
+    for (int i = K - 1; i > 0; --i) {
+        const float td = bd[0]; bd[0] = bd[i]; bd[i] = td;
+        const int ti = bi[0]; bi[0] = bi[i]; bi[i] = ti;
+        sift(i);
+    }
+    for (int i = P.drop; i < K; ++i) emit_result(P, q, i - P.drop, kout, bi[i], bd[i], qx, qy, qz);
 }
 
 int launch_knn(const KnnParams& P, cudaStream_t st) {
@@ -227,6 +287,8 @@ int launch_knn(const KnnParams& P, cudaStream_t st) {
         knn_ppf_kernel<1><<<ceil_div(P.m, KNN_WARPS), KNN_THREADS, smem, st>>>(P);
     }
     ROITR_CHECK_LAUNCH("knn_ppf_kernel");
+    knn_tie_fixup_kernel<<<ceil_div(P.m, 128), 128, 0, st>>>(P);
+    ROITR_CHECK_LAUNCH("knn_tie_fixup_kernel");
     return ROITR_OK;
 }
 

@@ -39,20 +39,30 @@ def run(pair, cfg, sd, device="cuda:0"):
             if li > 0:
                 add("%s L%d fps idx" % (side, li + 1), "mismatches", int((G[li]["down_idx"].cpu().long() != R[li]["down_idx"]).sum()), "exact")
             same = G[li]["idx"].cpu().long() == R[li]["idx"]
-            add("%s L%d knn idx" % (side, li + 1), "mismatch frac", float(1 - same.float().mean()), "ties")
+            add("%s L%d knn idx" % (side, li + 1), "mismatches", int((~same).sum()), "exact")
             add("%s L%d ppf" % (side, li + 1), "maxabs (agreeing idx)", float((G[li]["ppf"].cpu() - R[li]["ppf"])[same].abs().max()), "f1e-5")
             add("%s L%d enc feats" % (side, li + 1), "maxabs", _maxabs(G[li]["x"], R[li]["x"]), "feat")
         for li in range(4):
             add("%s L%d dec feats" % (side, li + 1), "maxabs", _maxabs(aux[side + "_dec"][li], raux[side + "_dec"][li]), "feat")
-    add("geo embedding src", "maxabs", _maxabs(aux["emb0"], raux["emb0"][0]), "feat")
-    add("geo embedding tgt", "maxabs", _maxabs(aux["emb1"], raux["emb1"][0]), "feat")
+    for nm, key in (("src", "emb0"), ("tgt", "emb1")):
+        eg, er = aux[key].cpu(), raux[key][0]
+        d = (eg - er).abs()
+        add("geo embedding " + nm, "maxabs", float(d.max()), "feat")
+        if d.max() > 1e-3:
+            n_, m_, c_ = [int(v) for v in np.unravel_index(int(d.argmax()), d.shape)]
+            add("geo embedding " + nm, "argmax (n,m,c) gpu ref rows>1e-3",
+                "%s %.4f %.4f bad pairs %d of %d; offdiag bad %d" % ((n_, m_, c_), eg[n_, m_, c_], er[n_, m_, c_],
+                int((d.amax(-1) > 1e-3).sum()), d.shape[0] * d.shape[1],
+                int(((d.amax(-1) > 1e-3) & ~torch.eye(d.shape[0], dtype=torch.bool)).sum())), "info")
     for k in ("src_nodes", "tgt_nodes"):
         add(k, "maxabs", _maxabs(out[k], ref[k]), "exactf")
     for k in ("src_node_feats", "tgt_node_feats", "src_point_feats", "tgt_point_feats"):
         add(k, "maxabs", _maxabs(out[k], ref[k]), "feat")
     for side in ("src", "tgt"):
         gi, ri = aux[side + "_node_knn_indices"].cpu().long(), raux[side + "_node_knn_indices"]
-        add(side + " partition knn idx", "mismatch frac", float((gi != ri).float().mean()), "ties")
+        # torch.topk's order among exactly equal distances is unspecified: rows must agree as sets, and mostly in order
+        add(side + " partition knn idx (as sets)", "rows differing", int((gi.sort(1)[0] != ri.sort(1)[0]).any(1).sum()), "exact")
+        add(side + " partition knn idx order", "permuted-row frac (exact ties)", float((gi != ri).any(1).float().mean()), "set")
         add(side + " partition masks", "mismatches", int((aux[side + "_node_knn_masks"].cpu() != raux[side + "_node_knn_masks"]).sum())
             + int((aux[side + "_node_masks"].cpu() != raux[side + "_node_masks"]).sum()), "exact")
     add("gt occ tgt", "maxabs", _maxabs(out["gt_tgt_node_occ"], ref["gt_tgt_node_occ"]), "f1e-5")
@@ -80,7 +90,9 @@ def run(pair, cfg, sd, device="cuda:0"):
     mine = torch.tensor([gpu_scores[(ti == a).nonzero().item(), (si == b).nonzero().item()] for a, b in g_pairs])
     add("coarse selection vs own scores", "max rel err of sorted values", float(((top - mine).abs() / top).max()) if kk else 0.0, "f1e-5")
 
-    common = [p for p in g_pairs if p in set(r_pairs)]
+    t_same = (aux["tgt_node_knn_indices"].cpu().long() == raux["tgt_node_knn_indices"]).all(1)
+    s_same = (aux["src_node_knn_indices"].cpu().long() == raux["src_node_knn_indices"]).all(1)
+    common = [p for p in g_pairs if p in set(r_pairs) and bool(t_same[p[0]]) and bool(s_same[p[1]])]
     gpos = {p: i for i, p in enumerate(g_pairs)}
     rpos = {p: i for i, p in enumerate(r_pairs)}
     if common:
@@ -88,7 +100,8 @@ def run(pair, cfg, sd, device="cuda:0"):
         ri = torch.tensor([rpos[p] for p in common])
         ms_g, ms_r = out["matching_scores"].cpu()[gi], ref["matching_scores"][ri]
         live = ms_r > -1e5
-        add("matching_scores (common patches)", "maxabs (unmasked)", float((ms_g - ms_r)[live].abs().max()), "f1e-3")
+        add("matching_scores (common patches)", "max |d|/(1+|ref|) (unmasked)",
+            float(((ms_g - ms_r).abs() / (1 + ms_r.abs()))[live].max()), "f1e-4")
         add("matching_scores masked pattern", "mismatches", int(((ms_g > -1e5) != live).sum()), "exact")
         add("patch knn points", "maxabs", _maxabs(out["tgt_node_corr_knn_points"].cpu()[gi], ref["tgt_node_corr_knn_points"][ri])
             + _maxabs(out["src_node_corr_knn_points"].cpu()[gi], ref["src_node_corr_knn_points"][ri]), "exactf")
