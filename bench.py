@@ -92,7 +92,9 @@ def cpu_reference_pairs_per_s(steps, warmup, n_points):
     from roitr_b200.synthetic import forward_args, synthetic_pair
     native.build()
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    # OpenMP kNN/FPS restatement uses every core; torch's intra-op pool is capped at 32 (the per-op tensors are small and
+    # 128 threads measured 12x SLOWER than 8 on the forward: 62 s vs 5 s per pair)
+    torch.set_num_threads(min(cores, 32))
     cfg, sd = _cfg(), _weights()
     pairs = [synthetic_pair(i, n_points) for i in range(min(POOL, max(1, steps)))]
     with torch.no_grad():

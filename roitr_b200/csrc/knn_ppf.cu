@@ -190,11 +190,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_ppf_kernel(const KnnParams P)
                     const float cd = __shfl_sync(FULL_MASK, d, l);
                     if (cd < tau[j]) {
                         const int ci = base + s + l;
-                        const unsigned le = __ballot_sync(FULL_MASK, ld[j] <= cd) & kmask;
-                        // equal to an element already in the list: the reference's order among equal distances is its
-                        // heap's, not ours -> recompute this query exactly
-                        if (__ballot_sync(FULL_MASK, ld[j] == cd) & kmask) tie[j] = true;
-                        const int ins = __popc(le);
+                        const int ins = __popc(__ballot_sync(FULL_MASK, ld[j] <= cd) & kmask);
                         const float up_d = __shfl_up_sync(FULL_MASK, ld[j], 1);
                         const int up_i = __shfl_up_sync(FULL_MASK, li[j], 1);
                         if (lane > ins) { ld[j] = up_d; li[j] = up_i; }
@@ -219,6 +215,11 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_ppf_kernel(const KnnParams P)
     for (int j = 0; j < QW; ++j) {
         const int q = q_cta0 + warp * QW + j;
         if (q >= P.m) continue;
+        // equal distances inside the final list: the reference's order among them is its heap's, not ours
+        {
+            const float nxt = __shfl_down_sync(FULL_MASK, ld[j], 1);
+            if (__ballot_sync(FULL_MASK, lane + 1 < K && ld[j] == nxt && ld[j] != 1e10f)) tie[j] = true;
+        }
         const int slot = lane - P.drop;
         if (slot < 0 || lane >= K) continue;
         if (tie[j]) {
@@ -229,20 +230,23 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_ppf_kernel(const KnnParams P)
     }
 }
 
-// Exact replay of the reference algorithm (sequential scan, max-heap with strict '<', heap sort:
-// knnquery_cuda_kernel.cu:21-48,86-107) for the queries the main kernel marked as tie-affected. Rare (about one query
-// per 20k x 20k call on random data), so one thread per marked query is fine.
-__global__ void knn_tie_fixup_kernel(const KnnParams P) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// Exact replay of the reference algorithm (sequential scan in index order, max-heap with strict '<', heap sort:
+// knnquery_cuda_kernel.cu:21-48,86-107) for the queries the main kernel marked as tie-affected (about one or two per
+// 20k x 20k call on random data). One WARP per marked query: the 32 lanes evaluate 32 consecutive points and filter
+// them against the current heap root (the root only decreases, so the filter is conservative); the few survivors are
+// pushed through the heap one by one, in index order, by lane 0 - exactly the reference's sequence of heap updates.
+constexpr int FIX_WARPS = 4;
+__global__ void __launch_bounds__(FIX_WARPS * 32) knn_tie_fixup_kernel(const KnnParams P) {
+    __shared__ float s_bd[FIX_WARPS][32];
+    __shared__ int s_bi[FIX_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = P.nslots, kout = K - P.drop;
-    if (q >= P.m || P.idx[(size_t)q * kout] >= 0) return;
-    const int s = find_segment(q, P.new_offset, P.b);
-    const int start = s == 0 ? 0 : __ldg(P.offset + s - 1), end = __ldg(P.offset + s);
-    const float qx = __ldg(P.qxyz + 3 * (size_t)q), qy = __ldg(P.qxyz + 3 * (size_t)q + 1), qz = __ldg(P.qxyz + 3 * (size_t)q + 2);
-    float bd[32];
-    int bi[32];
-    for (int i = 0; i < K; ++i) { bd[i] = 1e10f; bi[i] = start; }
-    auto sift = [&](int k) {
+    const int q_first = (blockIdx.x * FIX_WARPS + warp) * 32;
+    const int my_q = q_first + lane;
+    unsigned todo = __ballot_sync(FULL_MASK, my_q < P.m && P.idx[(size_t)my_q * kout] < 0);
+    float* bd = s_bd[warp];
+    int* bi = s_bi[warp];
+    auto sift = [&](int k) {  // lane 0 only
         int root = 0, child = 1;
         while (child < k) {
             if (child + 1 < k && bd[child + 1] > bd[child]) child++;
@@ -253,17 +257,39 @@ __global__ void knn_tie_fixup_kernel(const KnnParams P) {
             child = 2 * root + 1;
         }
     };
-    for (int i = start; i < end; ++i) {
-        const float d2 = sqdist_ref(qx - __ldg(P.xyz + 3 * (size_t)i), qy - __ldg(P.xyz + 3 * (size_t)i + 1),
-                                    qz - __ldg(P.xyz + 3 * (size_t)i + 2));
-        if (d2 < bd[0]) { bd[0] = d2; bi[0] = i; sift(K); }
+    while (todo) {
+        const int q = q_first + __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int sgm = find_segment(q, P.new_offset, P.b);
+        const int start = sgm == 0 ? 0 : __ldg(P.offset + sgm - 1), end = __ldg(P.offset + sgm);
+        const float qx = __ldg(P.qxyz + 3 * (size_t)q), qy = __ldg(P.qxyz + 3 * (size_t)q + 1), qz = __ldg(P.qxyz + 3 * (size_t)q + 2);
+        if (lane < K) { bd[lane] = 1e10f; bi[lane] = start; }
+        __syncwarp();
+        for (int base = start; base < end; base += 32) {
+            const int i = base + lane;
+            float d2 = CUDART_INF_F;
+            if (i < end)
+                d2 = sqdist_ref(qx - __ldg(P.xyz + 3 * (size_t)i), qy - __ldg(P.xyz + 3 * (size_t)i + 1),
+                                qz - __ldg(P.xyz + 3 * (size_t)i + 2));
+            unsigned cand = __ballot_sync(FULL_MASK, d2 < bd[0]);
+            while (cand) {
+                const int l = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const float cd = __shfl_sync(FULL_MASK, d2, l);
+                if (lane == 0 && cd < bd[0]) { bd[0] = cd; bi[0] = base + l; sift(K); }
+                __syncwarp();
+            }
+        }
+        if (lane == 0)
+            for (int i = K - 1; i > 0; --i) {
+                const float td = bd[0]; bd[0] = bd[i]; bd[i] = td;
+                const int ti = bi[0]; bi[0] = bi[i]; bi[i] = ti;
+                sift(i);
+            }
+        __syncwarp();
+        if (lane >= P.drop && lane < K) emit_result(P, q, lane - P.drop, kout, bi[lane], bd[lane], qx, qy, qz);
+        __syncwarp();
     }
-    for (int i = K - 1; i > 0; --i) {
-        const float td = bd[0]; bd[0] = bd[i]; bd[i] = td;
-        const int ti = bi[0]; bi[0] = bi[i]; bi[i] = ti;
-        sift(i);
-    }
-    for (int i = P.drop; i < K; ++i) emit_result(P, q, i - P.drop, kout, bi[i], bd[i], qx, qy, qz);
 }
 
 int launch_knn(const KnnParams& P, cudaStream_t st) {
@@ -287,7 +313,7 @@ int launch_knn(const KnnParams& P, cudaStream_t st) {
         knn_ppf_kernel<1><<<ceil_div(P.m, KNN_WARPS), KNN_THREADS, smem, st>>>(P);
     }
     ROITR_CHECK_LAUNCH("knn_ppf_kernel");
-    knn_tie_fixup_kernel<<<ceil_div(P.m, 128), 128, 0, st>>>(P);
+    knn_tie_fixup_kernel<<<ceil_div(P.m, FIX_WARPS * 32), FIX_WARPS * 32, 0, st>>>(P);
     ROITR_CHECK_LAUNCH("knn_tie_fixup_kernel");
     return ROITR_OK;
 }
