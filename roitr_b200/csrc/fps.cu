@@ -6,18 +6,24 @@
 // distance array `tmp` from global memory and finishes with an 11-level shared-memory tree (11 __syncthreads). FPS is a
 // chain of m dependent iterations, so what matters is the latency of one iteration.
 //
-// Here a cloud is owned by a CLUSTER of CL CTAs. Points, running min-distances and tie-break keys live in REGISTERS for
-// the whole kernel (PPT points per thread); an iteration is
-//   per-thread scan (PPT fused distance updates) -> 2x redux.sync per warp (max of the float bits, min of the key)
-//   -> one __syncthreads -> every warp re-reduces the <=16 warp candidates -> one DSMEM all-to-all of the CTA candidates
-//   + one cluster barrier -> every thread picks the winner (with its xyz carried along, so no global read on the chain).
+// Here a cloud is owned by a CLUSTER of CL CTAs. Coordinates, running min-distances and tie-break keys live in REGISTERS
+// for the whole kernel (PPT points per thread; a second copy of the CTA's coordinates sits in shared memory only so the
+// winner's xyz can be looked up by index). One iteration:
+//   1. per thread: PPT independent fused distance updates + an FMNMX tree                       (no select chains)
+//   2. per warp: redux.sync.max of the float bits; the lanes that hold the maximum resolve the tie-break key; redux.min
+//   3. one __syncthreads; every warp re-reduces the <=16 warp candidates redundantly (no second barrier)
+//   4. cluster exchange WITHOUT a cluster barrier: warp 0 pushes the CTA candidate (dist, key, xyz = 20 B) into every
+//      peer's shared memory with st.async, which also signals the peer's mbarrier (complete_tx); each CTA waits on its
+//      own mbarrier (try_wait), then picks the winner with two more redux. No fence, no barrier.cluster in the loop.
+//      (ncu on the first version, which used cooperative_groups cluster.sync(): ERRBAR + UCGABAR_ARV/WAIT + membar were
+//      ~50 % of all stall samples; profiles/r01_fps_v1_stalls.txt.)
 //
 // Bit-exactness with the reference, including exact-distance ties: the distance is the reference's FMA association
 // (sqdist_ref) with d = x_k - x_last; the reference's winner among equal maxima is the lowest k inside a thread
 // (strict '>' scanning k ascending, .cu:57-58) and then the lower SLOT at every level of its power-of-two tree
 // ('v2 > v1 ? i2 : i1', .cu:5-10), i.e. the smallest bit-reversed thread id. Both are encoded in a 31-bit key
 //   key(k) = bitrev_{log2 BS}((k-start) % BS) << 21 | (k-start) / BS ,   BS = reference block size for n_max
-// and the winner is (max distance, min key). k is recovered from the key, so candidates are (dist, key, x, y, z).
+// and the winner is (max distance, min key); k is recovered from the key.
 #include <cooperative_groups.h>
 
 #include "../../include/roitr_b200.h"
@@ -30,12 +36,14 @@ namespace {
 constexpr int FPS_THREADS = 512;
 constexpr int FPS_WARPS = FPS_THREADS / 32;
 constexpr int MAX_CL = 8;
+constexpr unsigned NO_KEY = 0xffffffffu;
+constexpr int XCHG_BYTES = 20;  // bits, key, x, y, z
 
 struct __align__(16) Cand {
-    unsigned bits;  // float bits of the running distance (>= 0, so unsigned order == float order)
+    int bits;       // float bits of the running distance; signed compare (valid distances >= 0, the -1 sentinel is < 0)
     unsigned key;   // tie-break key, smaller wins
     float x, y, z;
-    float pad0, pad1, pad2;
+    float pad[3];
 };
 
 struct FpsParams {
@@ -56,19 +64,46 @@ __host__ __device__ __forceinline__ int ref_block_log2(int n) {
     return p;
 }
 
-__device__ __forceinline__ bool better(unsigned b1, unsigned k1, unsigned b2, unsigned k2) {
-    return (b1 > b2) || (b1 == b2 && k1 < k2);
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+// 16-byte + 4-byte remote stores that also complete `bytes` on the remote mbarrier (async proxy; no fence needed:
+// the mbarrier phase completion orders the data for the waiter).
+__device__ __forceinline__ void st_async_v4(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t dst, uint32_t a, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst), "r"(a), "r"(bar)
+                 : "memory");
+}
+
+template <int N>
+__device__ __forceinline__ float tree_max(const float (&v)[N]) {
+    float t[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = v[i];
+#pragma unroll
+    for (int s = 1; s < N; s <<= 1)
+#pragma unroll
+        for (int i = 0; i + s < N; i += 2 * s) t[i] = fmaxf(t[i], t[i + s]);
+    return t[0];
 }
 
 template <int CL, int PPT>
 __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const FpsParams P) {
+    extern __shared__ __align__(16) float s_pts[];  // [PPT * FPS_THREADS][3]: this CTA's coordinates by local slot
+    __shared__ Cand s_cta[2][MAX_CL];
+    __shared__ int2 s_warp[2][FPS_WARPS];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (CL > 1) ? (int)cluster.block_rank() : 0;
     const int cloud = blockIdx.x / CL;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    __shared__ Cand s_warp[2][FPS_WARPS];
-    __shared__ Cand s_cta[2][MAX_CL];
 
     const int start_n = cloud == 0 ? 0 : __ldg(P.offset + cloud - 1);
     const int end_n = __ldg(P.offset + cloud);
@@ -94,9 +129,11 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const FpsPa
             pk[i] = (rev << 21) | (unsigned)(r >> bs_log2);
         } else {
             px[i] = py[i] = pz[i] = 0.f;
-            pd[i] = -1.f;       // never wins: a real point has distance >= 0 (float bits of -1 are handled below)
-            pk[i] = 0xffffffffu;
+            pd[i] = -1.f;  // min(d, -1) stays -1: never the maximum
+            pk[i] = NO_KEY;
         }
+        float* sp = s_pts + 3 * (size_t)(i * FPS_THREADS + tid);
+        sp[0] = px[i]; sp[1] = py[i]; sp[2] = pz[i];
     }
 
     float lx = 0.f, ly = 0.f, lz = 0.f;
@@ -112,73 +149,82 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const FpsPa
             P.new_xyz[3 * (size_t)start_m + 2] = lz;
         }
     }
-    if (CL > 1) cluster.sync();  // all CTAs of the cluster are resident before any DSMEM traffic
-
-    for (int j = start_m + 1; j < end_m; ++j) {
-        const int par = j & 1;
-        // ---- per-thread scan: update running distances, keep (max dist, min key) with its coordinates ----
-        unsigned bb = 0u, bk = 0xffffffffu;
-        float bx = 0.f, by = 0.f, bz = 0.f;
-        bool any = false;
-#pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-            const float d = sqdist_ref(px[i] - lx, py[i] - ly, pz[i] - lz);
-            const float d2 = fminf(d, pd[i]);
-            const bool valid = pk[i] != 0xffffffffu;
-            pd[i] = valid ? d2 : pd[i];
-            const unsigned bits = __float_as_uint(d2);
-            const bool take = valid && (!any || better(bits, pk[i], bb, bk));
-            bb = take ? bits : bb; bk = take ? pk[i] : bk;
-            bx = take ? px[i] : bx; by = take ? py[i] : by; bz = take ? pz[i] : bz;
-            any = any || valid;
+    if (CL > 1) {
+        if (tid == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            mbar_fence_init();
         }
-        // ---- warp: two redux.sync ----
-        const unsigned wmax = __reduce_max_sync(FULL_MASK, any ? bb : 0u);
-        const unsigned wkey = __reduce_min_sync(FULL_MASK, (any && bb == wmax) ? bk : 0xffffffffu);
-        if (any && bb == wmax && bk == wkey) {
-            Cand c; c.bits = bb; c.key = bk; c.x = bx; c.y = by; c.z = bz; c.pad0 = c.pad1 = c.pad2 = 0.f;
-            s_warp[par][warp] = c;
-        } else if (wkey == 0xffffffffu && lane == 0) {
-            Cand c; c.bits = 0u; c.key = 0xffffffffu; c.x = c.y = c.z = 0.f; c.pad0 = c.pad1 = c.pad2 = 0.f;
-            s_warp[par][warp] = c;  // warp with no valid point
-        }
+        cluster.sync();  // peers' mbarriers are initialised and all CTAs are resident before any DSMEM traffic
+    } else {
         __syncthreads();
-        // ---- CTA: every warp reduces the FPS_WARPS candidates redundantly (no second barrier) ----
-        unsigned cb = 0u, ck = 0xffffffffu;
-        if (lane < FPS_WARPS) { cb = s_warp[par][lane].bits; ck = s_warp[par][lane].key; }
-        const unsigned cmax = __reduce_max_sync(FULL_MASK, cb);
-        const unsigned ckey = __reduce_min_sync(FULL_MASK, (cb == cmax) ? ck : 0xffffffffu);
-        const unsigned wl = __ballot_sync(FULL_MASK, lane < FPS_WARPS && cb == cmax && ck == ckey);
-        const int wsrc = __ffs(wl) - 1;  // >= 0: at least one warp holds a valid point or all are sentinels
+    }
 
-        unsigned fbits, fkey;
-        if (CL == 1) {
-            const Cand w = s_warp[par][wsrc < 0 ? 0 : wsrc];
-            fbits = w.bits; fkey = w.key; lx = w.x; ly = w.y; lz = w.z;
-        } else {
-            if (warp == 0 && lane < CL) {
-                // all-to-all: lane r writes this CTA's candidate into CTA r's slot [par][rank]
-                const Cand w = s_warp[par][wsrc < 0 ? 0 : wsrc];
-                Cand* remote = cluster.map_shared_rank(&s_cta[par][rank], lane);
-                *remote = w;
-            }
-            cluster.sync();
-            unsigned b0 = 0u, k0 = 0xffffffffu;
-            int best = 0;
+    // recover (relative index, local slot) from a key: key = bitrev(t) << 21 | q with r = q * BS + t
+    auto key_to_rel = [&](unsigned key) {
+        const unsigned rev = key >> 21, qd = key & 0x1fffffu;
+        const unsigned t_ref = bs_log2 ? (__brev(rev) >> (32 - bs_log2)) : 0u;
+        return (int)(qd << bs_log2) + (int)t_ref;
+    };
+
+    int it = 0;
+    for (int j = start_m + 1; j < end_m; ++j, ++it) {
+        const int par = it & 1;
+        if (CL > 1 && tid == 0) mbar_expect_tx(&s_bar[par], CL * XCHG_BYTES);  // arm this iteration's exchange
+        // ---- 1. per-thread update + max ----
 #pragma unroll
-            for (int r = 0; r < CL; ++r) {
-                const unsigned rb = s_cta[par][r].bits, rk = s_cta[par][r].key;
-                if (r == 0 || better(rb, rk, b0, k0)) { b0 = rb; k0 = rk; best = r; }
-            }
-            fbits = b0; fkey = k0;
-            lx = s_cta[par][best].x; ly = s_cta[par][best].y; lz = s_cta[par][best].z;
+        for (int i = 0; i < PPT; ++i) pd[i] = fminf(sqdist_ref(px[i] - lx, py[i] - ly, pz[i] - lz), pd[i]);
+        const int tb = __float_as_int(tree_max<PPT>(pd));
+        // ---- 2. warp candidate ----
+        const int wmax = __reduce_max_sync(FULL_MASK, tb);
+        unsigned key = NO_KEY;
+        if (tb == wmax) {
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) key = (__float_as_int(pd[i]) == wmax) ? min(key, pk[i]) : key;
         }
-        (void)fbits;
+        const unsigned wkey = __reduce_min_sync(FULL_MASK, key);
+        if (lane == 0) s_warp[par][warp] = make_int2(wmax, (int)wkey);
+        __syncthreads();
+        // ---- 3. CTA candidate (every warp, redundantly) ----
+        int cb = (int)0x80000000;
+        unsigned ck = NO_KEY;
+        if (lane < FPS_WARPS) { const int2 w = s_warp[par][lane]; cb = w.x; ck = (unsigned)w.y; }
+        const int cmax = __reduce_max_sync(FULL_MASK, cb);
+        const unsigned ckey = __reduce_min_sync(FULL_MASK, cb == cmax ? ck : NO_KEY);
+
+        unsigned fkey;
+        if (CL == 1) {
+            fkey = ckey;
+            if (ckey != NO_KEY) {
+                const int rel = key_to_rel(ckey);  // CL == 1: local slot = (rel / 512) * 512 + rel % 512 = rel
+                lx = s_pts[3 * rel]; ly = s_pts[3 * rel + 1]; lz = s_pts[3 * rel + 2];
+            }
+        } else {
+            // ---- 4. cluster exchange: st.async + mbarrier ----
+            if (warp == 0 && lane < CL) {
+                float cx = 0.f, cy = 0.f, cz = 0.f;
+                if (ckey != NO_KEY) {
+                    const int rel = key_to_rel(ckey);
+                    const int slot = (rel / (CL * FPS_THREADS)) * FPS_THREADS + (rel % FPS_THREADS);
+                    cx = s_pts[3 * slot]; cy = s_pts[3 * slot + 1]; cz = s_pts[3 * slot + 2];
+                }
+                const uint32_t dst = map_to_rank(smem_u32(&s_cta[par][rank]), (uint32_t)lane);
+                const uint32_t rbar = map_to_rank(smem_u32(&s_bar[par]), (uint32_t)lane);
+                st_async_v4(dst, (uint32_t)cmax, ckey, __float_as_uint(cx), __float_as_uint(cy), rbar);
+                st_async_b32(dst + 16, __float_as_uint(cz), rbar);
+            }
+            mbar_wait(&s_bar[par], (it >> 1) & 1);
+            int rb = (int)0x80000000;
+            unsigned rk = NO_KEY;
+            if (lane < CL) { rb = s_cta[par][lane].bits; rk = s_cta[par][lane].key; }
+            const int fmax = __reduce_max_sync(FULL_MASK, rb);
+            fkey = __reduce_min_sync(FULL_MASK, rb == fmax ? rk : NO_KEY);
+            const int src = __ffs(__ballot_sync(FULL_MASK, lane < CL && rb == fmax && rk == fkey)) - 1;
+            const Cand& w = s_cta[par][src < 0 ? 0 : src];
+            lx = w.x; ly = w.y; lz = w.z;
+        }
         if (rank == 0 && tid == 0) {
-            // recover k from the key: key = bitrev(t) << 21 | q  with k - start = q * BS + t
-            const unsigned rev = fkey >> 21, qd = fkey & 0x1fffffu;
-            const unsigned t_ref = bs_log2 ? (__brev(rev) >> (32 - bs_log2)) : 0u;
-            P.idx[j] = start_n + (int)(qd << bs_log2) + (int)t_ref;
+            P.idx[j] = start_n + (fkey != NO_KEY ? key_to_rel(fkey) : 0);
             if (P.new_xyz) {
                 P.new_xyz[3 * (size_t)j] = lx; P.new_xyz[3 * (size_t)j + 1] = ly; P.new_xyz[3 * (size_t)j + 2] = lz;
             }
@@ -189,10 +235,16 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const FpsPa
 
 template <int CL, int PPT>
 int launch_fps(const FpsParams& P, cudaStream_t st) {
+    const int smem = PPT * FPS_THREADS * 12;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        ROITR_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<CL, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(P.b * CL);
     cfg.blockDim = dim3(FPS_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -217,8 +269,8 @@ extern "C" int roitr_furthestsampling_cfg(int b, int n_max, int n_seg_max, const
     FpsParams P;
     P.xyz = xyz; P.offset = offset; P.new_offset = new_offset; P.idx = idx; P.new_xyz = new_xyz; P.b = b;
     P.bs_shared_log2 = n_max > 0 ? ref_block_log2(n_max) : -1;
-    // capacity needed: CL * 512 * PPT >= n_seg_max. Latency mode (few clouds) prefers big clusters / small PPT,
-    // throughput mode (many clouds) prefers CL=1. Auto: keep roughly <= 148 CTAs in flight.
+    // capacity needed: CL * 512 * PPT >= n_seg_max. Latency mode (few clouds) prefers big clusters / few points per
+    // thread, throughput mode (many clouds) prefers small clusters. Auto: keep roughly <= 148 CTAs in flight.
     int cl = cluster_hint;
     if (cl != 1 && cl != 2 && cl != 4 && cl != 8) {
         cl = 8;
@@ -230,8 +282,13 @@ extern "C" int roitr_furthestsampling_cfg(int b, int n_max, int n_seg_max, const
 #define FPS_DISPATCH(CLV)                                                  \
     if (cl == CLV) {                                                       \
         if (per_thread <= 2) return launch_fps<CLV, 2>(P, st);             \
+        if (per_thread <= 3) return launch_fps<CLV, 3>(P, st);             \
         if (per_thread <= 4) return launch_fps<CLV, 4>(P, st);             \
+        if (per_thread <= 5) return launch_fps<CLV, 5>(P, st);             \
+        if (per_thread <= 6) return launch_fps<CLV, 6>(P, st);             \
         if (per_thread <= 8) return launch_fps<CLV, 8>(P, st);             \
+        if (per_thread <= 10) return launch_fps<CLV, 10>(P, st);           \
+        if (per_thread <= 12) return launch_fps<CLV, 12>(P, st);           \
         return launch_fps<CLV, 16>(P, st);                                 \
     }
     FPS_DISPATCH(1)
