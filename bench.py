@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one JSON line on rank 0)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithm on the host CPU cores
 
-A step = one RIGA_v2.forward over one synthetic pair of BASELINE.json configs[1] (2 x 20 000 points, Gaussian blobs,
-seeded weights). N > 1 (torchrun, one rank per GPU): pairs are independent units, rank r processes its own
+A step = RIGA_v2.forward over a batch of B (default 8) independent synthetic pairs of BASELINE.json configs[1]
+(2 x 20 000 points each, Gaussian blobs, seeded weights), issued as one CUDA graph. N > 1 (torchrun, one rank per GPU): pairs are independent units, rank r processes its own
 pairs (weak scaling), NCCL is used only for the barrier, the max-over-ranks time and the gather of per-pair result
 counts. `value` = pairs/s with inputs resident in HBM; `e2e` = the same metric through model.forward with pinned HOST
 buffers (H2D of the 9 inputs and D2H of the correspondences inside the timed region).
@@ -29,7 +29,7 @@ import torch  # noqa: E402
 N_POINTS = int(os.environ.get("ROITR_BENCH_POINTS", "20000"))
 WORKLOAD = "2x%d-pt synthetic pair, nsample 8/16/16/16 (k=16), full RIGA_v2 forward, 3DMatch head" % N_POINTS
 METRIC = "point-cloud pairs/s (2x20k pts, k=16)"
-POOL = 4   # distinct pairs cycled through (inputs differ from step to step)
+POOL = 4
 
 
 def _cfg():
@@ -124,12 +124,41 @@ def run_reference(args):
     return 0
 
 
+def op_work(name, ints):
+    """Algorithmic work of one entry-point call from its leading integer arguments (DESIGN.md §4 / SURVEY.md §8d).
+    -> (kind, amount): kind 'bytes' (compulsory bytes) or 'flop'."""
+    if name == "roitr_linear":
+        M, N, K = ints[:3]
+        return "flop", 2.0 * M * N * K
+    if name == "roitr_geo_embedding":
+        N, C = ints[:2]
+        return "flop", 8.0 * N * N * C * C
+    if name == "roitr_furthestsampling_cfg":
+        b, _, nseg = ints[:3]
+        return "bytes", b * (nseg * 12.0 + (nseg // 4) * 16.0)
+    if name == "roitr_knn_ppf_n":
+        b, m, k, drop, n = ints[:5]
+        return "bytes", n * 24.0 + m * 24.0 + m * k * 20.0
+    if name == "roitr_local_attention":
+        m, C, _, knb = ints[:4]
+        return "bytes", m * (2.0 * knb * C * 4 + 2 * C * 4)
+    if name == "roitr_geo_attention":
+        N, M, C = ints[:3]
+        return "bytes", 2.0 * N * M * C * 4 + 4.0 * N * C * 4
+    if name == "roitr_fine_matching":
+        P, _, _, C = ints[:4]
+        return "bytes", P * (2.0 * 64 * C * 4 + 65 * 65 * 4)
+    return "bytes", 0.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("ROITR_BENCH_BATCH", "8")), help="pairs per step per GPU")
+    ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -148,19 +177,21 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from roitr_b200 import _lib, model
-    from roitr_b200.synthetic import FORWARD_ARG_ORDER, synthetic_pair
+    from roitr_b200.synthetic import synthetic_pair
     cfg, sd = _cfg(), _weights()
     m = model.create_model(cfg)
     m.load_state_dict(sd, strict=True)
     m = m.to(dev).eval()
-    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    steps, warmup, B = max(1, args.steps), max(3, args.warmup), max(1, args.batch)
 
-    # rank r owns pairs r, r+world, ... (global pair index; outputs would be named by it)
-    host_pairs = [synthetic_pair(rank + world * i, N_POINTS) for i in range(POOL)]
-    pinned = [[p[k].pin_memory() for k in FORWARD_ARG_ORDER] for p in host_pairs]
-    resident = [[t.to(dev) for t in p] for p in pinned]
+    # rank r owns global pairs r, r+world, ... ; POOL distinct batches are cycled so inputs differ from step to step
+    NB = 2
+    host = [[synthetic_pair(rank + world * (j * B + i), N_POINTS) for i in range(B)] for j in range(NB)]
+    pinned = [[{k: v.pin_memory() for k, v in p.items()} for p in batch] for batch in host]
+    resident = [[{k: v.to(dev) for k, v in p.items()} for p in batch] for batch in pinned]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    h2d_bytes = sum(t.numel() * t.element_size() for t in pinned[0])
+    h2d_bytes = sum(t.numel() * t.element_size() for p in pinned[0] for t in p.values())
+    runner = m.batch_runner(B, N_POINTS, N_POINTS, graph=not args.no_graph)
 
     def barrier():
         torch.cuda.synchronize()
@@ -168,12 +199,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_loop(e2e, n_steps, timed_ops=()):
-        """returns (sum of per-step event ms, wall seconds between the barriers, d2h bytes/step, counts)"""
-        ev, d2h, counts = [], 0, []
-        _lib.TIMED.clear()
-        for k in timed_ops:
-            _lib.TIMED[k] = []
+    def run_loop(e2e, n_steps, r=runner):
+        ev, d2h, ncorr = [], 0, 0
         _lib.reset_stats()
         barrier()
         t0 = time.perf_counter()
@@ -182,32 +209,55 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if e2e:
-                args_dev = [t.to(dev, non_blocking=True) for t in pinned[i % POOL]]
-                out = m(*args_dev)
-                res = [out[k].cpu() for k in ("tgt_corr_points", "src_corr_points", "corr_scores")]
-                d2h = sum(t.numel() * t.element_size() for t in res)
+                r.load(pinned[i % NB])                       # H2D of the 9 inputs of every pair
+                r.run()
+                outs = r.results()                           # D2H of the counts (sync), exact-size outputs
+                res = [o[k].cpu() for o in outs for k in ("tgt_corr_points", "src_corr_points", "corr_scores")]
+                d2h = sum(t.numel() * t.element_size() for t in res) + 12 * B
+                ncorr = sum(int(o["corr_scores"].shape[0]) for o in outs)
             else:
-                out = m(*resident[i % POOL])
+                r.load(resident[i % NB])                     # device-to-device: inputs already resident in HBM
+                r.run()
             b.record()
             ev.append((a, b))
-            counts.append(int(out["corr_scores"].shape[0]))
         barrier()
         wall = time.perf_counter() - t0
-        return sum(a.elapsed_time(b) for a, b in ev), wall, d2h, counts
+        return sum(a.elapsed_time(b) for a, b in ev), wall, d2h, ncorr
 
     run_loop(False, warmup)
-    DOMINANT = "roitr_furthestsampling_cfg"
     with ClockSampler(local) as clk:
-        ms_dev, wall, _, counts = run_loop(False, steps, timed_ops=(DOMINANT,))
-    launches = _lib.STATS["launches"]
-    dom = _lib.TIMED.get(DOMINANT, [])
-    dom_ms = [a.elapsed_time(b) for a, b in dom]
-    calls = dict(_lib.STATS["calls"])
+        ms_dev, wall, _, _ = run_loop(False, steps)
+    counts = runner.results(full=False)
     run_loop(True, 2)
-    ms_e2e, _, d2h_bytes, _ = run_loop(True, steps)
+    ms_e2e, _, d2h_bytes, ncorr = run_loop(True, steps)
+
+    # instrumented EAGER replica of the same step: per-entry-point CUDA-event durations, launch count, algorithmic work
+    eager = m.batch_runner(B, N_POINTS, N_POINTS, graph=False)
+    eager.load(resident[0]); eager.run(); torch.cuda.synchronize()
+    _lib.TIMED.clear()
+    for k in _lib.KERNELS_PER_CALL:
+        _lib.TIMED[k] = []
+    _lib.reset_stats()
+    _lib.RECORD_ARGS = True
+    flush.zero_()
+    eager.load(resident[1 % NB]); eager.run(); torch.cuda.synchronize()
+    launches_per_step = _lib.STATS["launches"]
+    shares = {}
+    for name, evs in _lib.TIMED.items():
+        if not evs:
+            continue
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        work = {"bytes": 0.0, "flop": 0.0}
+        for ints in _lib.ARGS.get(name, []):
+            kind, amt = op_work(name, ints)
+            work[kind] += amt
+        shares[name] = {"ms": ms, "calls": len(evs), "bytes": work["bytes"], "flop": work["flop"]}
+    _lib.TIMED.clear()
+    _lib.RECORD_ARGS = False
+    eager_ms = sum(v["ms"] for v in shares.values())
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
-    c = torch.tensor([sum(counts)], dtype=torch.int64, device=dev)
+    c = torch.tensor([sum(x[2] for x in counts)], dtype=torch.int64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks, device-timed
         gathered = [torch.zeros_like(c) for _ in range(world)]
@@ -223,35 +273,34 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
-        # dominant kernel = fps_cluster_kernel (profiles/): algorithmic bytes per launch = n*12 (xyz read once) + m*4 (idx)
-        # + m*12 (sampled xyz); 6 launches per pair: 20000->5000, 5000->1250, 1250->312 for each cloud.
-        per_launch = []
-        n = N_POINTS
-        for _ in range(3):
-            per_launch.append(n * 12 + (n // 4) * 16)
-            n //= 4
-        alg_bytes = sum(per_launch) / len(per_launch)
-        avg_ms = sum(dom_ms) / max(1, len(dom_ms))
-        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+        src = "measured" if peaks.get("hbm_gbs") else "fallback"
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tf_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        top = max(shares, key=lambda k: shares[k]["ms"])
+        tv = shares[top]
+        if tv["flop"] > 0:
+            ach = tv["flop"] / (tv["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak}
+        else:
+            ach = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
+        roof.update({"kernel": top, "traffic": None, "peak_source": src, "avg_launch_ms": tv["ms"] / tv["calls"],
+                     "launches_timed": tv["calls"], "share_of_step": tv["ms"] / eager_ms if eager_ms else None,
+                     "how": "CUDA events around every entry-point call in an eager replica of the timed step (the timed "
+                            "step itself is one CUDA graph); algorithmic work per DESIGN.md §4 / SURVEY.md §8d"})
         line = {
-            "metric": METRIC, "value": world * steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": world * B * steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "parallelism": "independent pairs x%d" % world,
-                       "l2": "256 MiB flush between steps (outside the timed events); %d distinct pairs cycled" % POOL,
-                       "mode": "eager, one pair in flight per GPU"},
-            "e2e": {"value": world * steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "parallelism": "independent pairs x%d" % world,
+                       "l2": "256 MiB flush between steps (outside the timed events); %d distinct batches cycled" % NB,
+                       "mode": ("one CUDA graph per step" if not args.no_graph else "eager") + ", %d pairs in flight per GPU" % B},
+            "e2e": {"value": world * B * steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches, "clocks": clk.summary(),
-            "roofline": {"kernel": "fps_cluster_kernel (roitr_furthestsampling_cfg)", "bound": "hbm",
-                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_timed": len(dom_ms),
-                         "share_of_step": sum(dom_ms) / ms_dev if ms_dev else None,
-                         "note": "latency-bound dependent chain (m iterations); compulsory bytes are ~0.3 MB per launch, "
-                                 "so the HBM fraction is ~0 by construction (SURVEY.md §8d); see DESIGN.md"},
-            "result_check": {"correspondences_per_pair": total_corr / (world * steps)},
-            "wall_s_between_barriers": wall, "op_calls": calls,
+            "gpu_launches": launches_per_step * steps, "clocks": clk.summary(), "roofline": roof,
+            "kernel_shares_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])},
+            "result_check": {"correspondences_per_pair": total_corr / (world * B), "e2e_correspondences_last_step": ncorr},
+            "wall_s_between_barriers": wall,
         }
         if not args.no_cpu_baseline:
             v, dt, cores = cpu_reference_pairs_per_s(2, 0, N_POINTS)

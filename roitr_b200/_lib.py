@@ -67,6 +67,8 @@ KERNELS_PER_CALL = {
 }
 STATS = {"launches": 0, "calls": {}}
 TIMED = {}        # entry-point name -> list of (start_event, end_event); filled only for names present as keys
+RECORD_ARGS = False
+ARGS = {}         # entry-point name -> list of leading integer arguments per call (bench.py's work model)
 
 
 def reset_stats():
@@ -74,6 +76,7 @@ def reset_stats():
     STATS["calls"] = {}
     for k in TIMED:
         TIMED[k] = []
+    ARGS.clear()
 
 
 def call(name, *args):
@@ -90,5 +93,13 @@ def call(name, *args):
         timed.append((e0, e1))
     if rc != 0:
         raise RoitrError("%s failed (rc=%d): %s" % (name, rc, lib().roitr_last_error().decode()))
+    if RECORD_ARGS:
+        ints = []
+        for a in args:
+            if isinstance(a, c_int):
+                ints.append(a.value)
+            else:
+                break
+        ARGS.setdefault(name, []).append(ints)
     STATS["launches"] += KERNELS_PER_CALL.get(name, 1)
     STATS["calls"][name] = STATS["calls"].get(name, 0) + 1

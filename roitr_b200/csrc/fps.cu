@@ -237,7 +237,7 @@ template <int CL, int PPT>
 int launch_fps(const FpsParams& P, cudaStream_t st) {
     const int smem = PPT * FPS_THREADS * 12;
     static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    if (!attr_set) {  // dynamic + static shared memory can exceed the 48 KB default from PPT = 8 on
         ROITR_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<CL, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }

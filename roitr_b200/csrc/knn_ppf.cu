@@ -89,7 +89,7 @@ __device__ __forceinline__ void emit_result(const KnnParams& P, int q, int slot,
 }
 
 template <int QW>
-__global__ void __launch_bounds__(KNN_THREADS) knn_ppf_kernel(const KnnParams P) {
+__global__ void __launch_bounds__(KNN_THREADS, 3) knn_ppf_kernel(const KnnParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tile0 = reinterpret_cast<float*>(smem_raw);
     float* tile1 = reinterpret_cast<float*>(smem_raw + TILE_BYTES);
@@ -265,19 +265,27 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) knn_tie_fixup_kernel(const Knn
         const float qx = __ldg(P.qxyz + 3 * (size_t)q), qy = __ldg(P.qxyz + 3 * (size_t)q + 1), qz = __ldg(P.qxyz + 3 * (size_t)q + 2);
         if (lane < K) { bd[lane] = 1e10f; bi[lane] = start; }
         __syncwarp();
-        for (int base = start; base < end; base += 32) {
-            const int i = base + lane;
-            float d2 = CUDART_INF_F;
-            if (i < end)
-                d2 = sqdist_ref(qx - __ldg(P.xyz + 3 * (size_t)i), qy - __ldg(P.xyz + 3 * (size_t)i + 1),
-                                qz - __ldg(P.xyz + 3 * (size_t)i + 2));
-            unsigned cand = __ballot_sync(FULL_MASK, d2 < bd[0]);
-            while (cand) {
-                const int l = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const float cd = __shfl_sync(FULL_MASK, d2, l);
-                if (lane == 0 && cd < bd[0]) { bd[0] = cd; bi[0] = base + l; sift(K); }
-                __syncwarp();
+        constexpr int U = 8;  // 8 x 32 points per outer step: the independent loads overlap their L2 latency
+        for (int base = start; base < end; base += 32 * U) {
+            float d2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + 32 * u + lane;
+                d2[u] = CUDART_INF_F;
+                if (i < end)
+                    d2[u] = sqdist_ref(qx - __ldg(P.xyz + 3 * (size_t)i), qy - __ldg(P.xyz + 3 * (size_t)i + 1),
+                                       qz - __ldg(P.xyz + 3 * (size_t)i + 2));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {  // still strictly in index order
+                unsigned cand = __ballot_sync(FULL_MASK, d2[u] < bd[0]);
+                while (cand) {
+                    const int l = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const float cd = __shfl_sync(FULL_MASK, d2[u], l);
+                    if (lane == 0 && cd < bd[0]) { bd[0] = cd; bi[0] = base + 32 * u + l; sift(K); }
+                    __syncwarp();
+                }
             }
         }
         if (lane == 0)
@@ -291,6 +299,8 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) knn_tie_fixup_kernel(const Knn
         __syncwarp();
     }
 }
+
+int g_skip_fixup = 0;  // debug only (roitr_debug_skip_knn_fixup): leave the -1 markers in place to count flagged queries
 
 int launch_knn(const KnnParams& P, cudaStream_t st) {
     if (P.m == 0) return ROITR_OK;
@@ -313,6 +323,7 @@ int launch_knn(const KnnParams& P, cudaStream_t st) {
         knn_ppf_kernel<1><<<ceil_div(P.m, KNN_WARPS), KNN_THREADS, smem, st>>>(P);
     }
     ROITR_CHECK_LAUNCH("knn_ppf_kernel");
+    if (g_skip_fixup) return ROITR_OK;
     knn_tie_fixup_kernel<<<ceil_div(P.m, FIX_WARPS * 32), FIX_WARPS * 32, 0, st>>>(P);
     ROITR_CHECK_LAUNCH("knn_tie_fixup_kernel");
     return ROITR_OK;
@@ -340,6 +351,8 @@ static int knn_common(int b, int m, int nslots, int drop, const float* xyz, cons
     P.n_total = n_total > 0 ? n_total : 0x7fffffff;
     return launch_knn(P, (cudaStream_t)stream);
 }
+
+extern "C" int roitr_debug_skip_knn_fixup(int skip) { g_skip_fixup = skip; return 0; }
 
 extern "C" int roitr_knnquery_n(int b, int m, int nsample, int n_total, const float* xyz, const float* new_xyz,
                                 const int* offset, const int* new_offset, int* idx, float* dist2, void* stream) {

@@ -91,25 +91,50 @@ def _offsets(ends, device):
     return torch.tensor(ends, dtype=torch.int32, device=device)
 
 
-def encode(W, pts, feats, nrm, ends, fps_cluster=0):
-    """enc1..enc4 for a batch of clouds concatenated along dim 0 (``ends`` = host list of cumulative sizes)."""
-    dev = pts.device
+class Plan:
+    """Host-side schedule for a batch of ``B`` pairs with fixed cloud sizes: every size and every ``offset`` tensor the
+    kernels need, computed once (the reference recomputes them with .item() syncs on every forward, model/model.py:59-63).
+    Clouds are laid out [src_0 .. src_{B-1}, tgt_0 .. tgt_{B-1}] along dim 0. Nothing here depends on the data, so a
+    forward driven by a Plan issues no host<->device traffic until its outputs are read and can be CUDA-graph captured."""
+
+    def __init__(self, n_src, n_tgt, B, device, fps_cluster=0):
+        self.B, self.n_src, self.n_tgt, self.device, self.fps_cluster = B, n_src, n_tgt, device, fps_cluster
+        sizes = [n_src] * B + [n_tgt] * B
+        self.levels = []
+        for li in range(4):
+            if STRIDES[li] != 1:
+                sizes = [n // STRIDES[li] for n in sizes]
+            ends = [sum(sizes[: i + 1]) for i in range(len(sizes))]
+            self.levels.append(dict(sizes=list(sizes), ends=ends, total=ends[-1], n_max=max(sizes), o=_offsets(ends, device)))
+        self.one = {}
+
+    def starts(self, li, cloud):
+        e = self.levels[li]["ends"]
+        return (0 if cloud == 0 else e[cloud - 1]), e[cloud]
+
+    def single_offset(self, n):
+        if n not in self.one:
+            self.one[n] = _offsets([n], self.device)
+        return self.one[n]
+
+
+def encode(W, plan, pts, feats, nrm):
+    """enc1..enc4 for all 2B clouds of the plan at once (segment-batched kernels)."""
     levels = []
-    o = _offsets(ends, dev)
     x = feats
+    o = plan.levels[0]["o"]
     for li in range(4):
         p = "backbone.enc%d" % (li + 1)
         k = NSAMPLE[li]
+        L = plan.levels[li]
         if STRIDES[li] != 1:
-            sizes = [e - s for s, e in zip([0] + ends[:-1], ends)]
-            new_sizes = [n // STRIDES[li] for n in sizes]
-            new_ends = [sum(new_sizes[: i + 1]) for i in range(len(new_sizes))]
-            no = _offsets(new_ends, dev)
-            down_idx, n_p = ops.fps(pts, o, no, max(sizes), new_ends[-1], per_segment_rule=True, cluster=fps_cluster)
+            no = L["o"]
+            down_idx, n_p = ops.fps(pts, o, no, plan.levels[li - 1]["n_max"], L["total"], per_segment_rule=True,
+                                    cluster=plan.fps_cluster)
             n_n = ops.gather_rows(nrm, down_idx)
             gidx, gppf, _ = ops.knn_ppf(k, pts, nrm, n_p, n_n, o, no)
             x = local_ppf_transformer(W, p + ".0.transformer", x, down_idx, gidx, gppf)
-            pts, nrm, o, ends = n_p, n_n, no, new_ends
+            pts, nrm, o = n_p, n_n, no
             idx, ppf, _ = ops.knn_ppf(k, pts, nrm, pts, nrm, o, o)
         else:
             down_idx = None
@@ -117,7 +142,7 @@ def encode(W, pts, feats, nrm, ends, fps_cluster=0):
             x = local_ppf_transformer(W, p + ".0.transformer", x, None, idx, ppf)
         for bi in range(1, BLOCKS[li]):
             x = block(W, "%s.%d" % (p, bi), x, idx, ppf)
-        levels.append(dict(p=pts, n=nrm, x=x, o=o, ends=list(ends), idx=idx, ppf=ppf, down_idx=down_idx))
+        levels.append(dict(p=pts, n=nrm, x=x, o=o, idx=idx, ppf=ppf, down_idx=down_idx))
     return levels
 
 
@@ -202,84 +227,206 @@ def geometric_transformer(W, architecture, pts0, pts1, f0, f1, sigma_d=0.2, sigm
 
 
 # ------------------------------------------------------------------------------------------------ backbone
+def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=None):
+    """RIPointTransformer.forward (model/model.py:187-237) for all pairs of the plan. Returns per-level batched tensors,
+    the decoded level-1 features and, per pair, (src_nodes, src_node_feats, tgt_node_feats)."""
+    B = plan.B
+    L = encode(W, plan, pts, feats, nrm)
+    dec = decode(W, L)
+    per_pair = []
+    # index-chain composition of the FPS indices (model/model.py:233-235); indices are global rows of the batch
+    d3 = L[1]["down_idx"].long()[L[2]["down_idx"].long()]
+    d4 = d3[L[3]["down_idx"].long()]
+    for b in range(B):
+        s0, s1 = plan.starts(3, b)
+        t0, t1 = plan.starts(3, B + b)
+        s_g, t_g, embs = geometric_transformer(W, architecture, L[3]["p"][s0:s1], L[3]["p"][t0:t1], L[3]["x"][s0:s1],
+                                               L[3]["x"][t0:t1])
+        # node coordinates come from the (possibly deformed) source cloud: src_deformed is the batch of src clouds only
+        s_nodes = ops.gather_rows(src_deformed, d4[s0:s1])
+        per_pair.append(dict(src_nodes=s_nodes, src_g=s_g, tgt_g=t_g, tgt_nodes=L[3]["p"][t0:t1], embs=embs if aux is not None else None))
+    if aux is not None:
+        aux.update(levels=L, dec=dec, node_idx=d4)
+    return L, dec, per_pair
+
+
 def backbone_forward(W, architecture, s_pxon, t_pxon, src_deformed, aux=None):
     """RIPointTransformer.forward: -> (s_p4, s_g_x4, src_deformed_pcd, s_x1, t_p4, t_g_x4, t_p1, t_x1)."""
-    s_p, s_x, s_o, s_n = s_pxon
-    t_p, t_x, t_o, t_n = t_pxon
-    S = encode(W, s_p, s_x, s_n, [int(s_p.shape[0])])
-    T = encode(W, t_p, t_x, t_n, [int(t_p.shape[0])])
-    s_g, t_g, embs = geometric_transformer(W, architecture, S[3]["p"], T[3]["p"], S[3]["x"], T[3]["x"])
-    s_dec, t_dec = decode(W, S), decode(W, T)
-    d3 = S[1]["down_idx"].long()[S[2]["down_idx"].long()]          # index-chain composition (model/model.py:233-234)
-    d4 = d3[S[3]["down_idx"].long()]
-    s_nodes = ops.gather_rows(src_deformed, d4)
-    if aux is not None:
-        aux.update(src_levels=S, tgt_levels=T, src_node_idx=d4, src_dec=s_dec, tgt_dec=t_dec, emb0=embs[0], emb1=embs[1])
-    return s_nodes, s_g, src_deformed, s_dec[0], T[3]["p"], t_g, T[0]["p"], t_dec[0]
+    s_p, s_x, _, s_n = s_pxon
+    t_p, t_x, _, t_n = t_pxon
+    ns, nt = int(s_p.shape[0]), int(t_p.shape[0])
+    plan = Plan(ns, nt, 1, s_p.device)
+    L, dec, pp = backbone_batch(W, architecture, plan, torch.cat([s_p, t_p]), torch.cat([s_x, t_x]), torch.cat([s_n, t_n]),
+                                src_deformed, aux)
+    q = pp[0]
+    return q["src_nodes"], q["src_g"], src_deformed, dec[0][:ns], q["tgt_nodes"], q["tgt_g"], t_p, dec[0][ns:]
 
 
 # ------------------------------------------------------------------------------------------------ pipeline
-def riga_forward(W, cfg, src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, tgt_normals, rot, trans, src_raw_pcd,
-                 aux=None):
-    """RIGA_v2.forward (eval). Returns the reference's 22-key dict (exact-size tensors; one host sync at the end)."""
+def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
+    """RIGA_v2.forward (eval) for the B pairs of ``plan``. Inputs are the concatenated clouds
+    [src_raw_0..src_raw_{B-1}, tgt_0..tgt_{B-1}] (pts/feats/nrm), the concatenated (deformed) source clouds ``src_pcd``
+    and rot (B,3,3) / trans (B,3,1). No host sync. Returns a list of per-pair dicts of PADDED tensors plus a (B,3) int32
+    device tensor of counts [P, n_gt, n_corr]."""
     four_d = cfg["benchmark"] not in ("3DMatch", "3DLoMatch")
     if four_d:
         raise NotImplementedError("AdaptiveSuperPointMatching (4DMatch head) is scheduled after the 3DMatch path; see DESIGN.md")
-    dev = src_pcd.device
+    B, Ns, Nt = plan.B, plan.n_src, plan.n_tgt
     K = int(cfg["point_per_patch"])
-    Ns, Nt = src_raw_pcd.shape[0], tgt_pcd.shape[0]
-    so, to = _offsets([Ns], dev), _offsets([Nt], dev)
-    (src_nodes, src_nf, src_pts, src_pf, tgt_nodes, tgt_nf, tgt_pts, tgt_pf) = backbone_forward(
-        W, cfg["transformer_architecture"], [src_raw_pcd, src_feats, so, src_normals],
-        [tgt_pcd, tgt_feats, to, tgt_normals], src_pcd, aux)
-    src_nf = ops.row_epilogue(_lin(W, "coarse_proj", src_nf), mode=ops.MODE_L2NORM)
-    tgt_nf = ops.row_epilogue(_lin(W, "coarse_proj", tgt_nf), mode=ops.MODE_L2NORM)
-    src_pf, tgt_pf = _lin(W, "fine_proj", src_pf), _lin(W, "fine_proj", tgt_pf)
-
-    # 2. partition + ground-truth bookkeeping
-    _, s_nm, s_ki, s_km = ops.point_to_node(src_pts, src_nodes, K)
-    _, t_nm, t_ki, t_km = ops.point_to_node(tgt_pts, tgt_nodes, K)
-    Ms, Mt = src_nodes.shape[0], tgt_nodes.shape[0]
-    ov, ov_flag = ops.node_overlaps(tgt_nodes, src_nodes, t_ki, s_ki, t_km, s_km, t_nm, s_nm, tgt_pts, src_pts, rot,
-                                    trans, float(cfg["matching_radius"]))
-    gt_flat, gt_count = ops.compact_flags(ov_flag, Mt * Ms)
-    gt_idx, gt_ov = ops.corr_gather(Mt * Ms, Ms, gt_flat, gt_count, ov)
-    t_pad = ops.pad_transform(tgt_pts)
-    s_pad_t = ops.pad_transform(src_pts, rot, trans)
-    o_t, o_s = _offsets([Nt + 1], dev), _offsets([Ns + 1], dev)
-    _, _, t_nn = ops.knn_ppf(1, s_pad_t, None, t_pad, None, o_s, o_t, drop_first=0, want_ppf=False, want_dist=True)
-    _, _, s_nn = ops.knn_ppf(1, t_pad, None, s_pad_t, None, o_t, o_s, drop_first=0, want_ppf=False, want_dist=True)
-    t_occ = ops.node_occlusion(t_ki, t_km, t_nm, t_nn.view(-1))
-    s_occ = ops.node_occlusion(s_ki, s_km, s_nm, s_nn.view(-1))
-
-    # 3. coarse matching   (called as (tgt, src), model/RIGA_v2.py:121)
+    L, dec, per_pair = backbone_batch(W, cfg["transformer_architecture"], plan, pts, feats, nrm, src_pcd, aux)
+    pf_all = _lin(W, "fine_proj", dec[0])                                # all points of all clouds at once
     Pmax = int(cfg["num_est_coarse_corr"])
-    t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, t_nm, s_nm, Pmax, dual=True)
+    topk = int(cfg["fine_matching_topk"])
+    cap = Pmax * K * topk
+    outs, counts = [], []
+    o_t, o_s = plan.single_offset(Nt + 1), plan.single_offset(Ns + 1)
+    for b in range(B):
+        q = per_pair[b]
+        src_pts, tgt_pts = src_pcd[b * Ns:(b + 1) * Ns], pts[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
+        src_pf, tgt_pf = pf_all[b * Ns:(b + 1) * Ns], pf_all[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
+        src_nodes, tgt_nodes = q["src_nodes"], q["tgt_nodes"]
+        src_nf = ops.row_epilogue(_lin(W, "coarse_proj", q["src_g"]), mode=ops.MODE_L2NORM)
+        tgt_nf = ops.row_epilogue(_lin(W, "coarse_proj", q["tgt_g"]), mode=ops.MODE_L2NORM)
+        # 2. partition + ground-truth bookkeeping
+        _, s_nm, s_ki, s_km = ops.point_to_node(src_pts, src_nodes, K)
+        _, t_nm, t_ki, t_km = ops.point_to_node(tgt_pts, tgt_nodes, K)
+        Ms, Mt = src_nodes.shape[0], tgt_nodes.shape[0]
+        ov, ov_flag = ops.node_overlaps(tgt_nodes, src_nodes, t_ki, s_ki, t_km, s_km, t_nm, s_nm, tgt_pts, src_pts, rot[b],
+                                        trans[b], float(cfg["matching_radius"]))
+        gt_flat, gt_count = ops.compact_flags(ov_flag, Mt * Ms)
+        gt_idx, gt_ov = ops.corr_gather(Mt * Ms, Ms, gt_flat, gt_count, ov)
+        t_pad = ops.pad_transform(tgt_pts)
+        s_pad_t = ops.pad_transform(src_pts, rot[b], trans[b])
+        _, _, t_nn = ops.knn_ppf(1, s_pad_t, None, t_pad, None, o_s, o_t, drop_first=0, want_ppf=False, want_dist=True)
+        _, _, s_nn = ops.knn_ppf(1, t_pad, None, s_pad_t, None, o_t, o_s, drop_first=0, want_ppf=False, want_dist=True)
+        t_occ = ops.node_occlusion(t_ki, t_km, t_nm, t_nn.view(-1))
+        s_occ = ops.node_occlusion(s_ki, s_km, s_nm, s_nn.view(-1))
+        # 3. coarse matching   (called as (tgt, src), model/RIGA_v2.py:121)
+        t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, t_nm, s_nm, Pmax, dual=True)
+        # 4-6. fine scoring + OT + fine matching
+        scores, flags = ops.fine_matching(tgt_pf, src_pf, t_ki, s_ki, t_km, s_km, t_ci, s_ci, p_count,
+                                          W["optimal_transport.alpha"].view(1), 100, topk,
+                                          bool(cfg["fine_matching_mutual"]), float(cfg["fine_matching_confidence_threshold"]))
+        c_flat, c_count = ops.compact_flags(flags, cap)
+        t_cp, s_cp, c_sc = ops.fine_gather(cap, c_flat, c_count, scores, t_ci, s_ci, t_ki, s_ki, tgt_pts, src_pts)
+        counts.append(torch.cat([p_count, gt_count, c_count]))
+        outs.append(dict(src_points=src_pts, tgt_points=tgt_pts, src_nodes=src_nodes, tgt_nodes=tgt_nodes,
+                         src_point_feats=src_pf, tgt_point_feats=tgt_pf, src_node_feats=src_nf, tgt_node_feats=tgt_nf,
+                         gt_idx=gt_idx, gt_ov=gt_ov, gt_tgt_node_occ=t_occ, gt_src_node_occ=s_occ, s_ci=s_ci, t_ci=t_ci,
+                         s_ki=s_ki, t_ki=t_ki, s_km=s_km, t_km=t_km, s_nm=s_nm, t_nm=t_nm, node_sc=node_sc,
+                         matching_scores=scores, t_cp=t_cp, s_cp=s_cp, c_sc=c_sc, c_flat=c_flat, cap=cap))
+    return outs, torch.stack(counts)
 
-    # 4-6. fine scoring + OT + fine matching
-    scores, flags = ops.fine_matching(tgt_pf, src_pf, t_ki, s_ki, t_km, s_km, t_ci, s_ci, p_count,
-                                      W["optimal_transport.alpha"].view(1), 100, int(cfg["fine_matching_topk"]),
-                                      bool(cfg["fine_matching_mutual"]), float(cfg["fine_matching_confidence_threshold"]))
-    cap = Pmax * K * int(cfg["fine_matching_topk"])
-    c_flat, c_count = ops.compact_flags(flags, cap)
-    t_cp, s_cp, c_sc = ops.fine_gather(cap, c_flat, c_count, scores, t_ci, s_ci, t_ki, s_ki, tgt_pts, src_pts)
 
-    counts = torch.cat([p_count, gt_count, c_count]).tolist()       # the one host sync
+def finalize(o, counts, Ns, Nt, aux=None):
+    """Trim one pair's padded outputs to the reference's exact-size 22-key dict (host-side counts)."""
     P, n_gt, n_c = counts
-    n_c = min(n_c, cap)
-    s_ci, t_ci = s_ci[:P].long(), t_ci[:P].long()
-    s_cki, t_cki = s_ki.long()[s_ci], t_ki.long()[t_ci]
+    n_c = min(n_c, o["cap"])
+    s_ci, t_ci = o["s_ci"][:P].long(), o["t_ci"][:P].long()
+    s_cki, t_cki = o["s_ki"].long()[s_ci], o["t_ki"].long()[t_ci]
     out = dict(
-        src_points=src_pts, tgt_points=tgt_pts, src_nodes=src_nodes, tgt_nodes=tgt_nodes,
-        src_point_feats=src_pf, tgt_point_feats=tgt_pf, src_node_feats=src_nf, tgt_node_feats=tgt_nf,
-        gt_node_corr_indices=gt_idx[:n_gt], gt_node_corr_overlaps=gt_ov[:n_gt], gt_tgt_node_occ=t_occ, gt_src_node_occ=s_occ,
-        src_node_corr_indices=s_ci, tgt_node_corr_indices=t_ci,
-        src_node_corr_knn_points=ops.gather_rows(src_pts, s_cki, pad_row=Ns),
-        tgt_node_corr_knn_points=ops.gather_rows(tgt_pts, t_cki, pad_row=Nt),
-        src_node_corr_knn_masks=s_km.bool()[s_ci], tgt_node_corr_knn_masks=t_km.bool()[t_ci],
-        matching_scores=scores[:P], tgt_corr_points=t_cp[:n_c], src_corr_points=s_cp[:n_c], corr_scores=c_sc[:n_c])
+        src_points=o["src_points"], tgt_points=o["tgt_points"], src_nodes=o["src_nodes"], tgt_nodes=o["tgt_nodes"],
+        src_point_feats=o["src_point_feats"], tgt_point_feats=o["tgt_point_feats"], src_node_feats=o["src_node_feats"],
+        tgt_node_feats=o["tgt_node_feats"], gt_node_corr_indices=o["gt_idx"][:n_gt], gt_node_corr_overlaps=o["gt_ov"][:n_gt],
+        gt_tgt_node_occ=o["gt_tgt_node_occ"], gt_src_node_occ=o["gt_src_node_occ"], src_node_corr_indices=s_ci,
+        tgt_node_corr_indices=t_ci,
+        src_node_corr_knn_points=ops.gather_rows(o["src_points"], s_cki, pad_row=Ns),
+        tgt_node_corr_knn_points=ops.gather_rows(o["tgt_points"], t_cki, pad_row=Nt),
+        src_node_corr_knn_masks=o["s_km"].bool()[s_ci], tgt_node_corr_knn_masks=o["t_km"].bool()[t_ci],
+        matching_scores=o["matching_scores"][:P], tgt_corr_points=o["t_cp"][:n_c], src_corr_points=o["s_cp"][:n_c],
+        corr_scores=o["c_sc"][:n_c])
     if aux is not None:
-        aux.update(node_corr_scores=node_sc[:P], src_node_knn_indices=s_ki, tgt_node_knn_indices=t_ki,
-                   src_node_masks=s_nm.bool(), tgt_node_masks=t_nm.bool(), src_node_knn_masks=s_km.bool(),
-                   tgt_node_knn_masks=t_km.bool(), corr_flat=c_flat[:n_c])
+        aux.update(node_corr_scores=o["node_sc"][:P], src_node_knn_indices=o["s_ki"], tgt_node_knn_indices=o["t_ki"],
+                   src_node_masks=o["s_nm"].bool(), tgt_node_masks=o["t_nm"].bool(), src_node_knn_masks=o["s_km"].bool(),
+                   tgt_node_knn_masks=o["t_km"].bool(), corr_flat=o["c_flat"][:n_c])
     return out
+
+
+def riga_forward(W, cfg, src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, tgt_normals, rot, trans, src_raw_pcd,
+                 aux=None):
+    """RIGA_v2.forward (eval) for one pair: the reference's 22-key dict of exact-size tensors (one host sync at the end)."""
+    Ns, Nt = src_raw_pcd.shape[0], tgt_pcd.shape[0]
+    plan = Plan(Ns, Nt, 1, src_pcd.device)
+    outs, counts = riga_batch(W, cfg, plan, torch.cat([src_raw_pcd, tgt_pcd]), torch.cat([src_feats, tgt_feats]),
+                              torch.cat([src_normals, tgt_normals]), src_pcd, rot.reshape(1, 3, 3).contiguous(),
+                              trans.reshape(1, 3, 1).contiguous(), aux)
+    out = finalize(outs[0], counts[0].tolist(), Ns, Nt, aux)          # the one host sync
+    if aux is not None:   # per-cloud views of the batched intermediates, in the layout tests/parity.py expects
+        L, dec = aux["levels"], aux["dec"]
+        def cloud(c):
+            lv = []
+            for li in range(4):
+                a, b_ = plan.starts(li, c)
+                pa = 0 if li == 0 else plan.starts(li - 1, c)[0]
+                lv.append(dict(p=L[li]["p"][a:b_], x=L[li]["x"][a:b_], ppf=L[li]["ppf"][a:b_], idx=L[li]["idx"][a:b_] - a,
+                               down_idx=None if L[li]["down_idx"] is None else L[li]["down_idx"][a:b_] - pa))
+            return lv, [dec[li][plan.starts(li, c)[0]:plan.starts(li, c)[1]] for li in range(4)]
+        aux["src_levels"], aux["src_dec"] = cloud(0)
+        aux["tgt_levels"], aux["tgt_dec"] = cloud(1)
+        aux["src_node_idx"] = aux["node_idx"][plan.starts(3, 0)[0]:plan.starts(3, 0)[1]]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ batched execution
+class BatchRunner:
+    """Runs RIGA_v2.forward for a fixed-shape batch of B pairs per step, optionally as ONE CUDA graph.
+
+    A pair is an independent unit of work, so throughput comes from keeping many pairs in flight: every
+    segment-batched kernel (kNN+PPF, FPS clusters, local attention, linears) sees all 2B clouds at once, and the
+    latency-bound FPS chains of all clouds run concurrently on different SMs. Inputs live in static device buffers
+    (``load`` copies into them); ``run`` issues no host<->device traffic; ``results`` performs the single D2H read of
+    the per-pair counts and trims the padded outputs to the reference's 22-key dicts.
+    """
+
+    INPUT_KEYS = ("pts", "feats", "nrm", "src_pcd", "rot", "trans")
+
+    def __init__(self, W, cfg, B, n_src, n_tgt, device, graph=True, fps_cluster=0):
+        self.W, self.cfg, self.B, self.Ns, self.Nt, self.device = W, cfg, B, n_src, n_tgt, device
+        self.plan = Plan(n_src, n_tgt, B, device, fps_cluster)
+        tot = B * (n_src + n_tgt)
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        self.inp = dict(pts=f(tot, 3), feats=f(tot, 1), nrm=f(tot, 3), src_pcd=f(B * n_src, 3), rot=f(B, 3, 3), trans=f(B, 3, 1))
+        self.graph = None
+        self.outs = self.counts = None
+        self._want_graph = graph
+
+    def load(self, pairs, non_blocking=True):
+        """pairs: list of B dicts with the 9 RIGA_v2.forward inputs (host pinned or device tensors)."""
+        B, Ns, Nt = self.B, self.Ns, self.Nt
+        assert len(pairs) == B
+        i = self.inp
+        for b, p in enumerate(pairs):
+            i["pts"][b * Ns:(b + 1) * Ns].copy_(p["src_raw_pcd"], non_blocking=non_blocking)
+            i["pts"][B * Ns + b * Nt:B * Ns + (b + 1) * Nt].copy_(p["tgt_pcd"], non_blocking=non_blocking)
+            i["feats"][b * Ns:(b + 1) * Ns].copy_(p["src_feats"], non_blocking=non_blocking)
+            i["feats"][B * Ns + b * Nt:B * Ns + (b + 1) * Nt].copy_(p["tgt_feats"], non_blocking=non_blocking)
+            i["nrm"][b * Ns:(b + 1) * Ns].copy_(p["src_normals"], non_blocking=non_blocking)
+            i["nrm"][B * Ns + b * Nt:B * Ns + (b + 1) * Nt].copy_(p["tgt_normals"], non_blocking=non_blocking)
+            i["src_pcd"][b * Ns:(b + 1) * Ns].copy_(p["src_pcd"], non_blocking=non_blocking)
+            i["rot"][b].copy_(p["rot"], non_blocking=non_blocking)
+            i["trans"][b].copy_(p["trans"], non_blocking=non_blocking)
+
+    def _body(self):
+        i = self.inp
+        return riga_batch(self.W, self.cfg, self.plan, i["pts"], i["feats"], i["nrm"], i["src_pcd"], i["rot"], i["trans"])
+
+    def run(self):
+        if self._want_graph and self.graph is None:
+            # one eager pass first: lazily-set kernel attributes and allocator warm-up must not happen under capture
+            self.outs, self.counts = self._body()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.outs, self.counts = self._body()
+            self.graph = g
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.outs, self.counts = self._body()
+
+    def results(self, full=True):
+        """One D2H read of the (B,3) counts; returns the list of per-pair output dicts (exact sizes)."""
+        counts = self.counts.tolist()
+        if not full:
+            return counts
+        return [finalize(self.outs[b], counts[b], self.Ns, self.Nt) for b in range(self.B)]
