@@ -107,6 +107,12 @@ int roitr_gather_rows(long long rows, int c, const void* index, int index_is_i64
 int roitr_linear(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index, const float* W,
                  int ldw, const float* bias, float* C, int ldc, int relu, void* stream);
 
+/* Same contract as roitr_linear, computed on the tensor cores: tcgen05.mma kind::tf32 with 3xTF32 split precision
+ * (x = hi + lo exactly; hi*hi + hi*lo + lo*hi accumulated in fp32 TMEM; relative error ~2^-21, fp32-grade). One CTA per
+ * 128 x {64,128,256} output tile, operands split on the fly into 128B-swizzled shared memory, 2-stage pipeline. */
+int roitr_linear_tc(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index, const float* W,
+                    int ldw, const float* bias, float* C, int ldc, int relu, void* stream);
+
 /* out = [L2norm] [ReLU] ( [LayerNorm_{gamma,beta,eps=1e-5}] (x + res_pre[res_pre_index]) + res_post ), one row of C<=1024
  * floats per warp. mode bits: 1 LayerNorm, 2 ReLU, 4 x / max(|x|_2, 1e-12). Any of the residuals may be NULL. */
 int roitr_row_epilogue(int M, int C, const float* x, const float* res_pre, const int* res_pre_index, const float* gamma,

@@ -1,0 +1,277 @@
+// Tensor-core dense layer for sm_100a: C[M,N] = (A [+ A2])[M,K] W[N,K]^T + bias (+ReLU), fp32 in / fp32 out,
+// computed on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) with 3xTF32 split precision.
+//
+// Why split precision: the parity bar is fp32 results within 1e-4 of the reference. A single TF32 product keeps 11
+// mantissa bits (~5e-4 relative on K=256 contractions: too coarse). Each fp32 operand is split exactly into
+//     x = hi + lo,   hi = x with the low 13 mantissa bits cleared (a valid TF32 number),   lo = x - hi  (exact in fp32)
+// and the product is accumulated in fp32 (TMEM) as  hi*hi + hi*lo + lo*hi  (lo is truncated to TF32 by the MMA, the
+// lo*lo term is dropped): relative error ~2^-21, i.e. fp32-grade, at 3 MMAs per K-step (measured against an fp64
+// reference in tests/test_gemm_gpu.py).
+//
+// Structure (one CTA = 128 threads = one 128 x BN output tile, BN in {64,128,256}):
+//   loader (all threads)   global fp32 -> registers -> split -> 128B-swizzled K-major smem tiles A_hi/A_lo/B_hi/B_lo
+//                          (K chunks of 32 floats = one 128-byte swizzle row), 2 stages
+//   MMA (thread 0)         per chunk: 4 K-steps x 3 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8), then
+//                          tcgen05.commit -> mbarrier; the next chunk's loads overlap the asynchronous MMAs
+//   epilogue (4 warps)     tcgen05.ld 32x32b.x32 (warp w owns TMEM lanes 32w..32w+31 = rows), bias / ReLU, 128-byte row
+//                          segments to global
+// Operand rows may be gathered (a_index) or be the sum of two matrices (a_add), as in roitr_linear.
+#include "../../include/roitr_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_THREADS = 128;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;            // floats per chunk = 128 bytes = one swizzle row
+constexpr int TC_STAGES = 2;
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): K-major, SWIZZLE_128B, 8-row atoms of
+// 1024 B stacked along M/N (SBO = 1024 B), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);         // start address        bits [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset  bits [16,30) (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset   bits [32,46)
+    d |= (uint64_t)1 << 46;                              // version              bits [46,48)
+    d |= (uint64_t)2 << 61;                              // layout type 2 = SWIZZLE_128B, bits [61,64)
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of the 16-byte chunk `c` (0..7) of row `r` inside a K-major SWIZZLE_128B tile (Swizzle<3,4,3>)
+__device__ __forceinline__ uint32_t sw128_offset(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned char* lo_tile, int r, int c, float4 v) {
+    // hi = x rounded to the nearest TF32 (add half an ulp of the 13 dropped bits, then clear them); lo = x - hi is exact
+    float4 h, l;
+    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
+    const uint32_t o = sw128_offset(r, c);
+    *reinterpret_cast<float4*>(hi_tile + o) = h;
+    *reinterpret_cast<float4*>(lo_tile + o) = l;
+}
+
+struct TcParams {
+    int M, N, K;
+    const float* A; const float* A2; int lda; const int* a_index;
+    const float* W; int ldw; const float* bias;
+    float* C; int ldc; int relu;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment: align manually (the launch reserves 1 KB of slack)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // per stage: A_hi (16 KB) | A_lo (16 KB) | B_hi (BN*128 B) | B_lo (BN*128 B)
+    constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    __shared__ __align__(8) uint64_t mma_bar[TC_STAGES];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+
+    if (tid == 0) {
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = s_tmem;
+
+    // loader row assignment: thread t owns A row t and B rows t, t+128 (BN=256) / t (BN<=128, t < BN)
+    const int am = m0 + tid;
+    long long arow = -1;
+    if (am < P.M) arow = P.a_index ? (long long)__ldg(P.a_index + am) : (long long)am;
+    const bool vecA = (P.lda % 4 == 0) && ((uintptr_t)P.A % 16 == 0) && (!P.A2 || (uintptr_t)P.A2 % 16 == 0);
+    const bool vecW = (P.ldw % 4 == 0) && ((uintptr_t)P.W % 16 == 0);
+
+    auto load_row = [&](const float* base, const float* base2, long long row, int ld, int k0, bool vec, float4 (&v)[8]) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int k = k0 + 4 * c;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row >= 0) {
+                const float* p = base + row * ld + k;
+                if (vec && k + 3 < P.K) {
+                    x = __ldg(reinterpret_cast<const float4*>(p));
+                    if (base2) { const float4 y = __ldg(reinterpret_cast<const float4*>(base2 + row * ld + k)); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+                } else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (k + e < P.K) t[e] = __ldg(p + e) + (base2 ? __ldg(base2 + row * ld + k + e) : 0.f);
+                    x = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
+            v[c] = x;
+        }
+    };
+
+    const int nk = (P.K + TC_BK - 1) / TC_BK;
+    constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+    constexpr int BROWS = (BN + TC_THREADS - 1) / TC_THREADS;  // B rows per thread
+
+    for (int kc = 0; kc < nk; ++kc) {
+        const int buf = kc & 1;
+        unsigned char* st = smem + buf * STAGE_BYTES;
+        // global loads of this chunk are issued before waiting for the stage to drain
+        float4 va[8], vb[BROWS][8];
+        load_row(P.A, P.A2, arow, P.lda, kc * TC_BK, vecA, va);
+#pragma unroll
+        for (int j = 0; j < BROWS; ++j) {
+            const int br = tid + j * TC_THREADS;
+            const long long wrow = (br < BN && n0 + br < P.N) ? (long long)(n0 + br) : -1;
+            load_row(P.W, nullptr, wrow, P.ldw, kc * TC_BK, vecW, vb[j]);
+        }
+        if (kc >= TC_STAGES) {  // the MMAs that read this stage (chunk kc-2) must have completed
+            mbar_wait(&mma_bar[buf], ((kc >> 1) - 1) & 1);
+            tc_fence_after();
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) split_store(st, st + A_BYTES, tid, c, va[c]);
+#pragma unroll
+        for (int j = 0; j < BROWS; ++j) {
+            const int br = tid + j * TC_THREADS;
+            if (br < BN) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) split_store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, br, c, vb[j][c]);
+            }
+        }
+        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_BYTES, b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {   // K = 8 tf32 = 32 bytes per MMA
+                const uint64_t dah = make_desc_sw128(a_hi + ks * 32), dal = make_desc_sw128(a_lo + ks * 32);
+                const uint64_t dbh = make_desc_sw128(b_hi + ks * 32), dbl = make_desc_sw128(b_lo + ks * 32);
+                umma_tf32(tmem_d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);   // small terms first
+                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&mma_bar[buf]);
+        }
+    }
+    // drain: the last commit covers every earlier MMA (commits complete in order)
+    {
+        const int last = nk - 1;
+        mbar_wait(&mma_bar[last & 1], (last >> 1) & 1);
+        tc_fence_after();
+    }
+    // ---- epilogue: warp w reads TMEM lanes 32w..32w+31 (= output rows), 32 columns at a time ----
+    const int row = m0 + warp * 32 + lane;
+    const bool vecC = (P.ldc % 4 == 0) && ((uintptr_t)P.C % 16 == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= P.N) break;   // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        if (row < P.M) {
+            float* dst = P.C + (long long)row * P.ldc + n0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int n = n0 + c0 + i;
+                if (n < P.N) {
+                    float x = v[i] + (P.bias ? __ldg(P.bias + n) : 0.f);
+                    v[i] = P.relu ? fmaxf(x, 0.f) : x;
+                }
+            }
+            if (vecC && n0 + c0 + 32 <= P.N) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (n0 + c0 + i < P.N) dst[i] = v[i];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, BN);
+}
+
+template <int BN>
+int launch_tc(const TcParams& P, cudaStream_t st) {
+    constexpr int smem = TC_STAGES * (2 * TC_BM * 128 + 2 * BN * 128) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        ROITR_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    dim3 grid(ceil_div(P.M, TC_BM), ceil_div(P.N, BN));
+    linear_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(P);
+    ROITR_CHECK_LAUNCH("linear_tc_kernel");
+    return ROITR_OK;
+}
+
+}  // namespace
+
+extern "C" int roitr_linear_tc(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
+                               const float* W, int ldw, const float* bias, float* C, int ldc, int relu, void* stream) {
+    ROITR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && A && W && C, "linear_tc: bad arguments M=%d N=%d K=%d", M, N, K);
+    ROITR_CHECK_ARG(lda >= K && ldc >= N && ldw >= K, "linear_tc: bad leading dimensions");
+    if (M == 0) return ROITR_OK;
+    TcParams P;
+    P.M = M; P.N = N; P.K = K; P.A = A; P.A2 = a_add; P.lda = lda; P.a_index = a_index; P.W = W; P.ldw = ldw; P.bias = bias;
+    P.C = C; P.ldc = ldc; P.relu = relu;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 64) return launch_tc<64>(P, st);
+    if (N <= 128) return launch_tc<128>(P, st);
+    return launch_tc<256>(P, st);
+}

@@ -246,7 +246,7 @@ def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=Non
         s_nodes = ops.gather_rows(src_deformed, d4[s0:s1])
         per_pair.append(dict(src_nodes=s_nodes, src_g=s_g, tgt_g=t_g, tgt_nodes=L[3]["p"][t0:t1], embs=embs if aux is not None else None))
     if aux is not None:
-        aux.update(levels=L, dec=dec, node_idx=d4)
+        aux.update(levels=L, dec=dec, node_idx=d4, emb0=per_pair[0]["embs"][0], emb1=per_pair[0]["embs"][1])
     return L, dec, per_pair
 
 

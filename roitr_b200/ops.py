@@ -19,8 +19,11 @@ def empty(*shape, dtype=torch.float32, like=None, device=None):
     return torch.empty(*shape, dtype=dtype, device=like.device if like is not None else device)
 
 
+USE_TENSOR_CORES = True     # roitr_linear_tc (tcgen05, 3xTF32) for K >= 16; the fp32 FFMA kernel otherwise
+
+
 def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=None, K=None, lda=None, ldw=None,
-           ldc=None):
+           ldc=None, tc=None):
     """out[M,N] = (a [+ a_add])[rows, :K] @ w[:N, :K]^T + bias. ``a``/``out`` may be column slices of wider buffers
     (pass lda/ldc); ``a_index`` gathers rows of ``a``."""
     N = w.shape[0]
@@ -32,7 +35,8 @@ def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=No
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     ldc = out.stride(0) if ldc is None else ldc
-    _lib.call("roitr_linear", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
+    use_tc = (USE_TENSOR_CORES if tc is None else tc) and K >= 16
+    _lib.call("roitr_linear_tc" if use_tc else "roitr_linear", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
               c_void(w), c_int(ldw), c_void(bias), c_void(out), c_int(ldc), c_int(1 if relu else 0), stream_ptr())
     return out
 
