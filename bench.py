@@ -130,7 +130,7 @@ def op_work(name, ints):
     if name in ("roitr_linear", "roitr_linear_tc"):
         M, N, K = ints[:3]
         return "flop", 2.0 * M * N * K
-    if name == "roitr_geo_embedding":
+    if name in ("roitr_geo_embedding", "roitr_geo_embedding_tc"):
         N, C = ints[:2]
         return "flop", 8.0 * N * N * C * C
     if name == "roitr_furthestsampling_cfg":

@@ -147,6 +147,12 @@ int roitr_geo_embedding(int N, int C, const float* pts, const int* nn3, const fl
                         const float* Wa, const float* ba, const float* div_term, float sigma_d, float sigma_a, float* E,
                         void* stream);
 
+/* Same result on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split precision, four accumulators per tile in TMEM).
+ * wpack: W_d and W_a pre-split into TF32 hi/lo and pre-swizzled into 32 KB SWIZZLE_128B blocks,
+ * layout [mat(d,a)][C/128][C/32][hi|lo][4096] floats (roitr_b200.engine.pack_tf32_sw128); fetched by bulk TMA. */
+int roitr_geo_embedding_tc(int N, int C, const float* pts, const int* nn3, const float* wpack, const float* bd,
+                           const float* ba, const float* div_term, float sigma_d, float sigma_a, float* E, void* stream);
+
 /* Attention core. E == NULL: MultiHeadAttention (geoattention.py:50-64) hidden = softmax(q k^T / sqrt(c)) v.
  * E != NULL (N == M): RPEMultiHeadAttention (geoattention.py:107-134) with gq (N,4,C) = folded positional queries
  * (gq[n,h,:] = W_p[h*c:(h+1)*c,:]^T q[n,h*c:(h+1)*c]) and bp = proj_p.bias; also G (N,4,C) = sum_m A-_nm E_nm where A- is

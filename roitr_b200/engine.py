@@ -17,6 +17,7 @@ import torch
 
 from . import ops
 
+GEO_EMBEDDING_TC = True      # tcgen05 3xTF32 kernel (csrc/geo_tc.cu); False = fp32 FFMA kernel (csrc/geo.cu)
 STRIDES = (1, 4, 4, 4)
 NSAMPLE = (8, 16, 16, 16)
 BLOCKS = (2, 3, 3, 3)
@@ -26,6 +27,26 @@ HEADS = 4
 # ------------------------------------------------------------------------------------------------ weight packing
 class Packed(dict):
     """name -> contiguous f32 CUDA tensor, plus derived (stacked / folded / transposed) weights."""
+
+
+def pack_tf32_sw128(Wm):
+    """(N,K) f32 -> (N/128, K/32, 2, 4096) f32: per (128-row, 32-column) block the TF32 hi part (round to nearest) and the
+    exact remainder lo = W - hi, each laid out as a K-major SWIZZLE_128B shared-memory tile (8-row atoms of 1024 B, 16-byte
+    chunk index XOR row%8), so that a kernel fetches a ready-to-use tcgen05 B operand with one bulk copy (csrc/geo_tc.cu)."""
+    N, K = Wm.shape
+    assert N % 128 == 0 and K % 32 == 0
+    Wm = Wm.contiguous()
+    hi = ((Wm.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    lo = Wm - hi
+
+    def tile(X):
+        T = X.view(N // 128, 128, K // 32, 32).permute(0, 2, 1, 3).reshape(N // 128, K // 32, 16, 8, 8, 4)
+        out = torch.empty_like(T)
+        ar = torch.arange(8, device=X.device)
+        for j in range(8):
+            out[:, :, :, j, ar ^ j, :] = T[:, :, :, j, :, :]
+        return out.reshape(N // 128, K // 32, 4096)
+    return torch.stack([tile(hi), tile(lo)], dim=2).contiguous()
 
 
 def pack_weights(state_dict, device, architecture):
@@ -48,6 +69,8 @@ def pack_weights(state_dict, device, architecture):
         g = "backbone.global_transformer"
         C = W[g + ".in_proj.weight"].shape[0]
         c = C // HEADS
+        W[g + ".embedding#wpack"] = torch.stack([pack_tf32_sw128(W[g + ".embedding.proj_d.weight"]),
+                                                 pack_tf32_sw128(W[g + ".embedding.proj_a.weight"])], 0).contiguous()
         for i, kind in enumerate(architecture):
             a = "%s.transformer.layers.%d.attention.attention" % (g, i)
             if kind == "self":
@@ -211,8 +234,12 @@ def geometric_transformer(W, architecture, pts0, pts1, f0, f1, sigma_d=0.2, sigm
     embs = []
     for pts in (pts0, pts1):
         nn3 = ops.geo_knn(pts, 3)
-        embs.append(ops.geo_embedding(pts, nn3, W[e + ".proj_d.weight"], W[e + ".proj_d.bias"], W[e + ".proj_a.weight"],
-                                      W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], sigma_d, sigma_a))
+        if GEO_EMBEDDING_TC:
+            embs.append(ops.geo_embedding_tc(pts, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
+                                             W[e + ".embedding.div_term"], sigma_d, sigma_a))
+        else:
+            embs.append(ops.geo_embedding(pts, nn3, W[e + ".proj_d.weight"], W[e + ".proj_d.bias"], W[e + ".proj_a.weight"],
+                                          W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], sigma_d, sigma_a))
     f0, f1 = _lin(W, g + ".in_proj", f0), _lin(W, g + ".in_proj", f1)
     pos0 = pos1 = None
     for i, kind in enumerate(architecture):

@@ -19,7 +19,7 @@ def empty(*shape, dtype=torch.float32, like=None, device=None):
     return torch.empty(*shape, dtype=dtype, device=like.device if like is not None else device)
 
 
-USE_TENSOR_CORES = True     # roitr_linear_tc (tcgen05, 3xTF32) for K >= 16; the fp32 FFMA kernel otherwise
+USE_TENSOR_CORES = False    # roitr_linear_tc (tcgen05, 3xTF32) is correct but, being thread-loaded and 2-stage, slower than FFMA on these skinny GEMMs (scripts/bench_gemm.py); opt in per call with tc=True
 
 
 def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=None, K=None, lda=None, ldw=None,
@@ -135,6 +135,14 @@ def geo_embedding(pts, nn3, Wd, bd, Wa, ba, div_term, sigma_d, sigma_a):
     E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device)
     _lib.call("roitr_geo_embedding", c_int(N), c_int(C), f32(pts), i32(nn3), f32(Wd), f32(bd), f32(Wa), f32(ba),
               f32(div_term), c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
+    return E
+
+
+def geo_embedding_tc(pts, nn3, wpack, bd, ba, div_term, sigma_d, sigma_a):
+    N, C = pts.shape[0], bd.shape[0]
+    E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device)
+    _lib.call("roitr_geo_embedding_tc", c_int(N), c_int(C), f32(pts), i32(nn3), f32(wpack), f32(bd), f32(ba), f32(div_term),
+              c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
     return E
 
 

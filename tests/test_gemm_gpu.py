@@ -52,3 +52,27 @@ def test_tc_and_ffma_agree_on_model_shapes():
         w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
         y1, y2 = ops.linear(a, w, None, tc=True), ops.linear(a, w, None, tc=False)
         assert (y1 - y2).abs().max().item() <= 5e-6 * y2.abs().max().item()
+
+
+@pytest.mark.parametrize("N", [16, 64, 312])
+def test_geo_embedding_tensor_core_matches_ffma_and_oracle(N):
+    from oracle import forward_ref as fr
+    from roitr_b200 import engine
+    from tests.helpers import weights
+    sd = weights(1)
+    e = "backbone.global_transformer.embedding"
+    g = torch.Generator().manual_seed(N)
+    pts = (torch.rand(N, 3, generator=g) * 3 - 1.5)
+    ref = fr.geometric_embedding(sd, e, pts[None])[0]
+    W = {k: sd[k].to(DEV) for k in sd if k.startswith(e)}
+    wpack = torch.stack([engine.pack_tf32_sw128(W[e + ".proj_d.weight"]), engine.pack_tf32_sw128(W[e + ".proj_a.weight"])], 0).contiguous()
+    p = pts.to(DEV)
+    nn3 = ops.geo_knn(p, 3)
+    a = ops.geo_embedding(p, nn3, W[e + ".proj_d.weight"], W[e + ".proj_d.bias"], W[e + ".proj_a.weight"], W[e + ".proj_a.bias"],
+                          W[e + ".embedding.div_term"], 0.2, 15.0)
+    b = ops.geo_embedding_tc(p, nn3, wpack, W[e + ".proj_d.bias"], W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], 0.2, 15.0)
+    torch.cuda.synchronize()
+    off = ~torch.eye(N, dtype=torch.bool)     # the diagonal distance is rounding noise (x2 - 2xy + y2), compare off-diagonal
+    assert (a.cpu() - ref)[off].abs().max().item() < 2e-5
+    assert (b.cpu() - ref)[off].abs().max().item() < 2e-5
+    assert (a - b).abs().max().item() < 2e-5
