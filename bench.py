@@ -145,6 +145,9 @@ def op_work(name, ints):
     if name == "roitr_geo_attention":
         N, M, C = ints[:3]
         return "bytes", 2.0 * N * M * C * 4 + 4.0 * N * C * 4
+    if name == "roitr_geo_attention_batched":
+        b, N, M, C = ints[:4]
+        return "bytes", b * (2.0 * N * M * C * 4 + 4.0 * N * C * 4)
     if name == "roitr_fine_matching":
         P, _, _, C = ints[:4]
         return "bytes", P * (2.0 * 64 * C * 4 + 65 * 65 * 4)

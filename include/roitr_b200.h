@@ -160,6 +160,12 @@ int roitr_geo_embedding_tc(int N, int C, const float* pts, const int* nn3, const
 int roitr_geo_attention(int N, int M, int C, int heads, const float* q, int ldq, const float* k, int ldk, const float* v,
                         int ldv, const float* E, const float* gq, const float* bp, float* hidden, float* G, void* stream);
 
+/* `batch` independent clouds per launch (blockIdx.y): q/k/v advance by q_bs/k_bs/v_bs elements per cloud; E (batch,N,M,C),
+ * gq, G (batch,N,4,C) and hidden (batch,N,C) are contiguous per cloud. */
+int roitr_geo_attention_batched(int batch, int N, int M, int C, int heads, const float* q, int ldq, long long q_bs,
+                                const float* k, int ldk, long long k_bs, const float* v, int ldv, long long v_bs,
+                                const float* E, const float* gq, const float* bp, float* hidden, float* G, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Matching head (lib/utils.py:428-471, model/modules.py:10-72,135-178,216-324, model/RIGA_v2.py:150-173).
  * ---------------------------------------------------------------------------------------------------------- */

@@ -224,12 +224,20 @@ struct GeoAttnParams {
     float* G;                    // (N, 4, C) or NULL
     int N, M;
     float sqrt_c;
+    long long q_bs, k_bs, v_bs;  // element strides between the clouds of a batch (blockIdx.y) for q / k / v
 };
 
 template <int C, bool RPE>
-__global__ void __launch_bounds__(256) geo_attention_kernel(const GeoAttnParams P) {
+__global__ void __launch_bounds__(256) geo_attention_kernel(const GeoAttnParams P_) {
     constexpr int CPL = C / 32, H = 4;
     extern __shared__ float sm[];
+    GeoAttnParams P = P_;
+    {   // batch element: every operand advances by one cloud
+        const long long b = blockIdx.y;
+        P.q += b * P.q_bs; P.k += b * P.k_bs; P.v += b * P.v_bs;
+        P.hidden += b * (long long)P.N * C;
+        if (RPE) { P.E += b * (long long)P.N * P.M * C; P.gq += b * (long long)P.N * H * C; P.G += b * (long long)P.N * H * C; }
+    }
     const int M = P.M;
     float* S = sm;               // [H][M] scores -> attention
     float* Sm = sm + H * M;      // [H][M] attention without self (RPE only)
@@ -334,11 +342,11 @@ __global__ void __launch_bounds__(256) geo_attention_kernel(const GeoAttnParams 
 }
 
 template <int C, bool RPE>
-int launch_attn(const GeoAttnParams& P, cudaStream_t st) {
+int launch_attn(const GeoAttnParams& P, int batch, cudaStream_t st) {
     const size_t smem = (size_t)(RPE ? 2 : 1) * 4 * P.M * sizeof(float);
     if (smem > 48 * 1024) ROITR_CUDA(cudaFuncSetAttribute(geo_attention_kernel<C, RPE>,
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    geo_attention_kernel<C, RPE><<<P.N, 256, smem, st>>>(P);
+    geo_attention_kernel<C, RPE><<<dim3(P.N, batch), 256, smem, st>>>(P);
     ROITR_CHECK_LAUNCH("geo_attention_kernel");
     return ROITR_OK;
 }
@@ -370,17 +378,24 @@ extern "C" int roitr_geo_embedding(int N, int C, const float* pts, const int* nn
     return ROITR_OK;
 }
 
+extern "C" int roitr_geo_attention_batched(int batch, int N, int M, int C, int heads, const float* q, int ldq,
+                                           long long q_bs, const float* k, int ldk, long long k_bs, const float* v,
+                                           int ldv, long long v_bs, const float* E, const float* gq, const float* bp,
+                                           float* hidden, float* G, void* stream) {
+    ROITR_CHECK_ARG(heads == 4 && (C == 256 || C == 512), "geo_attention: heads=4, C in {256,512} only");
+    ROITR_CHECK_ARG(batch >= 1 && N >= 1 && M >= 1 && q && k && v && hidden, "geo_attention: bad arguments");
+    ROITR_CHECK_ARG(!E || (gq && bp && G && N == M), "geo_attention: RPE needs gq, bp, G and N == M");
+    ROITR_CHECK_ARG(ldk % 4 == 0 && k_bs % 4 == 0 && ((uintptr_t)k % 16 == 0) && (!E || (uintptr_t)E % 16 == 0), "geo_attention: alignment");
+    GeoAttnParams P;
+    P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.E = E; P.gq = gq; P.bp = bp; P.hidden = hidden;
+    P.G = G; P.N = N; P.M = M; P.sqrt_c = sqrtf((float)(C / heads)); P.q_bs = q_bs; P.k_bs = k_bs; P.v_bs = v_bs;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 256) return E ? launch_attn<256, true>(P, batch, st) : launch_attn<256, false>(P, batch, st);
+    return E ? launch_attn<512, true>(P, batch, st) : launch_attn<512, false>(P, batch, st);
+}
+
 extern "C" int roitr_geo_attention(int N, int M, int C, int heads, const float* q, int ldq, const float* k, int ldk,
                                    const float* v, int ldv, const float* E, const float* gq, const float* bp,
                                    float* hidden, float* G, void* stream) {
-    ROITR_CHECK_ARG(heads == 4 && (C == 256 || C == 512), "geo_attention: heads=4, C in {256,512} only");
-    ROITR_CHECK_ARG(N >= 1 && M >= 1 && q && k && v && hidden, "geo_attention: bad arguments");
-    ROITR_CHECK_ARG(!E || (gq && bp && G && N == M), "geo_attention: RPE needs gq, bp, G and N == M");
-    ROITR_CHECK_ARG(ldk % 4 == 0 && ((uintptr_t)k % 16 == 0) && (!E || (uintptr_t)E % 16 == 0), "geo_attention: alignment");
-    GeoAttnParams P;
-    P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.E = E; P.gq = gq; P.bp = bp; P.hidden = hidden;
-    P.G = G; P.N = N; P.M = M; P.sqrt_c = sqrtf((float)(C / heads));
-    cudaStream_t st = (cudaStream_t)stream;
-    if (C == 256) return E ? launch_attn<256, true>(P, st) : launch_attn<256, false>(P, st);
-    return E ? launch_attn<512, true>(P, st) : launch_attn<512, false>(P, st);
+    return roitr_geo_attention_batched(1, N, M, C, heads, q, ldq, 0, k, ldk, 0, v, ldv, 0, E, gq, bp, hidden, G, stream);
 }

@@ -9,83 +9,114 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 256, BK = 8;
 
 // C[M,N] = (A [+ A2])[M,K] * W[N,K]^T (+ bias) (+ ReLU). A rows optionally gathered through a_index (int32).
-// 64x64 CTA tile, 16-wide K slices staged in shared memory (k-major, so the inner product reads two float4 per k),
-// 4x4 register micro-tile per thread.
-__global__ void __launch_bounds__(GEMM_THREADS)
+// 128 x BN CTA tile (BN = 128 or 64), 8-wide K slices double-buffered in shared memory (k-major), 8 x TN register
+// micro-tile per thread (TN = BN/16): 4 (BN=128) or 3 (BN=64) LDS.128 per 64 / 32 FFMA, so the FMA pipe, not shared
+// memory, is the limit. The micro-tile is split in 4-wide halves (rows ty*4.. and 64+ty*4.., cols tx*4.. and BN/2+tx*4..)
+// so that the float4 shared-memory reads of a quarter-warp hit distinct banks.
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 linear_kernel(int M, int N, int K, const float* __restrict__ A, const float* __restrict__ A2, int lda,
-              const int* __restrict__ a_index, const float* __restrict__ W, int ldw, const float* __restrict__ bias, float* __restrict__ C, int ldc,
-              int relu) {
-    __shared__ __align__(16) float As[2][BK][BM + 4];
-    __shared__ __align__(16) float Ws[2][BK][BN + 4];
+              const int* __restrict__ a_index, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+              float* __restrict__ C, int ldc, int relu) {
+    constexpr int BM = 128, TN = BN / 16, NH = TN / 4;   // NH column halves of 4
+    __shared__ __align__(16) float As[2][BK][BM];
+    __shared__ __align__(16) float Ws[2][BK][BN];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4 (m) x 4 (n)
+    const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
 
-    // loader mapping: 64 rows x 16 k = 1024 elements per operand, 4 per thread: row = tid/4, k = (tid%4)*4..+3
-    const int lrow = tid >> 2, lk = (tid & 3) * 4;
+    // loaders: A tile 128 rows x 8 k = 256 float4 -> one per thread (row = tid/2, k half = tid%2);
+    //          W tile BN rows x 8 k -> BN*2 float4: threads < 2*BN
+    const int lrow = tid >> 1, lk = (tid & 1) * 4;
     const int am = m0 + lrow;
     long long arow = -1;
     if (am < M) arow = a_index ? (long long)__ldg(a_index + am) : (long long)am;
     const int wn = n0 + lrow;
+    const bool w_thread = lrow < BN;
+    const bool vecA = (lda % 4 == 0) && ((uintptr_t)A % 16 == 0) && (!A2 || (uintptr_t)A2 % 16 == 0);
+    const bool vecW = (ldw % 4 == 0) && ((uintptr_t)W % 16 == 0);
 
-    float acc[4][4];
+    auto ld4 = [&](const float* base, const float* base2, long long row, int ld, int k, bool vec) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < 0) return x;
+        const float* p = base + row * ld + k;
+        if (vec && k + 3 < K) {
+            x = __ldg(reinterpret_cast<const float4*>(p));
+            if (base2) { const float4 y = __ldg(reinterpret_cast<const float4*>(base2 + row * ld + k)); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    auto load_tile = [&](int kt, float (&ra)[4], float (&rw)[4]) {
-        const int k = kt * BK + lk;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            ra[i] = (arow >= 0 && k + i < K) ? __ldg(A + arow * lda + k + i) : 0.f;
-            if (A2 && arow >= 0 && k + i < K) ra[i] += __ldg(A2 + arow * lda + k + i);  // x + pos (geoattention.py:43-44)
-            rw[i] = (wn < N && k + i < K) ? __ldg(W + (long long)wn * ldw + k + i) : 0.f;
+            for (int e = 0; e < 4; ++e)
+                if (k + e < K) t[e] = __ldg(p + e) + (base2 ? __ldg(base2 + row * ld + k + e) : 0.f);   // x + pos (geoattention.py:43-44)
+            x = make_float4(t[0], t[1], t[2], t[3]);
         }
+        return x;
     };
-    auto store_tile = [&](int buf, const float (&ra)[4], const float (&rw)[4]) {
+    float acc[8][TN];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            As[buf][lk + i][lrow] = ra[i];
-            Ws[buf][lk + i][lrow] = rw[i];
-        }
-    };
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     const int nkt = (K + BK - 1) / BK;
-    float ra[4], rw[4];
-    load_tile(0, ra, rw);
-    store_tile(0, ra, rw);
+    float4 ra = ld4(A, A2, arow, lda, lk, vecA);
+    float4 rw = w_thread ? ld4(W, nullptr, wn < N ? (long long)wn : -1, ldw, lk, vecW) : make_float4(0.f, 0.f, 0.f, 0.f);
+    As[0][lk][lrow] = ra.x; As[0][lk + 1][lrow] = ra.y; As[0][lk + 2][lrow] = ra.z; As[0][lk + 3][lrow] = ra.w;
+    if (w_thread) { Ws[0][lk][lrow] = rw.x; Ws[0][lk + 1][lrow] = rw.y; Ws[0][lk + 2][lrow] = rw.z; Ws[0][lk + 3][lrow] = rw.w; }
     __syncthreads();
     for (int kt = 0; kt < nkt; ++kt) {
         const int buf = kt & 1;
-        if (kt + 1 < nkt) load_tile(kt + 1, ra, rw);  // global loads in flight during the math
+        if (kt + 1 < nkt) {   // global loads in flight during the math
+            ra = ld4(A, A2, arow, lda, (kt + 1) * BK + lk, vecA);
+            if (w_thread) rw = ld4(W, nullptr, wn < N ? (long long)wn : -1, ldw, (kt + 1) * BK + lk, vecW);
+        }
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[TN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int h = 0; h < NH; ++h) {
+                const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][h * (BN / 2) + tx * 4]);
+                bv[4 * h] = b.x; bv[4 * h + 1] = b.y; bv[4 * h + 2] = b.z; bv[4 * h + 3] = b.w;
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
-        if (kt + 1 < nkt) store_tile(buf ^ 1, ra, rw);
+        if (kt + 1 < nkt) {
+            const int nb = buf ^ 1;
+            As[nb][lk][lrow] = ra.x; As[nb][lk + 1][lrow] = ra.y; As[nb][lk + 2][lrow] = ra.z; As[nb][lk + 3][lrow] = ra.w;
+            if (w_thread) { Ws[nb][lk][lrow] = rw.x; Ws[nb][lk + 1][lrow] = rw.y; Ws[nb][lk + 2][lrow] = rw.z; Ws[nb][lk + 3][lrow] = rw.w; }
+        }
         __syncthreads();
     }
+    const bool vecC = (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (m >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= N) continue;
-            float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
-            if (relu) v = fmaxf(v, 0.f);
-            C[(long long)m * ldc + n] = v;
+        for (int h = 0; h < NH; ++h) {
+            const int n = n0 + h * (BN / 2) + tx * 4;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = acc[i][4 * h + j] + ((bias && n + j < N) ? __ldg(bias + n + j) : 0.f);
+                if (relu) v[j] = fmaxf(v[j], 0.f);
+            }
+            float* dst = C + (long long)m * ldc + n;
+            if (vecC && n + 3 < N) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < N) dst[j] = v[j];
+            }
         }
     }
 }
@@ -191,9 +222,15 @@ extern "C" int roitr_linear(int M, int N, int K, const float* A, const float* a_
     ROITR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && A && W && C, "linear: bad arguments M=%d N=%d K=%d", M, N, K);
     ROITR_CHECK_ARG(lda >= K && ldc >= N && ldw >= K, "linear: bad leading dimensions");
     if (M == 0) return ROITR_OK;
-    dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
-    linear_kernel<<<grid, GEMM_THREADS, 0, (cudaStream_t)stream>>>(M, N, K, A, a_add, lda, a_index, W, ldw, bias, C, ldc,
-                                                                   relu);
+    if (N <= 64) {
+        dim3 grid(ceil_div(M, 128), 1);
+        linear_kernel<64><<<grid, GEMM_THREADS, 0, (cudaStream_t)stream>>>(M, N, K, A, a_add, lda, a_index, W, ldw, bias, C,
+                                                                          ldc, relu);
+    } else {
+        dim3 grid(ceil_div(M, 128), ceil_div(N, 128));
+        linear_kernel<128><<<grid, GEMM_THREADS, 0, (cudaStream_t)stream>>>(M, N, K, A, a_add, lda, a_index, W, ldw, bias, C,
+                                                                           ldc, relu);
+    }
     ROITR_CHECK_LAUNCH("linear_kernel");
     return ROITR_OK;
 }

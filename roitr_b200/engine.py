@@ -253,6 +253,74 @@ def geometric_transformer(W, architecture, pts0, pts1, f0, f1, sigma_d=0.2, sigm
     return _lin(W, g + ".out_proj", f0), _lin(W, g + ".out_proj", f1), embs
 
 
+def _self_layer_batch(W, lp, x, E, nb, N):
+    """RPETransformerLayer for `nb` clouds of N superpoints stacked along dim 0 (x: (nb*N, C), E: (nb, N, N, C))."""
+    a = lp + ".attention.attention"
+    C = x.shape[1]
+    c = C // HEADS
+    R = x.shape[0]
+    qkv = ops.linear(x, W[a + "#Wqkv"], W[a + "#bqkv"])
+    gq = torch.empty(R, HEADS * C, dtype=torch.float32, device=x.device)
+    for h in range(HEADS):
+        ops.linear(qkv[:, h * c:(h + 1) * c], W[a + "#WpT"][h], None, out=gq[:, h * C:(h + 1) * C], M=R, K=c)
+    hidden, G = ops.geo_attention_batched(nb, N, N, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], C, E=E, gq=gq,
+                                          bp=W[a + ".proj_p.bias"])
+    Wvp, bvp = W[a + ".proj_vp.weight"], W[a + ".proj_vp.bias"]
+    G2 = G.view(R, HEADS * C)
+    pos = torch.empty(R, C, dtype=torch.float32, device=x.device)
+    for h in range(HEADS):
+        ops.linear(G2[:, h * C:(h + 1) * C], Wvp[h * c:(h + 1) * c], bvp[h * c:(h + 1) * c], out=pos[:, h * c:(h + 1) * c],
+                   M=R, K=C)
+    y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
+    pos = _ln(W, lp + ".attention.pos_norm", _lin(W, lp + ".attention.pos_linear", pos), mode=ops.MODE_LN)
+    return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
+
+
+def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
+    a = lp + ".attention.attention"
+    C = x.shape[1]
+    q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x)
+    k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y)
+    v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"])
+    hidden = ops.geo_attention_batched(nb, N, M, q, k, v, C)
+    z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
+    return _ffn(W, lp + ".output", z)
+
+
+def geometric_transformer_batch(W, architecture, B, pts0, pts1, f0, f1, sigma_d=0.2, sigma_a=15.0):
+    """GeometricTransformer.forward (geotransformer.py:94-133) for B pairs at once: pts0/f0 = the B source clouds
+    stacked (B*N0 rows), pts1/f1 = the B target clouds (B*N1 rows). Dense layers run on the stacked rows; the embedding
+    and attention kernels are per cloud (attention batched over blockIdx.y)."""
+    g = "backbone.global_transformer"
+    e = g + ".embedding"
+    C = W[g + ".in_proj.weight"].shape[0]
+    N0, N1 = pts0.shape[0] // B, pts1.shape[0] // B
+    embs = []
+    for pts, N in ((pts0, N0), (pts1, N1)):
+        E = torch.empty(B, N, N, C, dtype=torch.float32, device=pts.device)
+        for b in range(B):
+            pb = pts[b * N:(b + 1) * N]
+            nn3 = ops.geo_knn(pb, 3)
+            if GEO_EMBEDDING_TC:
+                ops.geo_embedding_tc(pb, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
+                                     W[e + ".embedding.div_term"], sigma_d, sigma_a, out=E[b])
+            else:
+                ops.geo_embedding(pb, nn3, W[e + ".proj_d.weight"], W[e + ".proj_d.bias"], W[e + ".proj_a.weight"],
+                                  W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], sigma_d, sigma_a, out=E[b])
+        embs.append(E)
+    f0, f1 = _lin(W, g + ".in_proj", f0), _lin(W, g + ".in_proj", f1)
+    pos0 = pos1 = None
+    for i, kind in enumerate(architecture):
+        lp = "%s.transformer.layers.%d" % (g, i)
+        if kind == "self":
+            f0, pos0 = _self_layer_batch(W, lp, f0, embs[0], B, N0)
+            f1, pos1 = _self_layer_batch(W, lp, f1, embs[1], B, N1)
+        else:
+            f0 = _cross_layer_batch(W, lp, f0, f1, pos0, pos1, B, N0, N1)
+            f1 = _cross_layer_batch(W, lp, f1, f0, pos1, pos0, B, N1, N0)
+    return _lin(W, g + ".out_proj", f0), _lin(W, g + ".out_proj", f1), embs
+
+
 # ------------------------------------------------------------------------------------------------ backbone
 def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=None):
     """RIPointTransformer.forward (model/model.py:187-237) for all pairs of the plan. Returns per-level batched tensors,
@@ -264,14 +332,16 @@ def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=Non
     # index-chain composition of the FPS indices (model/model.py:233-235); indices are global rows of the batch
     d3 = L[1]["down_idx"].long()[L[2]["down_idx"].long()]
     d4 = d3[L[3]["down_idx"].long()]
+    split = plan.starts(3, B)[0]             # level-4 rows: [B source clouds | B target clouds]
+    s_g_all, t_g_all, embs = geometric_transformer_batch(W, architecture, B, L[3]["p"][:split], L[3]["p"][split:],
+                                                         L[3]["x"][:split], L[3]["x"][split:])
     for b in range(B):
         s0, s1 = plan.starts(3, b)
         t0, t1 = plan.starts(3, B + b)
-        s_g, t_g, embs = geometric_transformer(W, architecture, L[3]["p"][s0:s1], L[3]["p"][t0:t1], L[3]["x"][s0:s1],
-                                               L[3]["x"][t0:t1])
         # node coordinates come from the (possibly deformed) source cloud: src_deformed is the batch of src clouds only
         s_nodes = ops.gather_rows(src_deformed, d4[s0:s1])
-        per_pair.append(dict(src_nodes=s_nodes, src_g=s_g, tgt_g=t_g, tgt_nodes=L[3]["p"][t0:t1], embs=embs if aux is not None else None))
+        per_pair.append(dict(src_nodes=s_nodes, src_g=s_g_all[s0:s1], tgt_g=t_g_all[t0 - split:t1 - split],
+                             tgt_nodes=L[3]["p"][t0:t1], embs=(embs[0][b], embs[1][b]) if aux is not None else None))
     if aux is not None:
         aux.update(levels=L, dec=dec, node_idx=d4, emb0=per_pair[0]["embs"][0], emb1=per_pair[0]["embs"][1])
     return L, dec, per_pair

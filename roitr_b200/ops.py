@@ -130,17 +130,17 @@ def geo_knn(pts, k=3):
     return nn
 
 
-def geo_embedding(pts, nn3, Wd, bd, Wa, ba, div_term, sigma_d, sigma_a):
+def geo_embedding(pts, nn3, Wd, bd, Wa, ba, div_term, sigma_d, sigma_a, out=None):
     N, C = pts.shape[0], Wd.shape[0]
-    E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device)
+    E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device) if out is None else out
     _lib.call("roitr_geo_embedding", c_int(N), c_int(C), f32(pts), i32(nn3), f32(Wd), f32(bd), f32(Wa), f32(ba),
               f32(div_term), c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
     return E
 
 
-def geo_embedding_tc(pts, nn3, wpack, bd, ba, div_term, sigma_d, sigma_a):
+def geo_embedding_tc(pts, nn3, wpack, bd, ba, div_term, sigma_d, sigma_a, out=None):
     N, C = pts.shape[0], bd.shape[0]
-    E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device)
+    E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device) if out is None else out
     _lib.call("roitr_geo_embedding_tc", c_int(N), c_int(C), f32(pts), i32(nn3), f32(wpack), f32(bd), f32(ba), f32(div_term),
               c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
     return E
@@ -154,6 +154,17 @@ def geo_attention(q, k, v, C, E=None, gq=None, bp=None):
     _lib.call("roitr_geo_attention", c_int(N), c_int(M), c_int(C), c_int(4), c_void(q), c_int(q.stride(0)), c_void(k),
               c_int(k.stride(0)), c_void(v), c_int(v.stride(0)), f32(E), f32(gq), f32(bp), f32(hidden), f32(G),
               stream_ptr())
+    return (hidden, G) if E is not None else hidden
+
+
+def geo_attention_batched(batch, N, M, q, k, v, C, E=None, gq=None, bp=None):
+    """q: rows of `batch` clouds of N queries each (stride N rows), k/v: `batch` clouds of M keys. Views with explicit
+    leading dims. Returns hidden (batch*N, C) [, G (batch*N, 4, C)]."""
+    hidden = torch.empty(batch * N, C, dtype=torch.float32, device=q.device)
+    G = torch.empty(batch * N, 4, C, dtype=torch.float32, device=q.device) if E is not None else None
+    _lib.call("roitr_geo_attention_batched", c_int(batch), c_int(N), c_int(M), c_int(C), c_int(4), c_void(q),
+              c_int(q.stride(0)), c_ll(N * q.stride(0)), c_void(k), c_int(k.stride(0)), c_ll(M * k.stride(0)), c_void(v),
+              c_int(v.stride(0)), c_ll(M * v.stride(0)), f32(E), f32(gq), f32(bp), f32(hidden), f32(G), stream_ptr())
     return (hidden, G) if E is not None else hidden
 
 
