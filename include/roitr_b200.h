@@ -189,6 +189,15 @@ int roitr_coarse_matching(int Mr, int Ms, int C, int k, int dual, const float* r
                           const unsigned char* ref_mask, const unsigned char* src_mask, const float* xy, float* work,
                           int* out_ref, int* out_src, float* out_score, int* out_count, void* stream);
 
+/* AdaptiveSuperPointMatching.forward (model/modules.py:81-123, 4DMatch head): sim = sqrt(clamp(2 - 2 a.b, 1e-12)) on valid
+ * superpoints; all pairs with sim <= threshold in row-major (torch.nonzero) order, or the min_num smallest (ascending) when
+ * fewer than min(min_num, #valid pairs) qualify; scores exp(-sim). Both candidate lists are built on the device and
+ * selected from the device-side counts (no host sync). xy = a @ b^T (Ma,Mb). work: 2*Ma*Mb floats + Ma*Mb bytes;
+ * iwork: cap + 3*min_num + 4 + roitr_compact_scratch_ints(Ma*Mb) ints. Outputs padded to cap (<= Ma*Mb). min_num <= 1024. */
+int roitr_coarse_matching_adaptive(int Ma, int Mb, int min_num, float threshold, const unsigned char* a_mask,
+                                   const unsigned char* b_mask, const float* xy, float* work, int* iwork, int cap,
+                                   int* out_a, int* out_b, float* out_score, int* out_count, void* stream);
+
 /* One CTA per superpoint correspondence p < *corr_count: gather the two 64-point patches' descriptors, scores =
  * Ft Fs^T / sqrt(C) (RIGA_v2.py:150-152), LearnableLogOptimalTransport (modules.py:28-68, num_iter Sinkhorn iterations
  * in shared memory) -> scores (Pmax,65,65); then FineMatching.compute_correspondence_matrix (modules.py:242-274) ->

@@ -649,3 +649,76 @@ extern "C" int roitr_fine_gather(int capacity, const int* flat, const int* count
     ROITR_CHECK_LAUNCH("fine_gather_kernel");
     return ROITR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ adaptive coarse matching
+// AdaptiveSuperPointMatching.forward (model/modules.py:81-123, 4DMatch head): sim = sqrt(clamp(2 - 2 a.b, 1e-12)) on the
+// valid superpoints; every pair with sim <= threshold in row-major (torch.nonzero) order, or - when fewer than
+// min(min_num, #valid pairs) qualify - the min_num smallest, ascending. Both candidate lists are produced on the device
+// (ordered compaction + flat top-k) and a last kernel picks one from the device-side counts: no host synchronisation.
+namespace {
+
+__global__ void adaptive_sim_kernel(int Ma, int Mb, const float* __restrict__ xy, const unsigned char* __restrict__ amask,
+                                    const unsigned char* __restrict__ bmask, float thr, float* __restrict__ sim,
+                                    float* __restrict__ key, unsigned char* __restrict__ flag) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)Ma * Mb) return;
+    const int i = (int)(e / Mb), j = (int)(e % Mb);
+    if (!(amask[i] && bmask[j])) { sim[e] = CUDART_INF_F; key[e] = -1.f; flag[e] = 0; return; }
+    // square_distance(normalized=True): 2 - 2 xy, clamp 1e-12 (lib/utils.py:149,155); then sqrt (modules.py:101)
+    const float d = __fsqrt_rn(fmaxf(__fsub_rn(2.0f, __fmul_rn(2.0f, __ldg(xy + e))), 1e-12f));
+    sim[e] = d;
+    key[e] = __uint_as_float(0x7f7fffffu - __float_as_uint(d));   // exact order-reversing map: largest key = smallest sim
+    flag[e] = d <= thr;
+}
+
+__global__ void adaptive_select_kernel(int Mb, int cap, const int* __restrict__ count_c, const int* __restrict__ flat_c,
+                                       const int* __restrict__ count_k, const int* __restrict__ row_k,
+                                       const int* __restrict__ col_k, const float* __restrict__ sim,
+                                       int* __restrict__ out_a, int* __restrict__ out_b, float* __restrict__ out_score,
+                                       int* __restrict__ out_count) {
+    const int nc = __ldg(count_c), nk = __ldg(count_k);
+    const bool use_topk = nc < nk;                                  // masks.sum() < min_num (modules.py:105)
+    const int n = use_topk ? nk : min(nc, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int a, b;
+        if (use_topk) { a = __ldg(row_k + i); b = __ldg(col_k + i); }
+        else { const int f = __ldg(flat_c + i); a = f / Mb; b = f % Mb; }
+        out_a[i] = a; out_b[i] = b;
+        out_score[i] = expf(-__ldg(sim + (size_t)a * Mb + b));      // corr_scores = exp(-corr_distances) (modules.py:112)
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = n;
+}
+
+}  // namespace
+
+extern "C" int roitr_coarse_matching_adaptive(int Ma, int Mb, int min_num, float threshold, const unsigned char* a_mask,
+                                              const unsigned char* b_mask, const float* xy, float* work, int* iwork,
+                                              int cap, int* out_a, int* out_b, float* out_score, int* out_count,
+                                              void* stream) {
+    // xy = a_feats @ b_feats^T (Ma x Mb) from roitr_linear. work: 2*Ma*Mb floats + Ma*Mb bytes (rounded up to floats).
+    // iwork: cap + 3*min_num + 4 + roitr_compact_scratch_ints(Ma*Mb) ints.
+    ROITR_CHECK_ARG(Ma >= 1 && Mb >= 1 && min_num >= 1 && min_num <= TOPK_MAX && cap >= min_num, "coarse_matching_adaptive: bad sizes");
+    ROITR_CHECK_ARG(a_mask && b_mask && xy && work && iwork && out_a && out_b && out_score && out_count, "coarse_matching_adaptive: null");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)Ma * Mb;
+    float* sim = work;
+    float* key = sim + n;
+    unsigned char* flag = reinterpret_cast<unsigned char*>(key + n);
+    int* flat_c = iwork;
+    int* row_k = flat_c + cap;
+    int* col_k = row_k + min_num;
+    float* val_k = reinterpret_cast<float*>(col_k + min_num);
+    int* count_c = reinterpret_cast<int*>(val_k + min_num);
+    int* count_k = count_c + 1;
+    int* scratch = count_k + 3;
+    adaptive_sim_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(Ma, Mb, xy, a_mask, b_mask, threshold, sim, key, flag);
+    const int nchunks = (int)ceil_div_ll(n, CMP_CHUNK);
+    compact_count_kernel<<<nchunks, 256, 0, st>>>(n, flag, scratch);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(nchunks, scratch, count_c);
+    compact_write_kernel<<<nchunks, 256, 0, st>>>(n, flag, scratch, flat_c, cap);
+    flat_topk_kernel<<<1, 1024, 0, st>>>((int)n, min_num, key, Mb, row_k, col_k, val_k, count_k);
+    adaptive_select_kernel<<<ceil_div(cap, 256) > 1024 ? 1024 : ceil_div(cap, 256), 256, 0, st>>>(Mb, cap, count_c, flat_c, count_k, row_k, col_k, sim,
+                                                                                                   out_a, out_b, out_score, out_count);
+    ROITR_CHECK_LAUNCH("coarse_matching_adaptive");
+    return ROITR_OK;
+}

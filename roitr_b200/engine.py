@@ -366,13 +366,14 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
     and rot (B,3,3) / trans (B,3,1). No host sync. Returns a list of per-pair dicts of PADDED tensors plus a (B,3) int32
     device tensor of counts [P, n_gt, n_corr]."""
     four_d = cfg["benchmark"] not in ("3DMatch", "3DLoMatch")
-    if four_d:
-        raise NotImplementedError("AdaptiveSuperPointMatching (4DMatch head) is scheduled after the 3DMatch path; see DESIGN.md")
     B, Ns, Nt = plan.B, plan.n_src, plan.n_tgt
     K = int(cfg["point_per_patch"])
     L, dec, per_pair = backbone_batch(W, cfg["transformer_architecture"], plan, pts, feats, nrm, src_pcd, aux)
     pf_all = _lin(W, "fine_proj", dec[0])                                # all points of all clouds at once
-    Pmax = int(cfg["num_est_coarse_corr"])
+    # 3DMatch: at most num_est_coarse_corr patch pairs. 4DMatch: every pair under the similarity threshold, i.e. up to
+    # Mt*Ms (model/modules.py:105-112); buffers are sized for that bound so the count can stay on the device.
+    M4s, M4t = plan.levels[3]["sizes"][0], plan.levels[3]["sizes"][B]
+    Pmax = M4s * M4t if four_d else int(cfg["num_est_coarse_corr"])
     topk = int(cfg["fine_matching_topk"])
     cap = Pmax * K * topk
     outs, counts = [], []
@@ -399,7 +400,11 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
         t_occ = ops.node_occlusion(t_ki, t_km, t_nm, t_nn.view(-1))
         s_occ = ops.node_occlusion(s_ki, s_km, s_nm, s_nn.view(-1))
         # 3. coarse matching   (called as (tgt, src), model/RIGA_v2.py:121)
-        t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, t_nm, s_nm, Pmax, dual=True)
+        if four_d:
+            t_ci, s_ci, node_sc, p_count = ops.coarse_matching_adaptive(tgt_nf, src_nf, t_nm, s_nm,
+                                                                        int(cfg["num_est_coarse_corr"]), 0.75, Pmax)
+        else:
+            t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, t_nm, s_nm, Pmax, dual=True)
         # 4-6. fine scoring + OT + fine matching
         scores, flags = ops.fine_matching(tgt_pf, src_pf, t_ki, s_ki, t_km, s_km, t_ci, s_ci, p_count,
                                           W["optimal_transport.alpha"].view(1), 100, topk,

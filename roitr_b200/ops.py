@@ -210,6 +210,25 @@ def coarse_matching(ref_feats, src_feats, ref_mask, src_mask, k, dual=True):
     return out_ref, out_src, out_score, count
 
 
+def coarse_matching_adaptive(a_feats, b_feats, a_mask, b_mask, min_num, threshold, cap):
+    Ma, Mb = a_feats.shape[0], b_feats.shape[0]
+    dev = a_feats.device
+    xy = linear(a_feats, b_feats)
+    n = Ma * Mb
+    work = torch.empty(2 * n + (n + 3) // 4, dtype=torch.float32, device=dev)
+    fn = _lib.lib().roitr_compact_scratch_ints
+    fn.restype = c_ll
+    iwork = torch.empty(cap + 3 * min_num + 4 + int(fn(c_ll(n))), dtype=torch.int32, device=dev)
+    out_a = torch.zeros(cap, dtype=torch.int32, device=dev)
+    out_b = torch.zeros(cap, dtype=torch.int32, device=dev)
+    out_score = torch.zeros(cap, dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.call("roitr_coarse_matching_adaptive", c_int(Ma), c_int(Mb), c_int(min_num), c_float(threshold), _u8(a_mask),
+              _u8(b_mask), f32(xy), f32(work), i32(iwork), c_int(cap), i32(out_a), i32(out_b), f32(out_score), i32(count),
+              stream_ptr())
+    return out_a, out_b, out_score, count
+
+
 def fine_matching(tgt_feat, src_feat, tgt_knn, src_knn, tgt_kmask, src_kmask, corr_t, corr_s, corr_count, alpha,
                   num_iter, topk, mutual, threshold):
     Pmax = corr_t.shape[0]

@@ -4,7 +4,7 @@ import torch
 
 from roitr_b200.synthetic import synthetic_pair
 from tests import parity
-from tests.helpers import CONFIG_3D, weights
+from tests.helpers import CONFIG_3D, CONFIG_4D, weights
 
 pytestmark = pytest.mark.gpu
 
@@ -26,4 +26,14 @@ def test_forward_ragged_sizes():
     pair["tgt_pcd"], pair["tgt_normals"], pair["tgt_feats"] = pair["tgt_pcd"][:2741].contiguous(), pair["tgt_normals"][:2741].contiguous(), pair["tgt_feats"][:2741].contiguous()
     rows, out, ref = parity.run(pair, CONFIG_3D, weights(1))
     print("\n" + parity.format_rows(rows))
+    assert not parity.failures(rows), parity.failures(rows)
+
+
+@pytest.mark.parametrize("n,index", [(1024, 2), (2048, 3)])
+def test_forward_parity_4dmatch(n, index):
+    """factor-2 backbone (C = 128/256/512/512) + AdaptiveSuperPointMatching + top-2 fine matching, deformed source."""
+    rows, out, ref = parity.run(synthetic_pair(index, n, deform=True), CONFIG_4D, weights(2))
+    print("\n" + parity.format_rows(rows))
+    for k in out:
+        assert out[k].dtype == ref[k].dtype and out[k].shape[1:] == ref[k].shape[1:], k
     assert not parity.failures(rows), parity.failures(rows)
