@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one JSON line on rank 0)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithm on the host CPU cores
 
-A step = RIGA_v2.forward over a batch of B (default 8) independent synthetic pairs of BASELINE.json configs[1]
+A step = RIGA_v2.forward over a batch of B (default 16) independent synthetic pairs of BASELINE.json configs[1]
 (2 x 20 000 points each, Gaussian blobs, seeded weights), issued as one CUDA graph. N > 1 (torchrun, one rank per GPU): pairs are independent units, rank r processes its own
 pairs (weak scaling), NCCL is used only for the barrier, the max-over-ranks time and the gather of per-pair result
 counts. `value` = pairs/s with inputs resident in HBM; `e2e` = the same metric through model.forward with pinned HOST
@@ -136,7 +136,7 @@ def op_work(name, ints):
     if name == "roitr_furthestsampling_cfg":
         b, _, nseg = ints[:3]
         return "bytes", b * (nseg * 12.0 + (nseg // 4) * 16.0)
-    if name == "roitr_knn_ppf_n":
+    if name in ("roitr_knn_ppf_n", "roitr_knn_ppf_grid"):
         b, m, k, drop, n = ints[:5]
         return "bytes", n * 24.0 + m * 24.0 + m * k * 20.0
     if name == "roitr_local_attention":
@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("ROITR_BENCH_BATCH", "8")), help="pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("ROITR_BENCH_BATCH", "16")), help="pairs per step per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

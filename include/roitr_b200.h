@@ -63,6 +63,21 @@ int roitr_knn_ppf_n(int b, int m, int k_out, int drop_first, int n_total, const 
                     float* dist, float* ppf, void* stream);
 
 /*
+ * Grid-accelerated form of roitr_knn_ppf_n: identical results (same distance arithmetic on every candidate, same
+ * (distance, index) order, same exact tie replay), but each query only visits the cells of a growing cube of a uniform
+ * grid over its segment until the k-th distance is provably smaller than anything outside the cube.
+ *   roitr_knn_grid_workspace_bytes(b, n)  bytes of device workspace for a reference set of b segments / n points
+ *   roitr_knn_grid_build(...)             bounding boxes, cell size, counting sort into cell order (4 small kernels);
+ *                                         the workspace can serve any number of queries against the same reference set
+ *   roitr_knn_ppf_grid(...)               as roitr_knn_ppf_n, with the workspace (256-byte aligned)
+ */
+long long roitr_knn_grid_workspace_bytes(int b, int n);
+int roitr_knn_grid_build(int b, int n, const float* xyz, const int* offset, void* workspace, void* stream);
+int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n_total, const float* xyz, const float* normals,
+                       const float* new_xyz, const float* new_normals, const int* offset, const int* new_offset,
+                       const void* workspace, int* idx, float* dist, float* ppf, void* stream);
+
+/*
  * Drop-in for  furthestsampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)
  * (cpp_wrappers/pointops/src/sampling/sampling_cuda_kernel.h:13; kernel .cu:14-129).
  * Iterative furthest point sampling per segment; first sample = first point of the segment; identical distance

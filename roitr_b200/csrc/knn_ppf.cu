@@ -20,6 +20,7 @@
 
 #include "../../include/roitr_b200.h"
 #include "common.cuh"
+#include "knn_grid.cuh"
 
 namespace {
 
@@ -300,6 +301,104 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) knn_tie_fixup_kernel(const Knn
     }
 }
 
+// ---- grid-accelerated exact kNN: one warp per query, candidates from the cells of a growing cube -------------------------
+// Same distance arithmetic, same (distance, index) order, same tie marking / replay as the brute-force kernel; candidates
+// arrive in cell order instead of index order, so admission and insertion compare (distance, index) lexicographically.
+__global__ void __launch_bounds__(KNN_THREADS, 4) knn_grid_kernel(const KnnParams P, const knngrid::SegHeader* __restrict__ hdr,
+                                                               const int* __restrict__ cell_start,
+                                                               const float4* __restrict__ sorted) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * KNN_WARPS + warp;
+    if (q >= P.m) return;
+    const int K = P.nslots, kout = K - P.drop;
+    const unsigned kmask = (K >= 32) ? FULL_MASK : ((1u << K) - 1u);
+    const int sgm = find_segment(q, P.new_offset, P.b);
+    const int qs = sgm == 0 ? 0 : __ldg(P.offset + sgm - 1);
+    const knngrid::SegHeader H = hdr[sgm];
+    const float qx = __ldg(P.qxyz + 3 * (size_t)q), qy = __ldg(P.qxyz + 3 * (size_t)q + 1), qz = __ldg(P.qxyz + 3 * (size_t)q + 2);
+    const int cx = knngrid::cell_coord(qx, H.ox, H.inv_h, H.nx), cy = knngrid::cell_coord(qy, H.oy, H.inv_h, H.ny),
+              cz = knngrid::cell_coord(qz, H.oz, H.inv_h, H.nz);
+    const int* cs = cell_start + H.cell_base;
+    const float4* pts = sorted + qs;
+
+    float ld = 1e10f, tau = 1e10f;
+    int li = qs, tau_i = qs;
+    bool tie = false;
+
+    auto scan_range = [&](int beg, int end) {
+        for (int p0 = beg; p0 < end; p0 += 32) {
+            const int p = p0 + lane;
+            float d = CUDART_INF_F;
+            int ci = 0;
+            if (p < end) {
+                const float4 v = __ldg(pts + p);
+                d = sqdist_ref(qx - v.x, qy - v.y, qz - v.z);
+                ci = __float_as_int(v.w);
+            }
+            unsigned mask = __ballot_sync(FULL_MASK, d <= tau);
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float cd = __shfl_sync(FULL_MASK, d, l);
+                const int cidx = __shfl_sync(FULL_MASK, ci, l);
+                if (cd == tau && tau != 1e10f) tie = true;     // boundary tie: the reference's choice depends on its heap
+                if (cd < tau || (cd == tau && cidx < tau_i)) {
+                    const bool before = (ld < cd) || (ld == cd && li < cidx);
+                    const int ins = __popc(__ballot_sync(FULL_MASK, before) & kmask);
+                    const float up_d = __shfl_up_sync(FULL_MASK, ld, 1);
+                    const int up_i = __shfl_up_sync(FULL_MASK, li, 1);
+                    if (lane > ins) { ld = up_d; li = up_i; }
+                    else if (lane == ins) { ld = cd; li = cidx; }
+                    const float tau_old = tau;
+                    tau = __shfl_sync(FULL_MASK, ld, K - 1);
+                    tau_i = __shfl_sync(FULL_MASK, li, K - 1);
+                    if (tau == tau_old && tau_old != 1e10f) tie = true;
+                }
+            }
+        }
+    };
+
+    for (int r = 0;; ++r) {
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, H.nx - 1);
+        for (int dz = -r; dz <= r; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= H.nz) continue;
+            for (int dy = -r; dy <= r; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= H.ny) continue;
+                const int row = (z * H.ny + y) * H.nx;
+                if (abs(dz) == r || abs(dy) == r) {               // face of the cube: the whole x span
+                    scan_range(__ldg(cs + row + x0), __ldg(cs + row + x1 + 1));
+                } else {                                         // interior row: only the two end cells
+                    if (cx - r >= 0) scan_range(__ldg(cs + row + cx - r), __ldg(cs + row + cx - r + 1));
+                    if (cx + r < H.nx) scan_range(__ldg(cs + row + cx + r), __ldg(cs + row + cx + r + 1));
+                }
+            }
+        }
+        // everything outside the cube of radius r is at least `bound` away from the query
+        const bool all = (cx - r <= 0) && (cx + r >= H.nx - 1) && (cy - r <= 0) && (cy + r >= H.ny - 1) && (cz - r <= 0) &&
+                         (cz + r >= H.nz - 1);
+        if (all) break;
+        float bound = CUDART_INF_F;
+        if (cx - r > 0) bound = fminf(bound, qx - (H.ox + (float)(cx - r) * H.h));
+        if (cx + r < H.nx - 1) bound = fminf(bound, (H.ox + (float)(cx + r + 1) * H.h) - qx);
+        if (cy - r > 0) bound = fminf(bound, qy - (H.oy + (float)(cy - r) * H.h));
+        if (cy + r < H.ny - 1) bound = fminf(bound, (H.oy + (float)(cy + r + 1) * H.h) - qy);
+        if (cz - r > 0) bound = fminf(bound, qz - (H.oz + (float)(cz - r) * H.h));
+        if (cz + r < H.nz - 1) bound = fminf(bound, (H.oz + (float)(cz + r + 1) * H.h) - qz);
+        bound -= 1e-4f * H.h;                                     // binning rounds (v - o) * inv_h: keep a safety margin
+        if (tau < 1e10f && bound > 0.f && tau < bound * bound * 0.99999f) break;
+    }
+    {   // equal distances inside the final list: the reference's order among them is its heap's
+        const float nxt = __shfl_down_sync(FULL_MASK, ld, 1);
+        if (__ballot_sync(FULL_MASK, lane + 1 < K && ld == nxt && ld != 1e10f)) tie = true;
+    }
+    const int slot = lane - P.drop;
+    if (slot < 0 || lane >= K) return;
+    if (tie) { if (slot == 0) P.idx[(size_t)q * kout] = -1; return; }
+    emit_result(P, q, slot, kout, li, ld, qx, qy, qz);
+}
+
 int g_skip_fixup = 0;  // debug only (roitr_debug_skip_knn_fixup): leave the -1 markers in place to count flagged queries
 
 int launch_knn(const KnnParams& P, cudaStream_t st) {
@@ -386,4 +485,56 @@ extern "C" int roitr_knn_ppf(int b, int m, int k_out, int drop_first, const floa
     ROITR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return roitr_knn_ppf_n(b, m, k_out, drop_first, n_total, xyz, normals, new_xyz, new_normals, offset, new_offset, idx,
                            dist, ppf, stream);
+}
+
+
+// ---- grid API -----------------------------------------------------------------------------------------------------------
+static size_t grid_hdr_bytes(int b) { return ((size_t)b * sizeof(knngrid::SegHeader) + 255) / 256 * 256; }
+static size_t grid_cells_bytes(int b) { return ((size_t)b * (knngrid::MAX_CELLS + 1) * sizeof(int) + 255) / 256 * 256; }
+
+extern "C" long long roitr_knn_grid_workspace_bytes(int b, int n) {
+    return (long long)(grid_hdr_bytes(b) + 2 * grid_cells_bytes(b) + (size_t)n * sizeof(float4));
+}
+
+extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* offset, void* workspace, void* stream) {
+    ROITR_CHECK_ARG(b >= 1 && n >= 0 && xyz && offset && workspace, "knn_grid_build: bad arguments");
+    ROITR_CHECK_ARG((uintptr_t)workspace % 256 == 0, "knn_grid_build: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* w = (unsigned char*)workspace;
+    auto* hdr = (knngrid::SegHeader*)w;
+    int* cell_start = (int*)(w + grid_hdr_bytes(b));
+    int* cursor = (int*)(w + grid_hdr_bytes(b) + grid_cells_bytes(b));
+    float4* sorted = (float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b));
+    ROITR_CUDA(cudaMemsetAsync(cursor, 0, grid_cells_bytes(b), st));
+    knngrid::grid_header_kernel<<<b, 256, 0, st>>>(b, xyz, offset, hdr);
+    if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 0);
+    knngrid::grid_scan_kernel<<<b, 1024, 0, st>>>(hdr, cursor, cell_start);
+    if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 1);
+    ROITR_CHECK_LAUNCH("knn_grid_build");
+    return ROITR_OK;
+}
+
+extern "C" int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n_total, const float* xyz,
+                                  const float* normals, const float* new_xyz, const float* new_normals, const int* offset,
+                                  const int* new_offset, const void* workspace, int* idx, float* dist, float* ppf,
+                                  void* stream) {
+    const int nslots = k_out + drop_first;
+    ROITR_CHECK_ARG(b >= 1 && m >= 0 && nslots >= 1 && nslots <= 32 && drop_first >= 0 && drop_first < nslots, "knn_ppf_grid: bad sizes");
+    ROITR_CHECK_ARG(xyz && new_xyz && offset && new_offset && idx && workspace, "knn_ppf_grid: null pointer");
+    ROITR_CHECK_ARG(!ppf || (normals && new_normals && (uintptr_t)ppf % 16 == 0), "knn_ppf_grid: ppf needs normals / alignment");
+    if (m == 0) return ROITR_OK;
+    KnnParams P;
+    P.xyz = xyz; P.nrm = normals; P.qxyz = new_xyz; P.qnrm = new_normals; P.offset = offset; P.new_offset = new_offset;
+    P.b = b; P.m = m; P.nslots = nslots; P.drop = drop_first; P.idx = idx; P.dist = dist; P.ppf = ppf; P.dist_squared = 0;
+    P.use_tma = 0; P.n_total = n_total;
+    const unsigned char* w = (const unsigned char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    knn_grid_kernel<<<ceil_div(m, KNN_WARPS), KNN_THREADS, 0, st>>>(P, (const knngrid::SegHeader*)w,
+                                                                  (const int*)(w + grid_hdr_bytes(b)),
+                                                                  (const float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b)));
+    ROITR_CHECK_LAUNCH("knn_grid_kernel");
+    if (g_skip_fixup) return ROITR_OK;
+    knn_tie_fixup_kernel<<<ceil_div(m, FIX_WARPS * 32), FIX_WARPS * 32, 0, st>>>(P);
+    ROITR_CHECK_LAUNCH("knn_tie_fixup_kernel");
+    return ROITR_OK;
 }

@@ -146,6 +146,9 @@ def encode(W, plan, pts, feats, nrm):
     levels = []
     x = feats
     o = plan.levels[0]["o"]
+    # one uniform grid per (large) reference set, shared by every kNN query against it (self, down-sampling, interpolation)
+    mk_grid = lambda li, p_, o_: ops.knn_grid_build(p_, o_) if plan.levels[li]["n_max"] >= ops.GRID_MIN_SEGMENT else None
+    grid = None
     for li in range(4):
         p = "backbone.enc%d" % (li + 1)
         k = NSAMPLE[li]
@@ -155,17 +158,19 @@ def encode(W, plan, pts, feats, nrm):
             down_idx, n_p = ops.fps(pts, o, no, plan.levels[li - 1]["n_max"], L["total"], per_segment_rule=True,
                                     cluster=plan.fps_cluster)
             n_n = ops.gather_rows(nrm, down_idx)
-            gidx, gppf, _ = ops.knn_ppf(k, pts, nrm, n_p, n_n, o, no)
+            gidx, gppf, _ = ops.knn_ppf(k, pts, nrm, n_p, n_n, o, no, grid=grid)
             x = local_ppf_transformer(W, p + ".0.transformer", x, down_idx, gidx, gppf)
             pts, nrm, o = n_p, n_n, no
-            idx, ppf, _ = ops.knn_ppf(k, pts, nrm, pts, nrm, o, o)
+            grid = mk_grid(li, pts, o)
+            idx, ppf, _ = ops.knn_ppf(k, pts, nrm, pts, nrm, o, o, grid=grid)
         else:
             down_idx = None
-            idx, ppf, _ = ops.knn_ppf(k, pts, nrm, pts, nrm, o, o)   # shared by the TD and the blocks of level 1
+            grid = mk_grid(li, pts, o)
+            idx, ppf, _ = ops.knn_ppf(k, pts, nrm, pts, nrm, o, o, grid=grid)   # shared by the TD and the blocks of level 1
             x = local_ppf_transformer(W, p + ".0.transformer", x, None, idx, ppf)
         for bi in range(1, BLOCKS[li]):
             x = block(W, "%s.%d" % (p, bi), x, idx, ppf)
-        levels.append(dict(p=pts, n=nrm, x=x, o=o, idx=idx, ppf=ppf, down_idx=down_idx))
+        levels.append(dict(p=pts, n=nrm, x=x, o=o, idx=idx, ppf=ppf, down_idx=down_idx, grid=grid))
     return levels
 
 
@@ -183,7 +188,7 @@ def decode(W, L):
         a = _ln(W, p + ".linear1.1", _lin(W, p + ".linear1.0", fine["x"]), mode=ops.MODE_LN | ops.MODE_RELU)
         b = _ln(W, p + ".linear2.1", _lin(W, p + ".linear2.0", xs[li + 1]), mode=ops.MODE_LN | ops.MODE_RELU)
         nn_idx, _, nn_dist = ops.knn_ppf(3, coarse["p"], None, fine["p"], None, coarse["o"], fine["o"], drop_first=0,
-                                         want_ppf=False, want_dist=True)
+                                         want_ppf=False, want_dist=True, grid=coarse["grid"])
         y = ops.interpolate(nn_idx, nn_dist, b, base=a)
         xs[li] = block(W, "backbone.dec%d.1" % (li + 1), y, fine["idx"], fine["ppf"])
     return xs
@@ -395,8 +400,10 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
         gt_idx, gt_ov = ops.corr_gather(Mt * Ms, Ms, gt_flat, gt_count, ov)
         t_pad = ops.pad_transform(tgt_pts)
         s_pad_t = ops.pad_transform(src_pts, rot[b], trans[b])
-        _, _, t_nn = ops.knn_ppf(1, s_pad_t, None, t_pad, None, o_s, o_t, drop_first=0, want_ppf=False, want_dist=True)
-        _, _, s_nn = ops.knn_ppf(1, t_pad, None, s_pad_t, None, o_t, o_s, drop_first=0, want_ppf=False, want_dist=True)
+        g_s = ops.knn_grid_build(s_pad_t, o_s) if Ns + 1 >= ops.GRID_MIN_SEGMENT else None
+        g_t = ops.knn_grid_build(t_pad, o_t) if Nt + 1 >= ops.GRID_MIN_SEGMENT else None
+        _, _, t_nn = ops.knn_ppf(1, s_pad_t, None, t_pad, None, o_s, o_t, drop_first=0, want_ppf=False, want_dist=True, grid=g_s)
+        _, _, s_nn = ops.knn_ppf(1, t_pad, None, s_pad_t, None, o_t, o_s, drop_first=0, want_ppf=False, want_dist=True, grid=g_t)
         t_occ = ops.node_occlusion(t_ki, t_km, t_nm, t_nn.view(-1))
         s_occ = ops.node_occlusion(s_ki, s_km, s_nm, s_nn.view(-1))
         # 3. coarse matching   (called as (tgt, src), model/RIGA_v2.py:121)

@@ -74,11 +74,29 @@ def concat_segment(x, g, offset):
     return out
 
 
-def knn_ppf(k, xyz, nrm, new_xyz, new_nrm, offset, new_offset, drop_first=1, want_ppf=True, want_dist=False):
+GRID_MIN_SEGMENT = 2048     # reference sets with at least this many points per segment get the grid-accelerated kNN
+
+
+def knn_grid_build(xyz, offset):
+    """Uniform-grid acceleration structure over a (segmented) reference set; reusable by every query against it."""
+    b, n = offset.shape[0], xyz.shape[0]
+    fn = _lib.lib().roitr_knn_grid_workspace_bytes
+    fn.restype = c_ll
+    ws = torch.empty(int(fn(c_int(b), c_int(n))), dtype=torch.uint8, device=xyz.device)
+    _lib.call("roitr_knn_grid_build", c_int(b), c_int(n), f32(xyz), i32(offset), ptr(ws), stream_ptr())
+    return ws
+
+
+def knn_ppf(k, xyz, nrm, new_xyz, new_nrm, offset, new_offset, drop_first=1, want_ppf=True, want_dist=False, grid=None):
     m = new_xyz.shape[0]
     idx = torch.empty(m, k, dtype=torch.int32, device=xyz.device)
     ppf = torch.empty(m, k, 4, dtype=torch.float32, device=xyz.device) if want_ppf else None
     dist = torch.empty(m, k, dtype=torch.float32, device=xyz.device) if want_dist else None
+    if grid is not None:
+        _lib.call("roitr_knn_ppf_grid", c_int(offset.shape[0]), c_int(m), c_int(k), c_int(drop_first), c_int(xyz.shape[0]),
+                  f32(xyz), f32(nrm) if want_ppf else None, f32(new_xyz), f32(new_nrm) if want_ppf else None, i32(offset),
+                  i32(new_offset), ptr(grid), i32(idx), f32(dist), f32(ppf), stream_ptr())
+        return idx, ppf, dist
     _lib.call("roitr_knn_ppf_n", c_int(offset.shape[0]), c_int(m), c_int(k), c_int(drop_first), c_int(xyz.shape[0]),
               f32(xyz), f32(nrm) if want_ppf else None, f32(new_xyz), f32(new_nrm) if want_ppf else None, i32(offset),
               i32(new_offset), i32(idx), f32(dist), f32(ppf), stream_ptr())

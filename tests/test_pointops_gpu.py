@@ -149,3 +149,49 @@ def test_interpolation_matches_oracle():
     ref = base + fr.interpolate3(coarse, fine, feat, oc, of)
     got = pointops.interpolation(coarse.to(DEV), fine.to(DEV), feat.to(DEV), oc.to(DEV), of.to(DEV), base=base.to(DEV))
     np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,m,k,drop,segs", [
+    (20000, 20000, 8, 1, None), (20000, 5000, 16, 1, None), (5000, 20000, 3, 0, None), (4096, 4096, 16, 1, None),
+    (9000, 2250, 16, 1, ([5000, 6000, 9000], [1250, 1500, 2250])), (3000, 3000, 31, 1, None), (2500, 40, 1, 0, None),
+])
+def test_grid_knn_equals_brute_force(n, m, k, drop, segs):
+    """The grid-accelerated kNN must return exactly what the brute-force kernel returns (indices, distances, PPF)."""
+    from roitr_b200 import ops
+    from roitr_b200.synthetic import synthetic_pair
+    pair = synthetic_pair(3, max(n, m))
+    xyz, nrm = pair["tgt_pcd"][:n].contiguous().to(DEV), pair["tgt_normals"][:n].contiguous().to(DEV)
+    if m == n:
+        q, qn = xyz, nrm
+    elif m < n:
+        sel = torch.arange(0, n, n // m)[:m]
+        q, qn = xyz[sel].contiguous(), nrm[sel].contiguous()
+    else:   # queries outside / around the reference set's bounding box too
+        q = (pair["src_pcd"][:m] * 1.3).contiguous().to(DEV)
+        qn = pair["src_normals"][:m].contiguous().to(DEV)
+    off, noff = (_i32([n]), _i32([m])) if segs is None else (_i32(segs[0]), _i32(segs[1]))
+    off, noff = off.to(DEV), noff.to(DEV)
+    want_ppf = drop == 1
+    a = ops.knn_ppf(k, xyz, nrm, q, qn, off, noff, drop_first=drop, want_ppf=want_ppf, want_dist=True)
+    grid = ops.knn_grid_build(xyz, off)
+    b = ops.knn_ppf(k, xyz, nrm, q, qn, off, noff, drop_first=drop, want_ppf=want_ppf, want_dist=True, grid=grid)
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    if want_ppf:
+        assert torch.equal(a[1], b[1])
+
+
+def test_grid_knn_lattice_ties_and_degenerate_clouds():
+    from roitr_b200 import ops
+    g = (torch.stack(torch.meshgrid(*[torch.arange(14.)] * 3, indexing="ij"), -1).reshape(-1, 3) * 0.1).contiguous().to(DEV)
+    off = _i32([g.shape[0]]).to(DEV)
+    idx_o, d2_o = native.knn(17, g.cpu(), g.cpu(), off.cpu(), off.cpu())
+    grid = ops.knn_grid_build(g, off)
+    idx, _, dist = ops.knn_ppf(17, g, None, g, None, off, off, drop_first=0, want_ppf=False, want_dist=True, grid=grid)
+    assert torch.equal(idx.cpu(), idx_o)
+    flat = torch.zeros(3000, 3); flat[:, 0] = torch.linspace(0, 1, 3000)      # all points on a line: ny = nz = 1
+    flat = flat.contiguous().to(DEV)
+    off = _i32([3000]).to(DEV)
+    a = ops.knn_ppf(5, flat, None, flat, None, off, off, drop_first=0, want_ppf=False, want_dist=True)
+    b = ops.knn_ppf(5, flat, None, flat, None, off, off, drop_first=0, want_ppf=False, want_dist=True, grid=ops.knn_grid_build(flat, off))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
