@@ -127,7 +127,7 @@ def run_reference(args):
 def op_work(name, ints):
     """Algorithmic work of one entry-point call from its leading integer arguments (DESIGN.md §4 / SURVEY.md §8d).
     -> (kind, amount): kind 'bytes' (compulsory bytes) or 'flop'."""
-    if name in ("roitr_linear", "roitr_linear_tc"):
+    if name in ("roitr_linear", "roitr_linear_tc", "roitr_linear_tc_packed"):
         M, N, K = ints[:3]
         return "flop", 2.0 * M * N * K
     if name in ("roitr_geo_embedding", "roitr_geo_embedding_tc"):

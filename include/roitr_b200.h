@@ -128,6 +128,13 @@ int roitr_linear(int M, int N, int K, const float* A, const float* a_add, int ld
 int roitr_linear_tc(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index, const float* W,
                     int ldw, const float* bias, float* C, int ldc, int relu, void* stream);
 
+/* The production tensor-core dense layer: persistent, warp-specialised (A loader warps, bulk-TMA weight producer, single-
+ * thread tcgen05 MMA issuer, epilogue warps; two TMEM accumulators so the epilogue of a tile overlaps the next tile).
+ * wpack = the weight pre-split into TF32 hi/lo and pre-swizzled by roitr_b200.engine.pack_linear_tc:
+ * [ceil(N/bn)][ceil(K/32)][hi|lo][bn*32] floats, zero padded, bn in {64,128}. Same contract as roitr_linear otherwise. */
+int roitr_linear_tc_packed(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
+                           const float* wpack, int bn, const float* bias, float* C, int ldc, int relu, void* stream);
+
 /* out = [L2norm] [ReLU] ( [LayerNorm_{gamma,beta,eps=1e-5}] (x + res_pre[res_pre_index]) + res_post ), one row of C<=1024
  * floats per warp. mode bits: 1 LayerNorm, 2 ReLU, 4 x / max(|x|_2, 1e-12). Any of the residuals may be NULL. */
 int roitr_row_epilogue(int M, int C, const float* x, const float* res_pre, const int* res_pre_index, const float* gamma,

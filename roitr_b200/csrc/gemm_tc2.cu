@@ -1,0 +1,285 @@
+// Persistent warp-specialised tensor-core dense layer (sm_100a):  C[M,N] = (A [+ A2])[M,K] W[N,K]^T + bias (+ReLU)
+// fp32 in / fp32 out, 3xTF32 split precision on tcgen05 (see gemm_tc.cu for the numerics).
+//
+// The dense layers of the forward are skinny (K = 64..512, N = 64..768) over very tall activations (up to 640 000 rows per
+// step): they are memory-streaming problems, so the kernel is organised to keep HBM/L2 requests in flight at all times:
+//
+//   warps 0-3   EPILOGUE   tcgen05.ld the finished accumulator (warp w = TMEM lanes 32w..), bias / ReLU, 128-byte row
+//                          segments to global; releases the accumulator (tmem_empty)
+//   warps 4-7   A LOADERS  one activation row per thread: 8 independent 16-byte loads per K chunk (optional row gather /
+//                          second addend), TF32 hi/lo split, 128B-swizzled shared-memory stores; run up to STAGES chunks
+//                          ahead of the tensor core
+//   warp 8      W PRODUCER the weights are static: pre-split and pre-swizzled at load time into per-(n-tile, K-chunk)
+//                          blocks, fetched with ONE bulk TMA copy per chunk (cp.async.bulk + mbarrier complete_tx)
+//   warp 9      MMA        one thread issues 4 K-steps x 3 tcgen05.mma.kind::tf32 per chunk and commits to the stage's
+//                          "empty" barrier; a second commit per tile hands the accumulator to the epilogue
+//
+// CTAs are persistent (grid = #SMs): each walks tiles (row tile, n tile) with a static stride. Two TMEM accumulators
+// alternate, so the epilogue of tile t overlaps the loads and MMAs of tile t+1.
+#include "../../include/roitr_b200.h"
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int T2_THREADS = 320;
+constexpr int T2_BM = 128, T2_BK = 32;
+constexpr int A_HALF = T2_BM * 128;     // 16 KB: hi or lo of a 128-row x 32-float chunk
+
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct Tc2Params {
+    int M, N, K;
+    const float* A; const float* A2; int lda; const int* a_index;
+    const float* wpack;     // [ceil(N/BN)][ceil(K/32)][hi|lo][BN rows x 128 B, SWIZZLE_128B], zero padded
+    const float* bias;
+    float* C; int ldc; int relu;
+    int tiles_m, tiles_n, nkc;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Params P) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int B_HALF = BN * 128;
+    constexpr int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_pad[4][32 * 33];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 128 + 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int total_tiles = P.tiles_m * P.tiles_n;
+    const int nkc = P.nkc;
+
+    if (warp >= 4 && warp < 8) {
+        // ================================================= A loaders =================================================
+        const int r = tid - 128;                                   // row of the tile owned by this thread
+        const bool vec = (P.lda % 4 == 0) && ((uintptr_t)P.A % 16 == 0) && (P.K % 4 == 0);
+        if (vec && !P.A2 && !P.a_index) {
+            // Streaming path: cp.async (LDGSTS) 16-byte copies straight into the swizzled operand tile, LOOK chunks ahead
+            // of the split pass, so STAGES-1 x 16 KB of loads are in flight per SM without holding registers. Each thread
+            // copies and later splits ONLY its own row, so per-thread cp.async groups are all the synchronisation needed.
+            constexpr int LOOK = STAGES - 1;
+            // this thread's chunk sequence: (tile, kc) pairs in order; `issue` runs LOOK steps ahead of `it`
+            int i_tile = blockIdx.x, i_kc = 0;
+            uint32_t i_it = 0;
+            auto issue_one = [&]() {
+                if (i_tile < total_tiles) {
+                    const int st = i_it % STAGES;
+                    mbar_wait(&empty_bar[st], ((i_it / STAGES) & 1) ^ 1);
+                    const int am = (i_tile / P.tiles_n) * T2_BM + r;
+                    const uint32_t dst = smem_u32(smem + st * STAGE_BYTES);
+                    const float* src = P.A + (long long)(am < P.M ? am : 0) * P.lda + i_kc * T2_BK;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int k = i_kc * T2_BK + 4 * c;
+                        cp_async16(dst + sw128_offset(r, c), src + 4 * c, (am < P.M && k < P.K) ? 16u : 0u);
+                    }
+                    ++i_it;
+                    if (++i_kc == nkc) { i_kc = 0; i_tile += gridDim.x; }
+                }
+                cp_async_commit();                                 // always commit: keeps the group count uniform
+            };
+#pragma unroll
+            for (int j = 0; j < LOOK; ++j) issue_one();
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    issue_one();
+                    cp_async_wait<LOOK>();                         // this thread's copies of chunk `it` have landed
+                    unsigned char* a_hi = smem + (it % STAGES) * STAGE_BYTES;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {                  // in-place split: raw -> TF32 hi (rounded), lo = raw - hi
+                        const uint32_t o = sw128_offset(r, c);
+                        split_store(a_hi, a_hi + A_HALF, r, c, *reinterpret_cast<const float4*>(a_hi + o));
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&full_bar[it % STAGES]);
+                }
+            }
+            cp_async_wait<0>();
+        } else {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int tm = tile / P.tiles_n;
+            const int am = tm * T2_BM + r;
+            long long arow = -1;
+            if (am < P.M) arow = P.a_index ? (long long)__ldg(P.a_index + am) : (long long)am;
+            const bool vec2 = vec && (!P.A2 || (uintptr_t)P.A2 % 16 == 0);
+            for (int kc = 0; kc < nkc; ++kc, ++it) {
+                const int st = it % STAGES;
+                float4 v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {                     // loads first: they fly while we wait for the stage
+                    const int k = kc * T2_BK + 4 * c;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (arow >= 0) {
+                        const float* p = P.A + arow * P.lda + k;
+                        if (vec2 && k + 3 < P.K) {
+                            x = __ldg(reinterpret_cast<const float4*>(p));
+                            if (P.A2) { const float4 y = __ldg(reinterpret_cast<const float4*>(P.A2 + arow * P.lda + k)); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+                        } else {
+                            float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (k + e < P.K) t[e] = __ldg(p + e) + (P.A2 ? __ldg(P.A2 + arow * P.lda + k + e) : 0.f);
+                            x = make_float4(t[0], t[1], t[2], t[3]);
+                        }
+                    }
+                    v[c] = x;
+                }
+                mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);
+                unsigned char* a_hi = smem + st * STAGE_BYTES;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) split_store(a_hi, a_hi + A_HALF, r, c, v[c]);
+                fence_proxy_async_smem();
+                mbar_arrive(&full_bar[st]);
+            }
+        }
+        }
+    } else if (warp == 8) {
+        // ================================================= W producer ================================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tn = tile % P.tiles_n;
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int st = it % STAGES;
+                    mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full_bar[st], 2 * B_HALF);
+                    tma_load_1d(smem + st * STAGE_BYTES + 2 * A_HALF, P.wpack + ((size_t)tn * nkc + kc) * (2 * B_HALF / 4),
+                                2 * B_HALF, &full_bar[st]);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================================================= MMA issuer ================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(T2_BM, BN);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const int acc = tcount & 1;
+                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);          // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem + (uint32_t)(acc * BN);
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int st = it % STAGES;
+                    mbar_wait(&full_bar[st], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t ah = smem_u32(smem + st * STAGE_BYTES), al = ah + A_HALF, bh = ah + 2 * A_HALF, bl = bh + B_HALF;
+#pragma unroll
+                    for (int ks = 0; ks < T2_BK / 8; ++ks) {
+                        const uint64_t dah = make_desc_sw128(ah + ks * 32), dal = make_desc_sw128(al + ks * 32);
+                        const uint64_t dbh = make_desc_sw128(bh + ks * 32), dbl = make_desc_sw128(bl + ks * 32);
+                        umma_tf32(d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(d, dah, dbl, idesc, 1u);
+                        umma_tf32(d, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[st]);                               // stage reusable when these MMAs retire
+                }
+                umma_commit(&tmem_full[acc]);                                  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ================================================= epilogue (warps 0-3) ======================================
+        // tcgen05.ld gives thread `lane` the 32 consecutive columns of ITS row; written directly that is 32 scattered
+        // 16-byte pieces per store instruction (32 LSU wavefronts). Each warp instead transposes the 32x32 block through
+        // its private shared-memory pad so that one store instruction writes 128 contiguous bytes of one row.
+        float* pad = s_pad[warp];                                   // [32][33]
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int tm = tile / P.tiles_n, tn = tile % P.tiles_n;
+            const int acc = tcount & 1;
+            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            tc_fence_after();
+            const int row0 = tm * T2_BM + warp * 32;
+            const int n0 = tn * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= P.N) break;
+                const int n = n0 + c0 + lane;
+                const float bv = (P.bias && n < P.N) ? __ldg(P.bias + n) : 0.f;   // one coalesced load per group
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pad[lane * 33 + i] = v[i];
+                __syncwarp();
+                if (n < P.N) {
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) {
+                        const int row = row0 + i;
+                        if (row < P.M) {
+                            float x = pad[i * 33 + lane] + bv;
+                            if (P.relu) x = fmaxf(x, 0.f);
+                            P.C[(long long)row * P.ldc + n] = x;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 2 * BN);
+}
+
+template <int BN, int STAGES>
+int launch_tc2(const Tc2Params& P, cudaStream_t st) {
+    constexpr int smem = STAGES * (2 * A_HALF + 2 * BN * 128) + 1024;   // + ~21 KB static (transpose pads, bias)
+    static bool attr = false;
+    static int num_sms = 0;
+    if (!attr) {
+        ROITR_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int dev = 0;
+        ROITR_CUDA(cudaGetDevice(&dev));
+        ROITR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr = true;
+    }
+    const int total = P.tiles_m * P.tiles_n;
+    const int grid = total < num_sms ? total : num_sms;
+    linear_tc2_kernel<BN, STAGES><<<grid, T2_THREADS, smem, st>>>(P);
+    ROITR_CHECK_LAUNCH("linear_tc2_kernel");
+    return ROITR_OK;
+}
+
+}  // namespace
+
+extern "C" int roitr_linear_tc_packed(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
+                                      const float* wpack, int bn, const float* bias, float* C, int ldc, int relu,
+                                      void* stream) {
+    ROITR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && A && wpack && C, "linear_tc_packed: bad arguments M=%d N=%d K=%d", M, N, K);
+    ROITR_CHECK_ARG(lda >= K && ldc >= N, "linear_tc_packed: bad leading dimensions");
+    ROITR_CHECK_ARG(bn == 64 || bn == 128, "linear_tc_packed: weights must be packed with 64- or 128-row tiles, got %d", bn);
+    ROITR_CHECK_ARG((uintptr_t)wpack % 16 == 0, "linear_tc_packed: wpack must be 16-byte aligned");
+    if (M == 0) return ROITR_OK;
+    Tc2Params P;
+    P.M = M; P.N = N; P.K = K; P.A = A; P.A2 = a_add; P.lda = lda; P.a_index = a_index; P.wpack = wpack; P.bias = bias; P.C = C;
+    P.ldc = ldc; P.relu = relu;
+    P.tiles_m = ceil_div(M, T2_BM); P.tiles_n = ceil_div(N, bn); P.nkc = ceil_div(K, T2_BK);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 64) return launch_tc2<64, 4>(P, st);
+    return launch_tc2<128, 3>(P, st);
+}

@@ -458,23 +458,61 @@ __global__ void __launch_bounds__(256) fine_patch_kernel(const FineParams P) {
     if (tid < FP1) { u[tid] = 0.f; v[tid] = 0.f; }
     __syncthreads();
     // ---- log-domain Sinkhorn (modules.py:21-26) ----
-    for (int it = 0; it < P.num_iter; ++it) {
-        for (int i = warp; i < FP1; i += 8) {   // u = log_mu - LSE_j(Z + v)
-            const float x0 = Z[i * FP1 + lane] + v[lane];
-            const float x1 = Z[i * FP1 + lane + 32] + v[lane + 32];
-            const float x2 = (lane == 0) ? Z[i * FP1 + 64] + v[64] : -CUDART_INF_F;
-            const float l = warp_lse3(x0, x1, x2);
-            if (lane == 0) u[i] = log_mu[i] - l;
+    // 200 dependent logsumexp sweeps per patch pair: keep them off shared memory and the serial path short. Warp w owns
+    // rows {w, w+8, ..} (row sweep) and columns {w, w+8, ..} (column sweep) of Z and holds them in REGISTERS for the whole
+    // loop (lane l has elements l, l+32 and - lane 0 - element 64); the 9 independent LSEs of a sweep are evaluated three
+    // at a time so their shuffle / MUFU latencies overlap; only u and v (65 floats each) go through shared memory, with
+    // one __syncthreads per sweep. exp/log use the ex2/lg2 hardware paths (relative error 2^-21, well inside the parity
+    // tolerance; the iteration is a contraction so errors do not accumulate).
+    {
+        constexpr int NR = 9;                                  // ceil(65 / 8) rows (columns) per warp
+        float zr[NR][3], zc[NR][3];
+#pragma unroll
+        for (int t = 0; t < NR; ++t) {
+            const int i = warp + 8 * t;
+            const bool ok = i < FP1;
+            zr[t][0] = ok ? Z[i * FP1 + lane] : 0.f;
+            zr[t][1] = ok ? Z[i * FP1 + lane + 32] : 0.f;
+            zr[t][2] = (ok && lane == 0) ? Z[i * FP1 + 64] : -CUDART_INF_F;
+            zc[t][0] = ok ? Z[lane * FP1 + i] : 0.f;
+            zc[t][1] = ok ? Z[(lane + 32) * FP1 + i] : 0.f;
+            zc[t][2] = (ok && lane == 0) ? Z[64 * FP1 + i] : -CUDART_INF_F;
         }
-        __syncthreads();
-        for (int j = warp; j < FP1; j += 8) {   // v = log_nu - LSE_i(Z + u)
-            const float x0 = Z[lane * FP1 + j] + u[lane];
-            const float x1 = Z[(lane + 32) * FP1 + j] + u[lane + 32];
-            const float x2 = (lane == 0) ? Z[64 * FP1 + j] + u[64] : -CUDART_INF_F;
-            const float l = warp_lse3(x0, x1, x2);
-            if (lane == 0) v[j] = log_nu[j] - l;
+        auto sweep = [&](const float (&z)[NR][3], const float* __restrict__ add, const float* __restrict__ marg,
+                         float* __restrict__ dst) {
+            const float a0 = add[lane], a1 = add[lane + 32], a2 = add[64];
+#pragma unroll
+            for (int g = 0; g < NR; g += 3) {
+                float x[3][3], mx[3], sm[3];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    x[t][0] = z[g + t][0] + a0; x[t][1] = z[g + t][1] + a1; x[t][2] = z[g + t][2] + a2;
+                    mx[t] = fmaxf(fmaxf(x[t][0], x[t][1]), x[t][2]);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) mx[t] = fmaxf(mx[t], __shfl_xor_sync(FULL_MASK, mx[t], o));
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                    sm[t] = __expf(x[t][0] - mx[t]) + __expf(x[t][1] - mx[t]) + __expf(x[t][2] - mx[t]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) sm[t] += __shfl_xor_sync(FULL_MASK, sm[t], o);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int i = warp + 8 * (g + t);
+                    if (lane == 0 && i < FP1) dst[i] = marg[i] - (__logf(sm[t]) + mx[t]);
+                }
+            }
+        };
+        for (int it = 0; it < P.num_iter; ++it) {
+            sweep(zr, v, log_mu, u);      // u = log_mu - LSE_j(Z + v)
+            __syncthreads();
+            sweep(zc, u, log_nu, v);      // v = log_nu - LSE_i(Z + u)
+            __syncthreads();
         }
-        __syncthreads();
     }
     // ---- output (P,65,65) log-assignment; keep it in Z for the matching step ----
     float* out = P.scores + (size_t)p * FP1 * FP1;

@@ -49,6 +49,28 @@ def pack_tf32_sw128(Wm):
     return torch.stack([tile(hi), tile(lo)], dim=2).contiguous()
 
 
+def pack_linear_tc(Wm):
+    """(N,K) f32 nn.Linear weight -> (packed, bn) for roitr_linear_tc_packed: rows padded to a multiple of bn (64 if
+    N <= 64 else 128), columns to a multiple of 32, then per (bn-row, 32-column) block the TF32 hi / lo parts as
+    SWIZZLE_128B tiles: (N/bn, K/32, 2, bn*32) floats."""
+    N, K = Wm.shape
+    bn = 64 if N <= 64 else 128
+    Np, Kp = -(-N // bn) * bn, -(-K // 32) * 32
+    Wp = torch.zeros(Np, Kp, dtype=torch.float32, device=Wm.device)
+    Wp[:N, :K] = Wm
+    hi = ((Wp.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    lo = Wp - hi
+
+    def tile(X):
+        T = X.view(Np // bn, bn, Kp // 32, 32).permute(0, 2, 1, 3).reshape(Np // bn, Kp // 32, bn // 8, 8, 8, 4)
+        out = torch.empty_like(T)
+        ar = torch.arange(8, device=X.device)
+        for j in range(8):
+            out[:, :, :, j, ar ^ j, :] = T[:, :, :, j, :, :]
+        return out.reshape(Np // bn, Kp // 32, bn * 32)
+    return torch.stack([tile(hi), tile(lo)], dim=2).contiguous(), bn
+
+
 def pack_weights(state_dict, device, architecture):
     W = Packed()
     for k, v in state_dict.items():
@@ -79,14 +101,20 @@ def pack_weights(state_dict, device, architecture):
                 Wp = W[a + ".proj_p.weight"]                                       # (C, C): p = Wp e + bp
                 # gq[n,h,:] = sum_{k in head h} q[n, h*c+k] * Wp[h*c+k, :]  ->  per head a (C x c) matrix, K = c
                 W[a + "#WpT"] = torch.stack([Wp[h * c:(h + 1) * c, :].t().contiguous() for h in range(HEADS)], 0).contiguous()
+        # tensor-core operand form of every dense-layer weight with a useful K (roitr_linear_tc_packed)
+        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv")) and W[k].dim() == 2 and W[k].shape[1] >= 16]:
+            W[k + "#tc"] = pack_linear_tc(W[k])
     finally:
         torch.backends.cuda.matmul.allow_tf32 = hp
     return W
 
 
 # ------------------------------------------------------------------------------------------------ local layers
+LINEAR_TC = True             # dense layers on tcgen05 (csrc/gemm_tc2.cu) when a packed weight exists; False = fp32 FFMA
+
+
 def _lin(W, p, x, **kw):
-    return ops.linear(x, W[p + ".weight"], W[p + ".bias"], **kw)
+    return ops.linear(x, W[p + ".weight"], W[p + ".bias"], wpack=W.get(p + ".weight#tc") if LINEAR_TC else None, **kw)
 
 
 def _ln(W, p, x, **kw):
@@ -97,7 +125,7 @@ def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf):
     """LocalPPFTransformer.forward (ppftransformer.py:243-253): (n,Cin) -> (m,Cout)."""
     C = W[p + ".in_proj.weight"].shape[0]
     f = _lin(W, p + ".in_proj", feats)
-    qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"])
+    qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], wpack=W.get(p + "#Wqkv#tc") if LINEAR_TC else None)
     h = ops.local_attention(qkv, C, node_idx, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"], W[p + "#Avp"], W[p + "#cvp"])
     t = _lin(W, p + ".transformer.linear", h)
     y = _ln(W, p + ".transformer.norm", t, res_pre=f, res_pre_index=node_idx, mode=ops.MODE_LN)
@@ -134,6 +162,11 @@ class Plan:
     def starts(self, li, cloud):
         e = self.levels[li]["ends"]
         return (0 if cloud == 0 else e[cloud - 1]), e[cloud]
+
+    def side_streams(self, n):
+        if len(getattr(self, "_streams", [])) < n:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n)]
+        return self._streams[:n]
 
     def single_offset(self, n):
         if n not in self.one:
@@ -264,7 +297,7 @@ def _self_layer_batch(W, lp, x, E, nb, N):
     C = x.shape[1]
     c = C // HEADS
     R = x.shape[0]
-    qkv = ops.linear(x, W[a + "#Wqkv"], W[a + "#bqkv"])
+    qkv = ops.linear(x, W[a + "#Wqkv"], W[a + "#bqkv"], wpack=W.get(a + "#Wqkv#tc") if LINEAR_TC else None)
     gq = torch.empty(R, HEADS * C, dtype=torch.float32, device=x.device)
     for h in range(HEADS):
         ops.linear(qkv[:, h * c:(h + 1) * c], W[a + "#WpT"][h], None, out=gq[:, h * C:(h + 1) * C], M=R, K=c)
@@ -284,9 +317,10 @@ def _self_layer_batch(W, lp, x, E, nb, N):
 def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     a = lp + ".attention.attention"
     C = x.shape[1]
-    q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x)
-    k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y)
-    v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"])
+    tcw = (lambda n: W.get(a + ".proj_%s.weight#tc" % n)) if LINEAR_TC else (lambda n: None)
+    q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x, wpack=tcw("q"))
+    k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, wpack=tcw("k"))
+    v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], wpack=tcw("v"))
     hidden = ops.geo_attention_batched(nb, N, M, q, k, v, C)
     z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", z)
@@ -381,9 +415,10 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
     Pmax = M4s * M4t if four_d else int(cfg["num_est_coarse_corr"])
     topk = int(cfg["fine_matching_topk"])
     cap = Pmax * K * topk
-    outs, counts = [], []
+    outs, counts = [None] * B, [None] * B
     o_t, o_s = plan.single_offset(Nt + 1), plan.single_offset(Ns + 1)
-    for b in range(B):
+
+    def head(b):
         q = per_pair[b]
         src_pts, tgt_pts = src_pcd[b * Ns:(b + 1) * Ns], pts[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
         src_pf, tgt_pf = pf_all[b * Ns:(b + 1) * Ns], pf_all[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
@@ -418,12 +453,28 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
                                           bool(cfg["fine_matching_mutual"]), float(cfg["fine_matching_confidence_threshold"]))
         c_flat, c_count = ops.compact_flags(flags, cap)
         t_cp, s_cp, c_sc = ops.fine_gather(cap, c_flat, c_count, scores, t_ci, s_ci, t_ki, s_ki, tgt_pts, src_pts)
-        counts.append(torch.cat([p_count, gt_count, c_count]))
-        outs.append(dict(src_points=src_pts, tgt_points=tgt_pts, src_nodes=src_nodes, tgt_nodes=tgt_nodes,
+        counts[b] = torch.cat([p_count, gt_count, c_count])
+        outs[b] = (dict(src_points=src_pts, tgt_points=tgt_pts, src_nodes=src_nodes, tgt_nodes=tgt_nodes,
                          src_point_feats=src_pf, tgt_point_feats=tgt_pf, src_node_feats=src_nf, tgt_node_feats=tgt_nf,
                          gt_idx=gt_idx, gt_ov=gt_ov, gt_tgt_node_occ=t_occ, gt_src_node_occ=s_occ, s_ci=s_ci, t_ci=t_ci,
                          s_ki=s_ki, t_ki=t_ki, s_km=s_km, t_km=t_km, s_nm=s_nm, t_nm=t_nm, node_sc=node_sc,
                          matching_scores=scores, t_cp=t_cp, s_cp=s_cp, c_sc=c_sc, c_flat=c_flat, cap=cap))
+    # The per-pair head is a chain of latency-bound, low-occupancy kernels (single-CTA top-k / scans, one CTA per patch
+    # for the Sinkhorn iterations) and pairs are independent: fork onto a few streams so several pairs' heads overlap.
+    streams = plan.side_streams(min(4, B)) if B > 1 else []
+    if not streams:
+        for b in range(B):
+            head(b)
+    else:
+        main = torch.cuda.current_stream()
+        fork = main.record_event()
+        for st in streams:
+            st.wait_event(fork)
+        for b in range(B):
+            with torch.cuda.stream(streams[b % len(streams)]):
+                head(b)
+        for st in streams:
+            main.wait_stream(st)
     return outs, torch.stack(counts)
 
 

@@ -23,7 +23,7 @@ USE_TENSOR_CORES = False    # roitr_linear_tc (tcgen05, 3xTF32) is correct but, 
 
 
 def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=None, K=None, lda=None, ldw=None,
-           ldc=None, tc=None):
+           ldc=None, tc=None, wpack=None):
     """out[M,N] = (a [+ a_add])[rows, :K] @ w[:N, :K]^T + bias. ``a``/``out`` may be column slices of wider buffers
     (pass lda/ldc); ``a_index`` gathers rows of ``a``."""
     N = w.shape[0]
@@ -35,6 +35,10 @@ def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=No
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     ldc = out.stride(0) if ldc is None else ldc
+    if wpack is not None:       # (packed weight, tile rows) from engine.pack_linear_tc: persistent tcgen05 kernel
+        _lib.call("roitr_linear_tc_packed", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
+                  f32(wpack[0]), c_int(wpack[1]), c_void(bias), c_void(out), c_int(ldc), c_int(1 if relu else 0), stream_ptr())
+        return out
     use_tc = (USE_TENSOR_CORES if tc is None else tc) and K >= 16
     _lib.call("roitr_linear_tc" if use_tc else "roitr_linear", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
               c_void(w), c_int(ldw), c_void(bias), c_void(out), c_int(ldc), c_int(1 if relu else 0), stream_ptr())

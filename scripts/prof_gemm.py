@@ -1,0 +1,10 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from roitr_b200 import ops, engine
+DEV = "cuda:0"
+M, N, K = 320000, 192, 64
+a = torch.randn(M, K, device=DEV); w = torch.randn(N, K, device=DEV); b = torch.randn(N, device=DEV); out = torch.empty(M, N, device=DEV)
+wp = engine.pack_linear_tc(w)
+for _ in range(3): ops.linear(a, w, b, out=out, wpack=wp)
+torch.cuda.synchronize()

@@ -76,3 +76,34 @@ def test_geo_embedding_tensor_core_matches_ffma_and_oracle(N):
     assert (a.cpu() - ref)[off].abs().max().item() < 2e-5
     assert (b.cpu() - ref)[off].abs().max().item() < 2e-5
     assert (a - b).abs().max().item() < 2e-5
+
+
+PACKED_SHAPES = SHAPES + [(640000, 192, 64), (40000, 768, 256), (10000, 512, 512), (129, 65, 33), (4992, 1024, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", PACKED_SHAPES)
+def test_linear_tc_packed_matches_fp64(M, N, K):
+    from roitr_b200 import engine
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    y = ops.linear(a, w, b, relu=(M % 2 == 0), wpack=engine.pack_linear_tc(w))
+    ref = _ref(a, w, b, M % 2 == 0)
+    err = (y.double() - ref).abs().max().item()
+    assert err <= 6e-6 * ref.abs().max().item() * max(1.0, (K / 256) ** 0.5), err
+
+
+def test_linear_tc_packed_strided_gather_add():
+    from roitr_b200 import engine
+    g = torch.Generator().manual_seed(6)
+    big = torch.randn(3000, 768, generator=g).to(DEV)
+    pos = torch.randn(3000, 768, generator=g).to(DEV)
+    w = (torch.randn(256, 256, generator=g) / 16).to(DEV)
+    idx = torch.randint(0, 3000, (1111,), generator=g).int().to(DEV)
+    out = torch.zeros(1111, 1024, device=DEV)
+    a, a2 = big[:, 256:512], pos[:, 256:512]
+    ops.linear(a, w, None, a_index=idx, a_add=a2, out=out[:, 512:768], M=1111, K=256, wpack=engine.pack_linear_tc(w))
+    ref = (a[idx.long()] + a2[idx.long()]).double() @ w.double().t()
+    assert (out[:, 512:768].double() - ref).abs().max().item() <= 6e-6 * ref.abs().max().item()
+    assert out[:, :512].abs().max().item() == 0 and out[:, 768:].abs().max().item() == 0
