@@ -87,11 +87,15 @@ def cpu_reference_pairs_per_s(steps, warmup, n_points):
     """The reference's algorithm on the host cores: oracle/forward_ref.py (plain PyTorch fp32) + oracle/pointops_ref.c
     (C/OpenMP restatement of the reference's two native kernels), all host threads. The reference has no CPU pointops path
     of its own, so this port is the CPU arm ("kind": "port")."""
+    cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and may use the whole host,
+    # so undo that BEFORE libgomp is loaded by the oracle's shared library
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     from oracle import forward_ref as fr
     from oracle import native
     from roitr_b200.synthetic import forward_args, synthetic_pair
-    native.build()
-    cores = os.cpu_count() or 1
+    native.build(force=False)
+    native.set_threads(cores)
     # OpenMP kNN/FPS restatement uses every core; torch's intra-op pool is capped at 32 (the per-op tensors are small and
     # 128 threads measured 12x SLOWER than 8 on the forward: 62 s vs 5 s per pair)
     torch.set_num_threads(min(cores, 32))
@@ -179,7 +183,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    from roitr_b200 import _lib, model
+    from roitr_b200 import _lib, model, sharding
     from roitr_b200.synthetic import synthetic_pair
     cfg, sd = _cfg(), _weights()
     m = model.create_model(cfg)
@@ -189,7 +193,7 @@ def main():
 
     # rank r owns global pairs r, r+world, ... ; POOL distinct batches are cycled so inputs differ from step to step
     NB = 2
-    host = [[synthetic_pair(rank + world * (j * B + i), N_POINTS) for i in range(B)] for j in range(NB)]
+    host = [[synthetic_pair(g, N_POINTS) for g in own] for own in sharding.owned_pairs(rank, world, B, NB)]
     pinned = [[{k: v.pin_memory() for k, v in p.items()} for p in batch] for batch in host]
     resident = [[{k: v.to(dev) for k, v in p.items()} for p in batch] for batch in pinned]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -259,16 +263,8 @@ def main():
     _lib.RECORD_ARGS = False
     eager_ms = sum(v["ms"] for v in shares.values())
 
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
-    c = torch.tensor([sum(x[2] for x in counts)], dtype=torch.int64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks, device-timed
-        gathered = [torch.zeros_like(c) for _ in range(world)]
-        dist.all_gather(gathered, c)                      # the (trivial) result gather
-        total_corr = int(sum(int(g) for g in gathered))
-    else:
-        total_corr = int(c)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e = sharding.max_over_ranks([ms_dev, ms_e2e], dist, dev)          # device-timed, max over ranks
+    total_corr = sum(sharding.gather_counts(sum(x[2] for x in counts), dist, dev))   # the (trivial) result gather
 
     if rank == 0:
         peaks = {}

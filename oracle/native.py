@@ -35,6 +35,8 @@ def lib():
         L.oracle_furthestsampling.restype = I
         L.oracle_fps_block_size.argtypes = [I]
         L.oracle_fps_block_size.restype = I
+        L.oracle_set_threads.argtypes = [I]
+        L.oracle_set_threads.restype = I
         _lib = L
     return _lib
 
@@ -60,6 +62,11 @@ def furthestsampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
                                        _chk(idx, torch.int32))
     if rc:
         raise RuntimeError("oracle_furthestsampling failed rc=%d" % rc)
+
+
+def set_threads(n: int) -> int:
+    """Host threads for the OpenMP loops (torchrun exports OMP_NUM_THREADS=1); returns the previous maximum."""
+    return int(lib().oracle_set_threads(int(n)))
 
 
 def fps_block_size(n_max: int) -> int:

@@ -103,6 +103,9 @@ static int ref_block_size(int work_size) {
 
 int oracle_fps_block_size(int n_max) { return ref_block_size(n_max); }
 
+/* host threads used by the OpenMP loops (results do not depend on it); returns the previous maximum */
+int oracle_set_threads(int n) { int old = omp_get_max_threads(); if (n > 0) omp_set_num_threads(n); return old; }
+
 /*
  * One "block" of bs emulated threads per batch element; tmp (n,) must arrive filled with 1e10
  * (pointops.py:22). Strided in-thread scan with strict '>' then the power-of-two tree with

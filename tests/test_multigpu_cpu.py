@@ -1,0 +1,84 @@
+"""The N>1 path on CPU: two `gloo` ranks exercise exactly the host logic bench.py / a multi-GPU deployment uses
+(roitr_b200/sharding.py): pair ownership, the max-over-ranks step time and the result-count gather. No GPU, no kernels:
+the data path has no collective, so this IS all the inter-rank traffic there is."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from roitr_b200 import sharding
+from roitr_b200.synthetic import synthetic_pair
+
+
+def test_ownership_is_a_partition():
+    for world in (1, 2, 4, 8):
+        for batch, nb in ((1, 1), (16, 2), (5, 3)):
+            seen = []
+            for r in range(world):
+                own = sharding.owned_pairs(r, world, batch, nb)
+                assert len(own) == nb and all(len(o) == batch for o in own)
+                for j, o in enumerate(own):
+                    for i, g in enumerate(o):
+                        assert sharding.owner_of(g, world) == (r, j * batch + i)
+                seen += [g for o in own for g in o]
+            assert sorted(seen) == list(range(world * batch * nb))
+    with pytest.raises(ValueError):
+        sharding.owned_pairs(2, 2, 1)
+
+
+def test_weak_scaling_throughput_formula():
+    assert sharding.job_throughput(16, 8, 10, 500.0) == pytest.approx(8 * 16 * 10 / 0.5)
+
+
+def test_single_process_paths_need_no_process_group():
+    assert sharding.max_over_ranks([3.0, 4.0]) == [3.0, 4.0]
+    assert sharding.gather_counts(7) == [7]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        own = sharding.owned_pairs(rank, world, 2, 2)
+        # the shard's inputs are a pure function of the GLOBAL pair index: any rank can regenerate any pair
+        first = synthetic_pair(own[0][0], 64)
+        checksum = float(first["src_pcd"].double().sum())
+        dist.barrier()
+        ms = sharding.max_over_ranks([10.0 + rank, 20.0 - rank], dist)          # slowest rank wins, per element
+        counts = sharding.gather_counts(100 + rank, dist)                       # rank order
+        flat = torch.tensor([g for o in own for g in o], dtype=torch.int64)
+        allidx = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(allidx, flat)
+        dist.barrier()
+        out.put((rank, ms, counts, [t.tolist() for t in allidx], own[0][0], checksum))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_shard_reduce_gather():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ms, counts, allidx, g0, checksum in got:
+        assert ms == [11.0, 20.0]
+        assert counts == [100, 101]
+        assert sorted(i for l in allidx for i in l) == list(range(8))          # disjoint and complete across ranks
+        assert allidx[rank][0] == g0 == rank
+        assert checksum == pytest.approx(float(synthetic_pair(g0, 64)["src_pcd"].double().sum()))
+    assert sharding.job_throughput(2, world, 2, max(m[1][0] for m in got)) == pytest.approx(8 / 0.011)
