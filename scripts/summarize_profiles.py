@@ -58,7 +58,8 @@ KEYS = [r"Kernel Name", r"Grid Size", r"gpu__time_duration.sum", r"dram__bytes_(
         r"sm__warps_active.avg.pct_of_peak", r"smsp__issue_active.avg.pct", r"sm__inst_executed.sum$", r"l1tex__data_bank_conflicts_pipe_lsu.sum$",
         r"sm__pipe_fma_cycles_active.avg.pct", r"sm__throughput.avg.pct", r"gpu__dram_throughput.avg.pct", r"lts__t_bytes.sum$", r"sm__pipe_tensor"]
 launches()
-for k in ("fps_cluster_kernel", "knn_ppf_kernel", "geo_embedding_kernel", "geo_embedding_tc_kernel", "linear_kernel", "fine_patch_kernel"):
+import glob
+for k in sorted(os.path.basename(f)[5:-8] for f in glob.glob(os.path.join(G, "prof_*.ncu-rep"))):
     raw("prof_%s.ncu-rep" % k, "%s_%s_raw.txt" % (tag, k), KEYS)
     source("prof_%s.ncu-rep" % k, "%s_%s_stalls.txt" % (tag, k))
 for f in ("bench.json",):
