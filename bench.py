@@ -137,6 +137,9 @@ def op_work(name, ints):
     if name in ("roitr_geo_embedding", "roitr_geo_embedding_tc"):
         N, C = ints[:2]
         return "flop", 8.0 * N * N * C * C
+    if name == "roitr_geo_embedding_tc_batched":
+        b, N, C = ints[:3]
+        return "flop", b * 8.0 * N * N * C * C
     if name == "roitr_furthestsampling_cfg":
         b, _, nseg = ints[:3]
         return "bytes", b * (nseg * 12.0 + (nseg // 4) * 16.0)
@@ -247,7 +250,12 @@ def main():
     _lib.reset_stats()
     _lib.RECORD_ARGS = True
     flush.zero_()
+    prof_range = os.environ.get("ROITR_PROFILE_RANGE") == "1"     # ncu --profile-from-start off: capture exactly one step
+    if prof_range:
+        torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStart()
     eager.load(resident[1 % NB]); eager.run(); torch.cuda.synchronize()
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches_per_step = _lib.STATS["launches"]
     shares = {}
     for name, evs in _lib.TIMED.items():

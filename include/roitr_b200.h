@@ -162,6 +162,8 @@ int roitr_local_attention(int m, int C, int heads, int knb, const float* q, int 
 
 /* k nearest superpoints of every superpoint on dist = sqrt(clamp(x2 - 2xy + y2, 0)) (topk(k+1)[1:], :120-124). k = 3. */
 int roitr_geo_knn(int N, int k, const float* pts, int* nn, void* stream);
+/* `batch` clouds of N superpoints stacked along dim 0 (pts (batch*N,3), nn (batch*N,k) with cloud-local indices). */
+int roitr_geo_knn_batched(int batch, int N, int k, const float* pts, int* nn, void* stream);
 
 /* E (N,N,C) = proj_d(sinusoid(dist/sigma_d)) + max_{r<3} proj_a(sinusoid(angle_r * 180/(sigma_a*pi)))
  * (GeometricStructureEmbedding.forward, :139-154); sinusoids are generated in-kernel. C multiple of 128. */
@@ -174,8 +176,44 @@ int roitr_geo_embedding(int N, int C, const float* pts, const int* nn3, const fl
  * layout [mat(d,a)][C/128][C/32][hi|lo][4096] floats (roitr_b200.engine.pack_tf32_sw128); fetched by bulk TMA. */
 int roitr_geo_embedding_tc(int N, int C, const float* pts, const int* nn3, const float* wpack, const float* bd,
                            const float* ba, const float* div_term, float sigma_d, float sigma_a, float* E, void* stream);
+/* `batch` clouds per launch (blockIdx.z): pts (batch*N,3), nn3 (batch*N,3) cloud-local, E (batch,N,N,C). */
+int roitr_geo_embedding_tc_batched(int batch, int N, int C, const float* pts, const int* nn3, const float* wpack,
+                                   const float* bd, const float* ba, const float* div_term, float sigma_d, float sigma_a,
+                                   float* E, void* stream);
 
-/* Attention core. E == NULL: MultiHeadAttention (geoattention.py:50-64) hidden = softmax(q k^T / sqrt(c)) v.
+/* Same E from weight-derived tables: F_d(t) = W_d s(t) + b_d and F_a(t) = W_a s(t) + b_a depend on the weights only, so
+ * they are sampled once per weight load on a uniform grid of step h = 1/inv_h (a power of two) in fp64
+ * (roitr_b200.engine.build_geo_tables) and evaluated per (n,m) scalar by 4-point Lagrange interpolation (error bound
+ * (3/128) h^4 max|d4F/dt4|, chosen <= 2.5e-7 at pack time). tab_a [C/64][rows_a][64], tab_d [C/64][rows_d][64], row r
+ * holds t = (r - 1) h. Scalars beyond the tables are evaluated directly from Wd / Wa (same contract as
+ * roitr_geo_embedding). pts (batch*N,3), nn3 (batch*N,3) cloud-local, E (batch,N,N,C). C multiple of 64. */
+long long roitr_geo_table_smem_rows(void);
+int roitr_geo_embedding_table(int batch, int N, int C, const float* pts, const int* nn3, const float* tab_a, int rows_a,
+                              const float* tab_d, int rows_d, float inv_h, const float* Wd, const float* bd,
+                              const float* Wa, const float* ba, const float* div_term, float sigma_d, float sigma_a,
+                              float* E, void* stream);
+
+/* Batched dense contraction on the tensor cores (tcgen05 3xTF32, the thread-loaded kernel of roitr_linear_tc) for
+ * operands that are activations: for every (o, i) in batch_outer x batch_inner
+ *     C_oi[M,N] = A_oi[M,K] W_oi[N,K]^T,   X_oi = X + o * sX_o + i * sX_i  (element strides)
+ * w_transposed != 0: W_oi is given as (K, >= N) row-major with leading dimension ldw (W_oi[n][k] = Wt[k * ldw + n]).
+ * Used for the global transformer's Q K^T (per cloud and head) and P V (V read transposed) - geoattention.py:50,62,107,128. */
+int roitr_gemm_tc_batched(int batch_outer, int batch_inner, int M, int N, int K, const float* A, int lda, long long sA_o,
+                          long long sA_i, const float* W, int ldw, long long sW_o, long long sW_i, int w_transposed,
+                          float* C, int ldc, long long sC_o, long long sC_i, void* stream);
+
+/* RPE self-attention between Q K^T and P V (geoattention.py:107-133), one streaming pass over E:
+ *   S = (qk + gq_h . E[n,m] + q_h . b_p,h) / sqrt(c);  P (batch,H,N,N) = softmax_m(S);
+ *   G (batch*N,H,C) = sum_m softmax_m(S without the diagonal)[m] E[n,m,:]   (the caller maps G through proj_vp per head).
+ * qk (batch,H,N,N) raw q.k; q: (batch*N rows, C) view with leading dim ldq and cloud stride q_bs; gq (batch*N,H,C) folded
+ * positional queries; bp = proj_p.bias. heads = 4, C in {256,512}. */
+int roitr_geo_self_scores(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq, long long q_bs,
+                          const float* E, const float* gq, const float* bp, float* P, float* G, void* stream);
+
+/* out[row,:] = softmax(qk[row,:] / scale_div) over M entries per row (MultiHeadAttention, geoattention.py:50-60). */
+int roitr_softmax_rows(long long rows, int M, const float* qk, float scale_div, float* out, void* stream);
+
+/* First-generation attention core (one SIMT kernel; kept as the reference implementation of the path above). E == NULL: MultiHeadAttention (geoattention.py:50-64) hidden = softmax(q k^T / sqrt(c)) v.
  * E != NULL (N == M): RPEMultiHeadAttention (geoattention.py:107-134) with gq (N,4,C) = folded positional queries
  * (gq[n,h,:] = W_p[h*c:(h+1)*c,:]^T q[n,h*c:(h+1)*c]) and bp = proj_p.bias; also G (N,4,C) = sum_m A-_nm E_nm where A- is
  * the softmax with the diagonal removed (the caller maps G through proj_vp per head). heads = 4, C in {256,512}. */
@@ -240,6 +278,9 @@ int roitr_fine_gather(int capacity, const int* flat, const int* count, const flo
 
 /* out (N+1,3): [pts ; zero row] (RIGA_v2.py:86-87), optionally mapped through p R^T + t (lib/utils.py:505). */
 int roitr_pad_transform(int N, const float* pts, const float* rot, const float* trans, float* out, void* stream);
+/* B equally sized clouds per launch: pts (B*N,3), rot (B,3,3) or NULL, trans (B,3), out (B*(N+1),3). */
+int roitr_pad_transform_batched(int B, int N, const float* pts, const float* rot, const float* trans, float* out,
+                                void* stream);
 
 /* get_node_occlusion_score tail (lib/utils.py:511-526) given the 1-NN distances of the padded clouds. */
 int roitr_node_occlusion(int M, int K, const int* knn, const unsigned char* kmask, const unsigned char* nmask,

@@ -32,10 +32,21 @@ struct TcParams {
     const float* A; const float* A2; int lda; const int* a_index;
     const float* W; int ldw; const float* bias;
     float* C; int ldc; int relu;
+    // batched form (blockIdx.z = outer * inner + inner index): element strides of A / W / C per outer and inner index
+    int inner;
+    long long sA_o, sA_i, sW_o, sW_i, sC_o, sC_i;
+    int w_transposed;       // W is given as Wt (K, >=N) row-major with leading dimension ldw: W[n][k] = Wt[k * ldw + n]
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P) {
+__global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_) {
+    TcParams P = P_;
+    {
+        const long long bo = blockIdx.z / P.inner, bi = blockIdx.z % P.inner;
+        P.A += bo * P.sA_o + bi * P.sA_i;
+        P.W += bo * P.sW_o + bi * P.sW_i;
+        P.C += bo * P.sC_o + bi * P.sC_i;
+    }
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment: align manually (the launch reserves 1 KB of slack)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -86,6 +97,20 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P)
         }
     };
 
+    // transposed weight operand: thread t owns output column n0+t and reads Wt[k][n0+t] (coalesced across threads)
+    auto load_row_t = [&](long long row, int k0, float4 (&v)[8]) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + 4 * c + e;
+                if (row >= 0 && k < P.K) t[e] = __ldg(P.W + (long long)k * P.ldw + row);
+            }
+            v[c] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    };
+
     const int nk = (P.K + TC_BK - 1) / TC_BK;
     constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
     constexpr int BROWS = (BN + TC_THREADS - 1) / TC_THREADS;  // B rows per thread
@@ -100,7 +125,8 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P)
         for (int j = 0; j < BROWS; ++j) {
             const int br = tid + j * TC_THREADS;
             const long long wrow = (br < BN && n0 + br < P.N) ? (long long)(n0 + br) : -1;
-            load_row(P.W, nullptr, wrow, P.ldw, kc * TC_BK, vecW, vb[j]);
+            if (P.w_transposed) load_row_t(wrow, kc * TC_BK, vb[j]);
+            else load_row(P.W, nullptr, wrow, P.ldw, kc * TC_BK, vecW, vb[j]);
         }
         if (kc >= TC_STAGES) {  // the MMAs that read this stage (chunk kc-2) must have completed
             mbar_wait(&mma_bar[buf], ((kc >> 1) - 1) & 1);
@@ -173,14 +199,14 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P)
 }
 
 template <int BN>
-int launch_tc(const TcParams& P, cudaStream_t st) {
+int launch_tc(const TcParams& P, cudaStream_t st, int batch = 1) {
     constexpr int smem = TC_STAGES * (2 * TC_BM * 128 + 2 * BN * 128) + 1024;
     static bool attr = false;
     if (!attr) {
         ROITR_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    dim3 grid(ceil_div(P.M, TC_BM), ceil_div(P.N, BN));
+    dim3 grid(ceil_div(P.M, TC_BM), ceil_div(P.N, BN), batch);
     linear_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(P);
     ROITR_CHECK_LAUNCH("linear_tc_kernel");
     return ROITR_OK;
@@ -196,8 +222,29 @@ extern "C" int roitr_linear_tc(int M, int N, int K, const float* A, const float*
     TcParams P;
     P.M = M; P.N = N; P.K = K; P.A = A; P.A2 = a_add; P.lda = lda; P.a_index = a_index; P.W = W; P.ldw = ldw; P.bias = bias;
     P.C = C; P.ldc = ldc; P.relu = relu;
+    P.inner = 1; P.sA_o = P.sA_i = P.sW_o = P.sW_i = P.sC_o = P.sC_i = 0; P.w_transposed = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64>(P, st);
     if (N <= 128) return launch_tc<128>(P, st);
     return launch_tc<256>(P, st);
+}
+
+extern "C" int roitr_gemm_tc_batched(int batch_outer, int batch_inner, int M, int N, int K, const float* A, int lda,
+                                     long long sA_o, long long sA_i, const float* W, int ldw, long long sW_o, long long sW_i,
+                                     int w_transposed, float* C, int ldc, long long sC_o, long long sC_i, void* stream) {
+    ROITR_CHECK_ARG(batch_outer >= 1 && batch_inner >= 1 && (long long)batch_outer * batch_inner <= 65535,
+                    "gemm_tc_batched: bad batch %d x %d", batch_outer, batch_inner);
+    ROITR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && A && W && C, "gemm_tc_batched: bad arguments M=%d N=%d K=%d", M, N, K);
+    ROITR_CHECK_ARG(lda >= K && ldc >= N && ldw >= (w_transposed ? N : K), "gemm_tc_batched: bad leading dimensions");
+    if (M == 0) return ROITR_OK;
+    TcParams P;
+    P.M = M; P.N = N; P.K = K; P.A = A; P.A2 = nullptr; P.lda = lda; P.a_index = nullptr; P.W = W; P.ldw = ldw; P.bias = nullptr;
+    P.C = C; P.ldc = ldc; P.relu = 0;
+    P.inner = batch_inner; P.sA_o = sA_o; P.sA_i = sA_i; P.sW_o = sW_o; P.sW_i = sW_i; P.sC_o = sC_o; P.sC_i = sC_i;
+    P.w_transposed = w_transposed;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int batch = batch_outer * batch_inner;
+    if (N <= 64) return launch_tc<64>(P, st, batch);
+    if (N <= 128) return launch_tc<128>(P, st, batch);
+    return launch_tc<256>(P, st, batch);
 }

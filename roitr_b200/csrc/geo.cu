@@ -36,6 +36,8 @@ __global__ void geo_knn_kernel(int N, const float* __restrict__ pts, int* __rest
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
+    pts += (size_t)blockIdx.y * N * 3;               // blockIdx.y = cloud of a batch (indices stay cloud-local)
+    nn += (size_t)blockIdx.y * N * (KP1 - 1);
     float a[3] = {__ldg(pts + 3 * n), __ldg(pts + 3 * n + 1), __ldg(pts + 3 * n + 2)};
     const float a2 = sq3(a);
     float bd[KP1];
@@ -353,12 +355,16 @@ int launch_attn(const GeoAttnParams& P, int batch, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int roitr_geo_knn(int N, int k, const float* pts, int* nn, void* stream) {
-    ROITR_CHECK_ARG(N >= 1 && pts && nn, "geo_knn: bad arguments");
+extern "C" int roitr_geo_knn_batched(int batch, int N, int k, const float* pts, int* nn, void* stream) {
+    ROITR_CHECK_ARG(batch >= 1 && batch <= 65535 && N >= 1 && pts && nn, "geo_knn: bad arguments");
     ROITR_CHECK_ARG(k == 3, "geo_knn: angle_k = 3 only (model/model.py:165), got %d", k);
-    geo_knn_kernel<4><<<ceil_div(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(N, pts, nn);
+    geo_knn_kernel<4><<<dim3(ceil_div(N * 32, 256), batch), 256, 0, (cudaStream_t)stream>>>(N, pts, nn);
     ROITR_CHECK_LAUNCH("geo_knn_kernel");
     return ROITR_OK;
+}
+
+extern "C" int roitr_geo_knn(int N, int k, const float* pts, int* nn, void* stream) {
+    return roitr_geo_knn_batched(1, N, k, pts, nn, stream);
 }
 
 extern "C" int roitr_geo_embedding(int N, int C, const float* pts, const int* nn3, const float* Wd, const float* bd,

@@ -1,0 +1,266 @@
+// Global transformer attention, second generation (sm_100a): the dense contractions (Q K^T and P V) run on tcgen05
+// (roitr_gemm_tc_batched, csrc/gemm_tc.cu); what is left is a streaming pass over the geometric embedding E.
+//
+// Replaces RPEMultiHeadAttention.forward (model/transformer/geoattention.py:101-136) and MultiHeadAttention.forward
+// (geoattention.py:43-66) between the q/k/v projections and the output linear:
+//
+//   QK[b,h,n,m] = q_h[n] . k_h[m]                                   tcgen05 batched GEMM (per cloud and head)
+//   self:  S = (QK + gq_h[n] . E[n,m] + q_h[n] . b_p,h) / sqrt(c)   this file, geo_self_scores_kernel
+//          P  = softmax_m(S)                 -> global, for P V
+//          G[n,h,:] = sum_m softmax_m(S with the diagonal removed)[m] E[n,m,:]      (position branch, :117-133)
+//   cross: P = softmax_m(QK / sqrt(c))                              this file, softmax_rows_kernel
+//   hidden[b,n,h*c:(h+1)*c] = P[b,h,n,:] V_h                        tcgen05 batched GEMM (V read transposed)
+//
+// geo_self_scores_kernel reads E exactly ONCE from HBM (the first generation, csrc/geo.cu, read it twice: 3.17 GB per
+// 16-cloud launch at 42 % of HBM peak, profiles/r01e_geo_attention_kernel_raw.txt): one CTA per query row n streams
+// the row's E[n,:,:] (M x C floats = 320 KB at M=312, C=256) through a two-stage shared-memory ring with bulk TMA copies
+// (cp.async.bulk + mbarrier) in chunks of ~48 KB. Per chunk: (A) scores of the chunk's keys from shared memory,
+// (B) chunk-level online softmax of the diagonal-free variant (running max / denominator per head, accumulators
+// rescaled once per chunk, i.e. ~7 times per row), (C) G accumulation from the same shared-memory chunk. The full softmax
+// that feeds P V is computed exactly (two-pass) at the end from the row's raw scores, which stay in shared memory.
+#include <math_constants.h>
+
+#include "../../include/roitr_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int GA_THREADS = 256;
+constexpr int GA_H = 4;
+constexpr int GA_CHUNK_BYTES = 48 * 1024;
+
+struct SelfParams {
+    const float* qk;       // (batch, H, N, M) raw q.k
+    const float* q; int ldq; long long q_bs;    // (batch*N rows, C) view for q . b_p
+    const float* E;        // (batch, N, M, C)
+    const float* gq;       // (batch*N, H, C)
+    const float* bp;       // (C)
+    float* P;              // (batch, H, N, M) softmax with self
+    float* G;              // (batch*N, H, C)
+    int N, M;
+    float sqrt_c;
+};
+
+// sum of 4 values over the warp with 6 shuffles instead of 20: after the two folding rounds each lane holds the partial
+// sum of ONE head (head = bit4*2 + bit3 of the lane), then a 3-step butterfly inside the 8-lane group finishes it.
+// Result: every lane of group g = lane>>3 ... holds the total of head ((lane>>4)&1)*2 + ((lane>>3)&1).
+__device__ __forceinline__ float reduce4_to_head(float a0, float a1, float a2, float a3, int lane) {
+    const bool hi16 = lane & 16;
+    // round 1: lanes with bit4 = 0 keep heads {0,1}, bit4 = 1 keep heads {2,3}
+    float s0 = hi16 ? a0 : a2, s1 = hi16 ? a1 : a3;        // what I send away
+    float k0 = hi16 ? a2 : a0, k1 = hi16 ? a3 : a1;        // what I keep
+    k0 += __shfl_xor_sync(FULL_MASK, s0, 16);
+    k1 += __shfl_xor_sync(FULL_MASK, s1, 16);
+    // round 2: bit3 = 0 keeps the first of the pair, bit3 = 1 the second
+    const bool hi8 = lane & 8;
+    float send = hi8 ? k0 : k1, keep = hi8 ? k1 : k0;
+    keep += __shfl_xor_sync(FULL_MASK, send, 8);
+    keep += __shfl_xor_sync(FULL_MASK, keep, 4);
+    keep += __shfl_xor_sync(FULL_MASK, keep, 2);
+    keep += __shfl_xor_sync(FULL_MASK, keep, 1);
+    return keep;
+}
+
+template <int C>
+__global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_kernel(const SelfParams P) {
+    constexpr int CPL = C / 32;            // channels per lane in phase A
+    constexpr int CPT = C / GA_THREADS;    // channels per thread in phase C
+    constexpr int H = GA_H;
+    constexpr int CHK = GA_CHUNK_BYTES / (C * 4);   // keys per chunk
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);              // 2 x [CHK][C]
+    float* S = ring + 2 * CHK * C;                                 // [H][M] raw scores of the row
+    float* pn = S + H * P.M;                                       // [CHK][H] chunk weights of the diagonal-free softmax
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ float s_alpha[H], s_mx[H], s_den[H];
+
+    const int n = blockIdx.x, b = blockIdx.y;
+    const int N = P.N, M = P.M;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* Erow = P.E + ((size_t)b * N + n) * (size_t)M * C;
+    const size_t rowid = (size_t)b * N + n;
+    const int nch = (M + CHK - 1) / CHK;
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    if (tid < H) { s_mx[tid] = -CUDART_INF_F; s_den[tid] = 0.f; }
+    __syncthreads();
+    auto issue = [&](int c) {   // thread 0: chunk c -> stage c & 1
+        const int rows = min(CHK, M - c * CHK);
+        const uint32_t bytes = (uint32_t)rows * C * 4;
+        mbar_expect_tx(&full[c & 1], bytes);
+        tma_load_1d(ring + (size_t)(c & 1) * CHK * C, Erow + (size_t)c * CHK * C, bytes, &full[c & 1]);
+    };
+    if (tid == 0) { issue(0); if (nch > 1) issue(1); }
+
+    // folded positional queries of this row: lane holds CPL consecutive channels of each head's gq
+    const int c0 = lane * CPL;
+    float gq[H][CPL];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) gq[h][i] = __ldg(P.gq + (rowid * H + h) * C + c0 + i);
+    // q_h . b_p,h per head (lanes of a head are the 8-lane groups: head = c0 / (C/H) = lane >> 3)
+    float qb = 0.f;
+    {
+        const float* q = P.q + (size_t)b * P.q_bs + (size_t)n * P.ldq;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) qb = fmaf(__ldg(q + c0 + i), __ldg(P.bp + c0 + i), qb);
+        qb += __shfl_xor_sync(FULL_MASK, qb, 1); qb += __shfl_xor_sync(FULL_MASK, qb, 2); qb += __shfl_xor_sync(FULL_MASK, qb, 4);
+    }
+    // the head whose total reduce4_to_head leaves in this lane, and that head's q.b_p
+    const int myh = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    const float qb_h = __shfl_sync(FULL_MASK, qb, myh * 8);
+    const float* qk_row = P.qk + (((size_t)b * H) * N + n) * M;     // + h * N * M
+
+    float G[CPT][H];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)
+#pragma unroll
+        for (int h = 0; h < H; ++h) G[u][h] = 0.f;
+
+    for (int c = 0; c < nch; ++c) {
+        const int m0 = c * CHK, rows = min(CHK, M - m0);
+        const float* Ec = ring + (size_t)(c & 1) * CHK * C;
+        mbar_wait(&full[c & 1], (c >> 1) & 1);
+        // ---- A: scores of the chunk's keys ----
+        for (int r = warp; r < rows; r += GA_THREADS / 32) {
+            const float* e = Ec + (size_t)r * C + c0;
+            float a[H] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < CPL / 4; ++i) {
+                const float4 t = *reinterpret_cast<const float4*>(e + 4 * i);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    a[h] = fmaf(gq[h][4 * i], t.x, a[h]); a[h] = fmaf(gq[h][4 * i + 1], t.y, a[h]);
+                    a[h] = fmaf(gq[h][4 * i + 2], t.z, a[h]); a[h] = fmaf(gq[h][4 * i + 3], t.w, a[h]);
+                }
+            }
+            const float sp = reduce4_to_head(a[0], a[1], a[2], a[3], lane);
+            if ((lane & 7) == 0) {
+                const int m = m0 + r;
+                const float se = __ldg(qk_row + (size_t)myh * N * M + m);
+                S[myh * M + m] = __fdiv_rn(se + (sp + qb_h), P.sqrt_c);
+            }
+        }
+        __syncthreads();
+        // ---- B: chunk-level online softmax of the diagonal-free variant (warp h < 4 owns head h) ----
+        if (warp < H) {
+            const int h = warp;
+            float cm = -CUDART_INF_F;
+            for (int r = lane; r < rows; r += 32)
+                if (m0 + r != n) cm = fmaxf(cm, S[h * M + m0 + r]);
+            cm = warp_max(cm);
+            const float old = s_mx[h];
+            const float nw = fmaxf(old, cm);
+            float sum = 0.f;
+            for (int r = lane; r < rows; r += 32) {
+                const float w = (m0 + r == n || nw == -CUDART_INF_F) ? 0.f : expf(S[h * M + m0 + r] - nw);
+                pn[r * H + h] = w;
+                sum += w;
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) {
+                const float alpha = (old == -CUDART_INF_F) ? 0.f : expf(old - nw);
+                s_alpha[h] = alpha;
+                s_mx[h] = nw;
+                s_den[h] = s_den[h] * alpha + sum;
+            }
+        }
+        __syncthreads();
+        // ---- C: G[h][ch] = G * alpha + sum_r pn[r][h] E[r][ch] ----
+        {
+            const float4 al = make_float4(s_alpha[0], s_alpha[1], s_alpha[2], s_alpha[3]);
+#pragma unroll
+            for (int u = 0; u < CPT; ++u) {
+                G[u][0] *= al.x; G[u][1] *= al.y; G[u][2] *= al.z; G[u][3] *= al.w;
+            }
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) {
+                const float4 w = *reinterpret_cast<const float4*>(pn + r * H);
+#pragma unroll
+                for (int u = 0; u < CPT; ++u) {
+                    const float e = Ec[(size_t)r * C + tid + u * GA_THREADS];
+                    G[u][0] = fmaf(w.x, e, G[u][0]); G[u][1] = fmaf(w.y, e, G[u][1]);
+                    G[u][2] = fmaf(w.z, e, G[u][2]); G[u][3] = fmaf(w.w, e, G[u][3]);
+                }
+            }
+        }
+        __syncthreads();                       // every thread is done with this stage (and with pn / s_alpha)
+        if (tid == 0 && c + 2 < nch) issue(c + 2);
+    }
+    // ---- G / denominator ----
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+            P.G[(rowid * H + h) * C + tid + u * GA_THREADS] = G[u][h] / s_den[h];
+    // ---- full softmax (with the diagonal) of the row's scores -> P (warp h < 4 owns head h) ----
+    if (warp < H) {
+        const int h = warp;
+        float mx = -CUDART_INF_F, den = 0.f;
+        for (int m = lane; m < M; m += 32) mx = fmaxf(mx, S[h * M + m]);
+        mx = warp_max(mx);
+        for (int m = lane; m < M; m += 32) den += expf(S[h * M + m] - mx);
+        den = warp_sum(den);
+        float* out = P.P + (((size_t)b * H + h) * N + n) * M;
+        for (int m = lane; m < M; m += 32) out[m] = expf(S[h * M + m] - mx) / den;
+    }
+}
+
+// cross attention: P[row,:] = softmax(QK[row,:] / sqrt(c)); one warp per row of M scores, in place allowed
+__global__ void softmax_rows_kernel(long long rows, int M, const float* __restrict__ qk, float sqrt_c, float* __restrict__ out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* s = qk + row * M;
+    float mx = -CUDART_INF_F, den = 0.f;
+    for (int m = lane; m < M; m += 32) mx = fmaxf(mx, __fdiv_rn(s[m], sqrt_c));
+    mx = warp_max(mx);
+    for (int m = lane; m < M; m += 32) den += expf(__fdiv_rn(s[m], sqrt_c) - mx);
+    den = warp_sum(den);
+    float* o = out + row * M;
+    for (int m = lane; m < M; m += 32) o[m] = expf(__fdiv_rn(s[m], sqrt_c) - mx) / den;
+}
+
+template <int C>
+int launch_self(const SelfParams& P, int batch, cudaStream_t st) {
+    constexpr int CHK = GA_CHUNK_BYTES / (C * 4);
+    const size_t smem = (size_t)2 * CHK * C * 4 + (size_t)GA_H * P.M * 4 + (size_t)CHK * GA_H * 4;
+    ROITR_CHECK_ARG(smem <= 226 * 1024, "geo_self_attention: %d keys do not fit the shared-memory score buffer", P.M);
+    static size_t configured = 0;
+    if (smem > configured) {
+        ROITR_CUDA(cudaFuncSetAttribute(geo_self_scores_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    geo_self_scores_kernel<C><<<dim3(P.N, batch), GA_THREADS, smem, st>>>(P);
+    ROITR_CHECK_LAUNCH("geo_self_scores_kernel");
+    return ROITR_OK;
+}
+
+}  // namespace
+
+extern "C" int roitr_geo_self_scores(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq,
+                                     long long q_bs, const float* E, const float* gq, const float* bp, float* P, float* G,
+                                     void* stream) {
+    ROITR_CHECK_ARG(heads == GA_H && (C == 256 || C == 512), "geo_self_scores: heads=4, C in {256,512} only");
+    ROITR_CHECK_ARG(batch >= 1 && batch <= 65535 && N >= 1 && qk && q && E && gq && bp && P && G, "geo_self_scores: bad arguments");
+    ROITR_CHECK_ARG((uintptr_t)E % 16 == 0, "geo_self_scores: E must be 16-byte aligned");
+    SelfParams S;
+    S.qk = qk; S.q = q; S.ldq = ldq; S.q_bs = q_bs; S.E = E; S.gq = gq; S.bp = bp; S.P = P; S.G = G; S.N = N; S.M = N;
+    S.sqrt_c = sqrtf((float)(C / heads));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 256) return launch_self<256>(S, batch, st);
+    return launch_self<512>(S, batch, st);
+}
+
+extern "C" int roitr_softmax_rows(long long rows, int M, const float* qk, float scale_div, float* out, void* stream) {
+    ROITR_CHECK_ARG(rows >= 0 && M >= 1 && qk && out, "softmax_rows: bad arguments");
+    if (rows == 0) return ROITR_OK;
+    softmax_rows_kernel<<<(unsigned)ceil_div_ll(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(rows, M, qk, scale_div, out);
+    ROITR_CHECK_LAUNCH("softmax_rows_kernel");
+    return ROITR_OK;
+}

@@ -1,0 +1,237 @@
+// Geometric structure embedding from weight-derived tables (sm_100a).
+//
+// E[n,m,:] = proj_d(sinusoid(D_nm / sigma_d)) + max_{r<3} proj_a(sinusoid(angle_nmr * factor_a))
+// (GeometricStructureEmbedding.forward, model/transformer/positional_encoding.py:139-154).
+//
+// Both terms are functions of ONE scalar per (n,m[,r]): F_d(t) = W_d s(t) + b_d and F_a(t) = W_a s(t) + b_a with s(t) the
+// 256-wide sinusoid vector of t. The reference evaluates them with an (N*N*4) x C x C GEMM (51 GFLOP per cloud at N=312);
+// csrc/geo_tc.cu does that GEMM on tcgen05 and is bound by shared-memory operand bandwidth at ~41 % tensor-pipe
+// (profiles/r01e). But F_d and F_a depend on the WEIGHTS only, so they are sampled once per load_state_dict on a uniform
+// grid of step h = 2^-4 (in fp64, roitr_b200.engine.build_geo_tables) and evaluated here by 4-point Lagrange (cubic)
+// interpolation:  |error| <= (3/128) h^4 max|F''''|  ~ 1e-7 for the grid chosen at pack time (the bound is computed from
+// the weights and checked there) - the size of one fp32 rounding of the result, and below the fp32 noise of the GEMM
+// (and of the reference's own rounded argument t * div_term). h is a power of two, so the cell index and the fraction
+// are exact in fp32. The max over the three angles and the bias adds are applied to the interpolated values; since
+// x -> fl(x + b) is monotone, max_r(a_r + b) == max_r(a_r) + b exactly.
+//
+// Layout: channels are processed in groups of 64; the tables are stored per group as rows of 64 floats (256 B), row r
+// holding t = (r - 1) h, so the four taps of cell i are rows i .. i+3. A CTA owns one channel group for its whole life:
+// it stages that group's angle table (t <= 12.25) and the head of the distance table in shared memory with two bulk TMA
+// copies, then walks (cloud, pair-block) work items. Distances beyond the staged head read the global table (L2), and
+// beyond the global table (D > ~100 m) the pair is evaluated directly from the weights, so results are defined for every
+// input.
+//
+// Per warp: 32 pairs at a time - lane p computes the geometry (distance, three angles: same arithmetic as geo_tc.cu) of
+// pair p; then for each pair the (cell, fraction) of the four scalars are broadcast with shuffles and every lane
+// interpolates ITS two channels (LDS.64 taps, conflict-free) and writes a float2: 256 contiguous bytes of E per warp.
+// Bound: shared-memory reads (16 taps x 256 B per pair and group) and issue slots; E is written exactly once (HBM).
+#include <math_constants.h>
+
+#include "../../include/roitr_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int GTB_THREADS = 256;
+constexpr int GTB_GROUP = 64;            // channels per group
+constexpr int GTB_ROW_BYTES = GTB_GROUP * 4;
+
+struct GeoTabParams {
+    const float* pts; const int* nn3;
+    const float* tab_a;      // [groups][rows_a][64]
+    const float* tab_d;      // [groups][rows_d][64]
+    const float* Wd; const float* bd; const float* Wa; const float* ba; const float* div_term;   // direct evaluation only
+    float* E;
+    int batch, N, C;
+    int rows_a, rows_d, rows_d_smem;
+    float inv_h, sigma_d, factor_a;
+    int ctas_per_group;
+};
+
+__device__ __forceinline__ float sq3t(const float* p) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])), __fmul_rn(p[2], p[2]));
+}
+
+// the four embedding scalars of pair (n, m): distance index and the three angle indices (positional_encoding.py:111-137)
+__device__ __forceinline__ void pair_scalars(const float* __restrict__ pts, const int* __restrict__ nn3, int n, int m,
+                                             float sigma_d, float factor_a, float (&t)[4]) {
+    float a[3] = {__ldg(pts + 3 * n), __ldg(pts + 3 * n + 1), __ldg(pts + 3 * n + 2)};
+    float b[3] = {__ldg(pts + 3 * m), __ldg(pts + 3 * m + 1), __ldg(pts + 3 * m + 2)};
+    {   // pairwise_distance (:24-33): sqrt(clamp(x2 - 2 xy + y2, 0)) with xy the matmul fma chain
+        const float xy = fmaf(a[2], b[2], fmaf(a[1], b[1], __fmul_rn(a[0], b[0])));
+        const float d2 = __fadd_rn(__fsub_rn(sq3t(a), __fmul_rn(2.0f, xy)), sq3t(b));
+        t[0] = __fdiv_rn(__fsqrt_rn(fmaxf(d2, 0.0f)), sigma_d);
+    }
+    const float ax = __fsub_rn(b[0], a[0]), ay = __fsub_rn(b[1], a[1]), az = __fsub_rn(b[2], a[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int q = __ldg(nn3 + 3 * n + k);
+        const float rx = __fsub_rn(__ldg(pts + 3 * q), a[0]), ry = __fsub_rn(__ldg(pts + 3 * q + 1), a[1]),
+                    rz = __fsub_rn(__ldg(pts + 3 * q + 2), a[2]);
+        const float cx = __fsub_rn(__fmul_rn(ry, az), __fmul_rn(rz, ay));
+        const float cy = __fsub_rn(__fmul_rn(rz, ax), __fmul_rn(rx, az));
+        const float cz = __fsub_rn(__fmul_rn(rx, ay), __fmul_rn(ry, ax));
+        const float sinv = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+        // torch.sum starts from +0: a zero dot product is +0 and atan2(0, +0) = 0 (not pi)
+        const float cosv = __fadd_rn(__fadd_rn(__fadd_rn(0.f, __fmul_rn(rx, ax)), __fmul_rn(ry, ay)), __fmul_rn(rz, az));
+        t[k + 1] = __fmul_rn(atan2f(sinv, cosv), factor_a);
+    }
+}
+
+// 4-point Lagrange weights at fraction u in [0,1) for nodes -1, 0, 1, 2
+__device__ __forceinline__ void lagrange4(float u, float (&w)[4]) {
+    const float um1 = u - 1.0f, um2 = u - 2.0f, up1 = u + 1.0f;
+    w[0] = -(1.0f / 6.0f) * u * um1 * um2;
+    w[1] = 0.5f * up1 * um1 * um2;
+    w[2] = -0.5f * up1 * u * um2;
+    w[3] = (1.0f / 6.0f) * up1 * u * um1;
+}
+
+// direct evaluation of (W s(t) + b) for this lane's two channels (only for scalars beyond every table)
+__device__ float2 direct_eval(const float* __restrict__ Wm, const float* __restrict__ bias, const float* __restrict__ div_term,
+                              int C, int ch, float t) {
+    float a0 = 0.f, a1 = 0.f;
+    const float* w0 = Wm + (size_t)ch * C;
+    const float* w1 = w0 + C;
+    for (int j = 0; j < C / 2; ++j) {
+        float sn, cs;
+        sincosf(__fmul_rn(t, __ldg(div_term + j)), &sn, &cs);
+        a0 = fmaf(__ldg(w0 + 2 * j + 1), cs, fmaf(__ldg(w0 + 2 * j), sn, a0));
+        a1 = fmaf(__ldg(w1 + 2 * j + 1), cs, fmaf(__ldg(w1 + 2 * j), sn, a1));
+    }
+    return make_float2(a0 + __ldg(bias + ch), a1 + __ldg(bias + ch + 1));
+}
+
+__global__ void __launch_bounds__(GTB_THREADS, 1) geo_embedding_table_kernel(const GeoTabParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_a = reinterpret_cast<float*>(smem_raw);                       // [rows_a][64]
+    float* s_d = s_a + (size_t)P.rows_a * GTB_GROUP;                      // [rows_d_smem][64]
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = blockIdx.x / P.ctas_per_group, slot = blockIdx.x % P.ctas_per_group;
+    const int N = P.N, C = P.C;
+    const float* g_d = P.tab_d + (size_t)group * P.rows_d * GTB_GROUP;    // this group's full distance table (global)
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // bulk copies are limited to < 1 MB each and need 16-byte multiples: rows are 256 B
+        const uint32_t bytes_a = (uint32_t)P.rows_a * GTB_ROW_BYTES, bytes_d = (uint32_t)P.rows_d_smem * GTB_ROW_BYTES;
+        mbar_expect_tx(&bar, bytes_a + bytes_d);
+        tma_load_1d(s_a, P.tab_a + (size_t)group * P.rows_a * GTB_GROUP, bytes_a, &bar);
+        tma_load_1d(s_d, g_d, bytes_d, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const long long npairs = (long long)N * N;
+    const long long blocks_per_cloud = (npairs + 255) / 256;               // a work item = 256 pairs (32 per warp)
+    const long long items = blocks_per_cloud * P.batch;
+    const int ch = group * GTB_GROUP + 2 * lane;
+    const int rows_a = P.rows_a, rows_ds = P.rows_d_smem, rows_d = P.rows_d;
+
+    for (long long item = slot; item < items; item += P.ctas_per_group) {
+        const int cloud = (int)(item / blocks_per_cloud);
+        const long long p0 = (item % blocks_per_cloud) * 256 + warp * 32;
+        const float* pts = P.pts + (size_t)cloud * N * 3;
+        const int* nn3 = P.nn3 + (size_t)cloud * N * 3;
+        float* E = P.E + (size_t)cloud * npairs * C;
+        // ---- lane = pair: geometry, cell index and fraction of the four scalars ----
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        const long long mine = p0 + lane;
+        if (mine < npairs) pair_scalars(pts, nn3, (int)(mine / N), (int)(mine % N), P.sigma_d, P.factor_a, t);
+        int ci[4];
+        float cu[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float x = t[k] * P.inv_h;                                // exact: inv_h is a power of two
+            const float fl = floorf(x);
+            cu[k] = x - fl;                                                // exact (Sterbenz / same binade)
+            ci[k] = (x < 2.0e9f) ? (int)fl : 0x7fffffff;
+        }
+        const int npw = (int)min((long long)32, npairs - p0);
+        for (int p = 0; p < npw; ++p) {
+            float2 acc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = __shfl_sync(FULL_MASK, ci[k], p);
+                const float u = __shfl_sync(FULL_MASK, cu[k], p);
+                float w[4];
+                lagrange4(u, w);
+                const float* tab;
+                bool ok = true;
+                if (k == 0) {
+                    if (i + 3 < rows_ds) tab = s_d + (size_t)i * GTB_GROUP;
+                    else if (i + 3 < rows_d) tab = g_d + (size_t)i * GTB_GROUP;
+                    else ok = false;
+                } else {
+                    ok = i + 3 < rows_a;
+                    tab = s_a + (size_t)i * GTB_GROUP;
+                }
+                if (ok) {
+                    const float2 v0 = *reinterpret_cast<const float2*>(tab + 2 * lane);
+                    const float2 v1 = *reinterpret_cast<const float2*>(tab + GTB_GROUP + 2 * lane);
+                    const float2 v2 = *reinterpret_cast<const float2*>(tab + 2 * GTB_GROUP + 2 * lane);
+                    const float2 v3 = *reinterpret_cast<const float2*>(tab + 3 * GTB_GROUP + 2 * lane);
+                    // inner nodes first (largest weights), outer corrections last
+                    acc[k].x = fmaf(w[3], v3.x, fmaf(w[0], v0.x, fmaf(w[2], v2.x, w[1] * v1.x)));
+                    acc[k].y = fmaf(w[3], v3.y, fmaf(w[0], v0.y, fmaf(w[2], v2.y, w[1] * v1.y)));
+                } else {   // beyond every table (warp-uniform branch): evaluate from the weights
+                    const float tv = __shfl_sync(FULL_MASK, t[k], p);
+                    acc[k] = (k == 0) ? direct_eval(P.Wd, P.bd, P.div_term, C, ch, tv)
+                                      : direct_eval(P.Wa, P.ba, P.div_term, C, ch, tv);
+                }
+            }
+            float2 o;
+            o.x = acc[0].x + fmaxf(fmaxf(acc[1].x, acc[2].x), acc[3].x);
+            o.y = acc[0].y + fmaxf(fmaxf(acc[1].y, acc[2].y), acc[3].y);
+            *reinterpret_cast<float2*>(E + (size_t)(p0 + p) * C + ch) = o;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" long long roitr_geo_table_smem_rows(void) {
+    // rows of 256 B that fit next to the static shared memory of the kernel (227 KB per CTA on sm_100a)
+    return (227 * 1024 - 1024) / GTB_ROW_BYTES;
+}
+
+extern "C" int roitr_geo_embedding_table(int batch, int N, int C, const float* pts, const int* nn3, const float* tab_a,
+                                         int rows_a, const float* tab_d, int rows_d, float inv_h, const float* Wd,
+                                         const float* bd, const float* Wa, const float* ba, const float* div_term,
+                                         float sigma_d, float sigma_a, float* E, void* stream) {
+    ROITR_CHECK_ARG(batch >= 1 && N >= 1 && pts && nn3 && tab_a && tab_d && Wd && bd && Wa && ba && div_term && E,
+                    "geo_embedding_table: bad arguments");
+    ROITR_CHECK_ARG(C % GTB_GROUP == 0 && C >= GTB_GROUP, "geo_embedding_table: C must be a multiple of %d, got %d", GTB_GROUP, C);
+    ROITR_CHECK_ARG(rows_a >= 8 && rows_d >= 8 && inv_h > 0.f, "geo_embedding_table: bad table shape");
+    ROITR_CHECK_ARG(((uintptr_t)tab_a | (uintptr_t)tab_d | (uintptr_t)E) % 16 == 0, "geo_embedding_table: 16-byte alignment");
+    const int max_rows = (int)roitr_geo_table_smem_rows();
+    ROITR_CHECK_ARG(rows_a + 8 <= max_rows, "geo_embedding_table: angle table of %d rows does not fit shared memory", rows_a);
+    GeoTabParams P;
+    P.pts = pts; P.nn3 = nn3; P.tab_a = tab_a; P.tab_d = tab_d; P.Wd = Wd; P.bd = bd; P.Wa = Wa; P.ba = ba;
+    P.div_term = div_term; P.E = E; P.batch = batch; P.N = N; P.C = C; P.rows_a = rows_a; P.rows_d = rows_d;
+    P.rows_d_smem = rows_d < max_rows - rows_a ? rows_d : max_rows - rows_a;
+    P.inv_h = inv_h; P.sigma_d = sigma_d;
+    P.factor_a = (float)(180.0 / ((double)sigma_a * 3.14159265358979323846));  // positional_encoding.py:99
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        ROITR_CUDA(cudaGetDevice(&dev));
+        ROITR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        ROITR_CUDA(cudaFuncSetAttribute(geo_embedding_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    }
+    const int groups = C / GTB_GROUP;
+    const long long items = (((long long)N * N + 255) / 256) * batch;
+    long long per = num_sms / groups;
+    if (per < 1) per = 1;
+    if (per > items) per = items;
+    P.ctas_per_group = (int)per;
+    const size_t smem = (size_t)(P.rows_a + P.rows_d_smem) * GTB_ROW_BYTES;
+    geo_embedding_table_kernel<<<groups * P.ctas_per_group, GTB_THREADS, smem, (cudaStream_t)stream>>>(P);
+    ROITR_CHECK_LAUNCH("geo_embedding_table_kernel");
+    return ROITR_OK;
+}

@@ -25,6 +25,11 @@ __global__ void pad_transform_kernel(int N, const float* __restrict__ pts, const
                                      const float* __restrict__ trans, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > N) return;
+    {   // blockIdx.y = pair of a batch: pts (B*N,3), rot (B,3,3), trans (B,3), out (B*(N+1),3)
+        const size_t b = blockIdx.y;
+        pts += b * (size_t)N * 3; out += b * (size_t)(N + 1) * 3;
+        if (rot) { rot += b * 9; trans += b * 3; }
+    }
     float x = 0.f, y = 0.f, z = 0.f;
     if (i < N) { x = __ldg(pts + 3 * i); y = __ldg(pts + 3 * i + 1); z = __ldg(pts + 3 * i + 2); }
     float o[3] = {x, y, z};
@@ -169,12 +174,17 @@ __global__ void corr_gather_kernel(const int* __restrict__ flat, const int* __re
 
 }  // namespace
 
-extern "C" int roitr_pad_transform(int N, const float* pts, const float* rot, const float* trans, float* out,
-                                   void* stream) {
-    ROITR_CHECK_ARG(N >= 0 && pts && out && (!rot || trans), "pad_transform: bad arguments");
-    pad_transform_kernel<<<ceil_div(N + 1, 256), 256, 0, (cudaStream_t)stream>>>(N, pts, rot, trans, out);
+extern "C" int roitr_pad_transform_batched(int B, int N, const float* pts, const float* rot, const float* trans,
+                                           float* out, void* stream) {
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && N >= 0 && pts && out && (!rot || trans), "pad_transform: bad arguments");
+    pad_transform_kernel<<<dim3(ceil_div(N + 1, 256), B), 256, 0, (cudaStream_t)stream>>>(N, pts, rot, trans, out);
     ROITR_CHECK_LAUNCH("pad_transform_kernel");
     return ROITR_OK;
+}
+
+extern "C" int roitr_pad_transform(int N, const float* pts, const float* rot, const float* trans, float* out,
+                                   void* stream) {
+    return roitr_pad_transform_batched(1, N, pts, rot, trans, out, stream);
 }
 
 extern "C" int roitr_node_occlusion(int M, int K, const int* knn, const unsigned char* kmask, const unsigned char* nmask,

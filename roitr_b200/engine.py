@@ -18,6 +18,8 @@ import torch
 from . import ops
 
 GEO_EMBEDDING_TC = True      # tcgen05 3xTF32 kernel (csrc/geo_tc.cu); False = fp32 FFMA kernel (csrc/geo.cu)
+GEO_EMBEDDING_TABLE = True   # batched path: weight-derived tables + cubic interpolation (csrc/geo_table.cu) instead of the GEMM
+GEO_TABLE_TOL = 2.5e-7       # interpolation error bound the table step is chosen for (one fp32 rounding of an O(1) value)
 STRIDES = (1, 4, 4, 4)
 NSAMPLE = (8, 16, 16, 16)
 BLOCKS = (2, 3, 3, 3)
@@ -71,6 +73,36 @@ def pack_linear_tc(Wm):
     return torch.stack([tile(hi), tile(lo)], dim=2).contiguous(), bn
 
 
+def build_geo_tables(Wd, bd, Wa, ba, div_term, sigma_a=15.0, t_d_max=512.0):
+    """Samples F_d(t) = W_d s(t) + b_d and F_a(t) = W_a s(t) + b_a (s = the interleaved [sin, cos] sinusoid vector of
+    SinusoidalPositionalEmbedding, positional_encoding.py:48-62) in fp64 on a uniform grid of step h = 2^-k for
+    csrc/geo_table.cu. k is the smallest value >= 4 whose 4-point Lagrange interpolation error bound
+    (3/128) h^4 max_c sum_j (|W[c,2j]| + |W[c,2j+1]|) div_j^4 is below GEO_TABLE_TOL for both matrices.
+    Returns dict(tab_a [C/64, rows_a, 64], tab_d [C/64, rows_d, 64], inv_h, bound). Row r holds t = (r - 1) h."""
+    C = Wd.shape[0]
+    dv = div_term.double()
+    w4 = (dv ** 4).repeat_interleave(2)                                   # per input column
+    m4 = max(float((Wd.double().abs() * w4).sum(1).max()), float((Wa.double().abs() * w4).sum(1).max()))
+    k = 4
+    while k < 8 and (3.0 / 128.0) * (2.0 ** (-4 * k)) * m4 > GEO_TABLE_TOL:
+        k += 1
+    bound = (3.0 / 128.0) * (2.0 ** (-4 * k)) * m4
+    if bound > 4 * GEO_TABLE_TOL:
+        raise ValueError("geometric-embedding weights too large for the tabulated evaluation (error bound %.2e); set "
+                         "engine.GEO_EMBEDDING_TABLE = False to use the tensor-core GEMM" % bound)
+    h = 2.0 ** (-k)
+    t_a_max = 180.0 / sigma_a + 0.25                                        # angle index <= 180 / sigma_a (:99)
+
+    def table(Wm, b, t_max):
+        rows = int(math.ceil(t_max / h)) + 5
+        t = (torch.arange(rows, dtype=torch.float64, device=Wm.device) - 1.0) * h
+        om = t[:, None] * dv[None, :]
+        emb = torch.stack([torch.sin(om), torch.cos(om)], dim=2).reshape(rows, -1)      # [sin, cos] interleaved (:60-61)
+        F = (emb @ Wm.double().t() + b.double()).float()                  # (rows, C)
+        return F.view(rows, C // 64, 64).permute(1, 0, 2).contiguous()
+    return dict(tab_a=table(Wa, ba, t_a_max), tab_d=table(Wd, bd, t_d_max), inv_h=1.0 / h, bound=bound)
+
+
 def pack_weights(state_dict, device, architecture):
     W = Packed()
     for k, v in state_dict.items():
@@ -93,6 +125,10 @@ def pack_weights(state_dict, device, architecture):
         c = C // HEADS
         W[g + ".embedding#wpack"] = torch.stack([pack_tf32_sw128(W[g + ".embedding.proj_d.weight"]),
                                                  pack_tf32_sw128(W[g + ".embedding.proj_a.weight"])], 0).contiguous()
+        if GEO_EMBEDDING_TABLE and C % 64 == 0:
+            W[g + ".embedding#tables"] = build_geo_tables(W[g + ".embedding.proj_d.weight"], W[g + ".embedding.proj_d.bias"],
+                                                          W[g + ".embedding.proj_a.weight"], W[g + ".embedding.proj_a.bias"],
+                                                          W[g + ".embedding.embedding.div_term"])
         for i, kind in enumerate(architecture):
             a = "%s.transformer.layers.%d.attention.attention" % (g, i)
             if kind == "self":
@@ -101,8 +137,20 @@ def pack_weights(state_dict, device, architecture):
                 Wp = W[a + ".proj_p.weight"]                                       # (C, C): p = Wp e + bp
                 # gq[n,h,:] = sum_{k in head h} q[n, h*c+k] * Wp[h*c+k, :]  ->  per head a (C x c) matrix, K = c
                 W[a + "#WpT"] = torch.stack([Wp[h * c:(h + 1) * c, :].t().contiguous() for h in range(HEADS)], 0).contiguous()
+                # the same per-head maps as ONE dense layer each (block-structured weights, exact zeros elsewhere), so that
+                # the batched path issues two tensor-core launches instead of eight skinny FFMA ones:
+                #   gq (R, H*C) = q (R, C) WpBig^T,  WpBig[h*C + j, h*c + k] = Wp[h*c + k, j]
+                #   pos (R, C)  = G (R, H*C) WvpBig^T + b_vp,  WvpBig[h*c + i, h*C + j] = Wvp[h*c + i, j]
+                Wvp = W[a + ".proj_vp.weight"]
+                big_p = torch.zeros(HEADS * C, C, dtype=torch.float32, device=device)
+                big_vp = torch.zeros(C, HEADS * C, dtype=torch.float32, device=device)
+                for h in range(HEADS):
+                    big_p[h * C:(h + 1) * C, h * c:(h + 1) * c] = Wp[h * c:(h + 1) * c, :].t()
+                    big_vp[h * c:(h + 1) * c, h * C:(h + 1) * C] = Wvp[h * c:(h + 1) * c, :]
+                W[a + "#WpBig"], W[a + "#WvpBig"] = big_p, big_vp
         # tensor-core operand form of every dense-layer weight with a useful K (roitr_linear_tc_packed)
-        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv")) and W[k].dim() == 2 and W[k].shape[1] >= 16]:
+        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("Big")) and W[k].dim() == 2
+                  and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
     finally:
         torch.backends.cuda.matmul.allow_tf32 = hp
@@ -110,6 +158,7 @@ def pack_weights(state_dict, device, architecture):
 
 
 # ------------------------------------------------------------------------------------------------ local layers
+ATTENTION_TC = True          # global attention: Q K^T / P V on tcgen05 + one streaming pass over E (csrc/geo_attn2.cu)
 LINEAR_TC = True             # dense layers on tcgen05 (csrc/gemm_tc2.cu) when a packed weight exists; False = fp32 FFMA
 
 
@@ -168,14 +217,22 @@ class Plan:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n)]
         return self._streams[:n]
 
+    def pad_offsets(self, n):
+        """Cumulative ends of B equal segments of n rows (the zero-padded clouds of the occlusion 1-NN)."""
+        key = ("pad", n)
+        if key not in self.one:
+            self.one[key] = _offsets([n * (i + 1) for i in range(self.B)], self.device)
+        return self.one[key]
+
     def single_offset(self, n):
         if n not in self.one:
             self.one[n] = _offsets([n], self.device)
         return self.one[n]
 
 
-def encode(W, plan, pts, feats, nrm):
-    """enc1..enc4 for all 2B clouds of the plan at once (segment-batched kernels)."""
+def encode(W, plan, pts, feats, nrm, on_nodes=None):
+    """enc1..enc4 for all 2B clouds of the plan at once (segment-batched kernels). ``on_nodes(levels, down_idx4, p4)`` is
+    called as soon as the level-4 superpoints exist (right after the last FPS), before the level-4 layers are issued."""
     levels = []
     x = feats
     o = plan.levels[0]["o"]
@@ -190,6 +247,8 @@ def encode(W, plan, pts, feats, nrm):
             no = L["o"]
             down_idx, n_p = ops.fps(pts, o, no, plan.levels[li - 1]["n_max"], L["total"], per_segment_rule=True,
                                     cluster=plan.fps_cluster)
+            if li == 3 and on_nodes is not None:
+                on_nodes(levels, down_idx, n_p)
             n_n = ops.gather_rows(nrm, down_idx)
             gidx, gppf, _ = ops.knn_ppf(k, pts, nrm, n_p, n_n, o, no, grid=grid)
             x = local_ppf_transformer(W, p + ".0.transformer", x, down_idx, gidx, gppf)
@@ -233,64 +292,6 @@ def _ffn(W, p, x):
     return _ln(W, p + ".norm", h, res_pre=x, mode=ops.MODE_LN)
 
 
-def _self_layer(W, lp, x, E):
-    a = lp + ".attention.attention"
-    C = x.shape[1]
-    c = C // HEADS
-    N = x.shape[0]
-    qkv = ops.linear(x, W[a + "#Wqkv"], W[a + "#bqkv"])
-    gq = torch.empty(N, HEADS * C, dtype=torch.float32, device=x.device)
-    for h in range(HEADS):
-        ops.linear(qkv[:, h * c:(h + 1) * c], W[a + "#WpT"][h], None, out=gq[:, h * C:(h + 1) * C], M=N, K=c)
-    hidden, G = ops.geo_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], C, E=E, gq=gq, bp=W[a + ".proj_p.bias"])
-    Wvp, bvp = W[a + ".proj_vp.weight"], W[a + ".proj_vp.bias"]
-    G2 = G.view(N, HEADS * C)
-    pos = torch.empty(N, C, dtype=torch.float32, device=x.device)
-    for h in range(HEADS):
-        ops.linear(G2[:, h * C:(h + 1) * C], Wvp[h * c:(h + 1) * c], bvp[h * c:(h + 1) * c], out=pos[:, h * c:(h + 1) * c],
-                   M=N, K=C)
-    y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
-    pos = _ln(W, lp + ".attention.pos_norm", _lin(W, lp + ".attention.pos_linear", pos), mode=ops.MODE_LN)
-    return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
-
-
-def _cross_layer(W, lp, x, y, pos_x, pos_y):
-    a = lp + ".attention.attention"
-    C = x.shape[1]
-    q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x)
-    k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y)
-    v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"])
-    hidden = ops.geo_attention(q, k, v, C)
-    z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
-    return _ffn(W, lp + ".output", z)
-
-
-def geometric_transformer(W, architecture, pts0, pts1, f0, f1, sigma_d=0.2, sigma_a=15.0):
-    """GeometricTransformer.forward (geotransformer.py:94-133); '0' = src, '1' = tgt as called at model/model.py:214."""
-    g = "backbone.global_transformer"
-    e = g + ".embedding"
-    embs = []
-    for pts in (pts0, pts1):
-        nn3 = ops.geo_knn(pts, 3)
-        if GEO_EMBEDDING_TC:
-            embs.append(ops.geo_embedding_tc(pts, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
-                                             W[e + ".embedding.div_term"], sigma_d, sigma_a))
-        else:
-            embs.append(ops.geo_embedding(pts, nn3, W[e + ".proj_d.weight"], W[e + ".proj_d.bias"], W[e + ".proj_a.weight"],
-                                          W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], sigma_d, sigma_a))
-    f0, f1 = _lin(W, g + ".in_proj", f0), _lin(W, g + ".in_proj", f1)
-    pos0 = pos1 = None
-    for i, kind in enumerate(architecture):
-        lp = "%s.transformer.layers.%d" % (g, i)
-        if kind == "self":
-            f0, pos0 = _self_layer(W, lp, f0, embs[0])
-            f1, pos1 = _self_layer(W, lp, f1, embs[1])
-        else:
-            f0 = _cross_layer(W, lp, f0, f1, pos0, pos1)
-            f1 = _cross_layer(W, lp, f1, f0, pos1, pos0)
-    return _lin(W, g + ".out_proj", f0), _lin(W, g + ".out_proj", f1), embs
-
-
 def _self_layer_batch(W, lp, x, E, nb, N):
     """RPETransformerLayer for `nb` clouds of N superpoints stacked along dim 0 (x: (nb*N, C), E: (nb, N, N, C))."""
     a = lp + ".attention.attention"
@@ -298,17 +299,23 @@ def _self_layer_batch(W, lp, x, E, nb, N):
     c = C // HEADS
     R = x.shape[0]
     qkv = ops.linear(x, W[a + "#Wqkv"], W[a + "#bqkv"], wpack=W.get(a + "#Wqkv#tc") if LINEAR_TC else None)
-    gq = torch.empty(R, HEADS * C, dtype=torch.float32, device=x.device)
-    for h in range(HEADS):
-        ops.linear(qkv[:, h * c:(h + 1) * c], W[a + "#WpT"][h], None, out=gq[:, h * C:(h + 1) * C], M=R, K=c)
-    hidden, G = ops.geo_attention_batched(nb, N, N, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], C, E=E, gq=gq,
-                                          bp=W[a + ".proj_p.bias"])
+    if LINEAR_TC:
+        gq = ops.linear(qkv[:, :C], W[a + "#WpBig"], None, wpack=W[a + "#WpBig#tc"])
+    else:
+        gq = torch.empty(R, HEADS * C, dtype=torch.float32, device=x.device)
+        for h in range(HEADS):
+            ops.linear(qkv[:, h * c:(h + 1) * c], W[a + "#WpT"][h], None, out=gq[:, h * C:(h + 1) * C], M=R, K=c)
+    attn = ops.attention_tc if ATTENTION_TC else ops.geo_attention_batched_compat
+    hidden, G = attn(nb, N, N, C, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], E=E, gq=gq, bp=W[a + ".proj_p.bias"])
     Wvp, bvp = W[a + ".proj_vp.weight"], W[a + ".proj_vp.bias"]
     G2 = G.view(R, HEADS * C)
-    pos = torch.empty(R, C, dtype=torch.float32, device=x.device)
-    for h in range(HEADS):
-        ops.linear(G2[:, h * C:(h + 1) * C], Wvp[h * c:(h + 1) * c], bvp[h * c:(h + 1) * c], out=pos[:, h * c:(h + 1) * c],
-                   M=R, K=C)
+    if LINEAR_TC:
+        pos = ops.linear(G2, W[a + "#WvpBig"], bvp, wpack=W[a + "#WvpBig#tc"])
+    else:
+        pos = torch.empty(R, C, dtype=torch.float32, device=x.device)
+        for h in range(HEADS):
+            ops.linear(G2[:, h * C:(h + 1) * C], Wvp[h * c:(h + 1) * c], bvp[h * c:(h + 1) * c], out=pos[:, h * c:(h + 1) * c],
+                       M=R, K=C)
     y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     pos = _ln(W, lp + ".attention.pos_norm", _lin(W, lp + ".attention.pos_linear", pos), mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
@@ -321,7 +328,7 @@ def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x, wpack=tcw("q"))
     k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, wpack=tcw("k"))
     v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], wpack=tcw("v"))
-    hidden = ops.geo_attention_batched(nb, N, M, q, k, v, C)
+    hidden = (ops.attention_tc if ATTENTION_TC else ops.geo_attention_batched_compat)(nb, N, M, C, q, k, v)
     z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", z)
 
@@ -336,16 +343,21 @@ def geometric_transformer_batch(W, architecture, B, pts0, pts1, f0, f1, sigma_d=
     N0, N1 = pts0.shape[0] // B, pts1.shape[0] // B
     embs = []
     for pts, N in ((pts0, N0), (pts1, N1)):
-        E = torch.empty(B, N, N, C, dtype=torch.float32, device=pts.device)
-        for b in range(B):
-            pb = pts[b * N:(b + 1) * N]
-            nn3 = ops.geo_knn(pb, 3)
-            if GEO_EMBEDDING_TC:
-                ops.geo_embedding_tc(pb, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
-                                     W[e + ".embedding.div_term"], sigma_d, sigma_a, out=E[b])
-            else:
-                ops.geo_embedding(pb, nn3, W[e + ".proj_d.weight"], W[e + ".proj_d.bias"], W[e + ".proj_a.weight"],
-                                  W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], sigma_d, sigma_a, out=E[b])
+        pts = pts.contiguous()
+        nn3 = ops.geo_knn_batched(B, N, pts, 3)
+        if GEO_EMBEDDING_TABLE and (e + "#tables") in W:
+            E = ops.geo_embedding_table(B, N, pts, nn3, W[e + "#tables"], W[e + ".proj_d.weight"], W[e + ".proj_d.bias"],
+                                        W[e + ".proj_a.weight"], W[e + ".proj_a.bias"], W[e + ".embedding.div_term"],
+                                        sigma_d, sigma_a)
+        elif GEO_EMBEDDING_TC:
+            E = ops.geo_embedding_tc_batched(B, N, pts, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
+                                             W[e + ".embedding.div_term"], sigma_d, sigma_a)
+        else:
+            E = torch.empty(B, N, N, C, dtype=torch.float32, device=pts.device)
+            for b in range(B):
+                ops.geo_embedding(pts[b * N:(b + 1) * N], nn3[b * N:(b + 1) * N], W[e + ".proj_d.weight"],
+                                  W[e + ".proj_d.bias"], W[e + ".proj_a.weight"], W[e + ".proj_a.bias"],
+                                  W[e + ".embedding.div_term"], sigma_d, sigma_a, out=E[b])
         embs.append(E)
     f0, f1 = _lin(W, g + ".in_proj", f0), _lin(W, g + ".in_proj", f1)
     pos0 = pos1 = None
@@ -361,28 +373,43 @@ def geometric_transformer_batch(W, architecture, B, pts0, pts1, f0, f1, sigma_d=
 
 
 # ------------------------------------------------------------------------------------------------ backbone
-def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=None):
+def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=None, on_nodes=None, on_global=None):
     """RIPointTransformer.forward (model/model.py:187-237) for all pairs of the plan. Returns per-level batched tensors,
-    the decoded level-1 features and, per pair, (src_nodes, src_node_feats, tgt_node_feats)."""
+    the decoded level-1 features and, per pair, (src_nodes, src_node_feats, tgt_node_feats).
+
+    Issue order is encoder -> global transformer -> decoder (the decoder does not consume the global transformer's
+    output, model/model.py:214-231), with two callbacks that let the caller fork independent work onto side streams:
+    ``on_nodes(per_pair_nodes)`` once the superpoints exist (after the last FPS) and ``on_global(per_pair)`` once the
+    conditioned superpoint features exist (before the decoder is issued)."""
     B = plan.B
-    L = encode(W, plan, pts, feats, nrm)
-    dec = decode(W, L)
-    per_pair = []
-    # index-chain composition of the FPS indices (model/model.py:233-235); indices are global rows of the batch
-    d3 = L[1]["down_idx"].long()[L[2]["down_idx"].long()]
-    d4 = d3[L[3]["down_idx"].long()]
     split = plan.starts(3, B)[0]             # level-4 rows: [B source clouds | B target clouds]
+    nodes = {}
+
+    def _nodes(levels, down_idx4, p4):
+        # index-chain composition of the FPS indices (model/model.py:233-235); indices are global rows of the batch
+        d3 = levels[1]["down_idx"].long()[levels[2]["down_idx"].long()]
+        d4 = d3[down_idx4.long()]
+        # node coordinates come from the (possibly deformed) source cloud: src_deformed is the batch of src clouds only
+        s_nodes_all = ops.gather_rows(src_deformed, d4[:split])
+        nodes.update(d4=d4, src=[s_nodes_all[plan.starts(3, b)[0]:plan.starts(3, b)[1]] for b in range(B)],
+                     tgt=[p4[plan.starts(3, B + b)[0]:plan.starts(3, B + b)[1]] for b in range(B)])
+        if on_nodes is not None:
+            on_nodes(nodes)
+
+    L = encode(W, plan, pts, feats, nrm, on_nodes=_nodes)
     s_g_all, t_g_all, embs = geometric_transformer_batch(W, architecture, B, L[3]["p"][:split], L[3]["p"][split:],
                                                          L[3]["x"][:split], L[3]["x"][split:])
+    per_pair = []
     for b in range(B):
         s0, s1 = plan.starts(3, b)
         t0, t1 = plan.starts(3, B + b)
-        # node coordinates come from the (possibly deformed) source cloud: src_deformed is the batch of src clouds only
-        s_nodes = ops.gather_rows(src_deformed, d4[s0:s1])
-        per_pair.append(dict(src_nodes=s_nodes, src_g=s_g_all[s0:s1], tgt_g=t_g_all[t0 - split:t1 - split],
-                             tgt_nodes=L[3]["p"][t0:t1], embs=(embs[0][b], embs[1][b]) if aux is not None else None))
+        per_pair.append(dict(src_nodes=nodes["src"][b], src_g=s_g_all[s0:s1], tgt_g=t_g_all[t0 - split:t1 - split],
+                             tgt_nodes=nodes["tgt"][b], embs=(embs[0][b], embs[1][b]) if aux is not None else None))
+    if on_global is not None:
+        on_global(per_pair, s_g_all, t_g_all)
+    dec = decode(W, L)
     if aux is not None:
-        aux.update(levels=L, dec=dec, node_idx=d4, emb0=per_pair[0]["embs"][0], emb1=per_pair[0]["embs"][1])
+        aux.update(levels=L, dec=dec, node_idx=nodes["d4"], emb0=per_pair[0]["embs"][0], emb1=per_pair[0]["embs"][1])
     return L, dec, per_pair
 
 
@@ -399,83 +426,138 @@ def backbone_forward(W, architecture, s_pxon, t_pxon, src_deformed, aux=None):
 
 
 # ------------------------------------------------------------------------------------------------ pipeline
+class _Fork:
+    """Side streams for per-pair work that is independent of the main-stream kernels (captured into the step's CUDA graph
+    as parallel branches). With no streams (B == 1) everything is issued inline on the current stream."""
+
+    def __init__(self, streams):
+        self.streams, self.main = streams, torch.cuda.current_stream()
+
+    def run(self, B, fn):
+        if not self.streams:
+            for b in range(B):
+                fn(b)
+            return
+        ev = self.main.record_event()
+        for st in self.streams:
+            st.wait_event(ev)
+        for b in range(B):
+            with torch.cuda.stream(self.streams[b % len(self.streams)]):
+                fn(b)
+
+    def run_one(self, fn):
+        """fn() on the first side stream (after everything issued so far on the main stream); returns an event that
+        marks its completion, or None when running inline."""
+        if not self.streams:
+            fn()
+            return None
+        st = self.streams[0]
+        st.wait_event(self.main.record_event())
+        with torch.cuda.stream(st):
+            fn()
+            return st.record_event()
+
+    def join(self):
+        for st in self.streams:
+            self.main.wait_stream(st)
+
+
+HEAD_STREAMS = 8
+
+
 def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
     """RIGA_v2.forward (eval) for the B pairs of ``plan``. Inputs are the concatenated clouds
     [src_raw_0..src_raw_{B-1}, tgt_0..tgt_{B-1}] (pts/feats/nrm), the concatenated (deformed) source clouds ``src_pcd``
     and rot (B,3,3) / trans (B,3,1). No host sync. Returns a list of per-pair dicts of PADDED tensors plus a (B,3) int32
-    device tensor of counts [P, n_gt, n_corr]."""
+    device tensor of counts [P, n_gt, n_corr].
+
+    The per-pair matching head is a chain of latency-bound, low-occupancy kernels (single-CTA top-k / scans, one CTA per
+    patch pair for the Sinkhorn iterations) and pairs are independent, so it runs on side streams in three stages, each
+    forked as early as its inputs exist: (1) partition + ground-truth bookkeeping after the last FPS (overlaps the level-4
+    encoder, the global transformer and the decoder), (2) coarse matching after the global transformer (overlaps the
+    decoder), (3) fine matching after the decoder."""
     four_d = cfg["benchmark"] not in ("3DMatch", "3DLoMatch")
     B, Ns, Nt = plan.B, plan.n_src, plan.n_tgt
     K = int(cfg["point_per_patch"])
-    L, dec, per_pair = backbone_batch(W, cfg["transformer_architecture"], plan, pts, feats, nrm, src_pcd, aux)
-    pf_all = _lin(W, "fine_proj", dec[0])                                # all points of all clouds at once
+    M4s, M4t = plan.levels[3]["sizes"][0], plan.levels[3]["sizes"][B]
     # 3DMatch: at most num_est_coarse_corr patch pairs. 4DMatch: every pair under the similarity threshold, i.e. up to
     # Mt*Ms (model/modules.py:105-112); buffers are sized for that bound so the count can stay on the device.
-    M4s, M4t = plan.levels[3]["sizes"][0], plan.levels[3]["sizes"][B]
     Pmax = M4s * M4t if four_d else int(cfg["num_est_coarse_corr"])
     topk = int(cfg["fine_matching_topk"])
     cap = Pmax * K * topk
-    outs, counts = [None] * B, [None] * B
-    o_t, o_s = plan.single_offset(Nt + 1), plan.single_offset(Ns + 1)
+    fork = _Fork(plan.side_streams(min(HEAD_STREAMS, B)) if B > 1 else [])
+    st = [dict() for _ in range(B)]          # per-pair state handed from stage to stage (same side stream per pair)
+    src_of = lambda b: src_pcd[b * Ns:(b + 1) * Ns]
+    tgt_of = lambda b: pts[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
 
-    def head(b):
-        q = per_pair[b]
-        src_pts, tgt_pts = src_pcd[b * Ns:(b + 1) * Ns], pts[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
-        src_pf, tgt_pf = pf_all[b * Ns:(b + 1) * Ns], pf_all[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
-        src_nodes, tgt_nodes = q["src_nodes"], q["tgt_nodes"]
-        src_nf = ops.row_epilogue(_lin(W, "coarse_proj", q["src_g"]), mode=ops.MODE_L2NORM)
-        tgt_nf = ops.row_epilogue(_lin(W, "coarse_proj", q["tgt_g"]), mode=ops.MODE_L2NORM)
-        # 2. partition + ground-truth bookkeeping
-        _, s_nm, s_ki, s_km = ops.point_to_node(src_pts, src_nodes, K)
-        _, t_nm, t_ki, t_km = ops.point_to_node(tgt_pts, tgt_nodes, K)
-        Ms, Mt = src_nodes.shape[0], tgt_nodes.shape[0]
-        ov, ov_flag = ops.node_overlaps(tgt_nodes, src_nodes, t_ki, s_ki, t_km, s_km, t_nm, s_nm, tgt_pts, src_pts, rot[b],
-                                        trans[b], float(cfg["matching_radius"]))
-        gt_flat, gt_count = ops.compact_flags(ov_flag, Mt * Ms)
-        gt_idx, gt_ov = ops.corr_gather(Mt * Ms, Ms, gt_flat, gt_count, ov)
-        t_pad = ops.pad_transform(tgt_pts)
-        s_pad_t = ops.pad_transform(src_pts, rot[b], trans[b])
+    # 0. occlusion 1-NN of the zero-padded clouds (lib/utils.py:505-509): depends on the inputs only, so it is issued first
+    # and for all pairs at once (one segment per pair)
+    occ = {}
+
+    def occlusion_nn():
+        o_s, o_t = plan.pad_offsets(Ns + 1), plan.pad_offsets(Nt + 1)
+        t_pad = ops.pad_transform_batched(B, Nt, pts[B * Ns:])
+        s_pad_t = ops.pad_transform_batched(B, Ns, src_pcd, rot, trans)
         g_s = ops.knn_grid_build(s_pad_t, o_s) if Ns + 1 >= ops.GRID_MIN_SEGMENT else None
         g_t = ops.knn_grid_build(t_pad, o_t) if Nt + 1 >= ops.GRID_MIN_SEGMENT else None
         _, _, t_nn = ops.knn_ppf(1, s_pad_t, None, t_pad, None, o_s, o_t, drop_first=0, want_ppf=False, want_dist=True, grid=g_s)
         _, _, s_nn = ops.knn_ppf(1, t_pad, None, s_pad_t, None, o_t, o_s, drop_first=0, want_ppf=False, want_dist=True, grid=g_t)
-        t_occ = ops.node_occlusion(t_ki, t_km, t_nm, t_nn.view(-1))
-        s_occ = ops.node_occlusion(s_ki, s_km, s_nm, s_nn.view(-1))
-        # 3. coarse matching   (called as (tgt, src), model/RIGA_v2.py:121)
-        if four_d:
-            t_ci, s_ci, node_sc, p_count = ops.coarse_matching_adaptive(tgt_nf, src_nf, t_nm, s_nm,
-                                                                        int(cfg["num_est_coarse_corr"]), 0.75, Pmax)
-        else:
-            t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, t_nm, s_nm, Pmax, dual=True)
-        # 4-6. fine scoring + OT + fine matching
-        scores, flags = ops.fine_matching(tgt_pf, src_pf, t_ki, s_ki, t_km, s_km, t_ci, s_ci, p_count,
-                                          W["optimal_transport.alpha"].view(1), 100, topk,
+        occ.update(t_nn=t_nn.view(B, Nt + 1), s_nn=s_nn.view(B, Ns + 1), keep=(t_pad, s_pad_t, g_s, g_t))
+    occ_done = fork.run_one(occlusion_nn)
+
+    def on_nodes(nodes):
+        def gt(b):   # 2. partition + ground-truth bookkeeping
+            q = st[b]
+            src_pts, tgt_pts, src_nodes, tgt_nodes = src_of(b), tgt_of(b), nodes["src"][b], nodes["tgt"][b]
+            _, s_nm, s_ki, s_km = ops.point_to_node(src_pts, src_nodes, K)
+            _, t_nm, t_ki, t_km = ops.point_to_node(tgt_pts, tgt_nodes, K)
+            Ms, Mt = src_nodes.shape[0], tgt_nodes.shape[0]
+            ov, ov_flag = ops.node_overlaps(tgt_nodes, src_nodes, t_ki, s_ki, t_km, s_km, t_nm, s_nm, tgt_pts, src_pts,
+                                            rot[b], trans[b], float(cfg["matching_radius"]))
+            gt_flat, gt_count = ops.compact_flags(ov_flag, Mt * Ms)
+            gt_idx, gt_ov = ops.corr_gather(Mt * Ms, Ms, gt_flat, gt_count, ov)
+            if occ_done is not None:
+                torch.cuda.current_stream().wait_event(occ_done)
+            q.update(src_points=src_pts, tgt_points=tgt_pts, src_nodes=src_nodes, tgt_nodes=tgt_nodes, s_nm=s_nm, s_ki=s_ki,
+                     s_km=s_km, t_nm=t_nm, t_ki=t_ki, t_km=t_km, gt_idx=gt_idx, gt_ov=gt_ov, gt_count=gt_count,
+                     gt_tgt_node_occ=ops.node_occlusion(t_ki, t_km, t_nm, occ["t_nn"][b]),
+                     gt_src_node_occ=ops.node_occlusion(s_ki, s_km, s_nm, occ["s_nn"][b]))
+        fork.run(B, gt)
+
+    def on_global(per_pair, s_g_all, t_g_all):
+        # coarse_proj + L2 normalisation for every superpoint of the batch at once (RIGA_v2.py:64-65)
+        s_nf_all = ops.row_epilogue(_lin(W, "coarse_proj", s_g_all), mode=ops.MODE_L2NORM)
+        t_nf_all = ops.row_epilogue(_lin(W, "coarse_proj", t_g_all), mode=ops.MODE_L2NORM)
+
+        def coarse(b):   # 3. coarse matching   (called as (tgt, src), model/RIGA_v2.py:121)
+            q = st[b]
+            src_nf, tgt_nf = s_nf_all[b * M4s:(b + 1) * M4s], t_nf_all[b * M4t:(b + 1) * M4t]
+            if four_d:
+                t_ci, s_ci, node_sc, p_count = ops.coarse_matching_adaptive(tgt_nf, src_nf, q["t_nm"], q["s_nm"],
+                                                                            int(cfg["num_est_coarse_corr"]), 0.75, Pmax)
+            else:
+                t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, q["t_nm"], q["s_nm"], Pmax, dual=True)
+            q.update(src_node_feats=src_nf, tgt_node_feats=tgt_nf, t_ci=t_ci, s_ci=s_ci, node_sc=node_sc, p_count=p_count)
+        fork.run(B, coarse)
+
+    L, dec, per_pair = backbone_batch(W, cfg["transformer_architecture"], plan, pts, feats, nrm, src_pcd, aux,
+                                      on_nodes=on_nodes, on_global=on_global)
+    pf_all = _lin(W, "fine_proj", dec[0])                                # all points of all clouds at once
+
+    def fine(b):   # 4-6. fine scoring + OT + fine matching
+        q = st[b]
+        src_pf, tgt_pf = pf_all[b * Ns:(b + 1) * Ns], pf_all[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
+        scores, flags = ops.fine_matching(tgt_pf, src_pf, q["t_ki"], q["s_ki"], q["t_km"], q["s_km"], q["t_ci"], q["s_ci"],
+                                          q["p_count"], W["optimal_transport.alpha"].view(1), 100, topk,
                                           bool(cfg["fine_matching_mutual"]), float(cfg["fine_matching_confidence_threshold"]))
         c_flat, c_count = ops.compact_flags(flags, cap)
-        t_cp, s_cp, c_sc = ops.fine_gather(cap, c_flat, c_count, scores, t_ci, s_ci, t_ki, s_ki, tgt_pts, src_pts)
-        counts[b] = torch.cat([p_count, gt_count, c_count])
-        outs[b] = (dict(src_points=src_pts, tgt_points=tgt_pts, src_nodes=src_nodes, tgt_nodes=tgt_nodes,
-                         src_point_feats=src_pf, tgt_point_feats=tgt_pf, src_node_feats=src_nf, tgt_node_feats=tgt_nf,
-                         gt_idx=gt_idx, gt_ov=gt_ov, gt_tgt_node_occ=t_occ, gt_src_node_occ=s_occ, s_ci=s_ci, t_ci=t_ci,
-                         s_ki=s_ki, t_ki=t_ki, s_km=s_km, t_km=t_km, s_nm=s_nm, t_nm=t_nm, node_sc=node_sc,
-                         matching_scores=scores, t_cp=t_cp, s_cp=s_cp, c_sc=c_sc, c_flat=c_flat, cap=cap))
-    # The per-pair head is a chain of latency-bound, low-occupancy kernels (single-CTA top-k / scans, one CTA per patch
-    # for the Sinkhorn iterations) and pairs are independent: fork onto a few streams so several pairs' heads overlap.
-    streams = plan.side_streams(min(4, B)) if B > 1 else []
-    if not streams:
-        for b in range(B):
-            head(b)
-    else:
-        main = torch.cuda.current_stream()
-        fork = main.record_event()
-        for st in streams:
-            st.wait_event(fork)
-        for b in range(B):
-            with torch.cuda.stream(streams[b % len(streams)]):
-                head(b)
-        for st in streams:
-            main.wait_stream(st)
-    return outs, torch.stack(counts)
+        t_cp, s_cp, c_sc = ops.fine_gather(cap, c_flat, c_count, scores, q["t_ci"], q["s_ci"], q["t_ki"], q["s_ki"],
+                                           q["tgt_points"], q["src_points"])
+        q.update(src_point_feats=src_pf, tgt_point_feats=tgt_pf, matching_scores=scores, t_cp=t_cp, s_cp=s_cp, c_sc=c_sc,
+                 c_flat=c_flat, cap=cap, counts=torch.cat([q["p_count"], q["gt_count"], c_count]))
+    fork.run(B, fine)
+    fork.join()
+    return st, torch.stack([q["counts"] for q in st])
 
 
 def finalize(o, counts, Ns, Nt, aux=None):

@@ -152,6 +152,31 @@ def geo_knn(pts, k=3):
     return nn
 
 
+def geo_knn_batched(batch, N, pts, k=3):
+    nn = torch.empty(batch * N, k, dtype=torch.int32, device=pts.device)
+    _lib.call("roitr_geo_knn_batched", c_int(batch), c_int(N), c_int(k), f32(pts), i32(nn), stream_ptr())
+    return nn
+
+
+def geo_embedding_tc_batched(batch, N, pts, nn3, wpack, bd, ba, div_term, sigma_d, sigma_a):
+    C = bd.shape[0]
+    E = torch.empty(batch, N, N, C, dtype=torch.float32, device=pts.device)
+    _lib.call("roitr_geo_embedding_tc_batched", c_int(batch), c_int(N), c_int(C), f32(pts), i32(nn3), f32(wpack), f32(bd),
+              f32(ba), f32(div_term), c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
+    return E
+
+
+def geo_embedding_table(batch, N, pts, nn3, tables, Wd, bd, Wa, ba, div_term, sigma_d, sigma_a):
+    """tables = engine.build_geo_tables(...). E (batch, N, N, C)."""
+    C = bd.shape[0]
+    ta, td = tables["tab_a"], tables["tab_d"]
+    E = torch.empty(batch, N, N, C, dtype=torch.float32, device=pts.device)
+    _lib.call("roitr_geo_embedding_table", c_int(batch), c_int(N), c_int(C), f32(pts), i32(nn3), f32(ta), c_int(ta.shape[1]),
+              f32(td), c_int(td.shape[1]), c_float(tables["inv_h"]), f32(Wd), f32(bd), f32(Wa), f32(ba), f32(div_term),
+              c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
+    return E
+
+
 def geo_embedding(pts, nn3, Wd, bd, Wa, ba, div_term, sigma_d, sigma_a, out=None):
     N, C = pts.shape[0], Wd.shape[0]
     E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device) if out is None else out
@@ -187,6 +212,45 @@ def geo_attention_batched(batch, N, M, q, k, v, C, E=None, gq=None, bp=None):
     _lib.call("roitr_geo_attention_batched", c_int(batch), c_int(N), c_int(M), c_int(C), c_int(4), c_void(q),
               c_int(q.stride(0)), c_ll(N * q.stride(0)), c_void(k), c_int(k.stride(0)), c_ll(M * k.stride(0)), c_void(v),
               c_int(v.stride(0)), c_ll(M * v.stride(0)), f32(E), f32(gq), f32(bp), f32(hidden), f32(G), stream_ptr())
+    return (hidden, G) if E is not None else hidden
+
+
+def geo_attention_batched_compat(batch, N, M, C, q, k, v, heads=4, E=None, gq=None, bp=None):
+    """First-generation SIMT attention core with the argument order of attention_tc."""
+    return geo_attention_batched(batch, N, M, q, k, v, C, E=E, gq=gq, bp=bp)
+
+
+def gemm_tc_batched(outer, inner, M, N, K, A, lda, sA, W, ldw, sW, C, ldc, sC, w_transposed=False):
+    """C_oi = A_oi W_oi^T on tcgen05 for outer x inner operand triples; sX = (outer stride, inner stride) in elements.
+    A / W / C may be views (pointers + explicit leading dimensions)."""
+    _lib.call("roitr_gemm_tc_batched", c_int(outer), c_int(inner), c_int(M), c_int(N), c_int(K), c_void(A), c_int(lda),
+              c_ll(sA[0]), c_ll(sA[1]), c_void(W), c_int(ldw), c_ll(sW[0]), c_ll(sW[1]), c_int(1 if w_transposed else 0),
+              c_void(C), c_int(ldc), c_ll(sC[0]), c_ll(sC[1]), stream_ptr())
+    return C
+
+
+def attention_tc(batch, N, M, C, q, k, v, heads=4, E=None, gq=None, bp=None):
+    """Attention core with Q K^T and P V on the tensor cores. q: rows of `batch` clouds of N queries (views with explicit
+    leading dimension), k / v: `batch` clouds of M keys. E (batch,N,N,C), gq (batch*N,heads,C), bp (C) select the RPE
+    self-attention. Returns hidden (batch*N, C) [, G (batch*N, heads, C)]."""
+    dev = q.device
+    c = C // heads
+    ldq, ldk, ldv = q.stride(0), k.stride(0), v.stride(0)
+    qk = torch.empty(batch, heads, N, M, dtype=torch.float32, device=dev)
+    gemm_tc_batched(batch, heads, N, M, c, q, ldq, (N * ldq, c), k, ldk, (M * ldk, c), qk, M, (heads * N * M, N * M))
+    G = None
+    if E is not None:
+        P = torch.empty_like(qk)
+        G = torch.empty(batch * N, heads, C, dtype=torch.float32, device=dev)
+        _lib.call("roitr_geo_self_scores", c_int(batch), c_int(N), c_int(C), c_int(heads), f32(qk), c_void(q), c_int(ldq),
+                  c_ll(N * ldq), f32(E), f32(gq), f32(bp), f32(P), f32(G), stream_ptr())
+    else:
+        P = qk
+        _lib.call("roitr_softmax_rows", c_ll(batch * heads * N), c_int(M), f32(qk), c_float(float(c) ** 0.5), f32(P),
+                  stream_ptr())
+    hidden = torch.empty(batch * N, C, dtype=torch.float32, device=dev)
+    gemm_tc_batched(batch, heads, N, c, M, P, M, (heads * N * M, N * M), v, ldv, (M * ldv, c), hidden, C, (N * C, c),
+                    w_transposed=True)
     return (hidden, G) if E is not None else hidden
 
 
@@ -278,6 +342,13 @@ def pad_transform(pts, rot=None, trans=None):
     N = pts.shape[0]
     out = torch.empty(N + 1, 3, dtype=torch.float32, device=pts.device)
     _lib.call("roitr_pad_transform", c_int(N), f32(pts), f32(rot), f32(trans), f32(out), stream_ptr())
+    return out
+
+
+def pad_transform_batched(B, N, pts, rot=None, trans=None):
+    """pts (B*N,3), rot (B,3,3), trans (B,3,1) -> (B*(N+1),3): every cloud followed by its (transformed) zero pad row."""
+    out = torch.empty(B * (N + 1), 3, dtype=torch.float32, device=pts.device)
+    _lib.call("roitr_pad_transform_batched", c_int(B), c_int(N), f32(pts), f32(rot), f32(trans), f32(out), stream_ptr())
     return out
 
 

@@ -107,3 +107,75 @@ def test_linear_tc_packed_strided_gather_add():
     ref = (a[idx.long()] + a2[idx.long()]).double() @ w.double().t()
     assert (out[:, 512:768].double() - ref).abs().max().item() <= 6e-6 * ref.abs().max().item()
     assert out[:, :512].abs().max().item() == 0 and out[:, 768:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("N,scale", [(16, 3.0), (64, 3.0), (312, 3.0), (97, 40.0), (64, 400.0)])
+def test_geo_embedding_table_matches_oracle_and_tensor_core(N, scale):
+    """Tabulated embedding (csrc/geo_table.cu): shared-memory tables (scale 3 m), the global-table path (distances up to
+    ~70 m at scale 40) and the direct evaluation beyond every table (scale 400), against the oracle and the GEMM kernel."""
+    from oracle import forward_ref as fr
+    from roitr_b200 import engine
+    from tests.helpers import weights
+    sd = weights(1)
+    e = "backbone.global_transformer.embedding"
+    g = torch.Generator().manual_seed(N)
+    B = 3
+    pts = (torch.rand(B * N, 3, generator=g) - 0.5) * scale
+    W = {k: sd[k].to(DEV) for k in sd if k.startswith(e)}
+    tables = engine.build_geo_tables(W[e + ".proj_d.weight"], W[e + ".proj_d.bias"], W[e + ".proj_a.weight"],
+                                     W[e + ".proj_a.bias"], W[e + ".embedding.div_term"])
+    assert tables["bound"] <= engine.GEO_TABLE_TOL
+    wpack = torch.stack([engine.pack_tf32_sw128(W[e + ".proj_d.weight"]), engine.pack_tf32_sw128(W[e + ".proj_a.weight"])], 0).contiguous()
+    p = pts.to(DEV)
+    nn3 = ops.geo_knn_batched(B, N, p, 3)
+    a = ops.geo_embedding_table(B, N, p, nn3, tables, W[e + ".proj_d.weight"], W[e + ".proj_d.bias"], W[e + ".proj_a.weight"],
+                                W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], 0.2, 15.0)
+    b = ops.geo_embedding_tc_batched(B, N, p, nn3, wpack, W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
+                                     W[e + ".embedding.div_term"], 0.2, 15.0)
+    torch.cuda.synchronize()
+    off = ~torch.eye(N, dtype=torch.bool)
+    # the fp32 evaluations (oracle, GEMM kernel) round the sinusoid argument t * div_term: their own error grows with t
+    tol = 2e-5 * max(1.0, scale / 3.0)
+    for c in range(B):
+        ref = fr.geometric_embedding(sd, e, pts[None, c * N:(c + 1) * N])[0]
+        assert (a[c].cpu() - ref)[off].abs().max().item() < tol
+        assert (a[c] - b[c]).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("N,M,C", [(312, 312, 256), (16, 16, 256), (15, 15, 256), (125, 125, 512), (40, 57, 256)])
+def test_attention_tensor_core_matches_first_generation(N, M, C):
+    """Q K^T / P V on tcgen05 + the streaming E pass (csrc/geo_attn2.cu) against the one-kernel SIMT attention core
+    (csrc/geo.cu) and an fp64 evaluation of geoattention.py:43-66,101-136."""
+    g = torch.Generator().manual_seed(N * 1000 + M)
+    B, H = 3, 4
+    c = C // H
+    qkv = torch.randn(B * N, 3 * C, generator=g).to(DEV)
+    kv = torch.randn(B * M, 2 * C, generator=g).to(DEV)
+    # cross attention (no E): q from one set of clouds, k / v from another
+    q, k, v = qkv[:, :C], kv[:, :C], kv[:, C:]
+    h_new = ops.attention_tc(B, N, M, C, q, k, v)
+    h_old = ops.geo_attention_batched(B, N, M, q, k, v, C)
+    q64, k64, v64 = (t.double().view(B, -1, H, c).permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = (torch.softmax(q64 @ k64.transpose(-1, -2) / c ** 0.5, -1) @ v64).permute(0, 2, 1, 3).reshape(B * N, C)
+    assert (h_new.double() - ref).abs().max().item() < 2e-5
+    assert (h_old.double() - ref).abs().max().item() < 2e-5
+    if N != M:
+        return
+    # RPE self attention
+    E = torch.randn(B, N, N, C, generator=g).to(DEV) * 0.5
+    gq = torch.randn(B * N, H, C, generator=g).to(DEV) * 0.1
+    bp = torch.randn(C, generator=g).to(DEV) * 0.1
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    h_new, G_new = ops.attention_tc(B, N, N, C, q, k, v, E=E, gq=gq, bp=bp)
+    h_old, G_old = ops.geo_attention_batched(B, N, N, q, k, v, C, E=E, gq=gq, bp=bp)
+    q64, k64, v64 = (t.double().view(B, N, H, c).permute(0, 2, 1, 3) for t in (q, k, v))
+    sp = torch.einsum("bnhc,bnmc->bhnm", gq.double().view(B, N, H, C), E.double())
+    qb = (q.double().view(B, N, H, c) * bp.double().view(1, 1, H, c)).sum(-1).permute(0, 2, 1)[..., None]
+    S = (q64 @ k64.transpose(-1, -2) + sp + qb) / c ** 0.5
+    ref_h = (torch.softmax(S, -1) @ v64).permute(0, 2, 1, 3).reshape(B * N, C)
+    Sm = S.masked_fill(torch.eye(N, dtype=torch.bool, device=DEV)[None, None], float("-inf"))
+    ref_G = torch.einsum("bhnm,bnmc->bnhc", torch.softmax(Sm, -1), E.double()).reshape(B * N, H, C)
+    assert (h_new.double() - ref_h).abs().max().item() < 3e-5
+    assert (G_new.double() - ref_G).abs().max().item() < 3e-5
+    assert (h_old.double() - ref_h).abs().max().item() < 3e-5
+    assert (G_old.double() - ref_G).abs().max().item() < 3e-5

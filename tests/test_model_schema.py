@@ -48,3 +48,31 @@ def test_no_cpu_fallback():
         m(x, x, torch.ones(64, 1), torch.ones(64, 1), x, x, torch.eye(3), torch.zeros(3, 1), x)
     with pytest.raises(RuntimeError):
         model.create_model(CONFIG_3D).train()(x, x, x, x, x, x, x, x, x)
+
+
+def test_geo_table_interpolation_bound_cpu():
+    """Host logic of the tabulated geometric embedding: the table step chosen by engine.build_geo_tables keeps the 4-point
+    Lagrange interpolation within its bound of the fp64 truth (emulating the kernel's fp32 arithmetic in numpy)."""
+    import numpy as np
+    import torch
+    from roitr_b200 import engine
+    from tests.helpers import weights
+    sd = weights(1)
+    e = "backbone.global_transformer.embedding"
+    Wd, bd, Wa, ba, dv = [sd[e + k] for k in (".proj_d.weight", ".proj_d.bias", ".proj_a.weight", ".proj_a.bias",
+                                               ".embedding.div_term")]
+    T = engine.build_geo_tables(Wd, bd, Wa, ba, dv)
+    assert T["bound"] <= engine.GEO_TABLE_TOL and T["inv_h"] == 2.0 ** round(np.log2(T["inv_h"]))
+    rng = np.random.default_rng(0)
+    for tab, Wm, b, tmax in ((T["tab_d"], Wd, bd, 200.0), (T["tab_a"], Wa, ba, 12.0)):
+        G, R, _ = tab.shape
+        full = tab.permute(1, 0, 2).reshape(R, -1).numpy()
+        t = rng.uniform(0, tmax, 4000).astype(np.float32)
+        x = t * np.float32(T["inv_h"]); fl = np.floor(x); u = (x - fl).astype(np.float32); i = fl.astype(np.int64)
+        w = [np.float32(-1 / 6) * u * (u - 1) * (u - 2), np.float32(.5) * (u + 1) * (u - 1) * (u - 2),
+             np.float32(-.5) * (u + 1) * u * (u - 2), np.float32(1 / 6) * (u + 1) * u * (u - 1)]
+        got = sum(w[k][:, None] * full[i + k] for k in range(4))
+        om = torch.tensor(t, dtype=torch.float64)[:, None] * dv.double()[None, :]
+        emb = torch.stack([torch.sin(om), torch.cos(om)], 2).reshape(len(t), -1)
+        truth = (emb @ Wm.double().t() + b.double()).numpy()
+        assert np.abs(got - truth).max() < 1e-6
