@@ -130,35 +130,47 @@ def run_reference(args):
 
 def op_work(name, ints):
     """Algorithmic work of one entry-point call from its leading integer arguments (DESIGN.md §4 / SURVEY.md §8d).
-    -> (kind, amount): kind 'bytes' (compulsory bytes) or 'flop'."""
+    -> (bytes, flop, bound): compulsory bytes, fp32-equivalent flops, and the roofline that bounds the kernel."""
     if name in ("roitr_linear", "roitr_linear_tc", "roitr_linear_tc_packed"):
-        M, N, K = ints[:3]
-        return "flop", 2.0 * M * N * K
+        M, N, K = ints[:3]     # skinny dense layers over tall activations: activations in + out (+ weights once)
+        return 4.0 * (M * K + M * N + N * K), 2.0 * M * N * K, "hbm"
+    if name == "roitr_gemm_tc_batched":
+        bo, bi, M, N, K = ints[:5]     # global attention Q K^T / P V tiles
+        return 4.0 * bo * bi * (M * K + N * K + M * N), 2.0 * bo * bi * M * N * K, "tensor"
     if name in ("roitr_geo_embedding", "roitr_geo_embedding_tc"):
         N, C = ints[:2]
-        return "flop", 8.0 * N * N * C * C
+        return 4.0 * N * N * C, 8.0 * N * N * C * C, "tensor"
     if name == "roitr_geo_embedding_tc_batched":
         b, N, C = ints[:3]
-        return "flop", b * 8.0 * N * N * C * C
+        return 4.0 * b * N * N * C, b * 8.0 * N * N * C * C, "tensor"
+    if name == "roitr_geo_embedding_table":
+        b, N, C = ints[:3]             # writes E once; the table itself stays in shared memory
+        return 4.0 * b * N * N * C, 0.0, "hbm"
+    if name == "roitr_geo_self_scores":
+        b, N, C = ints[:3]             # one streaming pass over E
+        return 4.0 * b * N * N * C, 4.0 * b * N * N * C, "hbm"
     if name == "roitr_furthestsampling_cfg":
         b, _, nseg = ints[:3]
-        return "bytes", b * (nseg * 12.0 + (nseg // 4) * 16.0)
+        return b * (nseg * 12.0 + (nseg // 4) * 16.0), 0.0, "hbm"
     if name in ("roitr_knn_ppf_n", "roitr_knn_ppf_grid"):
         b, m, k, drop, n = ints[:5]
-        return "bytes", n * 24.0 + m * 24.0 + m * k * 20.0
+        return n * 24.0 + m * 24.0 + m * k * 20.0, 0.0, "hbm"
     if name == "roitr_local_attention":
         m, C, _, knb = ints[:4]
-        return "bytes", m * (2.0 * knb * C * 4 + 2 * C * 4)
+        return m * (2.0 * knb * C * 4 + 2 * C * 4), 0.0, "hbm"
+    if name == "roitr_row_epilogue":
+        M, C = ints[:2]
+        return 4.0 * 3 * M * C, 0.0, "hbm"
     if name == "roitr_geo_attention":
         N, M, C = ints[:3]
-        return "bytes", 2.0 * N * M * C * 4 + 4.0 * N * C * 4
+        return 2.0 * N * M * C * 4 + 4.0 * N * C * 4, 0.0, "hbm"
     if name == "roitr_geo_attention_batched":
         b, N, M, C = ints[:4]
-        return "bytes", b * (2.0 * N * M * C * 4 + 4.0 * N * C * 4)
+        return b * (2.0 * N * M * C * 4 + 4.0 * N * C * 4), 0.0, "hbm"
     if name == "roitr_fine_matching":
         P, _, _, C = ints[:4]
-        return "bytes", P * (2.0 * 64 * C * 4 + 65 * 65 * 4)
-    return "bytes", 0.0
+        return P * (2.0 * 64 * C * 4 + 65 * 65 * 4), 0.0, "hbm"
+    return 0.0, 0.0, "hbm"
 
 
 def main():
@@ -242,7 +254,8 @@ def main():
     ms_e2e, _, d2h_bytes, ncorr = run_loop(True, steps)
 
     # instrumented EAGER replica of the same step: per-entry-point CUDA-event durations, launch count, algorithmic work
-    eager = m.batch_runner(B, N_POINTS, N_POINTS, graph=False)
+    # (serial=True: no side streams, so every call's event pair brackets that call alone)
+    eager = m.batch_runner(B, N_POINTS, N_POINTS, graph=False, serial=True)
     eager.load(resident[0]); eager.run(); torch.cuda.synchronize()
     _lib.TIMED.clear()
     for k in _lib.KERNELS_PER_CALL:
@@ -262,11 +275,11 @@ def main():
         if not evs:
             continue
         ms = sum(a.elapsed_time(b) for a, b in evs)
-        work = {"bytes": 0.0, "flop": 0.0}
+        work = {"bytes": 0.0, "flop": 0.0, "bound": "hbm"}
         for ints in _lib.ARGS.get(name, []):
-            kind, amt = op_work(name, ints)
-            work[kind] += amt
-        shares[name] = {"ms": ms, "calls": len(evs), "bytes": work["bytes"], "flop": work["flop"]}
+            nb, nf, bound = op_work(name, ints)
+            work["bytes"] += nb; work["flop"] += nf; work["bound"] = bound
+        shares[name] = {"ms": ms, "calls": len(evs), "bytes": work["bytes"], "flop": work["flop"], "bound": work["bound"]}
     _lib.TIMED.clear()
     _lib.RECORD_ARGS = False
     eager_ms = sum(v["ms"] for v in shares.values())
@@ -283,18 +296,34 @@ def main():
         src = "measured" if peaks.get("hbm_gbs") else "fallback"
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         tf_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        tf32_peak = tf_peak / 2.0     # dense TF32 is half the dense bf16 rate; the 3xTF32 kernels issue 3 MMAs per product
+
+        def roofline_of(names):
+            ms = sum(shares[n]["ms"] for n in names if n in shares)
+            nb = sum(shares[n]["bytes"] for n in names if n in shares)
+            nf = sum(shares[n]["flop"] for n in names if n in shares)
+            calls = sum(shares[n]["calls"] for n in names if n in shares)
+            bound = shares[names[0]]["bound"] if names[0] in shares else "hbm"
+            if not ms:
+                return None
+            if bound == "tensor":
+                ach = nf / (ms * 1e-3) / 1e12
+                r = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                     "tensor_pipe_frac_3xtf32": 3.0 * ach / tf32_peak}
+            else:
+                ach = nb / (ms * 1e-3) / 1e9
+                r = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
+            r.update({"kernel": "+".join(names), "traffic": None, "peak_source": src, "avg_launch_ms": ms / max(1, calls),
+                      "launches_timed": calls, "share_of_step": ms / eager_ms if eager_ms else None})
+            return r
         top = max(shares, key=lambda k: shares[k]["ms"])
-        tv = shares[top]
-        if tv["flop"] > 0:
-            ach = tv["flop"] / (tv["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak}
-        else:
-            ach = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
-        roof.update({"kernel": top, "traffic": None, "peak_source": src, "avg_launch_ms": tv["ms"] / tv["calls"],
-                     "launches_timed": tv["calls"], "share_of_step": tv["ms"] / eager_ms if eager_ms else None,
-                     "how": "CUDA events around every entry-point call in an eager replica of the timed step (the timed "
-                            "step itself is one CUDA graph); algorithmic work per DESIGN.md §4 / SURVEY.md §8d"})
+        roof = roofline_of([top])
+        roof["how"] = ("CUDA events around every entry-point call in a single-stream eager replica of the timed step (the timed "
+                       "step itself is one multi-stream CUDA graph); algorithmic work per DESIGN.md §4 / SURVEY.md §8d")
+        named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build"]),
+                 "global_attention_qk_pv": roofline_of(["roitr_gemm_tc_batched"]),
+                 "dense_layers": roofline_of(["roitr_linear_tc_packed"]),
+                 "fine_matching": roofline_of(["roitr_fine_matching"])}
         line = {
             "metric": METRIC, "value": world * B * steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",
@@ -305,6 +334,7 @@ def main():
             "e2e": {"value": world * B * steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches_per_step * steps, "clocks": clk.summary(), "roofline": roof,
+            "north_star_rooflines": named, "serial_replica_ms": round(eager_ms, 3),
             "kernel_shares_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])},
             "result_check": {"correspondences_per_pair": total_corr / (world * B), "e2e_correspondences_last_step": ncorr},
             "wall_s_between_barriers": wall,

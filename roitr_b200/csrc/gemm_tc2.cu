@@ -45,7 +45,50 @@ struct Tc2Params {
     const float* bias;
     float* C; int ldc; int relu;
     int tiles_m, tiles_n, nkc;
+    int ablate;             // debug only (roitr_debug_linear_ablate): 1 no C stores, 2 W fetched once, 4 no MMA, 8 no split, 16 no A loads
 };
+
+// Epilogue of one 32x32 accumulator block held as "thread = row, v[j] = column j" (the tcgen05.ld 32x32b layout): bias,
+// ReLU and the global store. The block is transposed through a per-warp shared-memory pad (row stride 36 floats: the
+// 16-byte writes of 8 consecutive rows and the 16-byte reads of one row both touch all 32 banks once) so that 8 lanes
+// write one 128-byte row segment with float4 stores: 8 store instructions per block, each covering 4 full lines.
+constexpr int PAD_STRIDE = 36;
+__device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, const float (&v)[32], int lane, int row0, int ncol0) {
+    const bool vec = (P.ldc % 4 == 0) && (P.N % 4 == 0) && ((uintptr_t)P.C % 16 == 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(pad + lane * PAD_STRIDE + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    if (vec) {
+        const int sub = lane >> 3, n = ncol0 + 4 * (lane & 7);
+        if (n < P.N && !(P.ablate & 1)) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (P.bias) b = __ldg(reinterpret_cast<const float4*>(P.bias + n));
+            float* dst = P.C + (long long)(row0 + sub) * P.ldc + n;
+            const long long step = 4ll * P.ldc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 x = *reinterpret_cast<const float4*>(pad + (4 * i + sub) * PAD_STRIDE + 4 * (lane & 7));
+                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+                if (P.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                if (row0 + 4 * i + sub < P.M) *reinterpret_cast<float4*>(dst + i * step) = x;
+            }
+        }
+    } else {
+        const int n = ncol0 + lane;
+        if (n < P.N && !(P.ablate & 1)) {
+            const float bv = P.bias ? __ldg(P.bias + n) : 0.f;
+            for (int i = 0; i < 32; ++i) {
+                if (row0 + i >= P.M) break;
+                float x = pad[i * PAD_STRIDE + lane] + bv;
+                if (P.relu) x = fmaxf(x, 0.f);
+                P.C[(long long)(row0 + i) * P.ldc + n] = x;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Params P) {
@@ -55,7 +98,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Para
     constexpr int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_pad[4][32 * 33];
+    __shared__ __align__(16) float s_pad[4][32 * PAD_STRIDE];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -205,7 +248,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Para
         // tcgen05.ld gives thread `lane` the 32 consecutive columns of ITS row; written directly that is 32 scattered
         // 16-byte pieces per store instruction (32 LSU wavefronts). Each warp instead transposes the 32x32 block through
         // its private shared-memory pad so that one store instruction writes 128 contiguous bytes of one row.
-        float* pad = s_pad[warp];                                   // [32][33]
+        float* pad = s_pad[warp];
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const int tm = tile / P.tiles_n, tn = tile % P.tiles_n;
@@ -217,25 +260,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Para
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (n0 + c0 >= P.N) break;
-                const int n = n0 + c0 + lane;
-                const float bv = (P.bias && n < P.N) ? __ldg(P.bias + n) : 0.f;   // one coalesced load per group
                 float v[32];
                 tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pad[lane * 33 + i] = v[i];
-                __syncwarp();
-                if (n < P.N) {
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        const int row = row0 + i;
-                        if (row < P.M) {
-                            float x = pad[i * 33 + lane] + bv;
-                            if (P.relu) x = fmaxf(x, 0.f);
-                            P.C[(long long)row * P.ldc + n] = x;
-                        }
-                    }
-                }
-                __syncwarp();
+                store_block32(P, pad, v, lane, row0, n0 + c0);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
@@ -244,6 +271,180 @@ __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Para
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 2 * BN);
+}
+
+// ---- streaming variant ------------------------------------------------------------------------------------------------
+// Same roles, but the activation loads are decoupled from the tensor core: raw fp32 chunks land in a RAW-deep ring with
+// cp.async (16 KB each; every thread copies and later splits ONLY its own 16-byte pieces, so the ring needs no barrier and
+// its look-ahead never waits for an MMA), and a separate OPS-deep ring holds the split hi/lo operands. The split of chunk
+// i therefore overlaps the MMAs of chunk i-1 and the HBM latency of chunks i+1 .. i+RAW-1. Pieces are mapped so that 8
+// consecutive lanes cover one 128-byte row segment (4 full lines per warp instruction) and 8 warps share the split pass.
+constexpr int T3_LOADERS = 256;
+constexpr int T3_THREADS = 128 + T3_LOADERS + 64;
+constexpr int RAW_BYTES = T2_BM * 128;
+
+template <int BN, int OPS, int RAW>
+__global__ void __launch_bounds__(T3_THREADS, 1) linear_tc3_kernel(const Tc2Params P) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int B_HALF = BN * 128;
+    constexpr int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
+    __shared__ __align__(8) uint64_t full_bar[OPS], empty_bar[OPS], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float s_pad[4][32 * PAD_STRIDE];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < OPS; ++i) { mbar_init(&full_bar[i], T3_LOADERS + 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int total_tiles = P.tiles_m * P.tiles_n;
+    const int nkc = P.nkc;
+    constexpr int W_LOADER0 = 4, W_PRODUCER = 4 + T3_LOADERS / 32, W_MMA = W_PRODUCER + 1;
+
+    if (warp >= W_LOADER0 && warp < W_PRODUCER) {
+        // ================================================= A loaders =================================================
+        const int t = tid - 128;
+        const int c = t & 7, r0 = t >> 3;                               // pieces (r0 + 32 j, c), j = 0..3
+        unsigned char* raw = smem + OPS * STAGE_BYTES;
+        const uint32_t raw_u32 = smem_u32(raw);
+        int i_tile = blockIdx.x, i_kc = 0;
+        uint32_t i_it = 0;
+        auto issue_one = [&]() {
+            if (i_tile < total_tiles) {
+                const uint32_t dst = raw_u32 + (i_it % RAW) * RAW_BYTES + (uint32_t)(r0 * 128 + c * 16);
+                const int k = i_kc * T2_BK + 4 * c;
+                const int am0 = (i_tile / P.tiles_n) * T2_BM + r0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int am = am0 + 32 * j;
+                    const bool ok = am < P.M && k < P.K;
+                    if (!(P.ablate & 16)) cp_async16(dst + j * 32 * 128, P.A + (ok ? (long long)am * P.lda + k : 0ll), ok ? 16u : 0u);
+                }
+                ++i_it;
+                if (++i_kc == nkc) { i_kc = 0; i_tile += gridDim.x; }
+            }
+            cp_async_commit();                                          // always commit: keeps the group count uniform
+        };
+#pragma unroll
+        for (int j = 0; j < RAW - 1; ++j) issue_one();
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int kc = 0; kc < nkc; ++kc, ++it) {
+                issue_one();                                            // refills the slot this thread drained last iteration
+                cp_async_wait<RAW - 1>();                               // this thread's pieces of chunk `it` have landed
+                const unsigned char* src = raw + (it % RAW) * RAW_BYTES + r0 * 128 + c * 16;
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * 32 * 128);
+                const int st = it % OPS;
+                mbar_wait(&empty_bar[st], ((it / OPS) & 1) ^ 1);        // MMAs of chunk it - OPS have retired
+                unsigned char* a_hi = smem + st * STAGE_BYTES;
+                if (!(P.ablate & 8)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) split_store(a_hi, a_hi + A_HALF, r0 + 32 * j, c, v[j]);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&full_bar[st]);
+            }
+        }
+        cp_async_wait<0>();
+    } else if (warp == W_PRODUCER) {
+        // ================================================= W producer ================================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tn = tile % P.tiles_n;
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int st = it % OPS;
+                    mbar_wait(&empty_bar[st], ((it / OPS) & 1) ^ 1);
+                    if ((P.ablate & 2) && it >= OPS) { mbar_arrive(&full_bar[st]); continue; }
+                    mbar_expect_tx(&full_bar[st], 2 * B_HALF);
+                    tma_load_1d(smem + st * STAGE_BYTES + 2 * A_HALF, P.wpack + ((size_t)tn * nkc + kc) * (2 * B_HALF / 4),
+                                2 * B_HALF, &full_bar[st]);
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ================================================= MMA issuer ================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(T2_BM, BN);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const int acc = tcount & 1;
+                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem + (uint32_t)(acc * BN);
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const int st = it % OPS;
+                    mbar_wait(&full_bar[st], (it / OPS) & 1);
+                    tc_fence_after();
+                    const uint32_t ah = smem_u32(smem + st * STAGE_BYTES), al = ah + A_HALF, bh = ah + 2 * A_HALF, bl = bh + B_HALF;
+                    if (!(P.ablate & 4)) {
+#pragma unroll
+                        for (int ks = 0; ks < T2_BK / 8; ++ks) {
+                            const uint64_t dah = make_desc_sw128(ah + ks * 32), dal = make_desc_sw128(al + ks * 32);
+                            const uint64_t dbh = make_desc_sw128(bh + ks * 32), dbl = make_desc_sw128(bl + ks * 32);
+                            umma_tf32(d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                            umma_tf32(d, dah, dbl, idesc, 1u);
+                            umma_tf32(d, dah, dbh, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[st]);
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else if (warp < 4) {
+        // ================================================= epilogue (warps 0-3) ======================================
+        float* pad = s_pad[warp];
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int tm = tile / P.tiles_n, tn = tile % P.tiles_n;
+            const int acc = tcount & 1;
+            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            tc_fence_after();
+            const int row0 = tm * T2_BM + warp * 32;
+            const int n0 = tn * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= P.N) break;
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                store_block32(P, pad, v, lane, row0, n0 + c0);
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 2 * BN);
+}
+
+template <int BN, int OPS, int RAW>
+int launch_tc3(const Tc2Params& P, cudaStream_t st) {
+    constexpr int smem = OPS * (2 * A_HALF + 2 * BN * 128) + RAW * RAW_BYTES + 1024;
+    static bool attr = false;
+    static int num_sms = 0;
+    if (!attr) {
+        ROITR_CUDA(cudaFuncSetAttribute(linear_tc3_kernel<BN, OPS, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int dev = 0;
+        ROITR_CUDA(cudaGetDevice(&dev));
+        ROITR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr = true;
+    }
+    const int total = P.tiles_m * P.tiles_n;
+    const int grid = total < num_sms ? total : num_sms;
+    linear_tc3_kernel<BN, OPS, RAW><<<grid, T3_THREADS, smem, st>>>(P);
+    ROITR_CHECK_LAUNCH("linear_tc3_kernel");
+    return ROITR_OK;
 }
 
 template <int BN, int STAGES>
@@ -267,6 +468,13 @@ int launch_tc2(const Tc2Params& P, cudaStream_t st) {
 
 }  // namespace
 
+static int g_ablate = 0;
+extern "C" int roitr_debug_linear_ablate(int mask) { g_ablate = mask; return 0; }
+static int g_tc3_variant = 0;  // debug only: ring depths of the 64-column streaming kernel (0: 3 operand / 3 raw, 1: 2/4, 2: 2/5)
+extern "C" int roitr_debug_linear_variant(int v) { g_tc3_variant = v; return 0; }
+static int g_force_tc2 = 0;   // debug only: route everything through the coupled-ring kernel (A/B timing)
+extern "C" int roitr_debug_force_linear_tc2(int on) { g_force_tc2 = on; return 0; }
+
 extern "C" int roitr_linear_tc_packed(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
                                       const float* wpack, int bn, const float* bias, float* C, int ldc, int relu,
                                       void* stream) {
@@ -277,9 +485,16 @@ extern "C" int roitr_linear_tc_packed(int M, int N, int K, const float* A, const
     if (M == 0) return ROITR_OK;
     Tc2Params P;
     P.M = M; P.N = N; P.K = K; P.A = A; P.A2 = a_add; P.lda = lda; P.a_index = a_index; P.wpack = wpack; P.bias = bias; P.C = C;
-    P.ldc = ldc; P.relu = relu;
+    P.ldc = ldc; P.relu = relu; P.ablate = g_ablate;
     P.tiles_m = ceil_div(M, T2_BM); P.tiles_n = ceil_div(N, bn); P.nkc = ceil_div(K, T2_BK);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool stream_ok = !a_add && !a_index && lda % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0;
+    if (stream_ok && !g_force_tc2) {
+        if (bn == 128) return launch_tc3<128, 2, 4>(P, st);
+        if (g_tc3_variant == 1) return launch_tc3<64, 2, 4>(P, st);
+        if (g_tc3_variant == 2) return launch_tc3<64, 2, 5>(P, st);
+        return launch_tc3<64, 3, 3>(P, st);
+    }
     if (bn == 64) return launch_tc2<64, 4>(P, st);
     return launch_tc2<128, 3>(P, st);
 }

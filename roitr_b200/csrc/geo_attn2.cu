@@ -27,7 +27,7 @@ namespace {
 
 constexpr int GA_THREADS = 256;
 constexpr int GA_H = 4;
-constexpr int GA_CHUNK_BYTES = 48 * 1024;
+constexpr int GA_CHUNK_BYTES = 32 * 1024;    // x 2 stages + scores: 3 CTAs (24 warps) per SM at C = 256
 
 struct SelfParams {
     const float* qk;       // (batch, H, N, M) raw q.k
@@ -62,7 +62,7 @@ __device__ __forceinline__ float reduce4_to_head(float a0, float a1, float a2, f
 }
 
 template <int C>
-__global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_kernel(const SelfParams P) {
+__global__ void __launch_bounds__(GA_THREADS, (C <= 256 ? 3 : 2)) geo_self_scores_kernel(const SelfParams P) {
     constexpr int CPL = C / 32;            // channels per lane in phase A
     constexpr int CPT = C / GA_THREADS;    // channels per thread in phase C
     constexpr int H = GA_H;

@@ -32,7 +32,7 @@
 
 namespace {
 
-constexpr int GTB_THREADS = 256;
+constexpr int GTB_THREADS = 1024;        // 32 independent warps: the pair loop is latency-bound (shuffle -> LDS -> FMA chains)
 constexpr int GTB_GROUP = 64;            // channels per group
 constexpr int GTB_ROW_BYTES = GTB_GROUP * 4;
 
@@ -128,14 +128,14 @@ __global__ void __launch_bounds__(GTB_THREADS, 1) geo_embedding_table_kernel(con
     mbar_wait(&bar, 0);
 
     const long long npairs = (long long)N * N;
-    const long long blocks_per_cloud = (npairs + 255) / 256;               // a work item = 256 pairs (32 per warp)
+    const long long blocks_per_cloud = (npairs + GTB_THREADS - 1) / GTB_THREADS;   // a work item = 32 pairs per warp
     const long long items = blocks_per_cloud * P.batch;
     const int ch = group * GTB_GROUP + 2 * lane;
     const int rows_a = P.rows_a, rows_ds = P.rows_d_smem, rows_d = P.rows_d;
 
     for (long long item = slot; item < items; item += P.ctas_per_group) {
         const int cloud = (int)(item / blocks_per_cloud);
-        const long long p0 = (item % blocks_per_cloud) * 256 + warp * 32;
+        const long long p0 = (item % blocks_per_cloud) * GTB_THREADS + warp * 32;
         const float* pts = P.pts + (size_t)cloud * N * 3;
         const int* nn3 = P.nn3 + (size_t)cloud * N * 3;
         float* E = P.E + (size_t)cloud * npairs * C;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(GTB_THREADS, 1) geo_embedding_table_kernel(con
             cu[k] = x - fl;                                                // exact (Sterbenz / same binade)
             ci[k] = (x < 2.0e9f) ? (int)fl : 0x7fffffff;
         }
-        const int npw = (int)min((long long)32, npairs - p0);
+        const int npw = (int)max((long long)0, min((long long)32, npairs - p0));
         for (int p = 0; p < npw; ++p) {
             float2 acc[4];
 #pragma unroll
@@ -225,7 +225,7 @@ extern "C" int roitr_geo_embedding_table(int batch, int N, int C, const float* p
         ROITR_CUDA(cudaFuncSetAttribute(geo_embedding_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     }
     const int groups = C / GTB_GROUP;
-    const long long items = (((long long)N * N + 255) / 256) * batch;
+    const long long items = (((long long)N * N + GTB_THREADS - 1) / GTB_THREADS) * batch;
     long long per = num_sms / groups;
     if (per < 1) per = 1;
     if (per > items) per = items;

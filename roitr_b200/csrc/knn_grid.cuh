@@ -16,7 +16,7 @@ namespace knngrid {
 
 constexpr int MAX_DIM = 40;                       // cells per axis (<= 64000 cells per segment)
 constexpr int MAX_CELLS = MAX_DIM * MAX_DIM * MAX_DIM;
-constexpr float TARGET_PER_CELL = 2.0f;           // average occupancy over the bounding box (clustered data: far more in dense cells)
+// target_per_cell (kernel argument): average occupancy over the bounding box; clustered data has far more in dense cells
 
 struct SegHeader {                                // one per segment (cloud)
     float ox, oy, oz, h, inv_h;
@@ -27,7 +27,7 @@ struct SegHeader {                                // one per segment (cloud)
 
 // ---- build ----------------------------------------------------------------------------------------------------------
 __global__ void grid_header_kernel(int b, const float* __restrict__ xyz, const int* __restrict__ offset,
-                                   SegHeader* __restrict__ hdr) {
+                                   SegHeader* __restrict__ hdr, float target_per_cell) {
     const int s = blockIdx.x;
     const int start = s == 0 ? 0 : __ldg(offset + s - 1), end = __ldg(offset + s);
     float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -52,7 +52,7 @@ __global__ void grid_header_kernel(int b, const float* __restrict__ xyz, const i
             if (n == 0) { l = 0.f; h = 0.f; }
             lo[a] = l; ext[a] = fmaxf(h - l, 1e-6f);
         }
-        float h = cbrtf(ext[0] * ext[1] * ext[2] * TARGET_PER_CELL / fmaxf((float)n, 1.f));
+        float h = cbrtf(ext[0] * ext[1] * ext[2] * target_per_cell / fmaxf((float)n, 1.f));
         h = fmaxf(h, fmaxf(ext[0], fmaxf(ext[1], ext[2])) / (float)MAX_DIM * 1.0001f);   // respect the dimension cap
         SegHeader H;
         H.ox = lo[0]; H.oy = lo[1]; H.oz = lo[2]; H.h = h; H.inv_h = 1.0f / h;

@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) knn_grid_kernel(const KnnParam
     emit_result(P, q, slot, kout, li, ld, qx, qy, qz);
 }
 
+float g_grid_target = 2.0f;   // average points per grid cell over the bounding box (roitr_debug_set_knn_grid_target)
 int g_skip_fixup = 0;  // debug only (roitr_debug_skip_knn_fixup): leave the -1 markers in place to count flagged queries
 
 int launch_knn(const KnnParams& P, cudaStream_t st) {
@@ -452,6 +453,7 @@ static int knn_common(int b, int m, int nslots, int drop, const float* xyz, cons
 }
 
 extern "C" int roitr_debug_skip_knn_fixup(int skip) { g_skip_fixup = skip; return 0; }
+extern "C" int roitr_debug_set_knn_grid_target(float per_cell) { if (per_cell > 0.f) g_grid_target = per_cell; return 0; }
 
 extern "C" int roitr_knnquery_n(int b, int m, int nsample, int n_total, const float* xyz, const float* new_xyz,
                                 const int* offset, const int* new_offset, int* idx, float* dist2, void* stream) {
@@ -506,7 +508,7 @@ extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* o
     int* cursor = (int*)(w + grid_hdr_bytes(b) + grid_cells_bytes(b));
     float4* sorted = (float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b));
     ROITR_CUDA(cudaMemsetAsync(cursor, 0, grid_cells_bytes(b), st));
-    knngrid::grid_header_kernel<<<b, 256, 0, st>>>(b, xyz, offset, hdr);
+    knngrid::grid_header_kernel<<<b, 256, 0, st>>>(b, xyz, offset, hdr, g_grid_target);
     if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 0);
     knngrid::grid_scan_kernel<<<b, 1024, 0, st>>>(hdr, cursor, cell_start);
     if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 1);

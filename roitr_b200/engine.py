@@ -191,6 +191,40 @@ def _offsets(ends, device):
     return torch.tensor(ends, dtype=torch.int32, device=device)
 
 
+class _Lane:
+    """A side stream that runs closures after given events and hands back (result, completion event). With no stream the
+    closure runs inline and the event is None (waiting on None is a no-op), so single-pair forwards stay single-stream."""
+
+    def __init__(self, stream):
+        self.stream = stream
+        self.used = False
+
+    def start(self):
+        if self.stream is not None:
+            self.stream.wait_event(torch.cuda.current_stream().record_event())   # after the step's inputs are in place
+            self.used = True
+
+    def run(self, fn, *after):
+        if self.stream is None:
+            return fn(), None
+        for ev in after:
+            if ev is not None:
+                self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            r = fn()
+            return r, self.stream.record_event()
+
+    def join(self):
+        if self.stream is not None and self.used:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def _wait(*events):
+    for ev in events:
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+
 class Plan:
     """Host-side schedule for a batch of ``B`` pairs with fixed cloud sizes: every size and every ``offset`` tensor the
     kernels need, computed once (the reference recomputes them with .item() syncs on every forward, model/model.py:59-63).
@@ -213,9 +247,20 @@ class Plan:
         return (0 if cloud == 0 else e[cloud - 1]), e[cloud]
 
     def side_streams(self, n):
+        if getattr(self, "serial", False):
+            return []
         if len(getattr(self, "_streams", [])) < n:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n)]
         return self._streams[:n]
+
+    def lanes(self):
+        """(sampling lane, neighbour-search lane): the two streams that carry the coordinate-only work of the backbone
+        (FPS chain; grids + kNN/PPF), or (None, None) when the plan runs everything inline on the current stream."""
+        if self.B <= 1 or getattr(self, "serial", False):
+            return _Lane(None), _Lane(None)
+        if not hasattr(self, "_lanes"):
+            self._lanes = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        return _Lane(self._lanes[0]), _Lane(self._lanes[1])
 
     def pad_offsets(self, n):
         """Cumulative ends of B equal segments of n rows (the zero-padded clouds of the occlusion 1-NN)."""
@@ -230,39 +275,74 @@ class Plan:
         return self.one[n]
 
 
-def encode(W, plan, pts, feats, nrm, on_nodes=None):
-    """enc1..enc4 for all 2B clouds of the plan at once (segment-batched kernels). ``on_nodes(levels, down_idx4, p4)`` is
-    called as soon as the level-4 superpoints exist (right after the last FPS), before the level-4 layers are issued."""
+def geometry(plan, pts, nrm, on_nodes=None):
+    """Everything in the backbone that depends on coordinates only, for all 2B clouds of the plan: the FPS chain, the
+    uniform grids, every kNN(+PPF) query (self, down-sampling, 3-NN up-sampling). None of it needs features, so for a
+    batch it is issued on two side streams (sampling lane: the latency-bound FPS chain; search lane: grids + kNN) and
+    overlaps the dense layers / attention of the main stream; every item carries the event that marks it ready.
+    ``on_nodes(levels, down_idx4, p4)`` is called on the sampling lane as soon as the level-4 superpoints exist."""
+    fps_lane, knn_lane = plan.lanes()
+    fps_lane.start(); knn_lane.start()
+    mk_grid = lambda li, p_, o_: ops.knn_grid_build(p_, o_) if plan.levels[li]["n_max"] >= ops.GRID_MIN_SEGMENT else None
+    G = [dict(p=pts, n=nrm, o=plan.levels[0]["o"], down_idx=None) for _ in range(1)]
+    # sampling lane: level li+1 points/normals from level li
+    for li in range(1, 4):
+        prev, L = G[li - 1], plan.levels[li]
+
+        def sample(prev=prev, L=L, li=li):
+            down_idx, n_p = ops.fps(prev["p"], prev["o"], L["o"], plan.levels[li - 1]["n_max"], L["total"],
+                                    per_segment_rule=True, cluster=plan.fps_cluster)
+            g = dict(p=n_p, n=ops.gather_rows(prev["n"], down_idx), o=L["o"], down_idx=down_idx)
+            if li == 3 and on_nodes is not None:
+                on_nodes(G + [g], down_idx, n_p)
+            return g
+        g, ev = fps_lane.run(sample)
+        g["ev_pts"] = ev
+        G.append(g)
+    G[0]["ev_pts"] = None
+    # search lane
+    for li in range(4):
+        g, k = G[li], NSAMPLE[li]
+
+        def search(g=g, k=k, li=li):
+            if li > 0:
+                up = G[li - 1]
+                g["gidx"], g["gppf"], _ = ops.knn_ppf(k, up["p"], up["n"], g["p"], g["n"], up["o"], g["o"], grid=up["grid"])
+        _, g["ev_down"] = knn_lane.run(search, g["ev_pts"])
+
+        def search_self(g=g, k=k, li=li):
+            g["grid"] = mk_grid(li, g["p"], g["o"])
+            g["idx"], g["ppf"], _ = ops.knn_ppf(k, g["p"], g["n"], g["p"], g["n"], g["o"], g["o"], grid=g["grid"])
+        _, g["ev_self"] = knn_lane.run(search_self)
+
+        def search_up(g=g, li=li):
+            if li > 0:      # 3-NN of the finer level's points among this level's points (interpolation, pointops.py:168-182)
+                fine = G[li - 1]
+                fine["up_idx"], _, fine["up_dist"] = ops.knn_ppf(3, g["p"], None, fine["p"], None, g["o"], fine["o"],
+                                                                 drop_first=0, want_ppf=False, want_dist=True, grid=g["grid"])
+        _, ev_up = knn_lane.run(search_up)
+        if li > 0:
+            G[li - 1]["ev_up"] = ev_up
+    return G, (fps_lane, knn_lane)
+
+
+def encode(W, plan, G, feats):
+    """enc1..enc4 for all 2B clouds of the plan at once (segment-batched kernels), consuming the geometry of ``G``."""
     levels = []
     x = feats
-    o = plan.levels[0]["o"]
-    # one uniform grid per (large) reference set, shared by every kNN query against it (self, down-sampling, interpolation)
-    mk_grid = lambda li, p_, o_: ops.knn_grid_build(p_, o_) if plan.levels[li]["n_max"] >= ops.GRID_MIN_SEGMENT else None
-    grid = None
     for li in range(4):
         p = "backbone.enc%d" % (li + 1)
-        k = NSAMPLE[li]
-        L = plan.levels[li]
-        if STRIDES[li] != 1:
-            no = L["o"]
-            down_idx, n_p = ops.fps(pts, o, no, plan.levels[li - 1]["n_max"], L["total"], per_segment_rule=True,
-                                    cluster=plan.fps_cluster)
-            if li == 3 and on_nodes is not None:
-                on_nodes(levels, down_idx, n_p)
-            n_n = ops.gather_rows(nrm, down_idx)
-            gidx, gppf, _ = ops.knn_ppf(k, pts, nrm, n_p, n_n, o, no, grid=grid)
-            x = local_ppf_transformer(W, p + ".0.transformer", x, down_idx, gidx, gppf)
-            pts, nrm, o = n_p, n_n, no
-            grid = mk_grid(li, pts, o)
-            idx, ppf, _ = ops.knn_ppf(k, pts, nrm, pts, nrm, o, o, grid=grid)
+        g = G[li]
+        if li > 0:
+            _wait(g["ev_down"])
+            x = local_ppf_transformer(W, p + ".0.transformer", x, g["down_idx"], g["gidx"], g["gppf"])
+            _wait(g["ev_self"])
         else:
-            down_idx = None
-            grid = mk_grid(li, pts, o)
-            idx, ppf, _ = ops.knn_ppf(k, pts, nrm, pts, nrm, o, o, grid=grid)   # shared by the TD and the blocks of level 1
-            x = local_ppf_transformer(W, p + ".0.transformer", x, None, idx, ppf)
+            _wait(g["ev_self"])        # (idx, ppf) shared by the TD and the blocks of level 1
+            x = local_ppf_transformer(W, p + ".0.transformer", x, None, g["idx"], g["ppf"])
         for bi in range(1, BLOCKS[li]):
-            x = block(W, "%s.%d" % (p, bi), x, idx, ppf)
-        levels.append(dict(p=pts, n=nrm, x=x, o=o, idx=idx, ppf=ppf, down_idx=down_idx, grid=grid))
+            x = block(W, "%s.%d" % (p, bi), x, g["idx"], g["ppf"])
+        levels.append(dict(p=g["p"], n=g["n"], x=x, o=g["o"], idx=g["idx"], ppf=g["ppf"], down_idx=g["down_idx"], g=g))
     return levels
 
 
@@ -276,12 +356,11 @@ def decode(W, L):
     xs = [None, None, None, block(W, "backbone.dec4.1", y, l4["idx"], l4["ppf"])]
     for li in (2, 1, 0):
         p = "backbone.dec%d.0" % (li + 1)
-        fine, coarse = L[li], L[li + 1]
+        fine = L[li]
         a = _ln(W, p + ".linear1.1", _lin(W, p + ".linear1.0", fine["x"]), mode=ops.MODE_LN | ops.MODE_RELU)
         b = _ln(W, p + ".linear2.1", _lin(W, p + ".linear2.0", xs[li + 1]), mode=ops.MODE_LN | ops.MODE_RELU)
-        nn_idx, _, nn_dist = ops.knn_ppf(3, coarse["p"], None, fine["p"], None, coarse["o"], fine["o"], drop_first=0,
-                                         want_ppf=False, want_dist=True, grid=coarse["grid"])
-        y = ops.interpolate(nn_idx, nn_dist, b, base=a)
+        _wait(fine["g"]["ev_up"])
+        y = ops.interpolate(fine["g"]["up_idx"], fine["g"]["up_dist"], b, base=a)
         xs[li] = block(W, "backbone.dec%d.1" % (li + 1), y, fine["idx"], fine["ppf"])
     return xs
 
@@ -396,7 +475,8 @@ def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=Non
         if on_nodes is not None:
             on_nodes(nodes)
 
-    L = encode(W, plan, pts, feats, nrm, on_nodes=_nodes)
+    G, lanes = geometry(plan, pts, nrm, on_nodes=_nodes)
+    L = encode(W, plan, G, feats)
     s_g_all, t_g_all, embs = geometric_transformer_batch(W, architecture, B, L[3]["p"][:split], L[3]["p"][split:],
                                                          L[3]["x"][:split], L[3]["x"][split:])
     per_pair = []
@@ -408,6 +488,8 @@ def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=Non
     if on_global is not None:
         on_global(per_pair, s_g_all, t_g_all)
     dec = decode(W, L)
+    for lane in lanes:
+        lane.join()
     if aux is not None:
         aux.update(levels=L, dec=dec, node_idx=nodes["d4"], emb0=per_pair[0]["embs"][0], emb1=per_pair[0]["embs"][1])
     return L, dec, per_pair
@@ -438,7 +520,7 @@ class _Fork:
             for b in range(B):
                 fn(b)
             return
-        ev = self.main.record_event()
+        ev = torch.cuda.current_stream().record_event()      # the issuing stream: main, or the lane that produced the inputs
         for st in self.streams:
             st.wait_event(ev)
         for b in range(B):
@@ -622,9 +704,10 @@ class BatchRunner:
 
     INPUT_KEYS = ("pts", "feats", "nrm", "src_pcd", "rot", "trans")
 
-    def __init__(self, W, cfg, B, n_src, n_tgt, device, graph=True, fps_cluster=0):
+    def __init__(self, W, cfg, B, n_src, n_tgt, device, graph=True, fps_cluster=0, serial=False):
         self.W, self.cfg, self.B, self.Ns, self.Nt, self.device = W, cfg, B, n_src, n_tgt, device
         self.plan = Plan(n_src, n_tgt, B, device, fps_cluster)
+        self.plan.serial = serial     # True: no side streams at all (bench.py's per-kernel timing replica)
         tot = B * (n_src + n_tgt)
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
         self.inp = dict(pts=f(tot, 3), feats=f(tot, 1), nrm=f(tot, 3), src_pcd=f(B * n_src, 3), rot=f(B, 3, 3), trans=f(B, 3, 1))

@@ -255,14 +255,15 @@ class RIGA_v2(nn.Module, _PackedMixin):
         return engine.riga_forward(W, self.cfg, *args, aux=_aux)
 
 
-    def batch_runner(self, batch_pairs, n_src, n_tgt, graph=True, fps_cluster=0):
+    def batch_runner(self, batch_pairs, n_src, n_tgt, graph=True, fps_cluster=0, serial=False):
         """Throughput API (not in the reference, which is batch_size=1 only): a engine.BatchRunner that evaluates
         ``batch_pairs`` independent pairs of fixed size per step, as one CUDA graph when ``graph`` is True."""
         if self.training:
             raise RuntimeError("inference only: call .eval()")
         W = self._packed("", self.cfg["transformer_architecture"])
         dev = next(self.parameters()).device
-        return engine.BatchRunner(W, self.cfg, batch_pairs, n_src, n_tgt, dev, graph=graph, fps_cluster=fps_cluster)
+        return engine.BatchRunner(W, self.cfg, batch_pairs, n_src, n_tgt, dev, graph=graph, fps_cluster=fps_cluster,
+                                  serial=serial)
 
 
 def create_model(config):

@@ -1,19 +1,34 @@
+"""Dense-layer micro-benchmark at the bench step's shapes (B = 16 pairs): coupled-ring kernel (linear_tc2) vs the
+streaming kernel (linear_tc3), with a 256 MiB L2 flush before every timed launch.
+usage: bench_gemm.py   (run on a GPU box; writes gpurun_out/bench_gemm.txt)"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import torch
-from roitr_b200 import ops
+from roitr_b200 import _lib, engine, ops
 DEV = "cuda:0"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
-def timeit(fn, iters=10):
-    for _ in range(3): fn()
+def timeit(fn, iters=7):
+    for _ in range(2): fn()
     ts = []
     for _ in range(iters):
         flush.zero_(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return sorted(ts)[len(ts) // 2]
-print("M,N,K, ffma_ms, tc_ms, tc_TFLOPs(fp32-equivalent), GB/s(A+C)")
-for (M, N, K) in [(320000, 64, 64), (320000, 192, 64), (80000, 384, 128), (80000, 128, 128), (20000, 768, 256), (20000, 256, 256), (5000, 256, 256), (320000, 256, 64), (4992, 768, 256), (312, 768, 256), (312, 512, 256)]:
-    a = torch.randn(M, K, device=DEV); w = torch.randn(N, K, device=DEV); b = torch.randn(N, device=DEV); out = torch.empty(M, N, device=DEV)
-    from roitr_b200 import engine; wp = engine.pack_linear_tc(w)
-    t1 = timeit(lambda: ops.linear(a, w, b, out=out, tc=False)); t2 = timeit(lambda: ops.linear(a, w, b, out=out, wpack=wp))
-    print("%d,%d,%d, %.4f, %.4f, %.1f, %.0f" % (M, N, K, t1, t2, 2.0 * M * N * K / t2 / 1e9, (M * K + M * N) * 4 / t2 / 1e6))
+out = open(os.path.join(ROOT, "gpurun_out", "bench_gemm.txt"), "w")
+def log(s):
+    print(s); out.write(s + "\n"); out.flush()
+log("M,N,K, tc2_ms, tc3_ms, tc3 GB/s(A+C), tc3 TFLOP/s(fp32-equivalent), max|tc3-tc2|")
+SHAPES = [(640000, 64, 64), (640000, 192, 64), (640000, 128, 64), (640000, 256, 64), (640000, 384, 128), (160000, 128, 128),
+          (160000, 384, 128), (160000, 256, 128), (160000, 768, 256), (40000, 256, 256), (40000, 768, 256), (9984, 256, 256),
+          (9984, 768, 256), (4992, 256, 256), (4992, 512, 256), (4992, 256, 512), (4992, 768, 256), (4992, 1024, 256), (4992, 256, 1024)]
+for (M, N, K) in SHAPES:
+    a = torch.randn(M, K, device=DEV); w = torch.randn(N, K, device=DEV) / K ** 0.5; b = torch.randn(N, device=DEV)
+    o2 = torch.empty(M, N, device=DEV); o3 = torch.empty(M, N, device=DEV)
+    wp = engine.pack_linear_tc(w)
+    _lib.lib().roitr_debug_force_linear_tc2(1)
+    t2 = timeit(lambda: ops.linear(a, w, b, out=o2, wpack=wp))
+    _lib.lib().roitr_debug_force_linear_tc2(0)
+    t3 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp))
+    log("%d,%d,%d, %.4f, %.4f, %.0f, %.1f, %.2e" % (M, N, K, t2, t3, (M * K + M * N) * 4 / t3 / 1e6, 2.0 * M * N * K / t3 / 1e9,
+                                               (o3 - o2).abs().max().item()))
