@@ -374,11 +374,20 @@ __device__ __forceinline__ float warp_lse3(float x0, float x1, float x2) {
     return logf(s) + m0;
 }
 
-__global__ void __launch_bounds__(256) fine_patch_kernel(const FineParams P) {
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+constexpr int FT = 288, FW = FT / 32;      // 8 warps own rows/columns 0..63 (4 threads each), warp 8 owns the dustbin row/column
+
+__global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
     __shared__ float Z[FP1 * FP1];
     __shared__ __align__(16) float At[32][FP + 4];
     __shared__ __align__(16) float Bs[32][FP + 4];
-    __shared__ float u[FP1], v[FP1], log_mu[FP1], log_nu[FP1];
+    __shared__ __align__(16) float u[FP1 + 3], v[FP1 + 3];
+    __shared__ float log_mu[FP1], log_nu[FP1];
     __shared__ int t_idx[FP], s_idx[FP];
     __shared__ unsigned char t_ok[FP], s_ok[FP];
     __shared__ unsigned char rowf[FP * FP];
@@ -396,47 +405,54 @@ __global__ void __launch_bounds__(256) fine_patch_kernel(const FineParams P) {
     }
     __syncthreads();
 
-    // ---- 64 x 64 x C scores (rows = tgt patch points, cols = src patch points) ----
-    const int tx = tid & 15, ty = tid >> 4;
+    // ---- 64 x 64 x C scores (rows = tgt patch points, cols = src patch points), threads 0..255 ----
+    const bool mm = tid < 256;
+    const int tx = tid & 15, ty = (tid >> 4) & 15;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int lrow = tid >> 2, lk = (tid & 3) * 8;
+    const int lrow = (tid >> 2) & 63, lk = (tid & 3) * 8;
     const int ti = t_idx[lrow], si = s_idx[lrow];
     for (int k0 = 0; k0 < P.C; k0 += 32) {
+        if (mm) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (ti < P.Nt) a = __ldg(reinterpret_cast<const float4*>(P.tgt_feat + (size_t)ti * P.C + k0 + lk) + h);
-            if (si < P.Ns) b = __ldg(reinterpret_cast<const float4*>(P.src_feat + (size_t)si * P.C + k0 + lk) + h);
-            At[lk + 4 * h][lrow] = a.x; At[lk + 4 * h + 1][lrow] = a.y; At[lk + 4 * h + 2][lrow] = a.z; At[lk + 4 * h + 3][lrow] = a.w;
-            Bs[lk + 4 * h][lrow] = b.x; Bs[lk + 4 * h + 1][lrow] = b.y; Bs[lk + 4 * h + 2][lrow] = b.z; Bs[lk + 4 * h + 3][lrow] = b.w;
+            for (int h = 0; h < 2; ++h) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (ti < P.Nt) a = __ldg(reinterpret_cast<const float4*>(P.tgt_feat + (size_t)ti * P.C + k0 + lk) + h);
+                if (si < P.Ns) b = __ldg(reinterpret_cast<const float4*>(P.src_feat + (size_t)si * P.C + k0 + lk) + h);
+                At[lk + 4 * h][lrow] = a.x; At[lk + 4 * h + 1][lrow] = a.y; At[lk + 4 * h + 2][lrow] = a.z; At[lk + 4 * h + 3][lrow] = a.w;
+                Bs[lk + 4 * h][lrow] = b.x; Bs[lk + 4 * h + 1][lrow] = b.y; Bs[lk + 4 * h + 2][lrow] = b.z; Bs[lk + 4 * h + 3][lrow] = b.w;
+            }
         }
         __syncthreads();
+        if (mm) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&At[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            for (int k = 0; k < 32; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(&At[k][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
         }
         __syncthreads();
     }
     // ---- padded, masked score matrix (modules.py:36-46) and marginals (:48-60) ----
     const float alpha = __ldg(P.alpha);
     const float NEG = -1e6f;
+    if (mm) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = ty * 4 + i, c = tx * 4 + j;
-            Z[r * FP1 + c] = (t_ok[r] && s_ok[c]) ? __fdiv_rn(acc[i][j], P.sqrt_c) : NEG;
-        }
+            for (int j = 0; j < 4; ++j) {
+                const int r = ty * 4 + i, c = tx * 4 + j;
+                Z[r * FP1 + c] = (t_ok[r] && s_ok[c]) ? __fdiv_rn(acc[i][j], P.sqrt_c) : NEG;
+            }
+    }
     if (tid < FP) {
         Z[tid * FP1 + FP] = t_ok[tid] ? alpha : NEG;   // dustbin column
         Z[FP * FP1 + tid] = s_ok[tid] ? alpha : NEG;   // dustbin row
@@ -455,56 +471,68 @@ __global__ void __launch_bounds__(256) fine_patch_kernel(const FineParams P) {
         log_mu[tid] = t_ok[tid] ? s_norm : NEG;
         log_nu[tid] = s_ok[tid] ? s_norm : NEG;
     }
-    if (tid < FP1) { u[tid] = 0.f; v[tid] = 0.f; }
+    if (tid < FP1 + 3) { u[tid] = 0.f; v[tid] = 0.f; }
     __syncthreads();
     // ---- log-domain Sinkhorn (modules.py:21-26) ----
-    // 200 dependent logsumexp sweeps per patch pair: keep them off shared memory and the serial path short. Warp w owns
-    // rows {w, w+8, ..} (row sweep) and columns {w, w+8, ..} (column sweep) of Z and holds them in REGISTERS for the whole
-    // loop (lane l has elements l, l+32 and - lane 0 - element 64); the 9 independent LSEs of a sweep are evaluated three
-    // at a time so their shuffle / MUFU latencies overlap; only u and v (65 floats each) go through shared memory, with
-    // one __syncthreads per sweep. exp/log use the ex2/lg2 hardware paths (relative error 2^-21, well inside the parity
-    // tolerance; the iteration is a contraction so errors do not accumulate).
+    // 200 dependent logsumexp sweeps per patch pair; the kernel's time is the instruction count of this loop, so a
+    // logsumexp is split over only FOUR threads: thread (i, q) of warps 0-7 holds elements 16q .. 16q+15 (+ the dustbin
+    // element for q = 3) of row i AND of column i of Z in registers for the whole loop, evaluates its 16-17 terms
+    // serially (independent FADD / FMNMX / FFMA / EX2 chains, no shuffles) and finishes with a 2-step butterfly; warp 8
+    // handles the dustbin row / column across its 32 lanes. Only u and v (65 floats each) go through shared memory, read
+    // as float4 broadcasts, one __syncthreads per sweep. exp(x - m) is ex2(fma(x, log2 e, -m log2 e)) and log is lg2 * ln 2
+    // (hardware paths, relative error 2^-21, well inside the parity tolerance; the iteration is a contraction so errors
+    // do not accumulate).
     {
-        constexpr int NR = 9;                                  // ceil(65 / 8) rows (columns) per warp
-        float zr[NR][3], zc[NR][3];
+        constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+        const int ri = (tid >> 2) & 63, q = tid & 3;
+        float zr[17], zc[17];
+        if (warp < 8) {
 #pragma unroll
-        for (int t = 0; t < NR; ++t) {
-            const int i = warp + 8 * t;
-            const bool ok = i < FP1;
-            zr[t][0] = ok ? Z[i * FP1 + lane] : 0.f;
-            zr[t][1] = ok ? Z[i * FP1 + lane + 32] : 0.f;
-            zr[t][2] = (ok && lane == 0) ? Z[i * FP1 + 64] : -CUDART_INF_F;
-            zc[t][0] = ok ? Z[lane * FP1 + i] : 0.f;
-            zc[t][1] = ok ? Z[(lane + 32) * FP1 + i] : 0.f;
-            zc[t][2] = (ok && lane == 0) ? Z[64 * FP1 + i] : -CUDART_INF_F;
+            for (int j = 0; j < 16; ++j) {
+                zr[j] = Z[ri * FP1 + q * 16 + j];
+                zc[j] = Z[(q * 16 + j) * FP1 + ri];
+            }
+            zr[16] = q == 3 ? Z[ri * FP1 + 64] : -CUDART_INF_F;
+            zc[16] = q == 3 ? Z[64 * FP1 + ri] : -CUDART_INF_F;
+        } else {
+            zr[0] = Z[64 * FP1 + lane]; zr[1] = Z[64 * FP1 + lane + 32]; zr[2] = lane == 0 ? Z[64 * FP1 + 64] : -CUDART_INF_F;
+            zc[0] = Z[lane * FP1 + 64]; zc[1] = Z[(lane + 32) * FP1 + 64]; zc[2] = lane == 0 ? Z[64 * FP1 + 64] : -CUDART_INF_F;
         }
-        auto sweep = [&](const float (&z)[NR][3], const float* __restrict__ add, const float* __restrict__ marg,
+        auto sweep = [&](const float (&z)[17], const float* __restrict__ add, const float* __restrict__ marg,
                          float* __restrict__ dst) {
-            const float a0 = add[lane], a1 = add[lane + 32], a2 = add[64];
+            if (warp < 8) {
+                float x[17];
 #pragma unroll
-            for (int g = 0; g < NR; g += 3) {
-                float x[3][3], mx[3], sm[3];
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    x[t][0] = z[g + t][0] + a0; x[t][1] = z[g + t][1] + a1; x[t][2] = z[g + t][2] + a2;
-                    mx[t] = fmaxf(fmaxf(x[t][0], x[t][1]), x[t][2]);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 a = *reinterpret_cast<const float4*>(add + q * 16 + 4 * j4);
+                    x[4 * j4] = z[4 * j4] + a.x; x[4 * j4 + 1] = z[4 * j4 + 1] + a.y;
+                    x[4 * j4 + 2] = z[4 * j4 + 2] + a.z; x[4 * j4 + 3] = z[4 * j4 + 3] + a.w;
                 }
+                x[16] = z[16] + add[64];
+                float m0 = fmaxf(x[0], x[1]), m1 = fmaxf(x[2], x[3]), m2 = fmaxf(x[4], x[5]), m3 = fmaxf(x[6], x[7]);
+                m0 = fmaxf(m0, fmaxf(x[8], x[9])); m1 = fmaxf(m1, fmaxf(x[10], x[11]));
+                m2 = fmaxf(m2, fmaxf(x[12], x[13])); m3 = fmaxf(m3, fmaxf(x[14], x[15]));
+                float m = fmaxf(fmaxf(m0, m1), fmaxf(fmaxf(m2, m3), x[16]));
+                m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 2));
+                const float nml = -m * L2E;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) mx[t] = fmaxf(mx[t], __shfl_xor_sync(FULL_MASK, mx[t], o));
-#pragma unroll
-                for (int t = 0; t < 3; ++t)
-                    sm[t] = __expf(x[t][0] - mx[t]) + __expf(x[t][1] - mx[t]) + __expf(x[t][2] - mx[t]);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) sm[t] += __shfl_xor_sync(FULL_MASK, sm[t], o);
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    const int i = warp + 8 * (g + t);
-                    if (lane == 0 && i < FP1) dst[i] = marg[i] - (__logf(sm[t]) + mx[t]);
+                for (int j = 0; j < 16; j += 4) {
+                    s0 += fast_ex2(fmaf(x[j], L2E, nml)); s1 += fast_ex2(fmaf(x[j + 1], L2E, nml));
+                    s2 += fast_ex2(fmaf(x[j + 2], L2E, nml)); s3 += fast_ex2(fmaf(x[j + 3], L2E, nml));
                 }
+                s0 += fast_ex2(fmaf(x[16], L2E, nml));
+                float sm = (s0 + s1) + (s2 + s3);
+                sm += __shfl_xor_sync(FULL_MASK, sm, 1);
+                sm += __shfl_xor_sync(FULL_MASK, sm, 2);
+                if (q == 0) dst[ri] = marg[ri] - fmaf(__log2f(sm), LN2, m);
+            } else {
+                const float x0 = z[0] + add[lane], x1 = z[1] + add[lane + 32], x2 = z[2] + add[64];
+                const float m = warp_max(fmaxf(fmaxf(x0, x1), x2));
+                const float nml = -m * L2E;
+                const float sm = warp_sum(fast_ex2(fmaf(x0, L2E, nml)) + fast_ex2(fmaf(x1, L2E, nml)) + fast_ex2(fmaf(x2, L2E, nml)));
+                if (lane == 0) dst[64] = marg[64] - fmaf(__log2f(sm), LN2, m);
             }
         };
         for (int it = 0; it < P.num_iter; ++it) {
@@ -516,7 +544,7 @@ __global__ void __launch_bounds__(256) fine_patch_kernel(const FineParams P) {
     }
     // ---- output (P,65,65) log-assignment; keep it in Z for the matching step ----
     float* out = P.scores + (size_t)p * FP1 * FP1;
-    for (int e = tid; e < FP1 * FP1; e += 256) {
+    for (int e = tid; e < FP1 * FP1; e += FT) {
         const int r = e / FP1, c = e % FP1;
         const float val = Z[e] + u[r] + v[c] - s_norm;
         Z[e] = val;
@@ -524,14 +552,14 @@ __global__ void __launch_bounds__(256) fine_patch_kernel(const FineParams P) {
     }
     __syncthreads();
     // ---- FineMatching (modules.py:242-274): exp, top-k along rows and columns, threshold, mutual, validity ----
-    for (int e = tid; e < FP * FP; e += 256) {
+    for (int e = tid; e < FP * FP; e += FT) {
         const int r = e >> 6, c = e & 63;
         Z[r * FP1 + c] = expf(Z[r * FP1 + c]);
         rowf[e] = 0;
     }
     __syncthreads();
     // row-wise top-k: warp per row, each lane holds columns lane and lane+32; ties -> lower index
-    for (int r = warp; r < FP; r += 8) {
+    for (int r = warp; r < FP; r += FW) {
         float a0 = Z[r * FP1 + lane], a1 = Z[r * FP1 + lane + 32];
         for (int t = 0; t < P.topk; ++t) {
             float bv = a0 >= a1 ? a0 : a1;
@@ -549,7 +577,7 @@ __global__ void __launch_bounds__(256) fine_patch_kernel(const FineParams P) {
     }
     __syncthreads();
     unsigned char* fl = P.flags + (size_t)p * FP * FP;
-    for (int c = warp; c < FP; c += 8) {
+    for (int c = warp; c < FP; c += FW) {
         float a0 = Z[lane * FP1 + c], a1 = Z[(lane + 32) * FP1 + c];
         unsigned colsel0 = 0, colsel1 = 0;  // whether my rows were selected by the column top-k
         for (int t = 0; t < P.topk; ++t) {
@@ -670,7 +698,7 @@ extern "C" int roitr_fine_matching(int Pmax, int Nt, int Ns, int C, const float*
     P.threshold = threshold; P.sqrt_c = sqrtf((float)C);
     cudaStream_t st = (cudaStream_t)stream;
     ROITR_CUDA(cudaMemsetAsync(flags, 0, (size_t)Pmax * FP * FP, st));
-    fine_patch_kernel<<<Pmax, 256, 0, st>>>(P);
+    fine_patch_kernel<<<Pmax, FT, 0, st>>>(P);
     ROITR_CHECK_LAUNCH("fine_patch_kernel");
     return ROITR_OK;
 }
