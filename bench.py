@@ -152,7 +152,7 @@ def op_work(name, ints):
     if name == "roitr_furthestsampling_cfg":
         b, _, nseg = ints[:3]
         return b * (nseg * 12.0 + (nseg // 4) * 16.0), 0.0, "hbm"
-    if name in ("roitr_knn_ppf_n", "roitr_knn_ppf_grid"):
+    if name in ("roitr_knn_ppf_n", "roitr_knn_ppf_grid", "roitr_knn_ppf_grid_q"):
         b, m, k, drop, n = ints[:5]
         return n * 24.0 + m * 24.0 + m * k * 20.0, 0.0, "hbm"
     if name == "roitr_local_attention":
@@ -320,7 +320,7 @@ def main():
         roof = roofline_of([top])
         roof["how"] = ("CUDA events around every entry-point call in a single-stream eager replica of the timed step (the timed "
                        "step itself is one multi-stream CUDA graph); algorithmic work per DESIGN.md §4 / SURVEY.md §8d")
-        named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build"]),
+        named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid_q", "roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build"]),
                  "global_attention_qk_pv": roofline_of(["roitr_gemm_tc_batched"]),
                  "dense_layers": roofline_of(["roitr_linear_tc_packed"]),
                  "fine_matching": roofline_of(["roitr_fine_matching"])}

@@ -76,6 +76,13 @@ int roitr_knn_grid_build(int b, int n, const float* xyz, const int* offset, void
 int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n_total, const float* xyz, const float* normals,
                        const float* new_xyz, const float* new_normals, const int* offset, const int* new_offset,
                        const void* workspace, int* idx, float* dist, float* ppf, void* stream);
+/* Same, with the visiting order of the queries taken from the QUERY set's own grid (`query_workspace`, built by
+ * roitr_knn_grid_build over new_xyz / new_offset; NULL = natural order, or the reference grid itself for self queries):
+ * one thread per query, neighbouring threads in neighbouring cells. Results are identical to roitr_knn_ppf_grid. */
+int roitr_knn_ppf_grid_q(int b, int m, int k_out, int drop_first, int n_total, const float* xyz, const float* normals,
+                         const float* new_xyz, const float* new_normals, const int* offset, const int* new_offset,
+                         const void* workspace, const void* query_workspace, int* idx, float* dist, float* ppf,
+                         void* stream);
 
 /*
  * Drop-in for  furthestsampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)

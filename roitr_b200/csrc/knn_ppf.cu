@@ -399,7 +399,138 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) knn_grid_kernel(const KnnParam
     emit_result(P, q, slot, kout, li, ld, qx, qy, qz);
 }
 
-float g_grid_target = 2.0f;   // average points per grid cell over the bounding box (roitr_debug_set_knn_grid_target)
+// ---- grid-accelerated exact kNN, one THREAD per query ----------------------------------------------------------------------
+// The warp-per-query kernel above spends its time in dependent loads: every row of every shell is a cell_start lookup
+// followed by a point fetch, ~45 serial round trips per query with 32 lanes sharing ~6 candidates. Here a thread owns a
+// query and keeps its k best (distance, index) pairs as a sorted list in REGISTERS (fully unrolled compare-exchange
+// insertion, K is a template parameter); memory latency is hidden by the other ~1000 resident queries of the SM instead
+// of by lanes. Queries are visited in the cell order of the QUERY set's own grid when one is given (for self queries
+// the same grid): the 32 queries of a warp then sit in the same or adjacent cells, walk nearly identical candidate
+// ranges (L1 hits, little divergence). Same distance arithmetic, same lexicographic (distance, index) order, same tie
+// marking / replay as the other kernels, so the result is bit-identical. Results are staged in shared memory and
+// emitted cooperatively (one (query, slot) pair per thread: contiguous index / PPF rows, PPF maths spread evenly).
+constexpr int KT_THREADS = 128;
+
+template <int K>
+__global__ void __launch_bounds__(KT_THREADS) knn_grid_thread_kernel(const KnnParams P, const knngrid::SegHeader* __restrict__ hdr,
+                                                                      const int* __restrict__ cell_start,
+                                                                      const float4* __restrict__ sorted,
+                                                                      const float4* __restrict__ qorder) {
+    __shared__ float s_d[KT_THREADS * K];
+    __shared__ int s_i[KT_THREADS * K];
+    __shared__ int s_q[KT_THREADS];
+    __shared__ float s_qp[KT_THREADS * 3];
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * KT_THREADS + tid;
+    int q = -1;
+    bool tie = false;
+    float bd[K];
+    int bi[K];
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (t < P.m) {
+        const int sgm = find_segment(t, P.new_offset, P.b);
+        if (qorder) {
+            const float4 v = __ldg(qorder + t);
+            q = __float_as_int(v.w); qx = v.x; qy = v.y; qz = v.z;
+        } else {
+            q = t;
+            qx = __ldg(P.qxyz + 3 * (size_t)q); qy = __ldg(P.qxyz + 3 * (size_t)q + 1); qz = __ldg(P.qxyz + 3 * (size_t)q + 2);
+        }
+        const int qs = sgm == 0 ? 0 : __ldg(P.offset + sgm - 1);
+        const knngrid::SegHeader H = hdr[sgm];
+        const int cx = knngrid::cell_coord(qx, H.ox, H.inv_h, H.nx), cy = knngrid::cell_coord(qy, H.oy, H.inv_h, H.ny),
+                  cz = knngrid::cell_coord(qz, H.oz, H.inv_h, H.nz);
+        const int* cs = cell_start + H.cell_base;
+        const float4* pts = sorted + qs;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { bd[j] = 1e10f; bi[j] = qs; }
+        float tau = 1e10f;
+        int tau_i = qs;
+
+        auto scan_range = [&](int beg, int end) {
+            for (int p = beg; p < end; ++p) {
+                const float4 v = __ldg(pts + p);
+                const float cd = sqdist_ref(qx - v.x, qy - v.y, qz - v.z);
+                if (cd <= tau) {
+                    const int ci = __float_as_int(v.w);
+                    if (cd == tau && tau != 1e10f) tie = true;     // boundary tie: the reference's choice depends on its heap
+                    if (cd < tau || ci < tau_i) {
+                        bd[K - 1] = cd; bi[K - 1] = ci;
+#pragma unroll
+                        for (int j = K - 1; j > 0; --j) {
+                            const bool sw = bd[j] < bd[j - 1] || (bd[j] == bd[j - 1] && bi[j] < bi[j - 1]);
+                            const float d0 = bd[j - 1], d1 = bd[j];
+                            const int i0 = bi[j - 1], i1 = bi[j];
+                            bd[j - 1] = sw ? d1 : d0; bd[j] = sw ? d0 : d1;
+                            bi[j - 1] = sw ? i1 : i0; bi[j] = sw ? i0 : i1;
+                        }
+                        const float tau_old = tau;
+                        tau = bd[K - 1]; tau_i = bi[K - 1];
+                        if (tau == tau_old && tau_old != 1e10f) tie = true;
+                    }
+                }
+            }
+        };
+
+        for (int r = 0;; ++r) {
+            const int x0 = max(cx - r, 0), x1 = min(cx + r, H.nx - 1);
+            for (int dz = -r; dz <= r; ++dz) {
+                const int z = cz + dz;
+                if (z < 0 || z >= H.nz) continue;
+                for (int dy = -r; dy <= r; ++dy) {
+                    const int y = cy + dy;
+                    if (y < 0 || y >= H.ny) continue;
+                    const int row = (z * H.ny + y) * H.nx;
+                    if (abs(dz) == r || abs(dy) == r) {               // face of the cube: the whole x span
+                        scan_range(__ldg(cs + row + x0), __ldg(cs + row + x1 + 1));
+                    } else {                                         // interior row: only the two end cells
+                        if (cx - r >= 0) scan_range(__ldg(cs + row + cx - r), __ldg(cs + row + cx - r + 1));
+                        if (cx + r < H.nx) scan_range(__ldg(cs + row + cx + r), __ldg(cs + row + cx + r + 1));
+                    }
+                }
+            }
+            // everything outside the cube of radius r is at least `bound` away from the query
+            const bool all = (cx - r <= 0) && (cx + r >= H.nx - 1) && (cy - r <= 0) && (cy + r >= H.ny - 1) && (cz - r <= 0) &&
+                             (cz + r >= H.nz - 1);
+            if (all) break;
+            float bound = CUDART_INF_F;
+            if (cx - r > 0) bound = fminf(bound, qx - (H.ox + (float)(cx - r) * H.h));
+            if (cx + r < H.nx - 1) bound = fminf(bound, (H.ox + (float)(cx + r + 1) * H.h) - qx);
+            if (cy - r > 0) bound = fminf(bound, qy - (H.oy + (float)(cy - r) * H.h));
+            if (cy + r < H.ny - 1) bound = fminf(bound, (H.oy + (float)(cy + r + 1) * H.h) - qy);
+            if (cz - r > 0) bound = fminf(bound, qz - (H.oz + (float)(cz - r) * H.h));
+            if (cz + r < H.nz - 1) bound = fminf(bound, (H.oz + (float)(cz + r + 1) * H.h) - qz);
+            bound -= 1e-4f * H.h;                                     // binning rounds (v - o) * inv_h: keep a safety margin
+            if (tau < 1e10f && bound > 0.f && tau < bound * bound * 0.99999f) break;
+        }
+        // equal distances inside the final list: the reference's order among them is its heap's
+#pragma unroll
+        for (int j = 0; j + 1 < K; ++j)
+            if (bd[j] == bd[j + 1] && bd[j] != 1e10f) tie = true;
+    }
+    // ---- stage and emit cooperatively ----
+    s_q[tid] = tie ? (-2 - q) : q;            // q >= 0: valid; -1: no query; <= -2: tie-marked query -2 - q
+    s_qp[3 * tid] = qx; s_qp[3 * tid + 1] = qy; s_qp[3 * tid + 2] = qz;
+#pragma unroll
+    for (int j = 0; j < K; ++j) { s_d[tid * K + j] = bd[j]; s_i[tid * K + j] = bi[j]; }
+    __syncthreads();
+    const int kout = K - P.drop;
+    for (int e = tid; e < KT_THREADS * kout; e += KT_THREADS) {
+        const int ql = e / kout, slot = e - ql * kout;
+        const int qq = s_q[ql];
+        if (qq == -1) continue;
+        if (qq <= -2) {
+            if (slot == 0) P.idx[(size_t)(-2 - qq) * kout] = -1;      // marker consumed by knn_tie_fixup_kernel
+            continue;
+        }
+        emit_result(P, qq, slot, kout, s_i[ql * K + slot + P.drop], s_d[ql * K + slot + P.drop], s_qp[3 * ql], s_qp[3 * ql + 1],
+                    s_qp[3 * ql + 2]);
+    }
+}
+
+int g_knn_thread = 1;         // debug only (roitr_debug_knn_thread_per_query): 0 = warp-per-query grid kernel everywhere, 1 = thread-per-query
+                              // for k <= 9 slots (measured: 2-4x faster there, slower for 17 slots), 2 = thread-per-query everywhere
+float g_grid_target = 1.0f;   // average points per grid cell over the bounding box (roitr_debug_set_knn_grid_target)
 int g_skip_fixup = 0;  // debug only (roitr_debug_skip_knn_fixup): leave the -1 markers in place to count flagged queries
 
 int launch_knn(const KnnParams& P, cudaStream_t st) {
@@ -516,10 +647,12 @@ extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* o
     return ROITR_OK;
 }
 
-extern "C" int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n_total, const float* xyz,
-                                  const float* normals, const float* new_xyz, const float* new_normals, const int* offset,
-                                  const int* new_offset, const void* workspace, int* idx, float* dist, float* ppf,
-                                  void* stream) {
+extern "C" int roitr_debug_knn_thread_per_query(int on) { g_knn_thread = on; return 0; }
+
+extern "C" int roitr_knn_ppf_grid_q(int b, int m, int k_out, int drop_first, int n_total, const float* xyz,
+                                    const float* normals, const float* new_xyz, const float* new_normals, const int* offset,
+                                    const int* new_offset, const void* workspace, const void* query_workspace, int* idx,
+                                    float* dist, float* ppf, void* stream) {
     const int nslots = k_out + drop_first;
     ROITR_CHECK_ARG(b >= 1 && m >= 0 && nslots >= 1 && nslots <= 32 && drop_first >= 0 && drop_first < nslots, "knn_ppf_grid: bad sizes");
     ROITR_CHECK_ARG(xyz && new_xyz && offset && new_offset && idx && workspace, "knn_ppf_grid: null pointer");
@@ -531,12 +664,33 @@ extern "C" int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n
     P.use_tma = 0; P.n_total = n_total;
     const unsigned char* w = (const unsigned char*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
-    knn_grid_kernel<<<ceil_div(m, KNN_WARPS), KNN_THREADS, 0, st>>>(P, (const knngrid::SegHeader*)w,
-                                                                  (const int*)(w + grid_hdr_bytes(b)),
-                                                                  (const float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b)));
+    const auto* hdr = (const knngrid::SegHeader*)w;
+    const int* cell_start = (const int*)(w + grid_hdr_bytes(b));
+    const float4* sorted = (const float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b));
+    // visiting order of the queries: the cell order of the query set's own grid (self queries: the same grid)
+    const unsigned char* qw = (const unsigned char*)query_workspace;
+    if (!qw && new_xyz == xyz && m == n_total) qw = w;
+    const float4* qorder = qw ? (const float4*)(qw + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b)) : nullptr;
+    const int grid = ceil_div(m, KT_THREADS);
+    bool done = true;
+    if (!g_knn_thread) done = false;
+    else if (nslots == 1) knn_grid_thread_kernel<1><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
+    else if (nslots == 3) knn_grid_thread_kernel<3><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
+    else if (nslots == 9) knn_grid_thread_kernel<9><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
+    else if (nslots == 17 && g_knn_thread > 1) knn_grid_thread_kernel<17><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
+    else done = false;
+    if (!done) knn_grid_kernel<<<ceil_div(m, KNN_WARPS), KNN_THREADS, 0, st>>>(P, hdr, cell_start, sorted);
     ROITR_CHECK_LAUNCH("knn_grid_kernel");
     if (g_skip_fixup) return ROITR_OK;
     knn_tie_fixup_kernel<<<ceil_div(m, FIX_WARPS * 32), FIX_WARPS * 32, 0, st>>>(P);
     ROITR_CHECK_LAUNCH("knn_tie_fixup_kernel");
     return ROITR_OK;
+}
+
+extern "C" int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n_total, const float* xyz,
+                                  const float* normals, const float* new_xyz, const float* new_normals, const int* offset,
+                                  const int* new_offset, const void* workspace, int* idx, float* dist, float* ppf,
+                                  void* stream) {
+    return roitr_knn_ppf_grid_q(b, m, k_out, drop_first, n_total, xyz, normals, new_xyz, new_normals, offset, new_offset,
+                                workspace, nullptr, idx, dist, ppf, stream);
 }

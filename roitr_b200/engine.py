@@ -305,13 +305,14 @@ def geometry(plan, pts, nrm, on_nodes=None):
         g, k = G[li], NSAMPLE[li]
 
         def search(g=g, k=k, li=li):
+            g["grid"] = mk_grid(li, g["p"], g["o"])      # also the visiting order of this level's points as queries
             if li > 0:
                 up = G[li - 1]
-                g["gidx"], g["gppf"], _ = ops.knn_ppf(k, up["p"], up["n"], g["p"], g["n"], up["o"], g["o"], grid=up["grid"])
+                g["gidx"], g["gppf"], _ = ops.knn_ppf(k, up["p"], up["n"], g["p"], g["n"], up["o"], g["o"], grid=up["grid"],
+                                                      qgrid=g["grid"])
         _, g["ev_down"] = knn_lane.run(search, g["ev_pts"])
 
         def search_self(g=g, k=k, li=li):
-            g["grid"] = mk_grid(li, g["p"], g["o"])
             g["idx"], g["ppf"], _ = ops.knn_ppf(k, g["p"], g["n"], g["p"], g["n"], g["o"], g["o"], grid=g["grid"])
         _, g["ev_self"] = knn_lane.run(search_self)
 
@@ -319,7 +320,8 @@ def geometry(plan, pts, nrm, on_nodes=None):
             if li > 0:      # 3-NN of the finer level's points among this level's points (interpolation, pointops.py:168-182)
                 fine = G[li - 1]
                 fine["up_idx"], _, fine["up_dist"] = ops.knn_ppf(3, g["p"], None, fine["p"], None, g["o"], fine["o"],
-                                                                 drop_first=0, want_ppf=False, want_dist=True, grid=g["grid"])
+                                                                 drop_first=0, want_ppf=False, want_dist=True, grid=g["grid"],
+                                                                 qgrid=fine["grid"])
         _, ev_up = knn_lane.run(search_up)
         if li > 0:
             G[li - 1]["ev_up"] = ev_up
@@ -582,8 +584,10 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
         s_pad_t = ops.pad_transform_batched(B, Ns, src_pcd, rot, trans)
         g_s = ops.knn_grid_build(s_pad_t, o_s) if Ns + 1 >= ops.GRID_MIN_SEGMENT else None
         g_t = ops.knn_grid_build(t_pad, o_t) if Nt + 1 >= ops.GRID_MIN_SEGMENT else None
-        _, _, t_nn = ops.knn_ppf(1, s_pad_t, None, t_pad, None, o_s, o_t, drop_first=0, want_ppf=False, want_dist=True, grid=g_s)
-        _, _, s_nn = ops.knn_ppf(1, t_pad, None, s_pad_t, None, o_t, o_s, drop_first=0, want_ppf=False, want_dist=True, grid=g_t)
+        _, _, t_nn = ops.knn_ppf(1, s_pad_t, None, t_pad, None, o_s, o_t, drop_first=0, want_ppf=False, want_dist=True, grid=g_s,
+                                 qgrid=g_t)
+        _, _, s_nn = ops.knn_ppf(1, t_pad, None, s_pad_t, None, o_t, o_s, drop_first=0, want_ppf=False, want_dist=True, grid=g_t,
+                                 qgrid=g_s)
         occ.update(t_nn=t_nn.view(B, Nt + 1), s_nn=s_nn.view(B, Ns + 1), keep=(t_pad, s_pad_t, g_s, g_t))
     occ_done = fork.run_one(occlusion_nn)
 

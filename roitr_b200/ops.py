@@ -78,7 +78,7 @@ def concat_segment(x, g, offset):
     return out
 
 
-GRID_MIN_SEGMENT = 2048     # reference sets with at least this many points per segment get the grid-accelerated kNN
+GRID_MIN_SEGMENT = 1024     # reference sets with at least this many points per segment get the grid-accelerated kNN
 
 
 def knn_grid_build(xyz, offset):
@@ -91,15 +91,18 @@ def knn_grid_build(xyz, offset):
     return ws
 
 
-def knn_ppf(k, xyz, nrm, new_xyz, new_nrm, offset, new_offset, drop_first=1, want_ppf=True, want_dist=False, grid=None):
+def knn_ppf(k, xyz, nrm, new_xyz, new_nrm, offset, new_offset, drop_first=1, want_ppf=True, want_dist=False, grid=None,
+            qgrid=None):
+    """Exact kNN (+PPF). ``grid``: uniform grid over the reference set (knn_grid_build); ``qgrid``: the query set's own
+    grid, used only as a cache-friendly visiting order of the queries (same results with or without it)."""
     m = new_xyz.shape[0]
     idx = torch.empty(m, k, dtype=torch.int32, device=xyz.device)
     ppf = torch.empty(m, k, 4, dtype=torch.float32, device=xyz.device) if want_ppf else None
     dist = torch.empty(m, k, dtype=torch.float32, device=xyz.device) if want_dist else None
     if grid is not None:
-        _lib.call("roitr_knn_ppf_grid", c_int(offset.shape[0]), c_int(m), c_int(k), c_int(drop_first), c_int(xyz.shape[0]),
+        _lib.call("roitr_knn_ppf_grid_q", c_int(offset.shape[0]), c_int(m), c_int(k), c_int(drop_first), c_int(xyz.shape[0]),
                   f32(xyz), f32(nrm) if want_ppf else None, f32(new_xyz), f32(new_nrm) if want_ppf else None, i32(offset),
-                  i32(new_offset), ptr(grid), i32(idx), f32(dist), f32(ppf), stream_ptr())
+                  i32(new_offset), ptr(grid), ptr(qgrid), i32(idx), f32(dist), f32(ppf), stream_ptr())
         return idx, ppf, dist
     _lib.call("roitr_knn_ppf_n", c_int(offset.shape[0]), c_int(m), c_int(k), c_int(drop_first), c_int(xyz.shape[0]),
               f32(xyz), f32(nrm) if want_ppf else None, f32(new_xyz), f32(new_nrm) if want_ppf else None, i32(offset),

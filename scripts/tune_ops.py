@@ -30,23 +30,28 @@ def log(s):
     print(s); out.write(s + "\n"); out.flush()
 
 ref = None
-for target in (2.0, 3.0, 4.0, 6.0, 8.0, 12.0, 16.0):
-    _lib.lib().roitr_debug_set_knn_grid_target(ctypes.c_float(target))
-    t_build = timeit(lambda: ops.knn_grid_build(pts, o))
-    grid = ops.knn_grid_build(pts, o)
-    t_self = timeit(lambda: ops.knn_ppf(8, pts, nrm, pts, nrm, o, o, grid=grid))
-    t_down = timeit(lambda: ops.knn_ppf(16, pts, nrm, q, qn, o, qo, grid=grid))
-    t_one = timeit(lambda: ops.knn_ppf(1, pts, None, pts.flip(0).contiguous(), None, o, o, drop_first=0, want_ppf=False, want_dist=True, grid=grid))
-    gq = ops.knn_grid_build(q, qo)
-    t_up = timeit(lambda: ops.knn_ppf(3, q, None, pts, None, qo, o, drop_first=0, want_ppf=False, want_dist=True, grid=gq))
-    idx = ops.knn_ppf(8, pts, nrm, pts, nrm, o, o, grid=grid)[0]
-    idx2 = ops.knn_ppf(16, pts, nrm, q, qn, o, qo, grid=grid)[0]
-    if ref is None:
-        ref = (idx.clone(), idx2.clone())
-    same = bool(torch.equal(idx, ref[0]) and torch.equal(idx2, ref[1]))
-    log("grid target %5.1f: build %.3f ms | self k=9 (640k q) %.3f ms | down k=17 (160k q) %.3f ms | k=1 (640k q incl. flip copy) %.3f ms | "
-        "interp k=3 (640k q, 160k refs) %.3f ms | identical to target 2: %s" % (target, t_build, t_self, t_down, t_one, t_up, same))
-_lib.lib().roitr_debug_set_knn_grid_target(ctypes.c_float(4.0))
+for thread_q in (0, 1):
+    _lib.lib().roitr_debug_knn_thread_per_query(thread_q)
+    for target in ((1.0, 1.5, 2.0) if not thread_q else (0.5, 1.0, 1.5, 2.0, 3.0, 4.0)):
+        _lib.lib().roitr_debug_set_knn_grid_target(ctypes.c_float(target))
+        t_build = timeit(lambda: ops.knn_grid_build(pts, o))
+        grid = ops.knn_grid_build(pts, o)
+        gq = ops.knn_grid_build(q, qo)
+        t_self = timeit(lambda: ops.knn_ppf(8, pts, nrm, pts, nrm, o, o, grid=grid))
+        t_down = timeit(lambda: ops.knn_ppf(16, pts, nrm, q, qn, o, qo, grid=grid, qgrid=gq))
+        t_down_n = timeit(lambda: ops.knn_ppf(16, pts, nrm, q, qn, o, qo, grid=grid))
+        t_one = timeit(lambda: ops.knn_ppf(1, pts, None, pts, None, o, o, drop_first=0, want_ppf=False, want_dist=True, grid=grid))
+        t_up = timeit(lambda: ops.knn_ppf(3, q, None, pts, None, qo, o, drop_first=0, want_ppf=False, want_dist=True, grid=gq, qgrid=grid))
+        t_up_n = timeit(lambda: ops.knn_ppf(3, q, None, pts, None, qo, o, drop_first=0, want_ppf=False, want_dist=True, grid=gq))
+        idx = ops.knn_ppf(8, pts, nrm, pts, nrm, o, o, grid=grid)[0]
+        idx2 = ops.knn_ppf(16, pts, nrm, q, qn, o, qo, grid=grid, qgrid=gq)[0]
+        if ref is None:
+            ref = (idx.clone(), idx2.clone())
+        same = bool(torch.equal(idx, ref[0]) and torch.equal(idx2, ref[1]))
+        log("thread-per-query %d grid target %5.1f: build %.3f ms | self k=9 (640k q) %.3f ms | down k=17 (160k q) %.3f (natural order %.3f) ms | "
+            "k=1 self (640k q) %.3f ms | interp k=3 (640k q, 160k refs) %.3f (natural order %.3f) ms | identical to warp kernel: %s"
+            % (thread_q, target, t_build, t_self, t_down, t_down_n, t_one, t_up, t_up_n, same))
+_lib.lib().roitr_debug_set_knn_grid_target(ctypes.c_float(1.0))
 # brute force vs grid on the 1250-point level
 M2 = M // 4
 q2o = torch.tensor([M2 * (i + 1) for i in range(2 * B)], dtype=torch.int32, device=dev)
