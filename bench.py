@@ -155,7 +155,7 @@ def op_work(name, ints):
     if name in ("roitr_knn_ppf_n", "roitr_knn_ppf_grid", "roitr_knn_ppf_grid_q"):
         b, m, k, drop, n = ints[:5]
         return n * 24.0 + m * 24.0 + m * k * 20.0, 0.0, "hbm"
-    if name == "roitr_local_attention":
+    if name in ("roitr_local_attention", "roitr_local_attention_ordered"):
         m, C, _, knb = ints[:4]
         return m * (2.0 * knb * C * 4 + 2 * C * 4), 0.0, "hbm"
     if name == "roitr_row_epilogue":

@@ -72,6 +72,7 @@ int roitr_knn_ppf_n(int b, int m, int k_out, int drop_first, int n_total, const 
  *   roitr_knn_ppf_grid(...)               as roitr_knn_ppf_n, with the workspace (256-byte aligned)
  */
 long long roitr_knn_grid_workspace_bytes(int b, int n);
+long long roitr_knn_grid_sorted_offset(int b);
 int roitr_knn_grid_build(int b, int n, const float* xyz, const int* offset, void* workspace, void* stream);
 int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n_total, const float* xyz, const float* normals,
                        const float* new_xyz, const float* new_normals, const int* offset, const int* new_offset,
@@ -162,6 +163,13 @@ int roitr_concat_segment(int M, int C, int b, const float* x, const float* g, co
 int roitr_local_attention(int m, int C, int heads, int knb, const float* q, int ldq, const float* k, int ldk,
                           const float* v, int ldv, const int* node_idx, const int* group_idx, const float* ppf,
                           const float* Ap, const float* cp, const float* Avp, const float* cvp, float* out, void* stream);
+/* Same, visiting the queries in the order of `order_xyzi` ((m,4) floats: the cell-sorted (x, y, z, index) array of the
+ * query set's grid, see roitr_knn_grid_sorted_offset; NULL = natural order). Results are identical; neighbouring
+ * queries share neighbours, so the K/V gathers hit L1. */
+int roitr_local_attention_ordered(int m, int C, int heads, int knb, const float* q, int ldq, const float* k, int ldk,
+                                  const float* v, int ldv, const int* node_idx, const int* group_idx, const float* ppf,
+                                  const float* Ap, const float* cp, const float* Avp, const float* cvp,
+                                  const float* order_xyzi, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Global geometric transformer (model/transformer/positional_encoding.py:94-154, geoattention.py:43-136).

@@ -629,6 +629,9 @@ extern "C" long long roitr_knn_grid_workspace_bytes(int b, int n) {
     return (long long)(grid_hdr_bytes(b) + 2 * grid_cells_bytes(b) + (size_t)n * sizeof(float4));
 }
 
+/* byte offset, inside a grid workspace of b segments, of the cell-sorted (x, y, z, index) float4 array */
+extern "C" long long roitr_knn_grid_sorted_offset(int b) { return (long long)(grid_hdr_bytes(b) + 2 * grid_cells_bytes(b)); }
+
 extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* offset, void* workspace, void* stream) {
     ROITR_CHECK_ARG(b >= 1 && n >= 0 && xyz && offset && workspace, "knn_grid_build: bad arguments");
     ROITR_CHECK_ARG((uintptr_t)workspace % 256 == 0, "knn_grid_build: workspace must be 256-byte aligned");

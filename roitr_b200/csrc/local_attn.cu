@@ -52,6 +52,7 @@ struct LocalAttnParams {
     const float* Ap; const float* cp;     // (C,4), (C)
     const float* Avp; const float* cvp;   // (C,4), (C)
     float* out;                    // (m, C)
+    const float4* order;           // (m,) cell-sorted (x, y, z, query index) of the query set's grid, or NULL (natural order)
     int m;
     float sqrt_c;
 };
@@ -62,7 +63,9 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= P.m) return;
-    const int qi = warp;
+    // visiting order: with the cell-sorted order of the query set's grid the queries resident on an SM are spatial
+    // neighbours, their k-neighbourhoods overlap and most K/V row gathers hit L1 instead of L2
+    const int qi = P.order ? __float_as_int(__ldg(P.order + warp).w) : warp;
     const int node = P.node_idx ? __ldg(P.node_idx + qi) : qi;
     const int c0 = lane * CPL;
 
@@ -153,19 +156,21 @@ int launch(const LocalAttnParams& P, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int roitr_local_attention(int m, int C, int heads, int knb, const float* q, int ldq, const float* k, int ldk,
-                                     const float* v, int ldv, const int* node_idx, const int* group_idx,
-                                     const float* ppf, const float* Ap, const float* cp, const float* Avp,
-                                     const float* cvp, float* out, void* stream) {
+extern "C" int roitr_local_attention_ordered(int m, int C, int heads, int knb, const float* q, int ldq, const float* k,
+                                             int ldk, const float* v, int ldv, const int* node_idx, const int* group_idx,
+                                             const float* ppf, const float* Ap, const float* cp, const float* Avp,
+                                             const float* cvp, const float* order_xyzi, float* out, void* stream) {
     ROITR_CHECK_ARG(heads == 4, "local_attention: 4 heads only (model/model.py:149), got %d", heads);
     ROITR_CHECK_ARG(q && k && v && group_idx && ppf && Ap && cp && Avp && cvp && out, "local_attention: null pointer");
     ROITR_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "local_attention: leading dims must be multiples of 4");
     ROITR_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)ppf | (uintptr_t)Ap | (uintptr_t)Avp) % 16 == 0,
                     "local_attention: pointers must be 16-byte aligned");
+    ROITR_CHECK_ARG((uintptr_t)order_xyzi % 16 == 0, "local_attention: order must be 16-byte aligned");
     if (m == 0) return ROITR_OK;
     LocalAttnParams P;
     P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.node_idx = node_idx; P.group_idx = group_idx;
     P.ppf = ppf; P.Ap = Ap; P.cp = cp; P.Avp = Avp; P.cvp = cvp; P.out = out; P.m = m;
+    P.order = reinterpret_cast<const float4*>(order_xyzi);
     P.sqrt_c = sqrtf((float)(C / heads));
     cudaStream_t st = (cudaStream_t)stream;
 #define LA(CV, KV) if (C == CV && knb == KV) return launch<CV, KV>(P, st)
@@ -173,4 +178,12 @@ extern "C" int roitr_local_attention(int m, int C, int heads, int knb, const flo
 #undef LA
     roitr_set_error("local_attention: unsupported C=%d k=%d (C in {64,128,256,512}, k in {8,16})", C, knb);
     return ROITR_ERR_UNSUPPORTED;
+}
+
+extern "C" int roitr_local_attention(int m, int C, int heads, int knb, const float* q, int ldq, const float* k, int ldk,
+                                     const float* v, int ldv, const int* node_idx, const int* group_idx,
+                                     const float* ppf, const float* Ap, const float* cp, const float* Avp,
+                                     const float* cvp, float* out, void* stream) {
+    return roitr_local_attention_ordered(m, C, heads, knb, q, ldq, k, ldk, v, ldv, node_idx, group_idx, ppf, Ap, cp, Avp, cvp,
+                                         nullptr, out, stream);
 }

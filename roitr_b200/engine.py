@@ -170,20 +170,21 @@ def _ln(W, p, x, **kw):
     return ops.row_epilogue(x, gamma=W[p + ".weight"], beta=W[p + ".bias"], **kw)
 
 
-def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf):
-    """LocalPPFTransformer.forward (ppftransformer.py:243-253): (n,Cin) -> (m,Cout)."""
+def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None):
+    """LocalPPFTransformer.forward (ppftransformer.py:243-253): (n,Cin) -> (m,Cout). ``order``: see ops.local_attention."""
     C = W[p + ".in_proj.weight"].shape[0]
     f = _lin(W, p + ".in_proj", feats)
     qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], wpack=W.get(p + "#Wqkv#tc") if LINEAR_TC else None)
-    h = ops.local_attention(qkv, C, node_idx, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"], W[p + "#Avp"], W[p + "#cvp"])
+    h = ops.local_attention(qkv, C, node_idx, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"], W[p + "#Avp"], W[p + "#cvp"],
+                            order=order)
     t = _lin(W, p + ".transformer.linear", h)
     y = _ln(W, p + ".transformer.norm", t, res_pre=f, res_pre_index=node_idx, mode=ops.MODE_LN)
     return _lin(W, p + ".out_proj", y)
 
 
-def block(W, p, x, idx, ppf):
+def block(W, p, x, idx, ppf, order=None):
     """RIPointTransformerBlock.forward (model/model.py:131-142) with cached (idx, ppf)."""
-    y = local_ppf_transformer(W, p + ".transformer.transformer", x, None, idx, ppf)
+    y = local_ppf_transformer(W, p + ".transformer.transformer", x, None, idx, ppf, order)
     return _ln(W, p + ".bn2", y, res_post=x, mode=ops.MODE_LN | ops.MODE_RELU)
 
 
@@ -335,16 +336,18 @@ def encode(W, plan, G, feats):
     for li in range(4):
         p = "backbone.enc%d" % (li + 1)
         g = G[li]
+        order = (g["grid"], g["o"].shape[0]) if g["grid"] is not None else None     # this level's points in cell order
         if li > 0:
             _wait(g["ev_down"])
-            x = local_ppf_transformer(W, p + ".0.transformer", x, g["down_idx"], g["gidx"], g["gppf"])
+            x = local_ppf_transformer(W, p + ".0.transformer", x, g["down_idx"], g["gidx"], g["gppf"], order)
             _wait(g["ev_self"])
         else:
             _wait(g["ev_self"])        # (idx, ppf) shared by the TD and the blocks of level 1
-            x = local_ppf_transformer(W, p + ".0.transformer", x, None, g["idx"], g["ppf"])
+            x = local_ppf_transformer(W, p + ".0.transformer", x, None, g["idx"], g["ppf"], order)
         for bi in range(1, BLOCKS[li]):
-            x = block(W, "%s.%d" % (p, bi), x, g["idx"], g["ppf"])
-        levels.append(dict(p=g["p"], n=g["n"], x=x, o=g["o"], idx=g["idx"], ppf=g["ppf"], down_idx=g["down_idx"], g=g))
+            x = block(W, "%s.%d" % (p, bi), x, g["idx"], g["ppf"], order)
+        levels.append(dict(p=g["p"], n=g["n"], x=x, o=g["o"], idx=g["idx"], ppf=g["ppf"], down_idx=g["down_idx"], g=g,
+                           order=order))
     return levels
 
 
@@ -355,7 +358,7 @@ def decode(W, L):
     g = _lin(W, p + ".linear2.0", ops.segment_mean(l4["x"], l4["o"]), relu=True)
     y = _ln(W, p + ".linear1.1", _lin(W, p + ".linear1.0", ops.concat_segment(l4["x"], g, l4["o"])),
             mode=ops.MODE_LN | ops.MODE_RELU)
-    xs = [None, None, None, block(W, "backbone.dec4.1", y, l4["idx"], l4["ppf"])]
+    xs = [None, None, None, block(W, "backbone.dec4.1", y, l4["idx"], l4["ppf"], l4["order"])]
     for li in (2, 1, 0):
         p = "backbone.dec%d.0" % (li + 1)
         fine = L[li]
@@ -363,7 +366,7 @@ def decode(W, L):
         b = _ln(W, p + ".linear2.1", _lin(W, p + ".linear2.0", xs[li + 1]), mode=ops.MODE_LN | ops.MODE_RELU)
         _wait(fine["g"]["ev_up"])
         y = ops.interpolate(fine["g"]["up_idx"], fine["g"]["up_dist"], b, base=a)
-        xs[li] = block(W, "backbone.dec%d.1" % (li + 1), y, fine["idx"], fine["ppf"])
+        xs[li] = block(W, "backbone.dec%d.1" % (li + 1), y, fine["idx"], fine["ppf"], fine["order"])
     return xs
 
 
@@ -414,43 +417,57 @@ def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     return _ffn(W, lp + ".output", z)
 
 
-def geometric_transformer_batch(W, architecture, B, pts0, pts1, f0, f1, sigma_d=0.2, sigma_a=15.0):
-    """GeometricTransformer.forward (geotransformer.py:94-133) for B pairs at once: pts0/f0 = the B source clouds
-    stacked (B*N0 rows), pts1/f1 = the B target clouds (B*N1 rows). Dense layers run on the stacked rows; the embedding
-    and attention kernels are per cloud (attention batched over blockIdx.y)."""
+def geometric_transformer_batch(W, architecture, B, pts, feats, split, sigma_d=0.2, sigma_a=15.0):
+    """GeometricTransformer.forward (geotransformer.py:94-133) for B pairs at once. ``pts`` / ``feats`` hold the level-4
+    superpoints of all 2B clouds, rows [0, split) = the B source clouds, the rest = the B target clouds. Dense layers run
+    on stacked rows. The self layers use the same weights for both clouds of a pair (geotransformer.py:40-41), so when
+    source and target clouds have the same number of superpoints all 2B clouds go through ONE launch per operation
+    (half the launches of this latency-bound section, twice the CTAs per launch); the cross layers are sequential
+    (feats1 attends to the already-updated feats0, :45-46) and run per direction."""
     g = "backbone.global_transformer"
     e = g + ".embedding"
     C = W[g + ".in_proj.weight"].shape[0]
-    N0, N1 = pts0.shape[0] // B, pts1.shape[0] // B
-    embs = []
-    for pts, N in ((pts0, N0), (pts1, N1)):
-        pts = pts.contiguous()
-        nn3 = ops.geo_knn_batched(B, N, pts, 3)
+    N0, N1 = split // B, (pts.shape[0] - split) // B
+    stacked = N0 == N1
+
+    def embed(p_, nb, N):
+        p_ = p_.contiguous()
+        nn3 = ops.geo_knn_batched(nb, N, p_, 3)
         if GEO_EMBEDDING_TABLE and (e + "#tables") in W:
-            E = ops.geo_embedding_table(B, N, pts, nn3, W[e + "#tables"], W[e + ".proj_d.weight"], W[e + ".proj_d.bias"],
-                                        W[e + ".proj_a.weight"], W[e + ".proj_a.bias"], W[e + ".embedding.div_term"],
-                                        sigma_d, sigma_a)
-        elif GEO_EMBEDDING_TC:
-            E = ops.geo_embedding_tc_batched(B, N, pts, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
-                                             W[e + ".embedding.div_term"], sigma_d, sigma_a)
-        else:
-            E = torch.empty(B, N, N, C, dtype=torch.float32, device=pts.device)
-            for b in range(B):
-                ops.geo_embedding(pts[b * N:(b + 1) * N], nn3[b * N:(b + 1) * N], W[e + ".proj_d.weight"],
-                                  W[e + ".proj_d.bias"], W[e + ".proj_a.weight"], W[e + ".proj_a.bias"],
-                                  W[e + ".embedding.div_term"], sigma_d, sigma_a, out=E[b])
-        embs.append(E)
-    f0, f1 = _lin(W, g + ".in_proj", f0), _lin(W, g + ".in_proj", f1)
-    pos0 = pos1 = None
+            return ops.geo_embedding_table(nb, N, p_, nn3, W[e + "#tables"], W[e + ".proj_d.weight"], W[e + ".proj_d.bias"],
+                                           W[e + ".proj_a.weight"], W[e + ".proj_a.bias"], W[e + ".embedding.div_term"],
+                                           sigma_d, sigma_a)
+        if GEO_EMBEDDING_TC:
+            return ops.geo_embedding_tc_batched(nb, N, p_, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
+                                                W[e + ".embedding.div_term"], sigma_d, sigma_a)
+        E = torch.empty(nb, N, N, C, dtype=torch.float32, device=p_.device)
+        for b in range(nb):
+            ops.geo_embedding(p_[b * N:(b + 1) * N], nn3[b * N:(b + 1) * N], W[e + ".proj_d.weight"], W[e + ".proj_d.bias"],
+                              W[e + ".proj_a.weight"], W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], sigma_d, sigma_a,
+                              out=E[b])
+        return E
+    if stacked:
+        E_all = embed(pts, 2 * B, N0)
+        embs = (E_all[:B], E_all[B:])
+    else:
+        embs = (embed(pts[:split], B, N0), embed(pts[split:], B, N1))
+    f = _lin(W, g + ".in_proj", feats)
+    pos = None
     for i, kind in enumerate(architecture):
         lp = "%s.transformer.layers.%d" % (g, i)
         if kind == "self":
-            f0, pos0 = _self_layer_batch(W, lp, f0, embs[0], B, N0)
-            f1, pos1 = _self_layer_batch(W, lp, f1, embs[1], B, N1)
+            if stacked:
+                f, pos = _self_layer_batch(W, lp, f, E_all, 2 * B, N0)
+            else:
+                f0, pos0 = _self_layer_batch(W, lp, f[:split], embs[0], B, N0)
+                f1, pos1 = _self_layer_batch(W, lp, f[split:], embs[1], B, N1)
+                f, pos = torch.cat([f0, f1]), torch.cat([pos0, pos1])
         else:
-            f0 = _cross_layer_batch(W, lp, f0, f1, pos0, pos1, B, N0, N1)
-            f1 = _cross_layer_batch(W, lp, f1, f0, pos1, pos0, B, N1, N0)
-    return _lin(W, g + ".out_proj", f0), _lin(W, g + ".out_proj", f1), embs
+            f0 = _cross_layer_batch(W, lp, f[:split], f[split:], pos[:split], pos[split:], B, N0, N1)
+            f1 = _cross_layer_batch(W, lp, f[split:], f0, pos[split:], pos[:split], B, N1, N0)
+            f = torch.cat([f0, f1])
+    out = _lin(W, g + ".out_proj", f)
+    return out[:split], out[split:], embs
 
 
 # ------------------------------------------------------------------------------------------------ backbone
@@ -479,8 +496,7 @@ def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=Non
 
     G, lanes = geometry(plan, pts, nrm, on_nodes=_nodes)
     L = encode(W, plan, G, feats)
-    s_g_all, t_g_all, embs = geometric_transformer_batch(W, architecture, B, L[3]["p"][:split], L[3]["p"][split:],
-                                                         L[3]["x"][:split], L[3]["x"][split:])
+    s_g_all, t_g_all, embs = geometric_transformer_batch(W, architecture, B, L[3]["p"], L[3]["x"], split)
     per_pair = []
     for b in range(B):
         s0, s1 = plan.starts(3, b)

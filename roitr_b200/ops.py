@@ -136,15 +136,25 @@ def interpolate(idx, dist, feat, base=None):
     return out
 
 
-def local_attention(qkv, C, node_idx, group_idx, ppf, Ap, cp, Avp, cvp):
+def grid_order_ptr(grid, b):
+    """Device address of the cell-sorted (x, y, z, index) array inside a grid workspace of b segments (None -> NULL)."""
+    if grid is None:
+        return ctypes.c_void_p(0)
+    fn = _lib.lib().roitr_knn_grid_sorted_offset
+    fn.restype = c_ll
+    return ctypes.c_void_p(grid.data_ptr() + int(fn(c_int(b))))
+
+
+def local_attention(qkv, C, node_idx, group_idx, ppf, Ap, cp, Avp, cvp, order=None):
+    """``order`` = (grid workspace of the QUERY set, number of segments): visit the queries in cell order."""
     m, knb = group_idx.shape
     out = torch.empty(m, C, dtype=torch.float32, device=qkv.device)
     ld = qkv.stride(0)
     base = qkv.data_ptr()
     P = ctypes.c_void_p
-    _lib.call("roitr_local_attention", c_int(m), c_int(C), c_int(4), c_int(knb), P(base), c_int(ld), P(base + 4 * C),
+    _lib.call("roitr_local_attention_ordered", c_int(m), c_int(C), c_int(4), c_int(knb), P(base), c_int(ld), P(base + 4 * C),
               c_int(ld), P(base + 8 * C), c_int(ld), i32(node_idx), i32(group_idx), f32(ppf), f32(Ap), f32(cp), f32(Avp),
-              f32(cvp), f32(out), stream_ptr())
+              f32(cvp), grid_order_ptr(*order) if order is not None else P(0), f32(out), stream_ptr())
     return out
 
 
