@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # see roitr_b200/__init__.py (before the CUDA context exists)
 import torch  # noqa: E402
 
 N_POINTS = int(os.environ.get("ROITR_BENCH_POINTS", "20000"))

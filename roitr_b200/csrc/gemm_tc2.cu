@@ -279,12 +279,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Para
 // its look-ahead never waits for an MMA), and a separate OPS-deep ring holds the split hi/lo operands. The split of chunk
 // i therefore overlaps the MMAs of chunk i-1 and the HBM latency of chunks i+1 .. i+RAW-1. Pieces are mapped so that 8
 // consecutive lanes cover one 128-byte row segment (4 full lines per warp instruction) and 8 warps share the split pass.
-constexpr int T3_LOADERS = 256;
-constexpr int T3_THREADS = 128 + T3_LOADERS + 64;
+//
+// LW = loader warps, MINB = CTAs per SM the register allocation is capped for. The "light" instantiations (one operand
+// stage, two raw stages, 4 loader warps, <= 64 registers: ~115 KB of shared memory and 20 K registers per CTA) exist so
+// that a dense layer can share an SM with the CTAs of other streams' kernels (FPS clusters, kNN, attention) instead of
+// waiting for 215 KB of shared memory and 38 K registers to become free on every SM at once.
 constexpr int RAW_BYTES = T2_BM * 128;
 
-template <int BN, int OPS, int RAW>
-__global__ void __launch_bounds__(T3_THREADS, 1) linear_tc3_kernel(const Tc2Params P) {
+template <int BN, int OPS, int RAW, int LW, int MINB>
+__global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(const Tc2Params P) {
+    constexpr int T3_LOADERS = LW * 32;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int B_HALF = BN * 128;
@@ -311,7 +315,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) linear_tc3_kernel(const Tc2Para
     if (warp >= W_LOADER0 && warp < W_PRODUCER) {
         // ================================================= A loaders =================================================
         const int t = tid - 128;
-        const int c = t & 7, r0 = t >> 3;                               // pieces (r0 + 32 j, c), j = 0..3
+        constexpr int RSTEP = LW * 4, NPIECE = T2_BM / RSTEP;           // pieces (r0 + RSTEP j, c), j = 0..NPIECE-1
+        const int c = t & 7, r0 = t >> 3;
         unsigned char* raw = smem + OPS * STAGE_BYTES;
         const uint32_t raw_u32 = smem_u32(raw);
         int i_tile = blockIdx.x, i_kc = 0;
@@ -322,10 +327,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) linear_tc3_kernel(const Tc2Para
                 const int k = i_kc * T2_BK + 4 * c;
                 const int am0 = (i_tile / P.tiles_n) * T2_BM + r0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int am = am0 + 32 * j;
+                for (int j = 0; j < NPIECE; ++j) {
+                    const int am = am0 + RSTEP * j;
                     const bool ok = am < P.M && k < P.K;
-                    if (!(P.ablate & 16)) cp_async16(dst + j * 32 * 128, P.A + (ok ? (long long)am * P.lda + k : 0ll), ok ? 16u : 0u);
+                    if (!(P.ablate & 16)) cp_async16(dst + j * RSTEP * 128, P.A + (ok ? (long long)am * P.lda + k : 0ll), ok ? 16u : 0u);
                 }
                 ++i_it;
                 if (++i_kc == nkc) { i_kc = 0; i_tile += gridDim.x; }
@@ -340,15 +345,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) linear_tc3_kernel(const Tc2Para
                 issue_one();                                            // refills the slot this thread drained last iteration
                 cp_async_wait<RAW - 1>();                               // this thread's pieces of chunk `it` have landed
                 const unsigned char* src = raw + (it % RAW) * RAW_BYTES + r0 * 128 + c * 16;
-                float4 v[4];
+                float4 v[NPIECE];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * 32 * 128);
+                for (int j = 0; j < NPIECE; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * RSTEP * 128);
                 const int st = it % OPS;
                 mbar_wait(&empty_bar[st], ((it / OPS) & 1) ^ 1);        // MMAs of chunk it - OPS have retired
                 unsigned char* a_hi = smem + st * STAGE_BYTES;
                 if (!(P.ablate & 8)) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) split_store(a_hi, a_hi + A_HALF, r0 + 32 * j, c, v[j]);
+                    for (int j = 0; j < NPIECE; ++j) split_store(a_hi, a_hi + A_HALF, r0 + RSTEP * j, c, v[j]);
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&full_bar[st]);
@@ -428,21 +433,24 @@ __global__ void __launch_bounds__(T3_THREADS, 1) linear_tc3_kernel(const Tc2Para
     if (warp == 0) tmem_dealloc(tmem, 2 * BN);
 }
 
-template <int BN, int OPS, int RAW>
+template <int BN, int OPS, int RAW, int LW, int MINB>
 int launch_tc3(const Tc2Params& P, cudaStream_t st) {
+    constexpr int T3_THREADS = 128 + LW * 32 + 64;
     constexpr int smem = OPS * (2 * A_HALF + 2 * BN * 128) + RAW * RAW_BYTES + 1024;
     static bool attr = false;
-    static int num_sms = 0;
+    static int num_sms = 0, per_sm = 1;
     if (!attr) {
-        ROITR_CUDA(cudaFuncSetAttribute(linear_tc3_kernel<BN, OPS, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ROITR_CUDA(cudaFuncSetAttribute(linear_tc3_kernel<BN, OPS, RAW, LW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0;
         ROITR_CUDA(cudaGetDevice(&dev));
         ROITR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        ROITR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linear_tc3_kernel<BN, OPS, RAW, LW, MINB>, T3_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
         attr = true;
     }
     const int total = P.tiles_m * P.tiles_n;
-    const int grid = total < num_sms ? total : num_sms;
-    linear_tc3_kernel<BN, OPS, RAW><<<grid, T3_THREADS, smem, st>>>(P);
+    const int grid = total < num_sms * per_sm ? total : num_sms * per_sm;
+    linear_tc3_kernel<BN, OPS, RAW, LW, MINB><<<grid, T3_THREADS, smem, st>>>(P);
     ROITR_CHECK_LAUNCH("linear_tc3_kernel");
     return ROITR_OK;
 }
@@ -470,7 +478,7 @@ int launch_tc2(const Tc2Params& P, cudaStream_t st) {
 
 static int g_ablate = 0;
 extern "C" int roitr_debug_linear_ablate(int mask) { g_ablate = mask; return 0; }
-static int g_tc3_variant = 0;  // debug only: ring depths of the 64-column streaming kernel (0: 3 operand / 3 raw, 1: 2/4, 2: 2/5)
+static int g_tc3_variant = 0;  // debug only: streaming-kernel configuration (0: deep rings, 1 CTA/SM; 1, 2: other ring depths at 64 columns; 3, 4: light, co-residency friendly)
 extern "C" int roitr_debug_linear_variant(int v) { g_tc3_variant = v; return 0; }
 static int g_force_tc2 = 0;   // debug only: route everything through the coupled-ring kernel (A/B timing)
 extern "C" int roitr_debug_force_linear_tc2(int on) { g_force_tc2 = on; return 0; }
@@ -490,10 +498,12 @@ extern "C" int roitr_linear_tc_packed(int M, int N, int K, const float* A, const
     cudaStream_t st = (cudaStream_t)stream;
     const bool stream_ok = !a_add && !a_index && lda % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0;
     if (stream_ok && !g_force_tc2) {
-        if (bn == 128) return launch_tc3<128, 2, 4>(P, st);
-        if (g_tc3_variant == 1) return launch_tc3<64, 2, 4>(P, st);
-        if (g_tc3_variant == 2) return launch_tc3<64, 2, 5>(P, st);
-        return launch_tc3<64, 3, 3>(P, st);
+        if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
+        if (g_tc3_variant == 4) return bn == 128 ? launch_tc3<128, 1, 3, 4, 3>(P, st) : launch_tc3<64, 2, 2, 4, 3>(P, st);
+        if (bn == 128) return launch_tc3<128, 2, 4, 8, 1>(P, st);
+        if (g_tc3_variant == 1) return launch_tc3<64, 2, 4, 8, 1>(P, st);
+        if (g_tc3_variant == 2) return launch_tc3<64, 2, 5, 8, 1>(P, st);
+        return launch_tc3<64, 3, 3, 8, 1>(P, st);
     }
     if (bn == 64) return launch_tc2<64, 4>(P, st);
     return launch_tc2<128, 3>(P, st);

@@ -254,6 +254,16 @@ class Plan:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n)]
         return self._streams[:n]
 
+    def global_lane(self):
+        """The stream that carries the global transformer next to the decoder (inline for single pairs / serial plans)."""
+        if self.B <= 1 or getattr(self, "serial", False):
+            return _Lane(None)
+        if not hasattr(self, "_glane"):
+            # high priority: its ~170 small launches are the critical path to coarse / fine matching; without it each of
+            # them queues behind whichever persistent decoder kernel currently owns the SMs
+            self._glane = torch.cuda.Stream(device=self.device, priority=-1)
+        return _Lane(self._glane)
+
     def lanes(self):
         """(sampling lane, neighbour-search lane): the two streams that carry the coordinate-only work of the backbone
         (FPS chain; grids + kNN/PPF), or (None, None) when the plan runs everything inline on the current stream."""
@@ -276,36 +286,40 @@ class Plan:
         return self.one[n]
 
 
-def geometry(plan, pts, nrm, on_nodes=None):
-    """Everything in the backbone that depends on coordinates only, for all 2B clouds of the plan: the FPS chain, the
-    uniform grids, every kNN(+PPF) query (self, down-sampling, 3-NN up-sampling). None of it needs features, so for a
-    batch it is issued on two side streams (sampling lane: the latency-bound FPS chain; search lane: grids + kNN) and
-    overlaps the dense layers / attention of the main stream; every item carries the event that marks it ready.
+def encode(W, plan, pts, feats, nrm, on_nodes=None):
+    """enc1..enc4 for all 2B clouds of the plan at once (segment-batched kernels).
+
+    Everything that depends on coordinates only - the FPS chain, the uniform grids, every kNN(+PPF) query (self,
+    down-sampling, 3-NN up-sampling) - needs no features, so for a batch it is issued on two side streams (sampling lane:
+    the latency-bound FPS chain; search lane: grids + kNN) and overlaps the dense layers / attention of the main stream;
+    every item carries the event that marks it ready. ISSUE ORDER matters even inside a CUDA graph (nodes captured later
+    were observed to start only after earlier-captured, still-blocked nodes had been dispatched; scripts/timeline.py), so
+    work is issued in the order it can start: search(0), sample(1), layers(0), search(1), sample(2), layers(1), ...
     ``on_nodes(levels, down_idx4, p4)`` is called on the sampling lane as soon as the level-4 superpoints exist."""
     fps_lane, knn_lane = plan.lanes()
     fps_lane.start(); knn_lane.start()
     mk_grid = lambda li, p_, o_: ops.knn_grid_build(p_, o_) if plan.levels[li]["n_max"] >= ops.GRID_MIN_SEGMENT else None
-    G = [dict(p=pts, n=nrm, o=plan.levels[0]["o"], down_idx=None) for _ in range(1)]
-    # sampling lane: level li+1 points/normals from level li
-    for li in range(1, 4):
+    G = [dict(p=pts, n=nrm, o=plan.levels[0]["o"], down_idx=None, ev_pts=None)]
+
+    def issue_sample(li):          # sampling lane: level li points / normals from level li - 1
         prev, L = G[li - 1], plan.levels[li]
 
-        def sample(prev=prev, L=L, li=li):
+        def sample():
             down_idx, n_p = ops.fps(prev["p"], prev["o"], L["o"], plan.levels[li - 1]["n_max"], L["total"],
                                     per_segment_rule=True, cluster=plan.fps_cluster)
             g = dict(p=n_p, n=ops.gather_rows(prev["n"], down_idx), o=L["o"], down_idx=down_idx)
+            # the level's points are ready here; what on_nodes issues behind them on this lane must not delay the search lane
+            g["ev_pts"] = torch.cuda.current_stream().record_event() if fps_lane.stream is not None else None
             if li == 3 and on_nodes is not None:
                 on_nodes(G + [g], down_idx, n_p)
             return g
-        g, ev = fps_lane.run(sample)
-        g["ev_pts"] = ev
+        g, _ = fps_lane.run(sample)
         G.append(g)
-    G[0]["ev_pts"] = None
-    # search lane
-    for li in range(4):
+
+    def issue_search(li):          # search lane: every kNN query whose queries or references are level li
         g, k = G[li], NSAMPLE[li]
 
-        def search(g=g, k=k, li=li):
+        def search():
             g["grid"] = mk_grid(li, g["p"], g["o"])      # also the visiting order of this level's points as queries
             if li > 0:
                 up = G[li - 1]
@@ -313,11 +327,11 @@ def geometry(plan, pts, nrm, on_nodes=None):
                                                       qgrid=g["grid"])
         _, g["ev_down"] = knn_lane.run(search, g["ev_pts"])
 
-        def search_self(g=g, k=k, li=li):
+        def search_self():
             g["idx"], g["ppf"], _ = ops.knn_ppf(k, g["p"], g["n"], g["p"], g["n"], g["o"], g["o"], grid=g["grid"])
         _, g["ev_self"] = knn_lane.run(search_self)
 
-        def search_up(g=g, li=li):
+        def search_up():
             if li > 0:      # 3-NN of the finer level's points among this level's points (interpolation, pointops.py:168-182)
                 fine = G[li - 1]
                 fine["up_idx"], _, fine["up_dist"] = ops.knn_ppf(3, g["p"], None, fine["p"], None, g["o"], fine["o"],
@@ -326,11 +340,9 @@ def geometry(plan, pts, nrm, on_nodes=None):
         _, ev_up = knn_lane.run(search_up)
         if li > 0:
             G[li - 1]["ev_up"] = ev_up
-    return G, (fps_lane, knn_lane)
 
-
-def encode(W, plan, G, feats):
-    """enc1..enc4 for all 2B clouds of the plan at once (segment-batched kernels), consuming the geometry of ``G``."""
+    issue_search(0)
+    issue_sample(1)
     levels = []
     x = feats
     for li in range(4):
@@ -348,7 +360,11 @@ def encode(W, plan, G, feats):
             x = block(W, "%s.%d" % (p, bi), x, g["idx"], g["ppf"], order)
         levels.append(dict(p=g["p"], n=g["n"], x=x, o=g["o"], idx=g["idx"], ppf=g["ppf"], down_idx=g["down_idx"], g=g,
                            order=order))
-    return levels
+        if li + 1 < 4:
+            issue_search(li + 1)
+            if li + 2 < 4:
+                issue_sample(li + 2)
+    return levels, (fps_lane, knn_lane)
 
 
 def decode(W, L):
@@ -417,18 +433,14 @@ def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     return _ffn(W, lp + ".output", z)
 
 
-def geometric_transformer_batch(W, architecture, B, pts, feats, split, sigma_d=0.2, sigma_a=15.0):
-    """GeometricTransformer.forward (geotransformer.py:94-133) for B pairs at once. ``pts`` / ``feats`` hold the level-4
-    superpoints of all 2B clouds, rows [0, split) = the B source clouds, the rest = the B target clouds. Dense layers run
-    on stacked rows. The self layers use the same weights for both clouds of a pair (geotransformer.py:40-41), so when
-    source and target clouds have the same number of superpoints all 2B clouds go through ONE launch per operation
-    (half the launches of this latency-bound section, twice the CTAs per launch); the cross layers are sequential
-    (feats1 attends to the already-updated feats0, :45-46) and run per direction."""
+def geometric_embedding_batch(W, B, pts, split, sigma_d=0.2, sigma_a=15.0):
+    """GeometricStructureEmbedding (positional_encoding.py:94-154) of the level-4 superpoints of all 2B clouds (rows
+    [0, split) = the B source clouds). Depends on coordinates only. Returns (E_all or None, (E_src, E_tgt)): when both
+    clouds of a pair have the same number of superpoints all 2B embeddings are one (2B, N, N, C) tensor."""
     g = "backbone.global_transformer"
     e = g + ".embedding"
     C = W[g + ".in_proj.weight"].shape[0]
     N0, N1 = split // B, (pts.shape[0] - split) // B
-    stacked = N0 == N1
 
     def embed(p_, nb, N):
         p_ = p_.contiguous()
@@ -446,17 +458,28 @@ def geometric_transformer_batch(W, architecture, B, pts, feats, split, sigma_d=0
                               W[e + ".proj_a.weight"], W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], sigma_d, sigma_a,
                               out=E[b])
         return E
-    if stacked:
+    if N0 == N1:
         E_all = embed(pts, 2 * B, N0)
-        embs = (E_all[:B], E_all[B:])
-    else:
-        embs = (embed(pts[:split], B, N0), embed(pts[split:], B, N1))
+        return E_all, (E_all[:B], E_all[B:])
+    return None, (embed(pts[:split], B, N0), embed(pts[split:], B, N1))
+
+
+def geometric_transformer_batch(W, architecture, B, feats, split, emb):
+    """GeometricTransformer.forward (geotransformer.py:94-133) for B pairs at once. ``feats`` holds the level-4 superpoint
+    features of all 2B clouds, rows [0, split) = the B source clouds, the rest = the B target clouds; ``emb`` is the
+    result of geometric_embedding_batch. Dense layers run on stacked rows. The self layers use the same weights for both
+    clouds of a pair (geotransformer.py:40-41), so when source and target clouds have the same number of superpoints all
+    2B clouds go through ONE launch per operation (half the launches of this latency-bound section, twice the CTAs per
+    launch); the cross layers are sequential (feats1 attends to the already-updated feats0, :45-46) and run per direction."""
+    g = "backbone.global_transformer"
+    E_all, embs = emb
+    N0, N1 = split // B, (feats.shape[0] - split) // B
     f = _lin(W, g + ".in_proj", feats)
     pos = None
     for i, kind in enumerate(architecture):
         lp = "%s.transformer.layers.%d" % (g, i)
         if kind == "self":
-            if stacked:
+            if E_all is not None:
                 f, pos = _self_layer_batch(W, lp, f, E_all, 2 * B, N0)
             else:
                 f0, pos0 = _self_layer_batch(W, lp, f[:split], embs[0], B, N0)
@@ -467,11 +490,12 @@ def geometric_transformer_batch(W, architecture, B, pts, feats, split, sigma_d=0
             f1 = _cross_layer_batch(W, lp, f[split:], f0, pos[split:], pos[:split], B, N1, N0)
             f = torch.cat([f0, f1])
     out = _lin(W, g + ".out_proj", f)
-    return out[:split], out[split:], embs
+    return out[:split], out[split:]
 
 
 # ------------------------------------------------------------------------------------------------ backbone
-def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=None, on_nodes=None, on_global=None):
+def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=None, on_nodes=None, on_global=None,
+                   join=True):
     """RIPointTransformer.forward (model/model.py:187-237) for all pairs of the plan. Returns per-level batched tensors,
     the decoded level-1 features and, per pair, (src_nodes, src_node_feats, tgt_node_feats).
 
@@ -493,24 +517,44 @@ def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=Non
                      tgt=[p4[plan.starts(3, B + b)[0]:plan.starts(3, B + b)[1]] for b in range(B)])
         if on_nodes is not None:
             on_nodes(nodes)
+        # the geometric structure embedding needs the superpoint coordinates only: it is issued here, on the sampling
+        # lane, and overlaps the encoder instead of sitting between the encoder and the global transformer
+        nodes["emb"] = geometric_embedding_batch(W, B, p4, split)
+        nodes["ev_emb"] = torch.cuda.current_stream().record_event() if B > 1 and not getattr(plan, "serial", False) else None
 
-    G, lanes = geometry(plan, pts, nrm, on_nodes=_nodes)
-    L = encode(W, plan, G, feats)
-    s_g_all, t_g_all, embs = geometric_transformer_batch(W, architecture, B, L[3]["p"], L[3]["x"], split)
+    L, lanes = encode(W, plan, pts, feats, nrm, on_nodes=_nodes)
     per_pair = []
-    for b in range(B):
-        s0, s1 = plan.starts(3, b)
-        t0, t1 = plan.starts(3, B + b)
-        per_pair.append(dict(src_nodes=nodes["src"][b], src_g=s_g_all[s0:s1], tgt_g=t_g_all[t0 - split:t1 - split],
-                             tgt_nodes=nodes["tgt"][b], embs=(embs[0][b], embs[1][b]) if aux is not None else None))
-    if on_global is not None:
-        on_global(per_pair, s_g_all, t_g_all)
+
+    def global_part():
+        s_g_all, t_g_all = geometric_transformer_batch(W, architecture, B, L[3]["x"], split, nodes["emb"])
+        embs = nodes["emb"][1]
+        for b in range(B):
+            s0, s1 = plan.starts(3, b)
+            t0, t1 = plan.starts(3, B + b)
+            per_pair.append(dict(src_nodes=nodes["src"][b], src_g=s_g_all[s0:s1], tgt_g=t_g_all[t0 - split:t1 - split],
+                                 tgt_nodes=nodes["tgt"][b], embs=(embs[0][b], embs[1][b]) if aux is not None else None))
+        if on_global is not None:
+            on_global(per_pair, s_g_all, t_g_all)
+    # The decoder does not consume the global transformer's output (model/model.py:214-231): the global transformer (a
+    # chain of ~170 small, latency-bound launches) runs on its own stream next to the decoder (few, bandwidth-bound ones).
+    glob = plan.global_lane()
+    ev_enc = torch.cuda.current_stream().record_event() if glob.stream is not None else None
+    glob.used = glob.stream is not None
+    glob.run(global_part, ev_enc, nodes.get("ev_emb"))
     dec = decode(W, L)
-    for lane in lanes:
-        lane.join()
+    plan.pending_lanes = lanes + (glob,)
+    if join:
+        join_lanes(plan)
     if aux is not None:
         aux.update(levels=L, dec=dec, node_idx=nodes["d4"], emb0=per_pair[0]["embs"][0], emb1=per_pair[0]["embs"][1])
     return L, dec, per_pair
+
+
+def join_lanes(plan):
+    """The current stream waits for every lane the backbone forked (required before a capture ends)."""
+    for lane in getattr(plan, "pending_lanes", ()):
+        lane.join()
+    plan.pending_lanes = ()
 
 
 def backbone_forward(W, architecture, s_pxon, t_pxon, src_deformed, aux=None):
@@ -643,7 +687,7 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
         fork.run(B, coarse)
 
     L, dec, per_pair = backbone_batch(W, cfg["transformer_architecture"], plan, pts, feats, nrm, src_pcd, aux,
-                                      on_nodes=on_nodes, on_global=on_global)
+                                      on_nodes=on_nodes, on_global=on_global, join=False)
     pf_all = _lin(W, "fine_proj", dec[0])                                # all points of all clouds at once
 
     def fine(b):   # 4-6. fine scoring + OT + fine matching
@@ -659,6 +703,7 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
                  c_flat=c_flat, cap=cap, counts=torch.cat([q["p_count"], q["gt_count"], c_count]))
     fork.run(B, fine)
     fork.join()
+    join_lanes(plan)
     return st, torch.stack([q["counts"] for q in st])
 
 
