@@ -132,7 +132,7 @@ def run_reference(args):
 def op_work(name, ints):
     """Algorithmic work of one entry-point call from its leading integer arguments (DESIGN.md §4 / SURVEY.md §8d).
     -> (bytes, flop, bound): compulsory bytes, fp32-equivalent flops, and the roofline that bounds the kernel."""
-    if name in ("roitr_linear", "roitr_linear_tc", "roitr_linear_tc_packed"):
+    if name in ("roitr_linear", "roitr_linear_tc", "roitr_linear_tc_packed", "roitr_linear_ln_tc_packed"):
         M, N, K = ints[:3]     # skinny dense layers over tall activations: activations in + out (+ weights once)
         return 4.0 * (M * K + M * N + N * K), 2.0 * M * N * K, "hbm"
     if name == "roitr_gemm_tc_batched":
@@ -323,7 +323,7 @@ def main():
                        "step itself is one multi-stream CUDA graph); algorithmic work per DESIGN.md §4 / SURVEY.md §8d")
         named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid_q", "roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build"]),
                  "global_attention_qk_pv": roofline_of(["roitr_gemm_tc_batched"]),
-                 "dense_layers": roofline_of(["roitr_linear_tc_packed"]),
+                 "dense_layers": roofline_of(["roitr_linear_tc_packed", "roitr_linear_ln_tc_packed"]),
                  "fine_matching": roofline_of(["roitr_fine_matching"])}
         line = {
             "metric": METRIC, "value": world * B * steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,

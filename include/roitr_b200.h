@@ -142,6 +142,14 @@ int roitr_linear_tc(int M, int N, int K, const float* A, const float* a_add, int
  * [ceil(N/bn)][ceil(K/32)][hi|lo][bn*32] floats, zero padded, bn in {64,128}. Same contract as roitr_linear otherwise. */
 int roitr_linear_tc_packed(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
                            const float* wpack, int bn, const float* bias, float* C, int ldc, int relu, void* stream);
+/* Dense layer with the row epilogue fused (one kernel instead of roitr_linear_tc_packed + roitr_row_epilogue):
+ *   C = act( LayerNorm_N( A W^T + bias + res_pre[res_pre_index] ) * gamma + beta + res_post ),  act = ReLU if relu
+ * (LocalRPEAttentionLayer output: attention.py:317-319; RIPointTransformerBlock: model/model.py:139-141; TransitionUp:
+ * model/model.py:103-105). N must be a multiple of 32 and fit one weight tile (N <= bn); res_pre / res_post rows have pitch
+ * ldr; res_pre_index (int32, optional) gathers res_pre rows. eps = 1e-5. */
+int roitr_linear_ln_tc_packed(int M, int N, int K, const float* A, int lda, const float* wpack, int bn, const float* bias,
+                              const float* gamma, const float* beta, const float* res_pre, const int* res_pre_index,
+                              const float* res_post, int ldr, int relu, float* C, int ldc, void* stream);
 
 /* out = [L2norm] [ReLU] ( [LayerNorm_{gamma,beta,eps=1e-5}] (x + res_pre[res_pre_index]) + res_post ), one row of C<=1024
  * floats per warp. mode bits: 1 LayerNorm, 2 ReLU, 4 x / max(|x|_2, 1e-12). Any of the residuals may be NULL. */

@@ -45,6 +45,9 @@ struct Tc2Params {
     const float* bias;
     float* C; int ldc; int relu;
     int tiles_m, tiles_n, nkc;
+    // fused row epilogue (streaming kernel, N <= one tile): out = act(LN(acc + bias + res_pre[idx]) * gamma + beta + res_post)
+    const float* ln_gamma; const float* ln_beta; const float* res_pre; const int* res_pre_index; const float* res_post;
+    int ln, ldr;            // ln != 0: LayerNorm over the N columns (eps 1e-5); ldr = row pitch of res_pre / res_post
     int ablate;             // debug only (roitr_debug_linear_ablate): 1 no C stores, 2 W fetched once, 4 no MMA, 8 no split, 16 no A loads
 };
 
@@ -53,8 +56,9 @@ struct Tc2Params {
 // 16-byte writes of 8 consecutive rows and the 16-byte reads of one row both touch all 32 banks once) so that 8 lanes
 // write one 128-byte row segment with float4 stores: 8 store instructions per block, each covering 4 full lines.
 constexpr int PAD_STRIDE = 36;
-__device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, const float (&v)[32], int lane, int row0, int ncol0) {
-    const bool vec = (P.ldc % 4 == 0) && (P.N % 4 == 0) && ((uintptr_t)P.C % 16 == 0);
+__device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, const float (&v)[32], int lane, int row0, int ncol0,
+                                              const float* bias, const float* post) {
+    const bool vec = (P.ldc % 4 == 0) && (P.N % 4 == 0) && ((uintptr_t)P.C % 16 == 0) && (!post || P.ldr % 4 == 0);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(pad + lane * PAD_STRIDE + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -63,24 +67,31 @@ __device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, co
         const int sub = lane >> 3, n = ncol0 + 4 * (lane & 7);
         if (n < P.N && !(P.ablate & 1)) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (P.bias) b = __ldg(reinterpret_cast<const float4*>(P.bias + n));
+            if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + n));
             float* dst = P.C + (long long)(row0 + sub) * P.ldc + n;
-            const long long step = 4ll * P.ldc;
+            const float* pp = post ? post + (long long)(row0 + sub) * P.ldr + n : nullptr;
+            const long long step = 4ll * P.ldc, pstep = 4ll * P.ldr;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float4 x = *reinterpret_cast<const float4*>(pad + (4 * i + sub) * PAD_STRIDE + 4 * (lane & 7));
                 x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+                const bool ok = row0 + 4 * i + sub < P.M;
+                if (pp && ok) {
+                    const float4 r = __ldg(reinterpret_cast<const float4*>(pp + i * pstep));
+                    x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+                }
                 if (P.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                if (row0 + 4 * i + sub < P.M) *reinterpret_cast<float4*>(dst + i * step) = x;
+                if (ok) *reinterpret_cast<float4*>(dst + i * step) = x;
             }
         }
     } else {
         const int n = ncol0 + lane;
         if (n < P.N && !(P.ablate & 1)) {
-            const float bv = P.bias ? __ldg(P.bias + n) : 0.f;
+            const float bv = bias ? __ldg(bias + n) : 0.f;
             for (int i = 0; i < 32; ++i) {
                 if (row0 + i >= P.M) break;
                 float x = pad[i * PAD_STRIDE + lane] + bv;
+                if (post) x += __ldg(post + (long long)(row0 + i) * P.ldr + n);
                 if (P.relu) x = fmaxf(x, 0.f);
                 P.C[(long long)(row0 + i) * P.ldc + n] = x;
             }
@@ -88,7 +99,9 @@ __device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, co
     }
     __syncwarp();
 }
-
+__device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, const float (&v)[32], int lane, int row0, int ncol0) {
+    store_block32(P, pad, v, lane, row0, ncol0, P.bias, nullptr);
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Params P) {
@@ -296,6 +309,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
     __shared__ __align__(8) uint64_t full_bar[OPS], empty_bar[OPS], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_pad[4][32 * PAD_STRIDE];
+    __shared__ __align__(16) float s_ln[3][BN];        // bias, gamma, beta of the fused LayerNorm epilogue
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -304,6 +318,14 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&s_tmem, 2 * BN);
+    if (P.ln && tid < 128) {
+        for (int i = tid; i < BN; i += 128) {
+            const bool in = i < P.N;
+            s_ln[0][i] = (in && P.bias) ? __ldg(P.bias + i) : 0.f;
+            s_ln[1][i] = in ? __ldg(P.ln_gamma + i) : 0.f;
+            s_ln[2][i] = in ? __ldg(P.ln_beta + i) : 0.f;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -417,12 +439,74 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
             tc_fence_after();
             const int row0 = tm * T2_BM + warp * 32;
             const int n0 = tn * BN;
+            const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+            if (P.ln) {
+                // Fused row epilogue (host guarantees one n-tile, N % 32 == 0). After tcgen05.ld a thread holds 32 columns
+                // of ITS row, so the LayerNorm statistics are thread-local: pass A adds bias and the (optionally gathered)
+                // pre-norm residual and writes the row back to TMEM while summing it, pass B sums the squared deviations,
+                // pass C normalises and hands 32x32 blocks to the transposed store (post-norm residual, ReLU, float4 rows).
+                const int row = row0 + lane;
+                const bool valid = row < P.M;
+                const float* pre = nullptr;
+                if (P.res_pre && valid)
+                    pre = P.res_pre + (P.res_pre_index ? (long long)__ldg(P.res_pre_index + row) : (long long)row) * P.ldr;
+                // one pass for both moments, shifted by the row's first value so that the subtraction sum2/N - (sum1/N)^2
+                // never cancels (|mean - shift| is of the order of the standard deviation)
+                float s1 = 0.f, s2 = 0.f, shift = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (n0 + c0 >= P.N) break;
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                store_block32(P, pad, v, lane, row0, n0 + c0);
+                for (int c0 = 0; c0 < P.N; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tbase + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = *reinterpret_cast<const float4*>(&s_ln[0][c0 + 4 * j]);
+                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                    if (pre) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(pre + c0) + j);
+                            v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                        }
+                    }
+                    if (c0 == 0) shift = v[0];
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float d0 = v[4 * j] - shift, d1 = v[4 * j + 1] - shift, d2 = v[4 * j + 2] - shift, d3 = v[4 * j + 3] - shift;
+                        a0 += d0; a1 += d1; a2 += d2; a3 += d3;
+                        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+                    }
+                    s1 += (a0 + a1) + (a2 + a3);
+                    s2 += (q0 + q1) + (q2 + q3);
+                    tmem_st32(tbase + c0, v);
+                }
+                const float inv_n = 1.0f / (float)P.N;
+                const float dm = s1 * inv_n;
+                const float mean = shift + dm;
+                const float sq = fmaxf(s2 - s1 * dm, 0.f);               // sum (x - mean)^2 = sum d^2 - (sum d)^2 / N
+                const float rstd = rsqrtf(sq / (float)P.N + 1e-5f);
+#pragma unroll 1
+                for (int c0 = 0; c0 < P.N; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tbase + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 g = *reinterpret_cast<const float4*>(&s_ln[1][c0 + 4 * j]);
+                        const float4 b = *reinterpret_cast<const float4*>(&s_ln[2][c0 + 4 * j]);
+                        v[4 * j] = (v[4 * j] - mean) * rstd * g.x + b.x; v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
+                        v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z; v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
+                    }
+                    store_block32(P, pad, v, lane, row0, c0, nullptr, P.res_post);
+                }
+            } else {
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if (n0 + c0 >= P.N) break;
+                    float v[32];
+                    tmem_ld32(tbase + c0, v);
+                    store_block32(P, pad, v, lane, row0, n0 + c0);
+                }
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
@@ -483,9 +567,10 @@ extern "C" int roitr_debug_linear_variant(int v) { g_tc3_variant = v; return 0; 
 static int g_force_tc2 = 0;   // debug only: route everything through the coupled-ring kernel (A/B timing)
 extern "C" int roitr_debug_force_linear_tc2(int on) { g_force_tc2 = on; return 0; }
 
-extern "C" int roitr_linear_tc_packed(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
-                                      const float* wpack, int bn, const float* bias, float* C, int ldc, int relu,
-                                      void* stream) {
+static int linear_tc_packed_impl(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
+                                 const float* wpack, int bn, const float* bias, float* C, int ldc, int relu,
+                                 const float* ln_gamma, const float* ln_beta, const float* res_pre, const int* res_pre_index,
+                                 const float* res_post, int ldr, void* stream) {
     ROITR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && A && wpack && C, "linear_tc_packed: bad arguments M=%d N=%d K=%d", M, N, K);
     ROITR_CHECK_ARG(lda >= K && ldc >= N, "linear_tc_packed: bad leading dimensions");
     ROITR_CHECK_ARG(bn == 64 || bn == 128, "linear_tc_packed: weights must be packed with 64- or 128-row tiles, got %d", bn);
@@ -494,9 +579,17 @@ extern "C" int roitr_linear_tc_packed(int M, int N, int K, const float* A, const
     Tc2Params P;
     P.M = M; P.N = N; P.K = K; P.A = A; P.A2 = a_add; P.lda = lda; P.a_index = a_index; P.wpack = wpack; P.bias = bias; P.C = C;
     P.ldc = ldc; P.relu = relu; P.ablate = g_ablate;
+    P.ln = ln_gamma != nullptr; P.ln_gamma = ln_gamma; P.ln_beta = ln_beta; P.res_pre = res_pre; P.res_pre_index = res_pre_index;
+    P.res_post = res_post; P.ldr = ldr;
     P.tiles_m = ceil_div(M, T2_BM); P.tiles_n = ceil_div(N, bn); P.nkc = ceil_div(K, T2_BK);
     cudaStream_t st = (cudaStream_t)stream;
     const bool stream_ok = !a_add && !a_index && lda % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0;
+    if (P.ln) {
+        ROITR_CHECK_ARG(stream_ok && P.tiles_n == 1 && N % 32 == 0 && ln_beta && ldr >= N && ldr % 4 == 0 &&
+                            ((uintptr_t)res_pre | (uintptr_t)res_post) % 16 == 0,
+                        "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile (N=%d, tile %d)", N, bn);
+        return bn == 64 ? launch_tc3<64, 3, 3, 8, 1>(P, st) : launch_tc3<128, 2, 4, 8, 1>(P, st);
+    }
     if (stream_ok && !g_force_tc2) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
         if (g_tc3_variant == 4) return bn == 128 ? launch_tc3<128, 1, 3, 4, 3>(P, st) : launch_tc3<64, 2, 2, 4, 3>(P, st);
@@ -507,4 +600,20 @@ extern "C" int roitr_linear_tc_packed(int M, int N, int K, const float* A, const
     }
     if (bn == 64) return launch_tc2<64, 4>(P, st);
     return launch_tc2<128, 3>(P, st);
+}
+
+extern "C" int roitr_linear_tc_packed(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
+                                      const float* wpack, int bn, const float* bias, float* C, int ldc, int relu,
+                                      void* stream) {
+    return linear_tc_packed_impl(M, N, K, A, a_add, lda, a_index, wpack, bn, bias, C, ldc, relu, nullptr, nullptr, nullptr,
+                                 nullptr, nullptr, 0, stream);
+}
+
+extern "C" int roitr_linear_ln_tc_packed(int M, int N, int K, const float* A, int lda, const float* wpack, int bn,
+                                         const float* bias, const float* gamma, const float* beta, const float* res_pre,
+                                         const int* res_pre_index, const float* res_post, int ldr, int relu, float* C,
+                                         int ldc, void* stream) {
+    ROITR_CHECK_ARG(gamma && beta, "linear_ln_tc_packed: gamma / beta required");
+    return linear_tc_packed_impl(M, N, K, A, nullptr, lda, nullptr, wpack, bn, bias, C, ldc, relu, gamma, beta, res_pre,
+                                 res_pre_index, res_post, ldr, stream);
 }

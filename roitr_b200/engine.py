@@ -170,22 +170,29 @@ def _ln(W, p, x, **kw):
     return ops.row_epilogue(x, gamma=W[p + ".weight"], beta=W[p + ".bias"], **kw)
 
 
-def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None):
-    """LocalPPFTransformer.forward (ppftransformer.py:243-253): (n,Cin) -> (m,Cout). ``order``: see ops.local_attention."""
+def _lin_ln(W, p, n, x, **kw):
+    """Linear p followed by LayerNorm n (+ residuals / ReLU), fused into the dense layer's epilogue where it fits."""
+    return ops.linear_ln(x, W[p + ".weight"], W[p + ".bias"], W.get(p + ".weight#tc") if LINEAR_TC else None,
+                         W[n + ".weight"], W[n + ".bias"], **kw)
+
+
+def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None, post=None):
+    """LocalPPFTransformer.forward (ppftransformer.py:243-253): (n,Cin) -> (m,Cout). ``order``: see ops.local_attention.
+    ``post`` = (LayerNorm prefix, res_post, relu): a row epilogue applied to the output (the block's bn2 + identity + ReLU)."""
     C = W[p + ".in_proj.weight"].shape[0]
     f = _lin(W, p + ".in_proj", feats)
     qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], wpack=W.get(p + "#Wqkv#tc") if LINEAR_TC else None)
     h = ops.local_attention(qkv, C, node_idx, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"], W[p + "#Avp"], W[p + "#cvp"],
                             order=order)
-    t = _lin(W, p + ".transformer.linear", h)
-    y = _ln(W, p + ".transformer.norm", t, res_pre=f, res_pre_index=node_idx, mode=ops.MODE_LN)
-    return _lin(W, p + ".out_proj", y)
+    y = _lin_ln(W, p + ".transformer.linear", p + ".transformer.norm", h, res_pre=f, res_pre_index=node_idx)
+    if post is None:
+        return _lin(W, p + ".out_proj", y)
+    return _lin_ln(W, p + ".out_proj", post[0], y, res_post=post[1], relu=post[2])
 
 
 def block(W, p, x, idx, ppf, order=None):
     """RIPointTransformerBlock.forward (model/model.py:131-142) with cached (idx, ppf)."""
-    y = local_ppf_transformer(W, p + ".transformer.transformer", x, None, idx, ppf, order)
-    return _ln(W, p + ".bn2", y, res_post=x, mode=ops.MODE_LN | ops.MODE_RELU)
+    return local_ppf_transformer(W, p + ".transformer.transformer", x, None, idx, ppf, order, post=(p + ".bn2", x, True))
 
 
 def _offsets(ends, device):
@@ -378,8 +385,8 @@ def decode(W, L):
     for li in (2, 1, 0):
         p = "backbone.dec%d.0" % (li + 1)
         fine = L[li]
-        a = _ln(W, p + ".linear1.1", _lin(W, p + ".linear1.0", fine["x"]), mode=ops.MODE_LN | ops.MODE_RELU)
-        b = _ln(W, p + ".linear2.1", _lin(W, p + ".linear2.0", xs[li + 1]), mode=ops.MODE_LN | ops.MODE_RELU)
+        a = _lin_ln(W, p + ".linear1.0", p + ".linear1.1", fine["x"], relu=True)
+        b = _lin_ln(W, p + ".linear2.0", p + ".linear2.1", xs[li + 1], relu=True)
         _wait(fine["g"]["ev_up"])
         y = ops.interpolate(fine["g"]["up_idx"], fine["g"]["up_dist"], b, base=a)
         xs[li] = block(W, "backbone.dec%d.1" % (li + 1), y, fine["idx"], fine["ppf"], fine["order"])

@@ -179,3 +179,35 @@ def test_attention_tensor_core_matches_first_generation(N, M, C):
     assert (G_new.double() - ref_G).abs().max().item() < 3e-5
     assert (h_old.double() - ref_h).abs().max().item() < 3e-5
     assert (G_old.double() - ref_G).abs().max().item() < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K,pre,gather,post,relu", [(20000, 64, 64, True, False, False, False), (5000, 128, 128, True, True, False, False),
+                                                       (4100, 64, 64, False, False, True, True), (1250, 128, 256, False, False, False, True),
+                                                       (777, 64, 128, True, True, True, True), (130, 128, 64, False, False, True, False)])
+def test_linear_ln_fused_matches_fp64(M, N, K, pre, gather, post, relu):
+    """roitr_linear_ln_tc_packed (LayerNorm / residuals / ReLU in the dense layer's epilogue) against fp64."""
+    from roitr_b200 import engine
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV), (0.1 * torch.randn(N, generator=g)).to(DEV)
+    R = 3 * M if gather else M
+    res_pre = torch.randn(R, N, generator=g).to(DEV) if pre else None
+    idx = torch.randint(0, R, (M,), generator=g).int().to(DEV) if gather else None
+    res_post = torch.randn(M, N, generator=g).to(DEV) if post else None
+    y = ops.linear_ln(a, w, b, engine.pack_linear_tc(w), gamma, beta, res_pre=res_pre, res_pre_index=idx, res_post=res_post, relu=relu)
+    t = a.double() @ w.double().t() + b.double()
+    if pre:
+        t = t + (res_pre[idx.long()] if gather else res_pre).double()
+    ref = torch.nn.functional.layer_norm(t, (N,), gamma.double(), beta.double(), 1e-5)
+    if post:
+        ref = ref + res_post.double()
+    if relu:
+        ref = torch.relu(ref)
+    assert (y.double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    # and it is the same function as the two-kernel path
+    t32 = ops.linear(a, w, b, wpack=engine.pack_linear_tc(w))
+    two = ops.row_epilogue(t32, res_pre=res_pre, res_pre_index=idx, gamma=gamma, beta=beta, res_post=res_post,
+                           mode=ops.MODE_LN | (ops.MODE_RELU if relu else 0))
+    assert (y - two).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
