@@ -87,7 +87,13 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P
     const int my_nb = (lane < KNB) ? __ldg(gi + lane) : 0;
 
     // ---- scores ----
-    float s[KNB];
+    // Lane l of a head computes the partial dot products of its CPL channels for all KNB neighbours; a halving butterfly
+    // over the 8 lanes of the head (exchange half of the values with lane^4, then lane^2, lane^1) leaves lane li with the
+    // COMPLETE dot product of neighbours li (and li + 8): 7 shuffles per 8 neighbours instead of 24, and the per-neighbour
+    // scalar work (positional term, division, exp) is done once per neighbour instead of once per lane.
+    constexpr int R = KNB / 8;
+    const int li = lane & 7;
+    float d[KNB];
 #pragma unroll
     for (int j0 = 0; j0 < KNB; j0 += 4) {
         float kr[4][CPL];
@@ -98,29 +104,69 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            float d = 0.f;
+            float t = 0.f;
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) d = fmaf(q[i], kr[u][i], d);
-            d = head_sum(d);
-            const float4 f = __ldg(pf + j0 + u);
-            const float sp = fmaf(qa3, f.w, fmaf(qa2, f.z, fmaf(qa1, f.y, fmaf(qa0, f.x, qb))));
-            s[j0 + u] = __fdiv_rn(d + sp, P.sqrt_c);  // attention.py:187: (e + p) / c ** 0.5
+            for (int i = 0; i < CPL; ++i) t = fmaf(q[i], kr[u][i], t);
+            d[j0 + u] = t;
         }
     }
-    // ---- softmax over the neighbourhood (per head; the 8 lanes of a head hold identical values) ----
-    float mx = s[0];
+    {
+        const bool b2 = li & 4, b1 = li & 2, b0 = li & 1;
 #pragma unroll
-    for (int j = 1; j < KNB; ++j) mx = fmaxf(mx, s[j]);
+        for (int r = 0; r < R; ++r) {
+            float* e = d + 8 * r;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float send = b2 ? e[t] : e[t + 4];
+                const float keep = b2 ? e[t + 4] : e[t];
+                e[t] = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const float send = b1 ? e[t] : e[t + 2];
+                const float keep = b1 ? e[t + 2] : e[t];
+                e[t] = keep + __shfl_xor_sync(FULL_MASK, send, 2);
+            }
+            {
+                const float send = b0 ? e[0] : e[1];
+                const float keep = b0 ? e[1] : e[0];
+                e[0] = keep + __shfl_xor_sync(FULL_MASK, send, 1);
+            }
+        }
+    }
+    // lane li now owns neighbours li + 8 r: score, softmax over the head's KNB values, positional weights
+    float sc[R];
+    float4 fr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        fr[r] = __ldg(pf + li + 8 * r);
+        const float sp = fmaf(qa3, fr[r].w, fmaf(qa2, fr[r].z, fmaf(qa1, fr[r].y, fmaf(qa0, fr[r].x, qb))));
+        sc[r] = __fdiv_rn(d[8 * r] + sp, P.sqrt_c);  // attention.py:187: (e + p) / c ** 0.5
+    }
+    float mx = sc[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) mx = fmaxf(mx, sc[r]);
+    mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, 4));
     float den = 0.f;
 #pragma unroll
-    for (int j = 0; j < KNB; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
+    for (int r = 0; r < R; ++r) { sc[r] = expf(sc[r] - mx); den += sc[r]; }
+    den = head_sum(den);
     const float inv = 1.0f / den;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;  // sum_j A_j ppf_j (per head)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        sc[r] *= inv;
+        w0 = fmaf(sc[r], fr[r].x, w0); w1 = fmaf(sc[r], fr[r].y, w1); w2 = fmaf(sc[r], fr[r].z, w2); w3 = fmaf(sc[r], fr[r].w, w3);
+    }
+    w0 = head_sum(w0); w1 = head_sum(w1); w2 = head_sum(w2); w3 = head_sum(w3);
 
     // ---- value aggregate ----
     float acc[CPL];
 #pragma unroll
     for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;  // sum_j A_j ppf_j
+    const int head_base = lane & 24;
 #pragma unroll
     for (int j0 = 0; j0 < KNB; j0 += 4) {
         float vr[4][CPL];
@@ -131,11 +177,10 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float a = s[j0 + u] * inv;
+            const int j = j0 + u;
+            const float a = __shfl_sync(FULL_MASK, sc[j >> 3], head_base | (j & 7));   // the weight lives in lane (head, j % 8)
 #pragma unroll
             for (int i = 0; i < CPL; ++i) acc[i] = fmaf(a, vr[u][i], acc[i]);
-            const float4 f = __ldg(pf + j0 + u);
-            w0 = fmaf(a, f.x, w0); w1 = fmaf(a, f.y, w1); w2 = fmaf(a, f.z, w2); w3 = fmaf(a, f.w, w3);
         }
     }
     float* o = P.out + (size_t)qi * C + c0;
