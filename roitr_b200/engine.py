@@ -120,6 +120,15 @@ def pack_weights(state_dict, device, architecture):
                 W[p + "#c" + nm] = (Wx @ be + bx).float().contiguous()            # (C,)
             W[p + "#Wqkv"] = torch.cat([W[a + ".proj_%s.weight" % t] for t in "qkv"], 0).contiguous()
             W[p + "#bqkv"] = torch.cat([W[a + ".proj_%s.bias" % t] for t in "qkv"], 0).contiguous()
+            # in_proj and the q/k/v projections as ONE dense layer on the layer's input x (exact fold, fp64):
+            #   [f | q | k | v] = x [W_in ; W_qkv W_in]^T + [b_in ; W_qkv b_in + b_qkv]
+            # one launch instead of two, x read once, f never re-read (used where the fused LayerNorm epilogue can take
+            # f as a strided residual: C <= 128, and where K is large enough for the tensor-core kernel)
+            Win, bin_ = W[p + ".in_proj.weight"].double(), W[p + ".in_proj.bias"].double()
+            if Win.shape[0] <= 128 and Win.shape[1] >= 16:
+                Wq, bq = W[p + "#Wqkv"].double(), W[p + "#bqkv"].double()
+                W[p + "#W4"] = torch.cat([Win, Wq @ Win], 0).float().contiguous()
+                W[p + "#b4"] = torch.cat([bin_, Wq @ bin_ + bq], 0).float().contiguous()
         g = "backbone.global_transformer"
         C = W[g + ".in_proj.weight"].shape[0]
         c = C // HEADS
@@ -149,7 +158,7 @@ def pack_weights(state_dict, device, architecture):
                     big_vp[h * c:(h + 1) * c, h * C:(h + 1) * C] = Wvp[h * c:(h + 1) * c, :]
                 W[a + "#WpBig"], W[a + "#WvpBig"] = big_p, big_vp
         # tensor-core operand form of every dense-layer weight with a useful K (roitr_linear_tc_packed)
-        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("Big")) and W[k].dim() == 2
+        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("Big")) and W[k].dim() == 2
                   and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
     finally:
@@ -180,8 +189,12 @@ def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None, pos
     """LocalPPFTransformer.forward (ppftransformer.py:243-253): (n,Cin) -> (m,Cout). ``order``: see ops.local_attention.
     ``post`` = (LayerNorm prefix, res_post, relu): a row epilogue applied to the output (the block's bn2 + identity + ReLU)."""
     C = W[p + ".in_proj.weight"].shape[0]
-    f = _lin(W, p + ".in_proj", feats)
-    qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], wpack=W.get(p + "#Wqkv#tc") if LINEAR_TC else None)
+    if LINEAR_TC and (p + "#W4#tc") in W:
+        fq = ops.linear(feats, W[p + "#W4"], W[p + "#b4"], wpack=W[p + "#W4#tc"])      # (n, 4C) = [f | q | k | v]
+        f, qkv = fq[:, :C], fq[:, C:]
+    else:
+        f = _lin(W, p + ".in_proj", feats)
+        qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], wpack=W.get(p + "#Wqkv#tc") if LINEAR_TC else None)
     h = ops.local_attention(qkv, C, node_idx, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"], W[p + "#Avp"], W[p + "#cvp"],
                             order=order)
     y = _lin_ln(W, p + ".transformer.linear", p + ".transformer.norm", h, res_pre=f, res_pre_index=node_idx)
@@ -613,7 +626,7 @@ class _Fork:
             self.main.wait_stream(st)
 
 
-HEAD_STREAMS = 8
+HEAD_STREAMS = 16
 
 
 def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):

@@ -51,15 +51,18 @@ def linear_ln(a, w, bias, wpack, gamma, beta, res_pre=None, res_pre_index=None, 
     M, K = a.shape
     N = w.shape[0]
     fused = (wpack is not None and N % 32 == 0 and N <= wpack[1] and a.stride(0) % 4 == 0 and K % 4 == 0 and
-             a.data_ptr() % 16 == 0 and a.stride(1) == 1)
+             a.data_ptr() % 16 == 0 and a.stride(1) == 1 and
+             (res_pre is None or res_post is None or res_pre.stride(0) == res_post.stride(0)))      # one residual pitch
     if not fused:
         t = linear(a, w, bias, wpack=wpack)
+        res_pre = res_pre.contiguous() if res_pre is not None else None
+        res_post = res_post.contiguous() if res_post is not None else None
         return row_epilogue(t, res_pre=res_pre, res_pre_index=res_pre_index, gamma=gamma, beta=beta, res_post=res_post,
                             mode=MODE_LN | (MODE_RELU if relu else 0))
     out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     ldr = (res_pre if res_pre is not None else res_post if res_post is not None else out).stride(0)
     _lib.call("roitr_linear_ln_tc_packed", c_int(M), c_int(N), c_int(K), c_void(a), c_int(a.stride(0)), f32(wpack[0]),
-              c_int(wpack[1]), c_void(bias), f32(gamma), f32(beta), f32(res_pre), i32(res_pre_index), f32(res_post), c_int(ldr),
+              c_int(wpack[1]), c_void(bias), f32(gamma), f32(beta), c_void(res_pre), i32(res_pre_index), c_void(res_post), c_int(ldr),
               c_int(1 if relu else 0), f32(out), c_int(N), stream_ptr())
     return out
 
