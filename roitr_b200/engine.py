@@ -125,10 +125,20 @@ def pack_weights(state_dict, device, architecture):
             # one launch instead of two, x read once, f never re-read (used where the fused LayerNorm epilogue can take
             # f as a strided residual: C <= 128, and where K is large enough for the tensor-core kernel)
             Win, bin_ = W[p + ".in_proj.weight"].double(), W[p + ".in_proj.bias"].double()
-            if Win.shape[0] <= 128 and Win.shape[1] >= 16:
-                Wq, bq = W[p + "#Wqkv"].double(), W[p + "#bqkv"].double()
+            Wq, bq = W[p + "#Wqkv"].double(), W[p + "#bqkv"].double()
+            Cp = Win.shape[0]
+            if Cp <= 128 and Win.shape[1] >= 16:
                 W[p + "#W4"] = torch.cat([Win, Wq @ Win], 0).float().contiguous()
                 W[p + "#b4"] = torch.cat([bin_, Wq @ bin_ + bq], 0).float().contiguous()
+            if Win.shape[1] >= 16:
+                # down-sampling layers (queries = a sampled subset of the rows): keys / values are needed for every row,
+                # f and q only for the sampled ones, so the fold is split into  [k | v] = x [W_kv W_in]^T  on all rows and
+                # [f | q] = x[node_idx] [W_in ; W_q W_in]^T  on the sampled rows (attention.py:176-181 computes q, k, v
+                # for all rows and gathers q afterwards)
+                W[p + "#Wkv"] = (Wq[Cp:] @ Win).float().contiguous()
+                W[p + "#bkv"] = (Wq[Cp:] @ bin_ + bq[Cp:]).float().contiguous()
+                W[p + "#Wfq"] = torch.cat([Win, Wq[:Cp] @ Win], 0).float().contiguous()
+                W[p + "#bfq"] = torch.cat([bin_, Wq[:Cp] @ bin_ + bq[:Cp]], 0).float().contiguous()
         g = "backbone.global_transformer"
         C = W[g + ".in_proj.weight"].shape[0]
         c = C // HEADS
@@ -158,7 +168,7 @@ def pack_weights(state_dict, device, architecture):
                     big_vp[h * c:(h + 1) * c, h * C:(h + 1) * C] = Wvp[h * c:(h + 1) * c, :]
                 W[a + "#WpBig"], W[a + "#WvpBig"] = big_p, big_vp
         # tensor-core operand form of every dense-layer weight with a useful K (roitr_linear_tc_packed)
-        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("Big")) and W[k].dim() == 2
+        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("#Wkv") or k.endswith("#Wfq") or k.endswith("Big")) and W[k].dim() == 2
                   and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
     finally:
@@ -189,14 +199,21 @@ def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None, pos
     """LocalPPFTransformer.forward (ppftransformer.py:243-253): (n,Cin) -> (m,Cout). ``order``: see ops.local_attention.
     ``post`` = (LayerNorm prefix, res_post, relu): a row epilogue applied to the output (the block's bn2 + identity + ReLU)."""
     C = W[p + ".in_proj.weight"].shape[0]
-    if LINEAR_TC and (p + "#W4#tc") in W:
-        fq = ops.linear(feats, W[p + "#W4"], W[p + "#b4"], wpack=W[p + "#W4#tc"])      # (n, 4C) = [f | q | k | v]
-        f, qkv = fq[:, :C], fq[:, C:]
+    if LINEAR_TC and node_idx is not None and (p + "#Wkv#tc") in W:
+        kv = ops.linear(feats, W[p + "#Wkv"], W[p + "#bkv"], wpack=W[p + "#Wkv#tc"])                       # (n, 2C) all rows
+        fq = ops.linear(feats, W[p + "#Wfq"], W[p + "#bfq"], wpack=W[p + "#Wfq#tc"], a_index=node_idx)     # (m, 2C) sampled rows
+        h = ops.local_attention((fq[:, C:], kv[:, :C], kv[:, C:]), C, None, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"],
+                                W[p + "#Avp"], W[p + "#cvp"], order=order)
+        f, node_idx = fq[:, :C], None
     else:
-        f = _lin(W, p + ".in_proj", feats)
-        qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], wpack=W.get(p + "#Wqkv#tc") if LINEAR_TC else None)
-    h = ops.local_attention(qkv, C, node_idx, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"], W[p + "#Avp"], W[p + "#cvp"],
-                            order=order)
+        if LINEAR_TC and (p + "#W4#tc") in W:
+            fq = ops.linear(feats, W[p + "#W4"], W[p + "#b4"], wpack=W[p + "#W4#tc"])      # (n, 4C) = [f | q | k | v]
+            f, qkv = fq[:, :C], fq[:, C:]
+        else:
+            f = _lin(W, p + ".in_proj", feats)
+            qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], wpack=W.get(p + "#Wqkv#tc") if LINEAR_TC else None)
+        h = ops.local_attention(qkv, C, node_idx, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"], W[p + "#Avp"], W[p + "#cvp"],
+                                order=order)
     y = _lin_ln(W, p + ".transformer.linear", p + ".transformer.norm", h, res_pre=f, res_pre_index=node_idx)
     if post is None:
         return _lin(W, p + ".out_proj", y)

@@ -170,12 +170,17 @@ def grid_order_ptr(grid, b):
 def local_attention(qkv, C, node_idx, group_idx, ppf, Ap, cp, Avp, cvp, order=None):
     """``order`` = (grid workspace of the QUERY set, number of segments): visit the queries in cell order."""
     m, knb = group_idx.shape
-    out = torch.empty(m, C, dtype=torch.float32, device=qkv.device)
-    ld = qkv.stride(0)
-    base = qkv.data_ptr()
     P = ctypes.c_void_p
-    _lib.call("roitr_local_attention_ordered", c_int(m), c_int(C), c_int(4), c_int(knb), P(base), c_int(ld), P(base + 4 * C),
-              c_int(ld), P(base + 8 * C), c_int(ld), i32(node_idx), i32(group_idx), f32(ppf), f32(Ap), f32(cp), f32(Avp),
+    if isinstance(qkv, tuple):      # (q, k, v) as separate (strided) views: q rows are addressed through node_idx, k / v by group_idx
+        q, k, v = qkv
+        dev = q.device
+        qa, ka, va = (P(q.data_ptr()), c_int(q.stride(0))), (P(k.data_ptr()), c_int(k.stride(0))), (P(v.data_ptr()), c_int(v.stride(0)))
+    else:
+        dev, ld, base = qkv.device, qkv.stride(0), qkv.data_ptr()
+        qa, ka, va = (P(base), c_int(ld)), (P(base + 4 * C), c_int(ld)), (P(base + 8 * C), c_int(ld))
+    out = torch.empty(m, C, dtype=torch.float32, device=dev)
+    _lib.call("roitr_local_attention_ordered", c_int(m), c_int(C), c_int(4), c_int(knb), qa[0], qa[1], ka[0], ka[1], va[0], va[1],
+              i32(node_idx), i32(group_idx), f32(ppf), f32(Ap), f32(cp), f32(Avp),
               f32(cvp), grid_order_ptr(*order) if order is not None else P(0), f32(out), stream_ptr())
     return out
 
