@@ -712,14 +712,20 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
         s_nf_all = ops.row_epilogue(_lin(W, "coarse_proj", s_g_all), mode=ops.MODE_L2NORM)
         t_nf_all = ops.row_epilogue(_lin(W, "coarse_proj", t_g_all), mode=ops.MODE_L2NORM)
 
+        # tgt . src^T of every pair in one batched tensor-core launch (the per-pair feature-similarity matrices)
+        C = s_nf_all.shape[1]
+        xy_all = torch.empty(B, M4t, M4s, dtype=torch.float32, device=s_nf_all.device)
+        ops.gemm_tc_batched(B, 1, M4t, M4s, C, t_nf_all, C, (M4t * C, 0), s_nf_all, C, (M4s * C, 0), xy_all, M4s, (M4t * M4s, 0))
+
         def coarse(b):   # 3. coarse matching   (called as (tgt, src), model/RIGA_v2.py:121)
             q = st[b]
             src_nf, tgt_nf = s_nf_all[b * M4s:(b + 1) * M4s], t_nf_all[b * M4t:(b + 1) * M4t]
             if four_d:
                 t_ci, s_ci, node_sc, p_count = ops.coarse_matching_adaptive(tgt_nf, src_nf, q["t_nm"], q["s_nm"],
-                                                                            int(cfg["num_est_coarse_corr"]), 0.75, Pmax)
+                                                                            int(cfg["num_est_coarse_corr"]), 0.75, Pmax, xy=xy_all[b])
             else:
-                t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, q["t_nm"], q["s_nm"], Pmax, dual=True)
+                t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, q["t_nm"], q["s_nm"], Pmax, dual=True,
+                                                                   xy=xy_all[b])
             q.update(src_node_feats=src_nf, tgt_node_feats=tgt_nf, t_ci=t_ci, s_ci=s_ci, node_sc=node_sc, p_count=p_count)
         fork.run(B, coarse)
 

@@ -321,10 +321,11 @@ def compact_flags(flags, capacity):
     return out, count
 
 
-def coarse_matching(ref_feats, src_feats, ref_mask, src_mask, k, dual=True):
+def coarse_matching(ref_feats, src_feats, ref_mask, src_mask, k, dual=True, xy=None):
     Mr, Ms, C = ref_feats.shape[0], src_feats.shape[0], ref_feats.shape[1]
     dev = ref_feats.device
-    xy = linear(ref_feats, src_feats)                       # (Mr, Ms) = ref @ src^T
+    if xy is None:
+        xy = linear(ref_feats, src_feats)                   # (Mr, Ms) = ref @ src^T
     work = torch.empty(Mr * Ms + 2 * (Mr + Ms), dtype=torch.float32, device=dev)
     out_ref = torch.zeros(k, dtype=torch.int32, device=dev)
     out_src = torch.zeros(k, dtype=torch.int32, device=dev)
@@ -336,10 +337,11 @@ def coarse_matching(ref_feats, src_feats, ref_mask, src_mask, k, dual=True):
     return out_ref, out_src, out_score, count
 
 
-def coarse_matching_adaptive(a_feats, b_feats, a_mask, b_mask, min_num, threshold, cap):
+def coarse_matching_adaptive(a_feats, b_feats, a_mask, b_mask, min_num, threshold, cap, xy=None):
     Ma, Mb = a_feats.shape[0], b_feats.shape[0]
     dev = a_feats.device
-    xy = linear(a_feats, b_feats)
+    if xy is None:
+        xy = linear(a_feats, b_feats)
     n = Ma * Mb
     work = torch.empty(2 * n + (n + 3) // 4, dtype=torch.float32, device=dev)
     fn = _lib.lib().roitr_compact_scratch_ints
