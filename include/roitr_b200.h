@@ -72,6 +72,12 @@ int roitr_knn_ppf_n(int b, int m, int k_out, int drop_first, int n_total, const 
  *   roitr_knn_ppf_grid(...)               as roitr_knn_ppf_n, with the workspace (256-byte aligned)
  */
 long long roitr_knn_grid_workspace_bytes(int b, int n);
+/* Surface normals of a (segmented) cloud: per point the `knn` (9, 17 or 33) nearest points of its own segment, itself
+ * included, their covariance and the eigenvector of its smallest eigenvalue (fp64), oriented towards `view_point`
+ * (3 HOST floats). Replaces Open3D estimate_normals(KDTreeSearchParamKNN(knn=33)) + normal_redirect
+ * (dataset/tdmatch.py:120-127, dataset/common.py:312-320). `workspace` = roitr_knn_grid_build over the same cloud. */
+int roitr_estimate_normals(int b, int n, int knn, const float* xyz, const int* offset, const void* workspace,
+                           const float* view_point, float* normals, void* stream);
 long long roitr_knn_grid_sorted_offset(int b);
 int roitr_knn_grid_build(int b, int n, const float* xyz, const int* offset, void* workspace, void* stream);
 int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n_total, const float* xyz, const float* normals,
@@ -318,6 +324,12 @@ int roitr_node_overlaps(int Mr, int Ms, int K, int Nr, int Nsrc, const float* re
                         float* work, float* overlap, unsigned char* flag, void* stream);
 int roitr_corr_gather(int capacity, int Ms, const int* flat, const int* count, const float* overlap, long long* out_idx,
                       float* out_ov, void* stream);
+
+/* Weighted Procrustes (lib/utils.py:159-218): per batch item the rigid transform (R (3,3) row-major, t (3)) that maps the
+ * src points (batch, n, 3) onto the tgt points under the weights (batch, n) (NULL = all ones; weights below weight_thresh
+ * count as zero; centroids use w / (sum w + eps)). R is always a proper rotation (the reference's sign det(V U^T) fix). */
+int roitr_weighted_procrustes(int batch, int n, const float* src, const float* tgt, const float* weights,
+                              float weight_thresh, float eps, float* R, float* t, void* stream);
 
 #ifdef __cplusplus
 }

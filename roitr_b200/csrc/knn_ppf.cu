@@ -411,6 +411,82 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) knn_grid_kernel(const KnnParam
 // emitted cooperatively (one (query, slot) pair per thread: contiguous index / PPF rows, PPF maths spread evenly).
 constexpr int KT_THREADS = 128;
 
+// The per-thread search: the K nearest reference points of (qx,qy,qz) inside segment `sgm`, as a list sorted by
+// (squared distance, index) in registers. `tie` is set when an exact-distance tie played any role (see above).
+template <int K>
+__device__ __forceinline__ void grid_search_thread(float qx, float qy, float qz, int qs, const knngrid::SegHeader& H,
+                                                   const int* __restrict__ cs, const float4* __restrict__ pts, float (&bd)[K],
+                                                   int (&bi)[K], bool& tie) {
+    const int cx = knngrid::cell_coord(qx, H.ox, H.inv_h, H.nx), cy = knngrid::cell_coord(qy, H.oy, H.inv_h, H.ny),
+              cz = knngrid::cell_coord(qz, H.oz, H.inv_h, H.nz);
+#pragma unroll
+    for (int j = 0; j < K; ++j) { bd[j] = 1e10f; bi[j] = qs; }
+    float tau = 1e10f;
+    int tau_i = qs;
+
+    auto scan_range = [&](int beg, int end) {
+        for (int p = beg; p < end; ++p) {
+            const float4 v = __ldg(pts + p);
+            const float cd = sqdist_ref(qx - v.x, qy - v.y, qz - v.z);
+            if (cd <= tau) {
+                const int ci = __float_as_int(v.w);
+                if (cd == tau && tau != 1e10f) tie = true;     // boundary tie: the reference's choice depends on its heap
+                if (cd < tau || ci < tau_i) {
+                    bd[K - 1] = cd; bi[K - 1] = ci;
+#pragma unroll
+                    for (int j = K - 1; j > 0; --j) {
+                        const bool sw = bd[j] < bd[j - 1] || (bd[j] == bd[j - 1] && bi[j] < bi[j - 1]);
+                        const float d0 = bd[j - 1], d1 = bd[j];
+                        const int i0 = bi[j - 1], i1 = bi[j];
+                        bd[j - 1] = sw ? d1 : d0; bd[j] = sw ? d0 : d1;
+                        bi[j - 1] = sw ? i1 : i0; bi[j] = sw ? i0 : i1;
+                    }
+                    const float tau_old = tau;
+                    tau = bd[K - 1]; tau_i = bi[K - 1];
+                    if (tau == tau_old && tau_old != 1e10f) tie = true;
+                }
+            }
+        }
+    };
+
+    for (int r = 0;; ++r) {
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, H.nx - 1);
+        for (int dz = -r; dz <= r; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= H.nz) continue;
+            for (int dy = -r; dy <= r; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= H.ny) continue;
+                const int row = (z * H.ny + y) * H.nx;
+                if (abs(dz) == r || abs(dy) == r) {               // face of the cube: the whole x span
+                    scan_range(__ldg(cs + row + x0), __ldg(cs + row + x1 + 1));
+                } else {                                         // interior row: only the two end cells
+                    if (cx - r >= 0) scan_range(__ldg(cs + row + cx - r), __ldg(cs + row + cx - r + 1));
+                    if (cx + r < H.nx) scan_range(__ldg(cs + row + cx + r), __ldg(cs + row + cx + r + 1));
+                }
+            }
+        }
+        // everything outside the cube of radius r is at least `bound` away from the query
+        const bool all = (cx - r <= 0) && (cx + r >= H.nx - 1) && (cy - r <= 0) && (cy + r >= H.ny - 1) && (cz - r <= 0) &&
+                         (cz + r >= H.nz - 1);
+        if (all) break;
+        float bound = CUDART_INF_F;
+        if (cx - r > 0) bound = fminf(bound, qx - (H.ox + (float)(cx - r) * H.h));
+        if (cx + r < H.nx - 1) bound = fminf(bound, (H.ox + (float)(cx + r + 1) * H.h) - qx);
+        if (cy - r > 0) bound = fminf(bound, qy - (H.oy + (float)(cy - r) * H.h));
+        if (cy + r < H.ny - 1) bound = fminf(bound, (H.oy + (float)(cy + r + 1) * H.h) - qy);
+        if (cz - r > 0) bound = fminf(bound, qz - (H.oz + (float)(cz - r) * H.h));
+        if (cz + r < H.nz - 1) bound = fminf(bound, (H.oz + (float)(cz + r + 1) * H.h) - qz);
+        bound -= 1e-4f * H.h;                                     // binning rounds (v - o) * inv_h: keep a safety margin
+        if (tau < 1e10f && bound > 0.f && tau < bound * bound * 0.99999f) break;
+    }
+    // equal distances inside the final list: the reference's order among them is its heap's
+#pragma unroll
+    for (int j = 0; j + 1 < K; ++j)
+        if (bd[j] == bd[j + 1] && bd[j] != 1e10f) tie = true;
+}
+
+
 template <int K>
 __global__ void __launch_bounds__(KT_THREADS) knn_grid_thread_kernel(const KnnParams P, const knngrid::SegHeader* __restrict__ hdr,
                                                                       const int* __restrict__ cell_start,
@@ -438,75 +514,7 @@ __global__ void __launch_bounds__(KT_THREADS) knn_grid_thread_kernel(const KnnPa
         }
         const int qs = sgm == 0 ? 0 : __ldg(P.offset + sgm - 1);
         const knngrid::SegHeader H = hdr[sgm];
-        const int cx = knngrid::cell_coord(qx, H.ox, H.inv_h, H.nx), cy = knngrid::cell_coord(qy, H.oy, H.inv_h, H.ny),
-                  cz = knngrid::cell_coord(qz, H.oz, H.inv_h, H.nz);
-        const int* cs = cell_start + H.cell_base;
-        const float4* pts = sorted + qs;
-#pragma unroll
-        for (int j = 0; j < K; ++j) { bd[j] = 1e10f; bi[j] = qs; }
-        float tau = 1e10f;
-        int tau_i = qs;
-
-        auto scan_range = [&](int beg, int end) {
-            for (int p = beg; p < end; ++p) {
-                const float4 v = __ldg(pts + p);
-                const float cd = sqdist_ref(qx - v.x, qy - v.y, qz - v.z);
-                if (cd <= tau) {
-                    const int ci = __float_as_int(v.w);
-                    if (cd == tau && tau != 1e10f) tie = true;     // boundary tie: the reference's choice depends on its heap
-                    if (cd < tau || ci < tau_i) {
-                        bd[K - 1] = cd; bi[K - 1] = ci;
-#pragma unroll
-                        for (int j = K - 1; j > 0; --j) {
-                            const bool sw = bd[j] < bd[j - 1] || (bd[j] == bd[j - 1] && bi[j] < bi[j - 1]);
-                            const float d0 = bd[j - 1], d1 = bd[j];
-                            const int i0 = bi[j - 1], i1 = bi[j];
-                            bd[j - 1] = sw ? d1 : d0; bd[j] = sw ? d0 : d1;
-                            bi[j - 1] = sw ? i1 : i0; bi[j] = sw ? i0 : i1;
-                        }
-                        const float tau_old = tau;
-                        tau = bd[K - 1]; tau_i = bi[K - 1];
-                        if (tau == tau_old && tau_old != 1e10f) tie = true;
-                    }
-                }
-            }
-        };
-
-        for (int r = 0;; ++r) {
-            const int x0 = max(cx - r, 0), x1 = min(cx + r, H.nx - 1);
-            for (int dz = -r; dz <= r; ++dz) {
-                const int z = cz + dz;
-                if (z < 0 || z >= H.nz) continue;
-                for (int dy = -r; dy <= r; ++dy) {
-                    const int y = cy + dy;
-                    if (y < 0 || y >= H.ny) continue;
-                    const int row = (z * H.ny + y) * H.nx;
-                    if (abs(dz) == r || abs(dy) == r) {               // face of the cube: the whole x span
-                        scan_range(__ldg(cs + row + x0), __ldg(cs + row + x1 + 1));
-                    } else {                                         // interior row: only the two end cells
-                        if (cx - r >= 0) scan_range(__ldg(cs + row + cx - r), __ldg(cs + row + cx - r + 1));
-                        if (cx + r < H.nx) scan_range(__ldg(cs + row + cx + r), __ldg(cs + row + cx + r + 1));
-                    }
-                }
-            }
-            // everything outside the cube of radius r is at least `bound` away from the query
-            const bool all = (cx - r <= 0) && (cx + r >= H.nx - 1) && (cy - r <= 0) && (cy + r >= H.ny - 1) && (cz - r <= 0) &&
-                             (cz + r >= H.nz - 1);
-            if (all) break;
-            float bound = CUDART_INF_F;
-            if (cx - r > 0) bound = fminf(bound, qx - (H.ox + (float)(cx - r) * H.h));
-            if (cx + r < H.nx - 1) bound = fminf(bound, (H.ox + (float)(cx + r + 1) * H.h) - qx);
-            if (cy - r > 0) bound = fminf(bound, qy - (H.oy + (float)(cy - r) * H.h));
-            if (cy + r < H.ny - 1) bound = fminf(bound, (H.oy + (float)(cy + r + 1) * H.h) - qy);
-            if (cz - r > 0) bound = fminf(bound, qz - (H.oz + (float)(cz - r) * H.h));
-            if (cz + r < H.nz - 1) bound = fminf(bound, (H.oz + (float)(cz + r + 1) * H.h) - qz);
-            bound -= 1e-4f * H.h;                                     // binning rounds (v - o) * inv_h: keep a safety margin
-            if (tau < 1e10f && bound > 0.f && tau < bound * bound * 0.99999f) break;
-        }
-        // equal distances inside the final list: the reference's order among them is its heap's
-#pragma unroll
-        for (int j = 0; j + 1 < K; ++j)
-            if (bd[j] == bd[j + 1] && bd[j] != 1e10f) tie = true;
+        grid_search_thread<K>(qx, qy, qz, qs, H, cell_start + H.cell_base, sorted + qs, bd, bi, tie);
     }
     // ---- stage and emit cooperatively ----
     s_q[tid] = tie ? (-2 - q) : q;            // q >= 0: valid; -1: no query; <= -2: tie-marked query -2 - q
@@ -526,6 +534,141 @@ __global__ void __launch_bounds__(KT_THREADS) knn_grid_thread_kernel(const KnnPa
         emit_result(P, qq, slot, kout, s_i[ql * K + slot + P.drop], s_d[ql * K + slot + P.drop], s_qp[3 * ql], s_qp[3 * ql + 1],
                     s_qp[3 * ql + 2]);
     }
+}
+
+// ---- surface normals: kNN + covariance + smallest-eigenvalue eigenvector, one thread per point ---------------------------
+// The step before the hot path: Open3D's estimate_normals(KDTreeSearchParamKNN(knn)) followed by
+// dataset/common.py:312-320 normal_redirect, as called in dataset/tdmatch.py:120-127. Per point: the knn nearest points of
+// its own cloud (the point itself included), the covariance of those points from first and second cumulants (what Open3D's
+// ComputeCovariance does), the eigenvector of the smallest eigenvalue by the non-iterative symmetric 3x3 solver Open3D
+// uses for fast_normal_computation (Eberly, "A Robust Eigensolver for 3x3 Symmetric Matrices"), all in fp64; then the
+// sign is chosen so that the normal points towards the view point. Fewer than 3 neighbours: (0, 0, 1) like Open3D.
+__device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3], double (&c)[3]) {
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+// eigenvector of the symmetric matrix A for eigenvalue ev: the largest cross product of two rows of A - ev I
+__device__ __forceinline__ void eigenvector0(const double (&A)[6], double ev, double (&out)[3]) {
+    const double r0[3] = {A[0] - ev, A[1], A[2]}, r1[3] = {A[1], A[3] - ev, A[4]}, r2[3] = {A[2], A[4], A[5] - ev};
+    double c01[3], c02[3], c12[3];
+    cross3(r0, r1, c01); cross3(r0, r2, c02); cross3(r1, r2, c12);
+    const double d0 = c01[0] * c01[0] + c01[1] * c01[1] + c01[2] * c01[2];
+    const double d1 = c02[0] * c02[0] + c02[1] * c02[1] + c02[2] * c02[2];
+    const double d2 = c12[0] * c12[0] + c12[1] * c12[1] + c12[2] * c12[2];
+    const double dm = fmax(d0, fmax(d1, d2));
+    const double* best = (d0 >= d1 && d0 >= d2) ? c01 : (d1 >= d2 ? c02 : c12);
+    const double inv = dm > 0.0 ? rsqrt(dm) : 0.0;
+    out[0] = best[0] * inv; out[1] = best[1] * inv; out[2] = best[2] * inv;
+}
+// second eigenvector, orthogonal to evec0, for eigenvalue ev (Eberly's ComputeEigenvector1)
+__device__ __forceinline__ void eigenvector1(const double (&A)[6], const double (&e0)[3], double ev, double (&out)[3]) {
+    double U[3], V[3];
+    if (fabs(e0[0]) > fabs(e0[1])) {
+        const double inv = 1.0 / sqrt(e0[0] * e0[0] + e0[2] * e0[2]);
+        U[0] = -e0[2] * inv; U[1] = 0.0; U[2] = e0[0] * inv;
+    } else {
+        const double inv = 1.0 / sqrt(e0[1] * e0[1] + e0[2] * e0[2]);
+        U[0] = 0.0; U[1] = e0[2] * inv; U[2] = -e0[1] * inv;
+    }
+    cross3(e0, U, V);
+    const double AU[3] = {A[0] * U[0] + A[1] * U[1] + A[2] * U[2], A[1] * U[0] + A[3] * U[1] + A[4] * U[2], A[2] * U[0] + A[4] * U[1] + A[5] * U[2]};
+    const double AV[3] = {A[0] * V[0] + A[1] * V[1] + A[2] * V[2], A[1] * V[0] + A[3] * V[1] + A[4] * V[2], A[2] * V[0] + A[4] * V[1] + A[5] * V[2]};
+    double m00 = U[0] * AU[0] + U[1] * AU[1] + U[2] * AU[2] - ev;
+    double m01 = U[0] * AV[0] + U[1] * AV[1] + U[2] * AV[2];
+    double m11 = V[0] * AV[0] + V[1] * AV[1] + V[2] * AV[2] - ev;
+    const double a00 = fabs(m00), a01 = fabs(m01), a11 = fabs(m11);
+    if (a00 >= a11) {
+        if (fmax(a00, a01) > 0.0) {
+            if (a00 >= a01) { m01 /= m00; m00 = 1.0 / sqrt(1.0 + m01 * m01); m01 *= m00; }
+            else { m00 /= m01; m01 = 1.0 / sqrt(1.0 + m00 * m00); m00 *= m01; }
+            for (int i = 0; i < 3; ++i) out[i] = m01 * U[i] - m00 * V[i];
+        } else { for (int i = 0; i < 3; ++i) out[i] = U[i]; }
+    } else {
+        if (fmax(a11, a01) > 0.0) {
+            if (a11 >= a01) { m01 /= m11; m11 = 1.0 / sqrt(1.0 + m01 * m01); m01 *= m11; }
+            else { m11 /= m01; m01 = 1.0 / sqrt(1.0 + m11 * m11); m11 *= m01; }
+            for (int i = 0; i < 3; ++i) out[i] = m11 * U[i] - m01 * V[i];
+        } else { for (int i = 0; i < 3; ++i) out[i] = U[i]; }
+    }
+}
+// unit eigenvector of the SMALLEST eigenvalue of the symmetric matrix {a00,a01,a02,a11,a12,a22}; false if A == 0
+__device__ bool smallest_eigenvector(const double (&Ain)[6], double (&n)[3]) {
+    double mx = 0.0;
+    for (int i = 0; i < 6; ++i) mx = fmax(mx, fabs(Ain[i]));
+    if (!(mx > 0.0)) return false;
+    double A[6];
+    for (int i = 0; i < 6; ++i) A[i] = Ain[i] / mx;
+    const double norm = A[1] * A[1] + A[2] * A[2] + A[4] * A[4];
+    if (norm > 0.0) {
+        const double q = (A[0] + A[3] + A[5]) / 3.0;
+        const double b00 = A[0] - q, b11 = A[3] - q, b22 = A[5] - q;
+        const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * norm) / 6.0);
+        const double c00 = b11 * b22 - A[4] * A[4], c01 = A[1] * b22 - A[4] * A[2], c02 = A[1] * A[4] - b11 * A[2];
+        const double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
+        const double half = fmin(fmax(0.5 * det, -1.0), 1.0);
+        const double angle = acos(half) / 3.0;
+        const double two_thirds_pi = 2.09439510239319549;
+        const double beta2 = 2.0 * cos(angle), beta0 = 2.0 * cos(angle + two_thirds_pi), beta1 = -(beta0 + beta2);
+        const double ev0 = q + p * beta0, ev1 = q + p * beta1, ev2 = q + p * beta2;   // ev0 <= ev1 <= ev2
+        if (half >= 0.0) {      // ev2 is the best separated eigenvalue: start from its eigenvector
+            double e2[3], e1[3];
+            eigenvector0(A, ev2, e2);
+            eigenvector1(A, e2, ev1, e1);
+            cross3(e1, e2, n);
+        } else {
+            eigenvector0(A, ev0, n);
+        }
+    } else {                    // diagonal matrix
+        const int k = (A[0] <= A[3] && A[0] <= A[5]) ? 0 : (A[3] <= A[5] ? 1 : 2);
+        n[0] = k == 0; n[1] = k == 1; n[2] = k == 2;
+    }
+    const double l = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (!(l > 0.0)) return false;
+    n[0] /= l; n[1] /= l; n[2] /= l;
+    return true;
+}
+
+template <int K>
+__global__ void __launch_bounds__(KT_THREADS) normals_kernel(int b, int n, const float* __restrict__ xyz, const int* __restrict__ offset,
+                                                            const knngrid::SegHeader* __restrict__ hdr,
+                                                            const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                                                            float vx, float vy, float vz, float* __restrict__ normals) {
+    const int t = blockIdx.x * KT_THREADS + threadIdx.x;
+    if (t >= n) return;
+    const int sgm = find_segment(t, offset, b);
+    const float4 me = __ldg(sorted + t);                            // points are visited in cell order
+    const int q = __float_as_int(me.w);
+    const int qs = sgm == 0 ? 0 : __ldg(offset + sgm - 1);
+    const knngrid::SegHeader H = hdr[sgm];
+    float bd[K];
+    int bi[K];
+    bool tie = false;
+    grid_search_thread<K>(me.x, me.y, me.z, qs, H, cell_start + H.cell_base, sorted + qs, bd, bi, tie);
+    double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+#pragma unroll 1
+    for (int j = 0; j < K; ++j) {
+        if (bd[j] >= 1e10f) break;                                   // unfilled slots (segment smaller than K)
+        const float* p = xyz + 3 * (size_t)bi[j];
+        const double x = (double)__ldg(p), y = (double)__ldg(p + 1), z = (double)__ldg(p + 2);
+        c[0] += x; c[1] += y; c[2] += z;
+        c[3] += x * x; c[4] += x * y; c[5] += x * z; c[6] += y * y; c[7] += y * z; c[8] += z * z;
+        ++cnt;
+    }
+    double nrm[3] = {0.0, 0.0, 1.0};
+    if (cnt >= 3) {
+        const double inv = 1.0 / (double)cnt;
+        for (int i = 0; i < 9; ++i) c[i] *= inv;
+        const double A[6] = {c[3] - c[0] * c[0], c[4] - c[0] * c[1], c[5] - c[0] * c[2], c[6] - c[1] * c[1], c[7] - c[1] * c[2],
+                             c[8] - c[2] * c[2]};
+        double e[3];
+        if (smallest_eigenvector(A, e)) { nrm[0] = e[0]; nrm[1] = e[1]; nrm[2] = e[2]; }
+    }
+    // normal_redirect (dataset/common.py:312-320): towards the view point
+    const double dot = ((double)vx - me.x) * nrm[0] + ((double)vy - me.y) * nrm[1] + ((double)vz - me.z) * nrm[2];
+    const double sgn = dot < 0.0 ? -1.0 : 1.0;
+    normals[3 * (size_t)q] = (float)(sgn * nrm[0]);
+    normals[3 * (size_t)q + 1] = (float)(sgn * nrm[1]);
+    normals[3 * (size_t)q + 2] = (float)(sgn * nrm[2]);
 }
 
 int g_knn_thread = 1;         // debug only (roitr_debug_knn_thread_per_query): 0 = warp-per-query grid kernel everywhere, 1 = thread-per-query
@@ -696,4 +839,23 @@ extern "C" int roitr_knn_ppf_grid(int b, int m, int k_out, int drop_first, int n
                                   void* stream) {
     return roitr_knn_ppf_grid_q(b, m, k_out, drop_first, n_total, xyz, normals, new_xyz, new_normals, offset, new_offset,
                                 workspace, nullptr, idx, dist, ppf, stream);
+}
+
+extern "C" int roitr_estimate_normals(int b, int n, int knn, const float* xyz, const int* offset, const void* workspace,
+                                      const float* view_point, float* normals, void* stream) {
+    ROITR_CHECK_ARG(b >= 1 && n >= 0 && xyz && offset && workspace && view_point && normals, "estimate_normals: bad arguments");
+    ROITR_CHECK_ARG(knn == 9 || knn == 17 || knn == 33, "estimate_normals: knn must be 9, 17 or 33 (Open3D call site: 33), got %d", knn);
+    if (n == 0) return ROITR_OK;
+    const unsigned char* w = (const unsigned char*)workspace;
+    const auto* hdr = (const knngrid::SegHeader*)w;
+    const int* cell_start = (const int*)(w + grid_hdr_bytes(b));
+    const float4* sorted = (const float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = ceil_div(n, KT_THREADS);
+    const float vx = view_point[0], vy = view_point[1], vz = view_point[2];
+    if (knn == 9) normals_kernel<9><<<grid, KT_THREADS, 0, st>>>(b, n, xyz, offset, hdr, cell_start, sorted, vx, vy, vz, normals);
+    else if (knn == 17) normals_kernel<17><<<grid, KT_THREADS, 0, st>>>(b, n, xyz, offset, hdr, cell_start, sorted, vx, vy, vz, normals);
+    else normals_kernel<33><<<grid, KT_THREADS, 0, st>>>(b, n, xyz, offset, hdr, cell_start, sorted, vx, vy, vz, normals);
+    ROITR_CHECK_LAUNCH("normals_kernel");
+    return ROITR_OK;
 }
