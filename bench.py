@@ -319,6 +319,15 @@ def main():
             return r
         top = max(shares, key=lambda k: shares[k]["ms"])
         roof = roofline_of([top])
+        try:        # DRAM bytes of that kernel from the committed ncu --set full capture (per launch, like `achieved`)
+            cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+            if cap:
+                l0 = cap["launches"][0]
+                roof["traffic"] = l0["dram_bytes"]
+                roof["traffic_detail"] = {"launch_MNK": l0["shape_MNK"], "algorithmic_bytes_of_that_launch": l0["algorithmic_bytes"],
+                                          "source": cap["source"]}
+        except Exception:
+            pass
         roof["how"] = ("CUDA events around every entry-point call in a single-stream eager replica of the timed step (the timed "
                        "step itself is one multi-stream CUDA graph); algorithmic work per DESIGN.md §4 / SURVEY.md §8d")
         named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid_q", "roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build"]),
