@@ -212,8 +212,10 @@ def main():
     host = [[synthetic_pair(g, N_POINTS) for g in own] for own in sharding.owned_pairs(rank, world, B, NB)]
     pinned = [[{k: v.pin_memory() for k, v in p.items()} for p in batch] for batch in host]
     resident = [[{k: v.to(dev) for k, v in p.items()} for p in batch] for batch in pinned]
+    from roitr_b200.engine import BatchRunner
+    collated = [BatchRunner.collate(batch) for batch in host]           # what a DataLoader's collate_fn hands over (pinned)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    h2d_bytes = sum(t.numel() * t.element_size() for p in pinned[0] for t in p.values())
+    h2d_bytes = sum(t.numel() * t.element_size() for p in pinned[0] for t in p.values())        # = bytes of collated[0]
     runner = m.batch_runner(B, N_POINTS, N_POINTS, graph=not args.no_graph)
 
     def barrier():
@@ -232,12 +234,11 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if e2e:
-                r.load(pinned[i % NB])                       # H2D of the 9 inputs of every pair
+                r.load_batched(collated[i % NB])             # H2D of the 9 inputs of every pair (collated pinned host batch)
                 r.run()
-                outs = r.results()                           # D2H of the counts (sync), exact-size outputs
-                res = [o[k].cpu() for o in outs for k in ("tgt_corr_points", "src_corr_points", "corr_scores")]
-                d2h = sum(t.numel() * t.element_size() for t in res) + 12 * B
-                ncorr = sum(int(o["corr_scores"].shape[0]) for o in outs)
+                res = r.correspondences()                    # D2H: counts (sync) + every pair's correspondences (sync)
+                d2h = sum(t.numel() * t.element_size() for trip in res for t in trip) + 12 * B
+                ncorr = sum(int(trip[2].shape[0]) for trip in res)
             else:
                 r.load(resident[i % NB])                     # device-to-device: inputs already resident in HBM
                 r.run()

@@ -839,6 +839,40 @@ class BatchRunner:
             i["rot"][b].copy_(p["rot"], non_blocking=non_blocking)
             i["trans"][b].copy_(p["trans"], non_blocking=non_blocking)
 
+    def load_batched(self, host, non_blocking=True):
+        """host: dict with the batch already collated on the host (pinned for asynchronous copies) in the runner's layout -
+        ``pts`` / ``feats`` / ``nrm`` = [src_raw_0..src_raw_{B-1}, tgt_0..tgt_{B-1}], ``src_pcd`` = the B source clouds,
+        ``rot`` (B,3,3), ``trans`` (B,3,1): six copies per step instead of nine per pair (see ``collate``)."""
+        for k in self.INPUT_KEYS:
+            self.inp[k].copy_(host[k], non_blocking=non_blocking)
+
+    @staticmethod
+    def collate(pairs, pin=True):
+        """List of B per-pair input dicts (the 9 RIGA_v2.forward inputs, host tensors) -> the batched host dict ``load_batched``
+        takes (what a DataLoader collate_fn would produce)."""
+        cat = lambda a, b: torch.cat([p[a] for p in pairs] + ([p[b] for p in pairs] if b else []))
+        out = dict(pts=cat("src_raw_pcd", "tgt_pcd"), feats=cat("src_feats", "tgt_feats"), nrm=cat("src_normals", "tgt_normals"),
+                   src_pcd=cat("src_pcd", None), rot=torch.stack([p["rot"] for p in pairs]),
+                   trans=torch.stack([p["trans"].reshape(3, 1) for p in pairs]))
+        return {k: (v.contiguous().pin_memory() if pin else v.contiguous()) for k, v in out.items()}
+
+    def correspondences(self):
+        """The step's result on the HOST with one device->host read of the counts and one of the payload: per pair
+        (tgt_corr_points (C,3), src_corr_points (C,3), corr_scores (C,)) - the three result entries of the 22-key dict."""
+        counts = self.counts.tolist()                                    # sync #1: (B,3) ints
+        ns = [min(c[2], self.outs[b]["cap"]) for b, c in enumerate(counts)]
+        packed = torch.cat([torch.cat([self.outs[b]["t_cp"][:n], self.outs[b]["s_cp"][:n], self.outs[b]["c_sc"][:n, None]], 1)
+                            for b, n in enumerate(ns)])                 # (sum C, 7) on the device
+        host = torch.empty(packed.shape, dtype=packed.dtype, pin_memory=True)
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                       # sync #2: the payload
+        out, o = [], 0
+        for n in ns:
+            blk = host[o:o + n]
+            out.append((blk[:, 0:3], blk[:, 3:6], blk[:, 6]))
+            o += n
+        return out
+
     def _body(self):
         i = self.inp
         return riga_batch(self.W, self.cfg, self.plan, i["pts"], i["feats"], i["nrm"], i["src_pcd"], i["rot"], i["trans"])

@@ -30,3 +30,23 @@ def test_batch_runner_equals_single_pair_forward(graph):
             for k in s:
                 assert o[k].shape == s[k].shape and o[k].dtype == s[k].dtype, k
                 assert torch.equal(o[k], s[k]), k      # same kernels, same arithmetic: bit-identical
+
+
+def test_collated_load_and_packed_correspondences_equal_results():
+    """The e2e path of bench.py (collated pinned host batch in, packed correspondences out) returns what results() returns."""
+    from roitr_b200.engine import BatchRunner
+    N, B = 2048, 3
+    m = model.create_model(CONFIG_3D)
+    m.load_state_dict(weights(1))
+    m = m.to(DEV).eval()
+    pairs = [synthetic_pair(20 + i, N) for i in range(B)]
+    r = m.batch_runner(B, N, N, graph=True)
+    r.load([{k: v.to(DEV) for k, v in p.items()} for p in pairs])
+    r.run()
+    ref = r.results()
+    r.load_batched(BatchRunner.collate(pairs))
+    r.run()
+    got = r.correspondences()
+    for (t, s, c), o in zip(got, ref):
+        assert torch.equal(t, o["tgt_corr_points"].cpu()) and torch.equal(s, o["src_corr_points"].cpu())
+        assert torch.equal(c, o["corr_scores"].cpu())
