@@ -147,7 +147,7 @@ def op_work(name, ints):
     if name == "roitr_geo_embedding_table":
         b, N, C = ints[:3]             # writes E once; the table itself stays in shared memory
         return 4.0 * b * N * N * C, 0.0, "hbm"
-    if name == "roitr_geo_self_scores":
+    if name in ("roitr_geo_self_scores", "roitr_geo_self_scores_ld"):
         b, N, C = ints[:3]             # one streaming pass over E
         return 4.0 * b * N * N * C, 4.0 * b * N * N * C, "hbm"
     if name == "roitr_furthestsampling_cfg":

@@ -238,6 +238,9 @@ int roitr_gemm_tc_batched(int batch_outer, int batch_inner, int M, int N, int K,
  * positional queries; bp = proj_p.bias. heads = 4, C in {256,512}. */
 int roitr_geo_self_scores(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq, long long q_bs,
                           const float* E, const float* gq, const float* bp, float* P, float* G, void* stream);
+/* Same with an explicit row pitch for gq (gq may be a column slice of a wider buffer, e.g. of the folded [q|k|v|gq] layer). */
+int roitr_geo_self_scores_ld(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq, long long q_bs,
+                             const float* E, const float* gq, int ldgq, const float* bp, float* P, float* G, void* stream);
 
 /* out[row,:] = softmax(qk[row,:] / scale_div) over M entries per row (MultiHeadAttention, geoattention.py:50-60). */
 int roitr_softmax_rows(long long rows, int M, const float* qk, float scale_div, float* out, void* stream);

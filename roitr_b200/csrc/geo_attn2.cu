@@ -33,7 +33,8 @@ struct SelfParams {
     const float* qk;       // (batch, H, N, M) raw q.k
     const float* q; int ldq; long long q_bs;    // (batch*N rows, C) view for q . b_p
     const float* E;        // (batch, N, M, C)
-    const float* gq;       // (batch*N, H, C)
+    const float* gq;       // (batch*N, H, C), row pitch ldgq floats
+    int ldgq;
     const float* bp;       // (C)
     float* P;              // (batch, H, N, M) softmax with self
     float* G;              // (batch*N, H, C)
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(GA_THREADS, (C <= 256 ? 3 : 2)) geo_self_score
 #pragma unroll
     for (int h = 0; h < H; ++h)
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) gq[h][i] = __ldg(P.gq + (rowid * H + h) * C + c0 + i);
+        for (int i = 0; i < CPL; ++i) gq[h][i] = __ldg(P.gq + rowid * (size_t)P.ldgq + h * C + c0 + i);
     // q_h . b_p,h per head (lanes of a head are the 8-lane groups: head = c0 / (C/H) = lane >> 3)
     float qb = 0.f;
     {
@@ -243,18 +244,24 @@ int launch_self(const SelfParams& P, int batch, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int roitr_geo_self_scores(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq,
-                                     long long q_bs, const float* E, const float* gq, const float* bp, float* P, float* G,
+extern "C" int roitr_geo_self_scores_ld(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq,
+                                     long long q_bs, const float* E, const float* gq, int ldgq, const float* bp, float* P, float* G,
                                      void* stream) {
     ROITR_CHECK_ARG(heads == GA_H && (C == 256 || C == 512), "geo_self_scores: heads=4, C in {256,512} only");
     ROITR_CHECK_ARG(batch >= 1 && batch <= 65535 && N >= 1 && qk && q && E && gq && bp && P && G, "geo_self_scores: bad arguments");
     ROITR_CHECK_ARG((uintptr_t)E % 16 == 0, "geo_self_scores: E must be 16-byte aligned");
     SelfParams S;
-    S.qk = qk; S.q = q; S.ldq = ldq; S.q_bs = q_bs; S.E = E; S.gq = gq; S.bp = bp; S.P = P; S.G = G; S.N = N; S.M = N;
+    S.qk = qk; S.q = q; S.ldq = ldq; S.q_bs = q_bs; S.E = E; S.gq = gq; S.ldgq = ldgq; S.bp = bp; S.P = P; S.G = G; S.N = N; S.M = N;
     S.sqrt_c = sqrtf((float)(C / heads));
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 256) return launch_self<256>(S, batch, st);
     return launch_self<512>(S, batch, st);
+}
+
+extern "C" int roitr_geo_self_scores(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq,
+                                     long long q_bs, const float* E, const float* gq, const float* bp, float* P, float* G,
+                                     void* stream) {
+    return roitr_geo_self_scores_ld(batch, N, C, heads, qk, q, ldq, q_bs, E, gq, heads * C, bp, P, G, stream);
 }
 
 extern "C" int roitr_softmax_rows(long long rows, int M, const float* qk, float scale_div, float* out, void* stream) {

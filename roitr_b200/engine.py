@@ -167,8 +167,18 @@ def pack_weights(state_dict, device, architecture):
                     big_p[h * C:(h + 1) * C, h * c:(h + 1) * c] = Wp[h * c:(h + 1) * c, :].t()
                     big_vp[h * c:(h + 1) * c, h * C:(h + 1) * C] = Wvp[h * c:(h + 1) * c, :]
                 W[a + "#WpBig"], W[a + "#WvpBig"] = big_p, big_vp
+                # two more exact folds (fp64) that take launches off the latency-bound chain:
+                #   [q | k | v | gq] = x [W_qkv ; WpBig W_q]^T + [b_qkv ; WpBig b_q]          (gq = q WpBig^T)
+                #   pos_linear(G WvpBig^T + b_vp) = G (W_pl WvpBig)^T + (W_pl b_vp + b_pl)
+                Wq_, bq_ = W[a + ".proj_q.weight"].double(), W[a + ".proj_q.bias"].double()
+                W[a + "#Wqkvg"] = torch.cat([W[a + "#Wqkv"].double(), big_p.double() @ Wq_], 0).float().contiguous()
+                W[a + "#bqkvg"] = torch.cat([W[a + "#bqkv"].double(), big_p.double() @ bq_], 0).float().contiguous()
+                pl = a[: -len(".attention")] + ".pos_linear"
+                Wpl, bpl = W[pl + ".weight"].double(), W[pl + ".bias"].double()
+                W[a + "#Wposf"] = (Wpl @ big_vp.double()).float().contiguous()
+                W[a + "#bposf"] = (Wpl @ W[a + ".proj_vp.bias"].double() + bpl).float().contiguous()
         # tensor-core operand form of every dense-layer weight with a useful K (roitr_linear_tc_packed)
-        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("#Wkv") or k.endswith("#Wfq") or k.endswith("Big")) and W[k].dim() == 2
+        for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("#Wkv") or k.endswith("#Wfq") or k.endswith("#Wqkvg") or k.endswith("#Wposf") or k.endswith("Big")) and W[k].dim() == 2
                   and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
     finally:
@@ -435,10 +445,11 @@ def _self_layer_batch(W, lp, x, E, nb, N):
     C = x.shape[1]
     c = C // HEADS
     R = x.shape[0]
-    qkv = ops.linear(x, W[a + "#Wqkv"], W[a + "#bqkv"], wpack=W.get(a + "#Wqkv#tc") if LINEAR_TC else None)
     if LINEAR_TC:
-        gq = ops.linear(qkv[:, :C], W[a + "#WpBig"], None, wpack=W[a + "#WpBig#tc"])
+        qkvg = ops.linear(x, W[a + "#Wqkvg"], W[a + "#bqkvg"], wpack=W[a + "#Wqkvg#tc"])     # (R, 3C + H*C)
+        qkv, gq = qkvg[:, :3 * C], qkvg[:, 3 * C:]
     else:
+        qkv = ops.linear(x, W[a + "#Wqkv"], W[a + "#bqkv"])
         gq = torch.empty(R, HEADS * C, dtype=torch.float32, device=x.device)
         for h in range(HEADS):
             ops.linear(qkv[:, h * c:(h + 1) * c], W[a + "#WpT"][h], None, out=gq[:, h * C:(h + 1) * C], M=R, K=c)
@@ -447,14 +458,14 @@ def _self_layer_batch(W, lp, x, E, nb, N):
     Wvp, bvp = W[a + ".proj_vp.weight"], W[a + ".proj_vp.bias"]
     G2 = G.view(R, HEADS * C)
     if LINEAR_TC:
-        pos = ops.linear(G2, W[a + "#WvpBig"], bvp, wpack=W[a + "#WvpBig#tc"])
+        pos = ops.linear(G2, W[a + "#Wposf"], W[a + "#bposf"], wpack=W[a + "#Wposf#tc"])      # pos_linear already applied
     else:
         pos = torch.empty(R, C, dtype=torch.float32, device=x.device)
         for h in range(HEADS):
             ops.linear(G2[:, h * C:(h + 1) * C], Wvp[h * c:(h + 1) * c], bvp[h * c:(h + 1) * c], out=pos[:, h * c:(h + 1) * c],
                        M=R, K=C)
     y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
-    pos = _ln(W, lp + ".attention.pos_norm", _lin(W, lp + ".attention.pos_linear", pos), mode=ops.MODE_LN)
+    pos = _ln(W, lp + ".attention.pos_norm", pos if LINEAR_TC else _lin(W, lp + ".attention.pos_linear", pos), mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
 
 

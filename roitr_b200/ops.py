@@ -282,8 +282,8 @@ def attention_tc(batch, N, M, C, q, k, v, heads=4, E=None, gq=None, bp=None):
     if E is not None:
         P = torch.empty_like(qk)
         G = torch.empty(batch * N, heads, C, dtype=torch.float32, device=dev)
-        _lib.call("roitr_geo_self_scores", c_int(batch), c_int(N), c_int(C), c_int(heads), f32(qk), c_void(q), c_int(ldq),
-                  c_ll(N * ldq), f32(E), f32(gq), f32(bp), f32(P), f32(G), stream_ptr())
+        _lib.call("roitr_geo_self_scores_ld", c_int(batch), c_int(N), c_int(C), c_int(heads), f32(qk), c_void(q), c_int(ldq),
+                  c_ll(N * ldq), f32(E), c_void(gq), c_int(gq.stride(0)), f32(bp), f32(P), f32(G), stream_ptr())
     else:
         P = qk
         _lib.call("roitr_softmax_rows", c_ll(batch * heads * N), c_int(M), f32(qk), c_float(float(c) ** 0.5), f32(P),
