@@ -50,3 +50,31 @@ def test_collated_load_and_packed_correspondences_equal_results():
     for (t, s, c), o in zip(got, ref):
         assert torch.equal(t, o["tgt_corr_points"].cpu()) and torch.equal(s, o["src_corr_points"].cpu())
         assert torch.equal(c, o["corr_scores"].cpu())
+
+
+@pytest.mark.parametrize("name,n_src,n_tgt,B", [("3dmatch_30k", 30000, 28000, 2), ("4dmatch_8k", 8000, 7000, 2)])
+def test_batch_runner_other_baseline_configs(name, n_src, n_tgt, B):
+    """BASELINE.json configs 3 and 5 (3DMatch-shaped ~30k clouds; 4DMatch-shaped ~8k non-rigid pair, factor-2 backbone and
+    the adaptive head) with UNEQUAL cloud sizes: the batched CUDA-graph path equals the single-pair forward bit for bit."""
+    from tests.helpers import CONFIG_4D
+    four_d = name.startswith("4d")
+    cfg = CONFIG_4D if four_d else CONFIG_3D
+    m = model.create_model(cfg)
+    m.load_state_dict(weights(2 if four_d else 1))
+    m = m.to(DEV).eval()
+    pairs = []
+    for i in range(B):
+        p = synthetic_pair(30 + i, n_src, deform=four_d)
+        p = dict(p)
+        for k in ("tgt_pcd", "tgt_feats", "tgt_normals"):
+            p[k] = p[k][:n_tgt].contiguous()
+        pairs.append(p)
+    singles = [m(*forward_args(p, DEV)) for p in pairs]
+    r = m.batch_runner(B, n_src, n_tgt, graph=True)
+    r.load([{k: v.to(DEV) for k, v in p.items()} for p in pairs])
+    r.run()
+    for o, s in zip(r.results(), singles):
+        assert set(o) == set(s)
+        for k in s:
+            assert o[k].shape == s[k].shape and torch.equal(o[k], s[k]), k
+    assert sum(int(s["corr_scores"].shape[0]) for s in singles) > 0
