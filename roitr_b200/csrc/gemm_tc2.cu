@@ -588,6 +588,7 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
         ROITR_CHECK_ARG(stream_ok && P.tiles_n == 1 && N % 32 == 0 && ln_beta && ldr >= N && ldr % 4 == 0 &&
                             ((uintptr_t)res_pre | (uintptr_t)res_post) % 16 == 0,
                         "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile (N=%d, tile %d)", N, bn);
+        if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
         return bn == 64 ? launch_tc3<64, 3, 3, 8, 1>(P, st) : launch_tc3<128, 2, 4, 8, 1>(P, st);
     }
     if (stream_ok && !g_force_tc2) {

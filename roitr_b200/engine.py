@@ -24,6 +24,8 @@ STRIDES = (1, 4, 4, 4)
 NSAMPLE = (8, 16, 16, 16)
 BLOCKS = (2, 3, 3, 3)
 HEADS = 4
+FPS_AFTER_KNN = False        # measured: the level-1 layers start 3 ms earlier but crawl next to the FPS clusters; 563 vs 569 pairs/s
+LIGHT_VARIANT = 3          # streaming dense-layer configuration used while the FPS clusters are resident (0 = none)
 
 
 # ------------------------------------------------------------------------------------------------ weight packing
@@ -348,7 +350,7 @@ def encode(W, plan, pts, feats, nrm, on_nodes=None):
     mk_grid = lambda li, p_, o_: ops.knn_grid_build(p_, o_) if plan.levels[li]["n_max"] >= ops.GRID_MIN_SEGMENT else None
     G = [dict(p=pts, n=nrm, o=plan.levels[0]["o"], down_idx=None, ev_pts=None)]
 
-    def issue_sample(li):          # sampling lane: level li points / normals from level li - 1
+    def issue_sample(li, *after):  # sampling lane: level li points / normals from level li - 1
         prev, L = G[li - 1], plan.levels[li]
 
         def sample():
@@ -360,7 +362,7 @@ def encode(W, plan, pts, feats, nrm, on_nodes=None):
             if li == 3 and on_nodes is not None:
                 on_nodes(G + [g], down_idx, n_p)
             return g
-        g, _ = fps_lane.run(sample)
+        g, _ = fps_lane.run(sample, *after)
         G.append(g)
 
     def issue_search(li):          # search lane: every kNN query whose queries or references are level li
@@ -389,13 +391,19 @@ def encode(W, plan, pts, feats, nrm, on_nodes=None):
             G[li - 1]["ev_up"] = ev_up
 
     issue_search(0)
-    issue_sample(1)
+    # The FPS chain starts only when the level-1 self kNN is done: resident FPS clusters leave room for 2-3 of its CTAs per
+    # SM instead of 9, which stretched it from 1.0 to 4.1 ms and with it the start of every level-1 layer (timeline r01j).
+    issue_sample(1, G[0]["ev_self"] if FPS_AFTER_KNN else None)
     levels = []
     x = feats
     for li in range(4):
         p = "backbone.enc%d" % (li + 1)
         g = G[li]
         order = (g["grid"], g["o"].shape[0]) if g["grid"] is not None else None     # this level's points in cell order
+        # Level 1 is issued while the FPS clusters (44 K registers + 61 KB shared memory on 128 of the 148 SMs for ~3.5 ms) are
+        # resident: the 215 KB / 57 K-register dense-layer CTAs cannot share an SM with them and would wait for the chain to
+        # finish, the "light" configuration (64 registers, 320 threads, ~115 KB) can.
+        ops.set_linear_variant(LIGHT_VARIANT if (li == 0 and fps_lane.stream is not None) else 0)
         if li > 0:
             _wait(g["ev_down"])
             x = local_ppf_transformer(W, p + ".0.transformer", x, g["down_idx"], g["gidx"], g["gppf"], order)
@@ -411,6 +419,7 @@ def encode(W, plan, pts, feats, nrm, on_nodes=None):
             issue_search(li + 1)
             if li + 2 < 4:
                 issue_sample(li + 2)
+    ops.set_linear_variant(0)
     return levels, (fps_lane, knn_lane)
 
 

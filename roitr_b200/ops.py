@@ -67,6 +67,12 @@ def linear_ln(a, w, bias, wpack, gamma, beta, res_pre=None, res_pre_index=None, 
     return out
 
 
+def set_linear_variant(v):
+    """Configuration of the streaming dense-layer kernel for the launches issued from now on (baked into a graph at capture):
+    0 = deep rings, one CTA per SM; 3 = light footprint that shares an SM with other kernels' CTAs."""
+    _lib.lib().roitr_debug_linear_variant(c_int(int(v)))
+
+
 def c_void(t):
     """Device pointer of a (possibly strided-view) f32 tensor: views into wider buffers are allowed here because the
     leading dimension is passed explicitly."""
