@@ -28,8 +28,6 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.roitr_last_error.restype = ctypes.c_char_p
         _lib.roitr_abi_version.restype = c_int
-        if os.environ.get("ROITR_FPS_MINB"):            # tuning knob: register cap of the FPS kernel (CTAs per SM)
-            _lib.roitr_debug_fps_min_blocks(int(os.environ["ROITR_FPS_MINB"]))
         if os.environ.get("ROITR_LINEAR_VARIANT"):      # tuning knob (scripts/): streaming dense-layer kernel configuration
             _lib.roitr_debug_linear_variant(int(os.environ["ROITR_LINEAR_VARIANT"]))
     return _lib

@@ -93,10 +93,9 @@ __device__ __forceinline__ float tree_max(const float (&v)[N]) {
     return t[0];
 }
 
-// MINB = CTAs per SM the register allocation is capped for: 2 keeps a CTA at <= 64 registers per thread (32 K registers, half
-// an SM's file), so that kernels of other streams can share the SM while the latency-bound FPS chain runs.
-template <int CL, int PPT, int MINB>
-__global__ void __launch_bounds__(FPS_THREADS, MINB) fps_cluster_kernel(const FpsParams P) {
+// (A 64-register build, two CTAs per SM, was measured: the spills land in the iteration loop, 4.3 -> 5.3 ms per step.)
+template <int CL, int PPT>
+__global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const FpsParams P) {
     extern __shared__ __align__(16) float s_pts[];  // [PPT * FPS_THREADS][3]: this CTA's coordinates by local slot
     __shared__ Cand s_cta[2][MAX_CL];
     __shared__ int2 s_warp[2][FPS_WARPS];
@@ -235,12 +234,12 @@ __global__ void __launch_bounds__(FPS_THREADS, MINB) fps_cluster_kernel(const Fp
     if (CL > 1) cluster.sync();  // no CTA exits while a peer may still write into its shared memory
 }
 
-template <int CL, int PPT, int MINB>
-int launch_fps_b(const FpsParams& P, cudaStream_t st) {
+template <int CL, int PPT>
+int launch_fps(const FpsParams& P, cudaStream_t st) {
     const int smem = PPT * FPS_THREADS * 12;
     static bool attr_set = false;
     if (!attr_set) {  // dynamic + static shared memory can exceed the 48 KB default from PPT = 8 on
-        ROITR_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<CL, PPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ROITR_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<CL, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -255,20 +254,11 @@ int launch_fps_b(const FpsParams& P, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ROITR_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CL, PPT, MINB>, P));
+    ROITR_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CL, PPT>, P));
     return ROITR_OK;
 }
 
-int g_fps_minb = 1;   // debug / tuning (roitr_debug_fps_min_blocks): 2 = light register footprint
-
-template <int CL, int PPT>
-int launch_fps(const FpsParams& P, cudaStream_t st) {
-    return g_fps_minb >= 2 ? launch_fps_b<CL, PPT, 2>(P, st) : launch_fps_b<CL, PPT, 1>(P, st);
-}
-
 }  // namespace
-
-extern "C" int roitr_debug_fps_min_blocks(int n) { g_fps_minb = n; return 0; }
 
 extern "C" int roitr_furthestsampling_cfg(int b, int n_max, int n_seg_max, const float* xyz, const int* offset,
                                           const int* new_offset, int* idx, float* new_xyz, int cluster_hint,

@@ -562,7 +562,7 @@ int launch_tc2(const Tc2Params& P, cudaStream_t st) {
 
 static int g_ablate = 0;
 extern "C" int roitr_debug_linear_ablate(int mask) { g_ablate = mask; return 0; }
-static int g_tc3_variant = 0;  // debug only: streaming-kernel configuration (0: deep rings, 1 CTA/SM; 1, 2: other ring depths at 64 columns; 3, 4: light, co-residency friendly)
+static int g_tc3_variant = 0;  // set per launch by the engine (roitr_debug_linear_variant): streaming-kernel configuration (0: deep rings, one CTA per SM; 3: light footprint, shares an SM with other kernels)
 extern "C" int roitr_debug_linear_variant(int v) { g_tc3_variant = v; return 0; }
 static int g_force_tc2 = 0;   // debug only: route everything through the coupled-ring kernel (A/B timing)
 extern "C" int roitr_debug_force_linear_tc2(int on) { g_force_tc2 = on; return 0; }
@@ -593,11 +593,7 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
     }
     if (stream_ok && !g_force_tc2) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
-        if (g_tc3_variant == 4) return bn == 128 ? launch_tc3<128, 1, 3, 4, 3>(P, st) : launch_tc3<64, 2, 2, 4, 3>(P, st);
-        if (bn == 128) return launch_tc3<128, 2, 4, 8, 1>(P, st);
-        if (g_tc3_variant == 1) return launch_tc3<64, 2, 4, 8, 1>(P, st);
-        if (g_tc3_variant == 2) return launch_tc3<64, 2, 5, 8, 1>(P, st);
-        return launch_tc3<64, 3, 3, 8, 1>(P, st);
+        return bn == 128 ? launch_tc3<128, 2, 4, 8, 1>(P, st) : launch_tc3<64, 3, 3, 8, 1>(P, st);
     }
     if (bn == 64) return launch_tc2<64, 4>(P, st);
     return launch_tc2<128, 3>(P, st);

@@ -32,8 +32,8 @@ for (M, N, K) in [(640000, 64, 64), (640000, 192, 64), (160000, 128, 128), (6400
     log("%d,%d,%d | " % (M, N, K) + " | ".join("%.4f" % t for t in ts))
     if N <= 64:
         vs = []
-        for v in (0, 1, 2):
+        for v in (0, 3):
             _lib.lib().roitr_debug_linear_variant(v)
             vs.append(timeit(lambda: ops.linear(a, w, b, out=o, wpack=wp)))
         _lib.lib().roitr_debug_linear_variant(0)
-        log("   ring variants (ops/raw 3/3, 2/4, 2/5): " + " | ".join("%.4f" % t for t in vs))
+        log("   configurations (deep rings, light footprint): " + " | ".join("%.4f" % t for t in vs))
