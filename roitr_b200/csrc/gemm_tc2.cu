@@ -71,17 +71,19 @@ __device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, co
             float* dst = P.C + (long long)(row0 + sub) * P.ldc + n;
             const float* pp = post ? post + (long long)(row0 + sub) * P.ldr + n : nullptr;
             const long long step = 4ll * P.ldc, pstep = 4ll * P.ldr;
+            float4 r[8];                                     // all eight residual segments in flight before the first use
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pp && row0 + 4 * i + sub < P.M) r[i] = __ldg(reinterpret_cast<const float4*>(pp + i * pstep));
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float4 x = *reinterpret_cast<const float4*>(pad + (4 * i + sub) * PAD_STRIDE + 4 * (lane & 7));
                 x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-                const bool ok = row0 + 4 * i + sub < P.M;
-                if (pp && ok) {
-                    const float4 r = __ldg(reinterpret_cast<const float4*>(pp + i * pstep));
-                    x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-                }
+                x.x += r[i].x; x.y += r[i].y; x.z += r[i].z; x.w += r[i].w;
                 if (P.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                if (ok) *reinterpret_cast<float4*>(dst + i * step) = x;
+                if (row0 + 4 * i + sub < P.M) *reinterpret_cast<float4*>(dst + i * step) = x;
             }
         }
     } else {
@@ -447,6 +449,21 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
                 // pass C normalises and hands 32x32 blocks to the transposed store (post-norm residual, ReLU, float4 rows).
                 const int row = row0 + lane;
                 const bool valid = row < P.M;
+                {   // the residual rows of this CTA's NEXT tile: requested now (L2 prefetch), consumed one tile later - each
+                    // thread reads its own row, so without this the 700-cycle miss latency is exposed twice per tile
+                    const int ntile = tile + gridDim.x;
+                    const int nrow = (ntile / P.tiles_n) * T2_BM + warp * 32 + lane;
+                    if (ntile < total_tiles && nrow < P.M) {
+                        if (P.res_pre) {
+                            const float* pr = P.res_pre + (P.res_pre_index ? (long long)__ldg(P.res_pre_index + nrow) : (long long)nrow) * P.ldr;
+                            for (int c = 0; c < P.N; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + c));
+                        }
+                        if (P.res_post) {
+                            const float* pq = P.res_post + (long long)nrow * P.ldr;
+                            for (int c = 0; c < P.N; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pq + c));
+                        }
+                    }
+                }
                 const float* pre = nullptr;
                 if (P.res_pre && valid)
                     pre = P.res_pre + (P.res_pre_index ? (long long)__ldg(P.res_pre_index + row) : (long long)row) * P.ldr;

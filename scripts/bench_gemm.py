@@ -32,3 +32,16 @@ for (M, N, K) in SHAPES:
     t3 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp))
     log("%d,%d,%d, %.4f, %.4f, %.0f, %.1f, %.2e" % (M, N, K, t2, t3, (M * K + M * N) * 4 / t3 / 1e6, 2.0 * M * N * K / t3 / 1e9,
                                                (o3 - o2).abs().max().item()))
+
+log("fused LayerNorm epilogue: M,N,K, plain_ms, row_epilogue_ms, fused_ms (res_pre), fused_ms (res_post+relu)")
+for (M, N, K) in [(640000, 64, 64), (160000, 128, 128)]:
+    a = torch.randn(M, K, device=DEV); w = torch.randn(N, K, device=DEV) / K ** 0.5; b = torch.randn(N, device=DEV)
+    g_, be = torch.ones(N, device=DEV), torch.zeros(N, device=DEV)
+    r = torch.randn(M, N, device=DEV)
+    wp = engine.pack_linear_tc(w)
+    o = torch.empty(M, N, device=DEV)
+    t0 = timeit(lambda: ops.linear(a, w, b, out=o, wpack=wp))
+    t1 = timeit(lambda: ops.row_epilogue(o, res_pre=r, gamma=g_, beta=be, mode=ops.MODE_LN))
+    t2 = timeit(lambda: ops.linear_ln(a, w, b, wp, g_, be, res_pre=r))
+    t3 = timeit(lambda: ops.linear_ln(a, w, b, wp, g_, be, res_post=r, relu=True))
+    log("%d,%d,%d, %.4f, %.4f, %.4f, %.4f" % (M, N, K, t0, t1, t2, t3))
