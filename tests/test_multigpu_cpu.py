@@ -82,3 +82,17 @@ def test_two_gloo_ranks_shard_reduce_gather():
         assert allidx[rank][0] == g0 == rank
         assert checksum == pytest.approx(float(synthetic_pair(g0, 64)["src_pcd"].double().sum()))
     assert sharding.job_throughput(2, world, 2, max(m[1][0] for m in got)) == pytest.approx(8 / 0.011)
+
+
+def test_collate_layout_matches_runner_inputs():
+    """BatchRunner.collate (the host-side batch layout of the e2e path): [src_0..src_{B-1}, tgt_0..tgt_{B-1}] per key."""
+    import torch
+    from roitr_b200.engine import BatchRunner
+    from roitr_b200.synthetic import synthetic_pair
+    pairs = [synthetic_pair(i, 256) for i in range(3)]
+    h = BatchRunner.collate(pairs, pin=False)
+    assert set(h) == set(BatchRunner.INPUT_KEYS)
+    assert h["pts"].shape == (6 * 256, 3) and h["src_pcd"].shape == (3 * 256, 3) and h["rot"].shape == (3, 3, 3) and h["trans"].shape == (3, 3, 1)
+    assert torch.equal(h["pts"][256:512], pairs[1]["src_raw_pcd"]) and torch.equal(h["pts"][3 * 256 + 512:], pairs[2]["tgt_pcd"])
+    assert torch.equal(h["nrm"][:256], pairs[0]["src_normals"]) and torch.equal(h["feats"][3 * 256:4 * 256], pairs[0]["tgt_feats"])
+    assert torch.equal(h["src_pcd"][512:], pairs[2]["src_pcd"]) and torch.equal(h["trans"][1].flatten(), pairs[1]["trans"].flatten())
