@@ -351,9 +351,9 @@ def main():
             "wall_s_between_barriers": wall,
         }
         if not args.no_cpu_baseline:
-            v, dt, cores = cpu_reference_pairs_per_s(2, 0, N_POINTS)
+            v, dt, cores = cpu_reference_pairs_per_s(6, 1, N_POINTS)      # bounded sample: ~10 s of CPU work after one warm-up pair
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                    "sample": "2 pairs of the named workload (%.1f s), oracle/forward_ref.py + pointops_ref.c" % dt}
+                                    "sample": "6 pairs of the named workload (%.1f s), oracle/forward_ref.py + pointops_ref.c" % dt}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
