@@ -590,7 +590,8 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
                                  const float* res_post, int ldr, void* stream) {
     ROITR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && A && wpack && C, "linear_tc_packed: bad arguments M=%d N=%d K=%d", M, N, K);
     ROITR_CHECK_ARG(lda >= K && ldc >= N, "linear_tc_packed: bad leading dimensions");
-    ROITR_CHECK_ARG(bn == 64 || bn == 128, "linear_tc_packed: weights must be packed with 64- or 128-row tiles, got %d", bn);
+    ROITR_CHECK_ARG(bn == 64 || bn == 128 || (bn == 256 && ln_gamma),
+                    "linear_tc_packed: weights must be packed with 64- or 128-row tiles (256 for the fused LayerNorm only), got %d", bn);
     ROITR_CHECK_ARG((uintptr_t)wpack % 16 == 0, "linear_tc_packed: wpack must be 16-byte aligned");
     if (M == 0) return ROITR_OK;
     Tc2Params P;
@@ -605,6 +606,9 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
         ROITR_CHECK_ARG(stream_ok && P.tiles_n == 1 && N % 32 == 0 && ln_beta && ldr >= N && ldr % 4 == 0 &&
                             ((uintptr_t)res_pre | (uintptr_t)res_post) % 16 == 0,
                         "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile (N=%d, tile %d)", N, bn);
+        // 256-column tile (EXPERIMENTAL, not used by the engine by default, see engine.LN256): the whole row of a 256-channel
+        // layer in one tile - one operand stage of 96 KB, four raw stages, both TMEM accumulators = all 512 columns
+        if (bn == 256) return launch_tc3<256, 1, 4, 8, 1>(P, st);
         if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
         return bn == 64 ? launch_tc3<64, 3, 3, 8, 1>(P, st) : launch_tc3<128, 2, 4, 8, 1>(P, st);
     }

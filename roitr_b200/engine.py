@@ -24,6 +24,9 @@ STRIDES = (1, 4, 4, 4)
 NSAMPLE = (8, 16, 16, 16)
 BLOCKS = (2, 3, 3, 3)
 HEADS = 4
+# EXPERIMENTAL, off: LayerNorm of the 256-channel layers (levels 3-4, global transformer) fused into a 256-column dense-layer
+# tile (csrc/gemm_tc2.cu launch_tc3<256,1,4,8,1>). Compiles; NOT yet run on a GPU (tests/test_experimental.py, opt-in).
+LN256 = False
 FPS_AFTER_KNN = False        # measured: the level-1 layers start 3 ms earlier but crawl next to the FPS clusters; 563 vs 569 pairs/s
 LIGHT_VARIANT = 3          # streaming dense-layer configuration used while the FPS clusters are resident (0 = none)
 
@@ -183,6 +186,8 @@ def pack_weights(state_dict, device, architecture):
         for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("#Wkv") or k.endswith("#Wfq") or k.endswith("#Wqkvg") or k.endswith("#Wposf") or k.endswith("Big")) and W[k].dim() == 2
                   and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
+            if LN256 and W[k].shape[0] == 256 and W[k].shape[1] % 32 == 0 and k.endswith(".weight"):
+                W[k + "#tc256"] = pack_linear_tc(W[k], 256)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = hp
     return W
@@ -204,7 +209,7 @@ def _ln(W, p, x, **kw):
 def _lin_ln(W, p, n, x, **kw):
     """Linear p followed by LayerNorm n (+ residuals / ReLU), fused into the dense layer's epilogue where it fits."""
     return ops.linear_ln(x, W[p + ".weight"], W[p + ".bias"], W.get(p + ".weight#tc") if LINEAR_TC else None,
-                         W[n + ".weight"], W[n + ".bias"], **kw)
+                         W[n + ".weight"], W[n + ".bias"], wpack_wide=W.get(p + ".weight#tc256") if LINEAR_TC else None, **kw)
 
 
 def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None, post=None):
@@ -444,8 +449,10 @@ def decode(W, L):
 
 # ------------------------------------------------------------------------------------------------ global transformer
 def _ffn(W, p, x):
-    h = _lin(W, p + ".squeeze", _lin(W, p + ".expand", x, relu=True))
-    return _ln(W, p + ".norm", h, res_pre=x, mode=ops.MODE_LN)
+    h = _lin(W, p + ".expand", x, relu=True)
+    if LN256:
+        return _lin_ln(W, p + ".squeeze", p + ".norm", h, res_pre=x)
+    return _ln(W, p + ".norm", _lin(W, p + ".squeeze", h), res_pre=x, mode=ops.MODE_LN)
 
 
 def _self_layer_batch(W, lp, x, E, nb, N):
@@ -473,7 +480,10 @@ def _self_layer_batch(W, lp, x, E, nb, N):
         for h in range(HEADS):
             ops.linear(G2[:, h * C:(h + 1) * C], Wvp[h * c:(h + 1) * c], bvp[h * c:(h + 1) * c], out=pos[:, h * c:(h + 1) * c],
                        M=R, K=C)
-    y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
+    if LN256:
+        y = _lin_ln(W, lp + ".attention.linear", lp + ".attention.norm", hidden, res_pre=x)
+    else:
+        y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     pos = _ln(W, lp + ".attention.pos_norm", pos if LINEAR_TC else _lin(W, lp + ".attention.pos_linear", pos), mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
 
@@ -486,7 +496,10 @@ def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, wpack=tcw("k"))
     v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], wpack=tcw("v"))
     hidden = (ops.attention_tc if ATTENTION_TC else ops.geo_attention_batched_compat)(nb, N, M, C, q, k, v)
-    z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
+    if LN256:
+        z = _lin_ln(W, lp + ".attention.linear", lp + ".attention.norm", hidden, res_pre=x)
+    else:
+        z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", z)
 
 
