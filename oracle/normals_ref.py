@@ -3,7 +3,7 @@
 Follows dataset/tdmatch.py:120-127 (Open3D ``estimate_normals(KDTreeSearchParamKNN(knn=33))`` on each cloud, then
 ``normal_redirect``) and dataset/common.py:312-320 (normal_redirect). Only tests/ may import this file.
 
-PARITY UNPINNED for the Open3D part: Open3D (third-party, pinned ``open3d==0.10.0.0`` in requirements.txt) is not under
+PARITY UNPINNED for the Open3D part: Open3D (third-party, pinned ``open3d==0.13.0`` in requirements.txt) is not under
 /root/reference and not installable here, so its published algorithm is restated: the knn nearest points of the query
 (itself included), population covariance from first/second cumulants (geometry/EstimateNormals.cpp ComputeCovariance),
 eigenvector of the smallest eigenvalue (ComputeNormal). The eigenvector is taken from numpy.linalg.eigh in float64, which
