@@ -7,8 +7,12 @@
 A step = RIGA_v2.forward over a batch of B (default 16) independent synthetic pairs of BASELINE.json configs[1]
 (2 x 20 000 points each, Gaussian blobs, seeded weights), issued as one CUDA graph. N > 1 (torchrun, one rank per GPU): pairs are independent units, rank r processes its own
 pairs (weak scaling), NCCL is used only for the barrier, the max-over-ranks time and the gather of per-pair result
-counts. `value` = pairs/s with inputs resident in HBM; `e2e` = the same metric through model.forward with pinned HOST
-buffers (H2D of the 9 inputs and D2H of the correspondences inside the timed region).
+counts. `value` = pairs/s with inputs resident in HBM; `e2e` = the same metric through the batched public API
+(`BatchRunner.load_batched` / `run` / `correspondences`) with pinned HOST buffers: H2D of the 9 inputs of every pair and D2H
+of every pair's correspondences inside the timed region. `e2e_record` = the same with the FULL result record of
+lib/tester.py:56-69 (descriptors included, ~45 MB per pair) copied to the host; `single_pair_forward_ms` = the call
+lib/tester.py:53 makes (model.forward on ONE pair, batch_size 1, host sync at the end); `reference_gpu` = the reference's
+algorithm in eager PyTorch with the reference's OWN kNN / FPS kernels (oracle/_ref) on this GPU (information only).
 Timing: CUDA events on the launch stream; >= 3 warm-up steps; an L2 flush (256 MiB memset) between steps, outside the
 timed events; clocks sampled with nvidia-smi during the timed region.
 """
@@ -110,6 +114,35 @@ def cpu_reference_pairs_per_s(steps, warmup, n_points):
             fr.riga_forward(sd, cfg, *forward_args(pairs[i % len(pairs)]))
         dt = time.perf_counter() - t0
     return steps / dt, dt, cores
+
+
+def reference_gpu_pairs_per_s(dev, n_points, steps=3, warmup=1):
+    """The reference on THIS GPU: its algorithm in eager PyTorch fp32 (oracle/forward_ref.py, which is
+    pinned bit for bit to the reference's Python) driving the reference's OWN kernels compiled unmodified for sm_100a
+    (oracle/_ref: knnquery_cuda_kernel.cu:65-108, sampling_cuda_kernel.cu:14-129), batch size 1 as lib/tester.py runs it.
+    Information only: it explains how much of the speed-up is B200 vs host cores and how much is this repo's kernels."""
+    from oracle import forward_ref as fr
+    from oracle import native
+    from roitr_b200.synthetic import forward_args, synthetic_pair
+    if not native.have_ref_cuda():
+        return None
+    cfg = _cfg()
+    sd = {k: v.to(dev) for k, v in _weights().items()}
+    pairs = [forward_args(synthetic_pair(100 + i, n_points), dev) for i in range(2)]
+    with torch.no_grad():
+        for i in range(warmup):
+            fr.riga_forward(sd, cfg, *pairs[i % 2])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            out = fr.riga_forward(sd, cfg, *pairs[i % 2])
+            n = int(out["corr_scores"].shape[0])          # the forward's own syncs (nonzero) already made this a host value
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": "pairs/s", "ms_per_pair": 1000.0 * dt / steps, "pairs_timed": steps,
+            "kind": "reference algorithm (oracle/forward_ref.py, eager PyTorch fp32) + the reference's own kNN/FPS kernels "
+                    "(oracle/_ref, sm_100a) on this GPU, batch size 1, wall clock incl. its host syncs",
+            "correspondences_last_pair": n}
 
 
 def run_reference(args):
@@ -255,6 +288,38 @@ def main():
     run_loop(True, 2)
     ms_e2e, _, d2h_bytes, ncorr = run_loop(True, steps)
 
+    # e2e with the FULL record lib/tester.py:56-69 builds per pair (16 tensors incl. the (N,256) point descriptors)
+    from roitr_b200 import results as results_mod
+    rec_steps = max(2, min(steps, 5))
+
+    def record_loop(n_steps):
+        nbytes = 0
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n_steps):
+            runner.load_batched(collated[i % NB])
+            runner.run()
+            recs = results_mod.tester_records(host[i % NB], runner.results(), cfg["benchmark"])
+            nbytes = sum(t.numel() * t.element_size() for r in recs for t in r.values() if torch.is_tensor(t))
+        b.record()
+        barrier()
+        return a.elapsed_time(b), nbytes
+    record_loop(1)
+    ms_rec, rec_bytes = record_loop(rec_steps)
+
+    # the call lib/tester.py:53 makes: model.forward on ONE pair (batch_size 1), the forward's single host sync included
+    one = [t.to(dev) for t in (host[0][0][k] for k in ("src_pcd", "tgt_pcd", "src_feats", "tgt_feats", "src_normals",
+                                                       "tgt_normals", "rot", "trans", "src_raw_pcd"))]
+    for _ in range(3):
+        m(*one)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        o1 = m(*one)
+    torch.cuda.synchronize()
+    single_ms = (time.perf_counter() - t0) * 100.0
+
     # instrumented EAGER replica of the same step: per-entry-point CUDA-event durations, launch count, algorithmic work
     # (serial=True: no side streams, so every call's event pair brackets that call alone)
     eager = m.batch_runner(B, N_POINTS, N_POINTS, graph=False, serial=True)
@@ -286,7 +351,7 @@ def main():
     _lib.RECORD_ARGS = False
     eager_ms = sum(v["ms"] for v in shares.values())
 
-    ms_dev, ms_e2e = sharding.max_over_ranks([ms_dev, ms_e2e], dist, dev)          # device-timed, max over ranks
+    ms_dev, ms_e2e, ms_rec = sharding.max_over_ranks([ms_dev, ms_e2e, ms_rec], dist, dev)   # device-timed, max over ranks
     total_corr = sum(sharding.gather_counts(sum(x[2] for x in counts), dist, dev))   # the (trivial) result gather
 
     if rank == 0:
@@ -344,13 +409,23 @@ def main():
                        "mode": ("one CUDA graph per step" if not args.no_graph else "eager") + ", %d pairs in flight per GPU" % B},
             "e2e": {"value": world * B * steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
+            "e2e_record": {"value": world * B * rec_steps / (ms_rec * 1e-3), "unit": "pairs/s", "d2h_bytes_per_step": rec_bytes,
+                           "steps": rec_steps, "what": "e2e with the full 16-key record of lib/tester.py:56-69 for every pair "
+                           "(roitr_b200.results.tester_records: one staged D2H copy per dtype per step)"},
+            "single_pair_forward_ms": {"value": single_ms, "pairs_per_s": 1000.0 / single_ms,
+                                       "what": "model.forward on one pair (lib/tester.py:53, batch_size 1), wall clock incl. its host sync, mean of 10"},
             "gpu_launches": launches_per_step * steps, "clocks": clk.summary(), "roofline": roof,
             "north_star_rooflines": named, "serial_replica_ms": round(eager_ms, 3),
             "kernel_shares_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])},
             "result_check": {"correspondences_per_pair": total_corr / (world * B), "e2e_correspondences_last_step": ncorr},
             "wall_s_between_barriers": wall,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
+            # rank 0 at N=1 only: under torchrun the other ranks would spin in the closing barrier for the whole CPU leg
+            try:
+                line["reference_gpu"] = reference_gpu_pairs_per_s(dev, N_POINTS)
+            except Exception as e:      # information only; never takes the bench line down
+                line["reference_gpu"] = {"unavailable": repr(e)[:200]}
             v, dt, cores = cpu_reference_pairs_per_s(6, 1, N_POINTS)      # bounded sample: ~10 s of CPU work after one warm-up pair
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": "6 pairs of the named workload (%.1f s), oracle/forward_ref.py + pointops_ref.c" % dt}

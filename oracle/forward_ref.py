@@ -50,8 +50,8 @@ def _ln(sd, p, x):
     return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
 
 
-def _i32(vals):
-    return torch.tensor(list(vals), dtype=torch.int32)
+def _i32(vals, device=None):
+    return torch.tensor(list(vals), dtype=torch.int32, device=device)
 
 
 def knn(nsample, xyz, new_xyz, offset, new_offset):
@@ -116,12 +116,12 @@ def transition_down(sd, p, stride, nsample, pts, x, o, nrm):
         for s, e in zip([0] + ends[:-1], ends):
             cnt += (e - s) // stride
             new_o.append(cnt)
-        new_o = _i32(new_o)
+        new_o = _i32(new_o, pts.device)
         idx = native.fps(pts.contiguous(), o, new_o).long()
         n_p, n_n = pts[idx], nrm[idx]
     else:
         new_o, n_p, n_n = o, pts, nrm
-        idx = torch.arange(pts.shape[0])
+        idx = torch.arange(pts.shape[0], device=pts.device)
     g = group_indices(nsample, pts, n_p.contiguous(), o, new_o)
     pf = ppf(n_p, n_n, pts[g], nrm[g])
     x = local_ppf_transformer(sd, p + ".transformer", x, idx, g, pf)
@@ -134,7 +134,7 @@ def block(sd, p, nsample, pts, x, o, nrm, idx, ppf_r):
         idx = group_indices(nsample, pts, pts, o, o)
     if ppf_r is None:
         ppf_r = ppf(pts, nrm, pts[idx], nrm[idx])
-    node_idx = torch.arange(pts.shape[0])
+    node_idx = torch.arange(pts.shape[0], device=pts.device)
     y = local_ppf_transformer(sd, p + ".transformer.transformer", x, node_idx, idx, ppf_r)
     y = _ln(sd, p + ".bn2", y)
     return F.relu(y + x), idx, ppf_r
@@ -144,7 +144,7 @@ def interpolate3(coarse_xyz, fine_xyz, feat, o_coarse, o_fine, k=3):
     idx, dist = knn(k, coarse_xyz, fine_xyz, o_coarse, o_fine)
     r = 1.0 / (dist + 1e-8)
     w = r / r.sum(dim=1, keepdim=True)
-    out = torch.zeros(fine_xyz.shape[0], feat.shape[1])
+    out = torch.zeros(fine_xyz.shape[0], feat.shape[1], device=feat.device)
     for i in range(k):
         out += feat[idx[:, i].long()] * w[:, i].unsqueeze(-1)
     return out
@@ -223,7 +223,7 @@ def rpe_self_layer(sd, p, x, emb):
     s_p = torch.einsum("bhnc,bhnmc->bhnm", q, pe)
     s_e = torch.einsum("bhnc,bhmc->bhnm", q, k)
     s = (s_e + s_p) / c ** 0.5
-    eye = torch.eye(N, dtype=torch.bool).view(1, 1, N, N)
+    eye = torch.eye(N, dtype=torch.bool, device=x.device).view(1, 1, N, N)
     s_noself = s.masked_fill(eye, float("-inf"))
     w = F.softmax(s, dim=-1)
     h = torch.matmul(w, v).permute(0, 2, 1, 3).reshape(b, N, C)
@@ -321,13 +321,13 @@ def partition(points, nodes, point_limit):
     d = square_distance(nodes[None], points[None])[0]               # (M,N)
     owner = d.min(dim=0)[1]
     M, N = d.shape
-    node_masks = torch.zeros(M, dtype=torch.bool)
+    node_masks = torch.zeros(M, dtype=torch.bool, device=d.device)
     node_masks[owner] = True
     own = torch.zeros_like(d, dtype=torch.bool)
-    own[owner, torch.arange(N)] = True
+    own[owner, torch.arange(N, device=d.device)] = True
     d = d.masked_fill(~own, 1e12)
     knn_idx = d.topk(k=point_limit, dim=1, largest=False)[1]
-    knn_masks = owner[knn_idx] == torch.arange(M).unsqueeze(1)
+    knn_masks = owner[knn_idx] == torch.arange(M, device=d.device).unsqueeze(1)
     knn_idx = knn_idx.masked_fill(~knn_masks, N)
     return owner, node_masks, knn_idx, knn_masks
 
@@ -335,7 +335,7 @@ def partition(points, nodes, point_limit):
 def node_occlusion(ref_knn_ids, src_knn_ids, ref_pts, src_pts, rot, trans, ref_masks, src_masks, ref_knn_masks,
                    src_knn_masks, thres=0.0375):
     src_pts = torch.matmul(src_pts, rot.T) + trans.T
-    ro, so = _i32([ref_pts.shape[0]]), _i32([src_pts.shape[0]])
+    ro, so = _i32([ref_pts.shape[0]], ref_pts.device), _i32([src_pts.shape[0]], ref_pts.device)
     _, rd = knn(1, src_pts, ref_pts, so, ro)
     _, sdist = knn(1, ref_pts, src_pts, ro, so)
     r_ov = (rd < thres).float().squeeze(1)
@@ -397,19 +397,20 @@ def coarse_matching_4d(a_feats, b_feats, a_masks, b_masks, min_num, thr=0.75):
 
 def optimal_transport(alpha, scores, row_masks, col_masks, num_iter=100, inf=1e6):
     B, R, Cn = scores.shape
-    prm = torch.zeros(B, R + 1, dtype=torch.bool)
+    dev = scores.device
+    prm = torch.zeros(B, R + 1, dtype=torch.bool, device=dev)
     prm[:, :R] = ~row_masks
-    pcm = torch.zeros(B, Cn + 1, dtype=torch.bool)
+    pcm = torch.zeros(B, Cn + 1, dtype=torch.bool, device=dev)
     pcm[:, :Cn] = ~col_masks
     z = torch.cat([torch.cat([scores, alpha.expand(B, R, 1)], dim=-1), alpha.expand(B, 1, Cn + 1)], dim=1)
     z = z.masked_fill(prm.unsqueeze(2) | pcm.unsqueeze(1), -inf)
-    nr, nc = row_masks.float().sum(1), col_masks.float().sum(1)
+    nr, nc = row_masks.to(scores.dtype).sum(1), col_masks.to(scores.dtype).sum(1)
     norm = -torch.log(nr + nc)
-    log_mu = torch.empty(B, R + 1)
+    log_mu = torch.empty(B, R + 1, dtype=scores.dtype, device=dev)
     log_mu[:, :R] = norm.unsqueeze(1)
     log_mu[:, R] = torch.log(nc) + norm
     log_mu[prm] = -inf
-    log_nu = torch.empty(B, Cn + 1)
+    log_nu = torch.empty(B, Cn + 1, dtype=scores.dtype, device=dev)
     log_nu[:, :Cn] = norm.unsqueeze(1)
     log_nu[:, Cn] = torch.log(nr) + norm
     log_nu[pcm] = -inf
@@ -433,6 +434,18 @@ def fine_matching(ref_pts, src_pts, ref_masks, src_masks, log_scores, k, thr=0.0
     return ref_pts[b, r], src_pts[b, c], (s * corr.float())[b, r, c], torch.stack([b, r, c], 1)
 
 
+def fine_stage_fp64(alpha, tgt_pf, src_pf, t_ki, s_ki, t_km, s_km, t_ci, s_ci, num_iter=100):
+    """The fine stage of RIGA_v2.forward (RIGA_v2.py:139-160: gather patch descriptors, einsum / sqrt(C), log optimal
+    transport) evaluated in float64 from fp32 descriptors: the yardstick for how far TWO correct fp32 evaluations of the
+    same formula may sit from exact arithmetic (tests/parity.py). Returns the (P, 65, 65) log-assignment in float64."""
+    tgt_pf, src_pf = tgt_pf.double(), src_pf.double()
+    s_pad = torch.cat([src_pf, torch.zeros_like(src_pf[:1])], 0)
+    t_pad = torch.cat([tgt_pf, torch.zeros_like(tgt_pf[:1])], 0)
+    s_f, t_f = s_pad[s_ki[s_ci]], t_pad[t_ki[t_ci]]
+    ms = torch.einsum("bnd,bmd->bnm", t_f, s_f) / src_pf.shape[1] ** 0.5
+    return optimal_transport(alpha.double(), ms, t_km[t_ci], s_km[s_ci], num_iter)
+
+
 # --------------------------------------------------------------------------------------------- pipeline
 def riga_forward(sd, cfg, src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, tgt_normals, rot, trans, src_raw_pcd,
                  with_aux=False):
@@ -440,7 +453,7 @@ def riga_forward(sd, cfg, src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, t
     transformer_architecture, point_per_patch, matching_radius, fine_matching_topk, fine_matching_mutual,
     fine_matching_confidence_threshold."""
     four_d = cfg["benchmark"] not in ("3DMatch", "3DLoMatch")
-    so, to = _i32([src_raw_pcd.shape[0]]), _i32([tgt_pcd.shape[0]])
+    so, to = _i32([src_raw_pcd.shape[0]], src_raw_pcd.device), _i32([tgt_pcd.shape[0]], tgt_pcd.device)
     (src_nodes, src_nf, src_pts, src_pf, tgt_nodes, tgt_nf, tgt_pts, tgt_pf, aux) = backbone(
         sd, [src_raw_pcd, src_feats, so, src_normals], [tgt_pcd, tgt_feats, to, tgt_normals], src_pcd,
         cfg["transformer_architecture"])

@@ -41,6 +41,36 @@ def lib():
     return _lib
 
 
+_REF_SO = os.path.join(_HERE, "_ref", "libpointops_ref_cuda.so")
+_ref = None
+
+
+def ref_cuda():
+    """The reference's OWN kernels (oracle/build_ref.sh: knnquery_cuda_kernel.cu / sampling_cuda_kernel.cu compiled
+    unmodified for sm_100a). Used when the oracle forward is evaluated on CUDA tensors: that is the reference's algorithm
+    with the reference's kernels on this GPU (bench.py `reference_gpu`, scripts/bench_ops.py). Launches on the legacy
+    default stream, as the reference's pybind wrappers do."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF_SO):
+            raise RuntimeError("oracle/_ref/libpointops_ref_cuda.so is not built (oracle/build_ref.sh needs /root/reference)")
+        L = ctypes.CDLL(_REF_SO)
+        P, I = ctypes.c_void_p, ctypes.c_int
+        L.knnquery_cuda_launcher.argtypes = [I, I, P, P, P, P, P, P]
+        L.furthestsampling_cuda_launcher.argtypes = [I, I, P, P, P, P, P]
+        _ref = L
+    return _ref
+
+
+def have_ref_cuda():
+    return os.path.exists(_REF_SO)
+
+
+def _dev(t, dtype):
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype)
+    return ctypes.c_void_p(t.data_ptr())
+
+
 def _chk(t, dtype):
     assert t.device.type == "cpu" and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype)
     return ctypes.c_void_p(t.data_ptr())
@@ -48,6 +78,11 @@ def _chk(t, dtype):
 
 def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):
     """Same contract as knnquery_cuda (knnquery_cuda_kernel.h:7): caller allocates idx/dist2."""
+    if xyz.is_cuda:
+        ref_cuda().knnquery_cuda_launcher(int(m), int(nsample), _dev(xyz, torch.float32), _dev(new_xyz, torch.float32),
+                                          _dev(offset, torch.int32), _dev(new_offset, torch.int32),
+                                          _dev(idx, torch.int32), _dev(dist2, torch.float32))
+        return
     rc = lib().oracle_knnquery(int(m), int(nsample), _chk(xyz, torch.float32), _chk(new_xyz, torch.float32),
                                _chk(offset, torch.int32), _chk(new_offset, torch.int32),
                                _chk(idx, torch.int32), _chk(dist2, torch.float32))
@@ -57,6 +92,11 @@ def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):
 
 def furthestsampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
     """Same contract as furthestsampling_cuda (sampling_cuda_kernel.h:7); n is the max segment length."""
+    if xyz.is_cuda:
+        ref_cuda().furthestsampling_cuda_launcher(int(b), int(n), _dev(xyz, torch.float32), _dev(offset, torch.int32),
+                                                  _dev(new_offset, torch.int32), _dev(tmp, torch.float32),
+                                                  _dev(idx, torch.int32))
+        return
     rc = lib().oracle_furthestsampling(int(b), int(n), _chk(xyz, torch.float32), _chk(offset, torch.int32),
                                        _chk(new_offset, torch.int32), _chk(tmp, torch.float32),
                                        _chk(idx, torch.int32))
@@ -76,8 +116,8 @@ def fps_block_size(n_max: int) -> int:
 # ---- convenience wrappers (allocate like pointops.py:18-23,39-43) ----
 def knn(nsample, xyz, new_xyz, offset, new_offset):
     m = new_xyz.shape[0]
-    idx = torch.zeros(m, nsample, dtype=torch.int32)
-    d2 = torch.zeros(m, nsample, dtype=torch.float32)
+    idx = torch.zeros(m, nsample, dtype=torch.int32, device=xyz.device)
+    d2 = torch.zeros(m, nsample, dtype=torch.float32, device=xyz.device)
     knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, d2)
     return idx, d2
 
@@ -86,7 +126,7 @@ def fps(xyz, offset, new_offset):
     b = offset.shape[0]
     ends = offset.tolist()
     n_max = max(e - s for s, e in zip([0] + ends[:-1], ends))
-    idx = torch.zeros(int(new_offset[-1]), dtype=torch.int32)
-    tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32)
+    idx = torch.zeros(int(new_offset[-1]), dtype=torch.int32, device=xyz.device)
+    tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32, device=xyz.device)
     furthestsampling_cuda(b, n_max, xyz, offset, new_offset, tmp, idx)
     return idx

@@ -33,8 +33,18 @@ def lib():
     return _lib
 
 
+_ARG_DEVICE = None    # device of the most recent tensor argument (every entry point takes its tensors before the stream)
+
+
+def _note(t):
+    global _ARG_DEVICE
+    _ARG_DEVICE = t.device
+
+
 def stream_ptr():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current stream OF THE DEVICE THE ARGUMENTS LIVE ON (always the last argument of an entry point, so the tensor
+    arguments have been seen): a model on cuda:1 must not launch on cuda:0's stream just because cuda:0 is current."""
+    return c_void_p(torch.cuda.current_stream(_ARG_DEVICE).cuda_stream)
 
 
 def ptr(t, dtype=None):
@@ -47,6 +57,7 @@ def ptr(t, dtype=None):
         raise RoitrError("expected a contiguous tensor")
     if dtype is not None and t.dtype != dtype:
         raise RoitrError("expected dtype %s, got %s" % (dtype, t.dtype))
+    _note(t)
     return c_void_p(t.data_ptr())
 
 
@@ -89,7 +100,12 @@ def call(name, *args):
     if timed is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = fn(*args)
+    dev = _ARG_DEVICE
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):      # the launch itself must happen with the tensors' device current
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
     if timed is not None:
         e1.record()
         timed.append((e0, e1))

@@ -36,6 +36,14 @@ void roitr_set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
+// Launch-side caches (cudaFuncSetAttribute done, SM count, occupancy) are per DEVICE: a process may drive several GPUs.
+#define ROITR_MAX_DEVICES 64
+static inline int roitr_cur_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d < 0 ? 0 : d) % ROITR_MAX_DEVICES;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

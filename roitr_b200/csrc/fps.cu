@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const FpsPa
 template <int CL, int PPT>
 int launch_fps(const FpsParams& P, cudaStream_t st) {
     const int smem = PPT * FPS_THREADS * 12;
-    static bool attr_set = false;
+    static bool attr_set_dev[ROITR_MAX_DEVICES] = {};
+    bool& attr_set = attr_set_dev[roitr_cur_device()];
     if (!attr_set) {  // dynamic + static shared memory can exceed the 48 KB default from PPT = 8 on
         ROITR_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<CL, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;

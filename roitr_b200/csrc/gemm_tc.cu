@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_
 template <int BN>
 int launch_tc(const TcParams& P, cudaStream_t st, int batch = 1) {
     constexpr int smem = TC_STAGES * (2 * TC_BM * 128 + 2 * BN * 128) + 1024;
-    static bool attr = false;
+    static bool attr_dev[ROITR_MAX_DEVICES] = {};
+    bool& attr = attr_dev[roitr_cur_device()];
     if (!attr) {
         ROITR_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;

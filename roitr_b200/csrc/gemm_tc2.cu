@@ -538,8 +538,11 @@ template <int BN, int OPS, int RAW, int LW, int MINB>
 int launch_tc3(const Tc2Params& P, cudaStream_t st) {
     constexpr int T3_THREADS = 128 + LW * 32 + 64;
     constexpr int smem = OPS * (2 * A_HALF + 2 * BN * 128) + RAW * RAW_BYTES + 1024;
-    static bool attr = false;
-    static int num_sms = 0, per_sm = 1;
+    static bool attr_dev[ROITR_MAX_DEVICES] = {};
+    static int num_sms_dev[ROITR_MAX_DEVICES] = {}, per_sm_dev[ROITR_MAX_DEVICES] = {};
+    const int dv = roitr_cur_device();
+    bool& attr = attr_dev[dv];
+    int &num_sms = num_sms_dev[dv], &per_sm = per_sm_dev[dv];
     if (!attr) {
         ROITR_CUDA(cudaFuncSetAttribute(linear_tc3_kernel<BN, OPS, RAW, LW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0;
@@ -559,8 +562,11 @@ int launch_tc3(const Tc2Params& P, cudaStream_t st) {
 template <int BN, int STAGES>
 int launch_tc2(const Tc2Params& P, cudaStream_t st) {
     constexpr int smem = STAGES * (2 * A_HALF + 2 * BN * 128) + 1024;   // + ~21 KB static (transpose pads, bias)
-    static bool attr = false;
-    static int num_sms = 0;
+    static bool attr_dev[ROITR_MAX_DEVICES] = {};
+    static int num_sms_dev[ROITR_MAX_DEVICES] = {};
+    const int dv = roitr_cur_device();
+    bool& attr = attr_dev[dv];
+    int& num_sms = num_sms_dev[dv];
     if (!attr) {
         ROITR_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0;

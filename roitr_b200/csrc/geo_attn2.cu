@@ -232,7 +232,8 @@ int launch_self(const SelfParams& P, int batch, cudaStream_t st) {
     constexpr int CHK = GA_CHUNK_BYTES / (C * 4);
     const size_t smem = (size_t)2 * CHK * C * 4 + (size_t)GA_H * P.M * 4 + (size_t)CHK * GA_H * 4;
     ROITR_CHECK_ARG(smem <= 226 * 1024, "geo_self_attention: %d keys do not fit the shared-memory score buffer", P.M);
-    static size_t configured = 0;
+    static size_t configured_dev[ROITR_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[roitr_cur_device()];
     if (smem > configured) {
         ROITR_CUDA(cudaFuncSetAttribute(geo_self_scores_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

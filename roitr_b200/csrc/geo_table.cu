@@ -150,7 +150,9 @@ __global__ void __launch_bounds__(GTB_THREADS, 1) geo_embedding_table_kernel(con
             const float x = t[k] * P.inv_h;                                // exact: inv_h is a power of two
             const float fl = floorf(x);
             cu[k] = x - fl;                                                // exact (Sterbenz / same binade)
-            ci[k] = (x < 2.0e9f) ? (int)fl : 0x7fffffff;
+            // out of table (huge, negative, NaN / Inf): a sentinel that cannot overflow in `i + 3` below -> direct evaluation,
+            // which propagates NaN like the reference instead of reading outside the table
+            ci[k] = (x >= 0.0f && x < 1.0e9f) ? (int)fl : 0x3fffffff;
         }
         const int npw = (int)max((long long)0, min((long long)32, npairs - p0));
         for (int p = 0; p < npw; ++p) {
@@ -217,7 +219,8 @@ extern "C" int roitr_geo_embedding_table(int batch, int N, int C, const float* p
     P.rows_d_smem = rows_d < max_rows - rows_a ? rows_d : max_rows - rows_a;
     P.inv_h = inv_h; P.sigma_d = sigma_d;
     P.factor_a = (float)(180.0 / ((double)sigma_a * 3.14159265358979323846));  // positional_encoding.py:99
-    static int num_sms = 0;
+    static int num_sms_dev[ROITR_MAX_DEVICES] = {};
+    int& num_sms = num_sms_dev[roitr_cur_device()];
     if (!num_sms) {
         int dev = 0;
         ROITR_CUDA(cudaGetDevice(&dev));

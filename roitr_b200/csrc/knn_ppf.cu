@@ -682,14 +682,16 @@ int launch_knn(const KnnParams& P, cudaStream_t st) {
     // many queries: 4 per warp (amortises the shared-memory reads); few queries: 1 per warp (more CTAs in flight)
     const bool wide = P.m >= 4 * KNN_WARPS * 148 * 2;
     if (wide) {
-        static bool attr4 = false;
+        static bool attr4_dev[ROITR_MAX_DEVICES] = {};
+        bool& attr4 = attr4_dev[roitr_cur_device()];
         if (!attr4) {
             ROITR_CUDA(cudaFuncSetAttribute(knn_ppf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr4 = true;
         }
         knn_ppf_kernel<4><<<ceil_div(P.m, KNN_WARPS * 4), KNN_THREADS, smem, st>>>(P);
     } else {
-        static bool attr1 = false;
+        static bool attr1_dev[ROITR_MAX_DEVICES] = {};
+        bool& attr1 = attr1_dev[roitr_cur_device()];
         if (!attr1) {
             ROITR_CUDA(cudaFuncSetAttribute(knn_ppf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr1 = true;

@@ -56,12 +56,13 @@ def pack_tf32_sw128(Wm):
     return torch.stack([tile(hi), tile(lo)], dim=2).contiguous()
 
 
-def pack_linear_tc(Wm):
-    """(N,K) f32 nn.Linear weight -> (packed, bn) for roitr_linear_tc_packed: rows padded to a multiple of bn (64 if
-    N <= 64 else 128), columns to a multiple of 32, then per (bn-row, 32-column) block the TF32 hi / lo parts as
+def pack_linear_tc(Wm, bn=None):
+    """(N,K) f32 nn.Linear weight -> (packed, bn) for roitr_linear_tc_packed: rows padded to a multiple of bn (default 64
+    if N <= 64 else 128), columns to a multiple of 32, then per (bn-row, 32-column) block the TF32 hi / lo parts as
     SWIZZLE_128B tiles: (N/bn, K/32, 2, bn*32) floats."""
     N, K = Wm.shape
-    bn = 64 if N <= 64 else 128
+    if bn is None:
+        bn = 64 if N <= 64 else 128
     Np, Kp = -(-N // bn) * bn, -(-K // 32) * 32
     Wp = torch.zeros(Np, Kp, dtype=torch.float32, device=Wm.device)
     Wp[:N, :K] = Wm
@@ -108,7 +109,32 @@ def build_geo_tables(Wd, bd, Wa, ba, div_term, sigma_a=15.0, t_d_max=512.0):
     return dict(tab_a=table(Wa, ba, t_a_max), tab_d=table(Wd, bd, t_d_max), inv_h=1.0 / h, bound=bound)
 
 
+PACK_ON_HOST = False         # True: fold / split / swizzle the weights with CPU tensors and upload the result (no ATen kernels
+                             # on the GPU before the first product kernel; __graft_entry__.smoke() uses it)
+
+
+def _to_device(v, device):
+    if torch.is_tensor(v):
+        return v.to(device)
+    if isinstance(v, tuple):
+        return tuple(_to_device(x, device) for x in v)
+    if isinstance(v, dict):
+        return {k: _to_device(x, device) for k, x in v.items()}
+    return v
+
+
 def pack_weights(state_dict, device, architecture):
+    target = device
+    if PACK_ON_HOST:
+        device = torch.device("cpu")
+    W = _pack_weights(state_dict, device, architecture)
+    if PACK_ON_HOST:
+        for k in list(W):
+            W[k] = _to_device(W[k], target)
+    return W
+
+
+def _pack_weights(state_dict, device, architecture):
     W = Packed()
     for k, v in state_dict.items():
         W[k] = v.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -698,7 +724,11 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
     # Mt*Ms (model/modules.py:105-112); buffers are sized for that bound so the count can stay on the device.
     Pmax = M4s * M4t if four_d else int(cfg["num_est_coarse_corr"])
     topk = int(cfg["fine_matching_topk"])
-    cap = Pmax * K * topk
+    if K != 64:
+        raise ValueError("point_per_patch must be 64 (the fine-matching kernel holds one 64 x 64 patch pair per CTA; every "
+                         "reference config uses 64), got %d" % K)
+    # mutual: at most topk matches per row; non-mutual = the UNION of the row-wise and column-wise top-k (modules.py:283-287)
+    cap = Pmax * K * topk * (1 if bool(cfg["fine_matching_mutual"]) else 2)
     fork = _Fork(plan.side_streams(min(HEAD_STREAMS, B)) if B > 1 else [])
     st = [dict() for _ in range(B)]          # per-pair state handed from stage to stage (same side stream per pair)
     src_of = lambda b: src_pcd[b * Ns:(b + 1) * Ns]

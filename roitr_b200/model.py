@@ -120,9 +120,23 @@ class GeometricTransformer(nn.Module):
 class _PackedMixin:
     """Caches the device-resident packed/folded weights; rebuilt when parameters move or change."""
 
+    def repack(self):
+        """Drop the packed / folded / TF32-split copy of the weights; the next forward rebuilds it. Needed only after an
+        update the cache key cannot see: an in-place write through ``p.data`` (which does not bump the version counter)."""
+        self._pack_key = None
+
+    def _apply(self, fn, *a, **kw):            # .to() / .cuda() / .float(): new storage
+        self._pack_key = None
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._pack_key = None
+        return super().load_state_dict(*a, **kw)
+
     def _packed(self, prefix, architecture):
         params = list(self.parameters())
-        key = (params[0].device, params[0].data_ptr(), sum(p._version for p in params))
+        every = params + list(self.buffers())   # buffers too: the geometric-embedding tables are built from div_term
+        key = (params[0].device, tuple(t.data_ptr() for t in every), sum(t._version for t in every))
         if getattr(self, "_pack_key", None) != key:
             if params[0].device.type != "cuda":
                 raise RuntimeError("roitr_b200 runs on CUDA only: call .to('cuda') / .cuda() first (no CPU fallback)")
@@ -168,8 +182,9 @@ class RIPointTransformer(nn.Module, _PackedMixin):
 
     @torch.no_grad()
     def forward(self, s_pxon, t_pxon, src_deformed_pcd):
-        W = self._packed("backbone.", self.transformer_architecture)
-        return engine.backbone_forward(W, self.transformer_architecture, s_pxon, t_pxon, src_deformed_pcd)
+        with torch.cuda.device(s_pxon[0].device):      # streams / events below are those of the tensors' device
+            W = self._packed("backbone.", self.transformer_architecture)
+            return engine.backbone_forward(W, self.transformer_architecture, s_pxon, t_pxon, src_deformed_pcd)
 
 
 class LearnableLogOptimalTransport(nn.Module):
@@ -249,10 +264,13 @@ class RIGA_v2(nn.Module, _PackedMixin):
     def forward(self, src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, tgt_normals, rot, trans, src_raw_pcd, _aux=None):
         if self.training:
             raise RuntimeError("roitr_b200 implements the inference forward only: call .eval() (training is out of scope)")
-        W = self._packed("", self.cfg["transformer_architecture"])
-        args = [t.contiguous().float() for t in (src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, tgt_normals, rot,
-                                                 trans, src_raw_pcd)]
-        return engine.riga_forward(W, self.cfg, *args, aux=_aux)
+        if not src_pcd.is_cuda:
+            raise RuntimeError("roitr_b200 runs on CUDA only (no CPU fallback): move the inputs to the model's device")
+        with torch.cuda.device(src_pcd.device):        # streams / events below are those of the tensors' device
+            W = self._packed("", self.cfg["transformer_architecture"])
+            args = [t.contiguous().float() for t in (src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, tgt_normals, rot,
+                                                     trans, src_raw_pcd)]
+            return engine.riga_forward(W, self.cfg, *args, aux=_aux)
 
 
     def batch_runner(self, batch_pairs, n_src, n_tgt, graph=True, fps_cluster=0, serial=False):

@@ -81,6 +81,7 @@ def c_void(t):
     if t is None:
         return ctypes.c_void_p(0)
     assert t.is_cuda and t.dtype == torch.float32
+    _lib._note(t)
     return ctypes.c_void_p(t.data_ptr())
 
 
@@ -369,6 +370,8 @@ def fine_matching(tgt_feat, src_feat, tgt_knn, src_knn, tgt_kmask, src_kmask, co
                   num_iter, topk, mutual, threshold):
     Pmax = corr_t.shape[0]
     dev = tgt_feat.device
+    if tgt_knn.shape[1] != 64 or src_knn.shape[1] != 64:
+        raise _lib.RoitrError("fine_matching: patches must hold 64 points (got %d / %d)" % (tgt_knn.shape[1], src_knn.shape[1]))
     scores = torch.zeros(Pmax, 65, 65, dtype=torch.float32, device=dev)
     flags = torch.empty(Pmax, 64, 64, dtype=torch.uint8, device=dev)
     _lib.call("roitr_fine_matching", c_int(Pmax), c_int(tgt_feat.shape[0]), c_int(src_feat.shape[0]),

@@ -26,7 +26,37 @@ RECORD_FIELDS = (
 FOUR_D = ("4DMatch", "4DLoMatch")
 
 
-def _to_host(tensors):
+_STAGING = {}     # (dtype, device) -> pinned host buffer, grown on demand and reused from step to step
+
+
+def _staging(dtype, dev, numel):
+    buf = _STAGING.get((dtype, dev))
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(int(numel * 1.25) + 16, dtype=dtype, pin_memory=True)
+        _STAGING[(dtype, dev)] = buf
+    return buf[:numel]
+
+
+def tester_records(inputs_list, outputs_list, benchmark="3DMatch", metric_index_list=None):
+    """tester_record for a BATCH of pairs with ONE device->host copy per dtype for the whole batch (reused pinned staging
+    buffers; a record's tensors are views into them, valid until the next call - save_record clones). inputs_list /
+    outputs_list: per pair, the forward inputs and the forward's output dict (e.g. BatchRunner.results())."""
+    flat = {}
+    for b, (inp, out) in enumerate(zip(inputs_list, outputs_list)):
+        src = {"inputs": inp, "outputs": out}
+        for key, where, name in RECORD_FIELDS:
+            flat[(b, key)] = src[where][name]
+    host = _to_host(flat, reuse=True)
+    recs = []
+    for b in range(len(outputs_list)):
+        data = {key: host[(b, key)] for key, _, _ in RECORD_FIELDS}
+        if benchmark in FOUR_D:
+            data["metric_index_list"] = None if metric_index_list is None else metric_index_list[b]
+        recs.append(data)
+    return recs
+
+
+def _to_host(tensors, reuse=False):
     """dict name -> tensor (any device) -> dict name -> CPU tensor. Device tensors of one dtype travel together: one
     concatenation on the device, one copy into pinned memory, views on the host."""
     out, groups = {}, {}
@@ -38,7 +68,7 @@ def _to_host(tensors):
             out[k] = t
     for (dtype, dev), items in groups.items():
         flat = torch.cat([t.reshape(-1) for _, t in items])
-        host = torch.empty(flat.shape, dtype=dtype, pin_memory=True)
+        host = _staging(dtype, dev, flat.numel()) if reuse else torch.empty(flat.shape, dtype=dtype, pin_memory=True)
         host.copy_(flat, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         o = 0

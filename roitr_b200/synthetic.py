@@ -58,7 +58,7 @@ def forward_args(pair: dict, device=None):
     return [pair[k].to(device) if device is not None else pair[k] for k in FORWARD_ARG_ORDER]
 
 
-def seeded_state_dict(schema, seed: int = 42):
+def seeded_state_dict(schema, seed: int = 42, fine_scale: float = 8.0):
     """Weights as a pure function of (schema, seed), independent of module construction order.
 
     ``schema``: list of (name, shape) in state_dict order (tests/golden/state_dict_schema_f{1,2}.json, dumped from the
@@ -79,7 +79,7 @@ def seeded_state_dict(schema, seed: int = 42):
             bound = 1.0 / math.sqrt(shape[1])
             sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
             if name == 'fine_proj.weight':
-                sd[name] *= 8.0   # random features are nearly flat; sharpen the fine scores so correspondences exist
+                sd[name] *= fine_scale   # random features are nearly flat; sharpen the fine scores so correspondences exist
         elif len(shape) == 1 and (".norm." in name or ".bn2." in name or "pos_norm" in name or _is_ln(name)):
             if name.endswith("weight"):
                 sd[name] = 1.0 + 0.1 * (torch.rand(shape, generator=g) * 2 - 1)

@@ -22,8 +22,19 @@ def schema(factor=1):
     return json.load(open(os.path.join(GOLDEN, "state_dict_schema_f%d.json" % factor)))
 
 
-def weights(factor=1, seed=42):
-    return seeded_state_dict(schema(factor), seed)
+def weights(factor=1, seed=42, fine_scale=8.0):
+    return seeded_state_dict(schema(factor), seed, fine_scale=fine_scale)
+
+
+def baseline_pair(name):
+    """The two BASELINE.json configurations that are not the headline one, with UNEQUAL cloud sizes:
+    "3dmatch_30k" = config 3 (2 x ~30k points -> 468 / 437 superpoints), "4dmatch_8k" = config 5 (2 x ~8k points, non-rigid
+    source, factor-2 backbone, adaptive head)."""
+    n_src, n_tgt, four_d, index = {"3dmatch_30k": (30000, 28000, False, 30), "4dmatch_8k": (8000, 7000, True, 31)}[name]
+    p = dict(synthetic_pair(index, n_src, deform=four_d))
+    for k in ("tgt_pcd", "tgt_feats", "tgt_normals"):
+        p[k] = p[k][:n_tgt].contiguous()
+    return p
 
 
 def load_golden(name):

@@ -13,6 +13,9 @@ from roitr_b200 import model
 from roitr_b200.synthetic import forward_args
 
 
+FP64_PATCHES = 1024
+
+
 def _maxabs(a, b):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     if a.shape != b.shape:
@@ -62,14 +65,14 @@ def run(pair, cfg, sd, device="cuda:0"):
         gi, ri = aux[side + "_node_knn_indices"].cpu().long(), raux[side + "_node_knn_indices"]
         # torch.topk's order among exactly equal distances is unspecified: rows must agree as sets, and mostly in order
         add(side + " partition knn idx (as sets)", "rows differing", int((gi.sort(1)[0] != ri.sort(1)[0]).any(1).sum()), "exact")
-        add(side + " partition knn idx order", "permuted-row frac (exact ties)", float((gi != ri).any(1).float().mean()), "set")
+        add(side + " partition knn idx order", "permuted-row frac (exact ties)", float((gi != ri).any(1).float().mean()), "tiefrac")
         add(side + " partition masks", "mismatches", int((aux[side + "_node_knn_masks"].cpu() != raux[side + "_node_knn_masks"]).sum())
             + int((aux[side + "_node_masks"].cpu() != raux[side + "_node_masks"]).sum()), "exact")
     add("gt occ tgt", "maxabs", _maxabs(out["gt_tgt_node_occ"], ref["gt_tgt_node_occ"]), "f1e-5")
     add("gt occ src", "maxabs", _maxabs(out["gt_src_node_occ"], ref["gt_src_node_occ"]), "f1e-5")
     g_gt = {tuple(r): float(v) for r, v in zip(out["gt_node_corr_indices"].cpu().tolist(), out["gt_node_corr_overlaps"].cpu().tolist())}
     r_gt = {tuple(r): float(v) for r, v in zip(ref["gt_node_corr_indices"].tolist(), ref["gt_node_corr_overlaps"].tolist())}
-    add("gt node corr", "sym diff / ref", len(set(g_gt) ^ set(r_gt)) / max(1, len(r_gt)), "set")
+    add("gt node corr", "sym diff / ref", len(set(g_gt) ^ set(r_gt)) / max(1, len(r_gt)), "set0")
     add("gt node corr overlaps", "maxabs (common)", max([abs(g_gt[k] - r_gt[k]) for k in set(g_gt) & set(r_gt)] or [0.0]), "f1e-2")
     add("gt node corr order", "is nonzero order", float(out["gt_node_corr_indices"].cpu().tolist() == sorted(out["gt_node_corr_indices"].cpu().tolist())), "true")
 
@@ -87,8 +90,9 @@ def run(pair, cfg, sd, device="cuda:0"):
         add("coarse score matrix (from gpu feats)", "max rel err", float(((ref_scores - gpu_scores).abs() / ref_scores).max()), "f1e-3")
     g_pairs = list(zip(out["tgt_node_corr_indices"].cpu().tolist(), out["src_node_corr_indices"].cpu().tolist()))
     r_pairs = list(zip(ref["tgt_node_corr_indices"].tolist(), ref["src_node_corr_indices"].tolist()))
-    add("coarse P", "|gpu - ref| / ref", abs(len(g_pairs) - len(r_pairs)) / max(1, len(r_pairs)), "set" if four_d else "exact")
-    add("coarse selected pairs", "sym diff / P", len(set(g_pairs) ^ set(r_pairs)) / max(1, len(r_pairs)), "set")
+    add("coarse P", "|gpu - ref| / ref", abs(len(g_pairs) - len(r_pairs)) / max(1, len(r_pairs)), "set4d" if four_d else "exact")
+    add("coarse P", "gpu / ref", "%d / %d" % (len(g_pairs), len(r_pairs)), "info")
+    add("coarse selected pairs", "sym diff / P", len(set(g_pairs) ^ set(r_pairs)) / max(1, len(r_pairs)), "set4d" if four_d else "set0")
     # is the gpu selection the exact top-k of its OWN scores? (selection logic check, independent of flips)
     ti = torch.nonzero(tm).flatten()
     si = torch.nonzero(smk).flatten()
@@ -102,7 +106,8 @@ def run(pair, cfg, sd, device="cuda:0"):
 
     t_same = (aux["tgt_node_knn_indices"].cpu().long() == raux["tgt_node_knn_indices"]).all(1)
     s_same = (aux["src_node_knn_indices"].cpu().long() == raux["src_node_knn_indices"]).all(1)
-    common = [p for p in g_pairs if p in set(r_pairs) and bool(t_same[p[0]]) and bool(s_same[p[1]])]
+    r_set = set(r_pairs)
+    common = [p for p in g_pairs if p in r_set and bool(t_same[p[0]]) and bool(s_same[p[1]])]
     gpos = {p: i for i, p in enumerate(g_pairs)}
     rpos = {p: i for i, p in enumerate(r_pairs)}
     if common:
@@ -111,7 +116,7 @@ def run(pair, cfg, sd, device="cuda:0"):
         ms_g, ms_r = out["matching_scores"].cpu()[gi], ref["matching_scores"][ri]
         live = ms_r > -1e5
         add("matching_scores (common patches)", "max |d|/(1+|ref|) (unmasked)",
-            float(((ms_g - ms_r).abs() / (1 + ms_r.abs()))[live].max()), "f6e-4" if four_d else "f3e-4")
+            float(((ms_g - ms_r).abs() / (1 + ms_r.abs()))[live].max()), "info")
         add("matching_scores masked pattern", "mismatches", int(((ms_g > -1e5) != live).sum()), "exact")
         add("patch knn points", "maxabs", _maxabs(out["tgt_node_corr_knn_points"].cpu()[gi], ref["tgt_node_corr_knn_points"][ri])
             + _maxabs(out["src_node_corr_knn_points"].cpu()[gi], ref["src_node_corr_knn_points"][ri]), "exactf")
@@ -123,13 +128,72 @@ def run(pair, cfg, sd, device="cuda:0"):
         gk = {k: v for k, v in gk.items() if k[0] in cs}
         rk = {k: v for k, v in rk.items() if k[0] in cs}
         add("final corr (common patches)", "count gpu / ref", "%d / %d" % (len(gk), len(rk)), "info")
-        add("final corr (common patches)", "sym diff / ref", len(set(gk) ^ set(rk)) / max(1, len(rk)), "set")
+        add("final corr (common patches)", "sym diff / ref", len(set(gk) ^ set(rk)) / max(1, len(rk)), "flipset")
         add("final corr scores", "maxabs (common)", max([abs(gk[k] - rk[k]) for k in set(gk) & set(rk)] or [0.0]),
-            "f2e-4")
-        # flips must sit at a decision boundary: threshold 0.05 or a top-k rank tie
+            "info")
+        # a flip (entry present in one result only) must sit at a decision boundary of the reference's own scores: the
+        # confidence threshold, or a rank tie at the k-th / (k+1)-th score of its row or column (mutual top-k)
         thr = float(cfg["fine_matching_confidence_threshold"])
-        far = [k for k in set(gk) ^ set(rk) if abs((gk.get(k) or rk.get(k)) - thr) > 1e-3]
-        add("final corr flips away from threshold", "count", len(far), "info")
+        kk_ = int(cfg["fine_matching_topk"])
+        ms_ref_all = torch.exp(ref["matching_scores"][:, :-1, :-1])
+
+        def at_boundary(key):
+            pr, r, c = key
+            sc = gk.get(key) if key in gk else rk.get(key)
+            if abs(sc - thr) <= 1e-3:
+                return True
+            m_ = ms_ref_all[rpos[pr]]
+            v = float(m_[r, c])
+            if abs(v - thr) <= 1e-3:
+                return True
+            for line in (m_[r, :], m_[:, c]):
+                top = line.topk(min(kk_ + 1, line.numel()))[0]
+                if top.numel() > kk_ and abs(float(top[kk_ - 1] - top[kk_])) <= 1e-3 * max(float(top[kk_ - 1]), 1e-6):
+                    return True
+            return False
+        far = [k for k in set(gk) ^ set(rk) if not at_boundary(k)]
+        add("final corr flips away from a decision boundary", "count", len(far), "exact")
+
+        # ---- fp64 yardstick for the fine stage (verdict r01 weak #1): each implementation against the SAME formula in
+        # float64 evaluated from ITS OWN fp32 descriptors and patches, so the number is the fine stage's own rounding
+        # (einsum + 100 Sinkhorn iterations + exp), not upstream feature noise. CUDA must be within 1e-4 or no worse than
+        # the fp32 oracle (= the reference's arithmetic) is.
+        alpha = sd["optimal_transport.alpha"]
+        # patches are independent: at most FP64_PATCHES evenly strided ones per side keep the float64 evaluation to seconds
+        # when P is in the thousands (4DMatch head, P up to Mt*Ms)
+        sel_g = torch.arange(0, len(g_pairs), max(1, -(-len(g_pairs) // FP64_PATCHES)))
+        sel_r = torch.arange(0, len(r_pairs), max(1, -(-len(r_pairs) // FP64_PATCHES)))
+        g64 = fr.fine_stage_fp64(alpha, out["tgt_point_feats"].cpu(), out["src_point_feats"].cpu(),
+                                 aux["tgt_node_knn_indices"].cpu().long(), aux["src_node_knn_indices"].cpu().long(),
+                                 aux["tgt_node_knn_masks"].cpu(), aux["src_node_knn_masks"].cpu(),
+                                 out["tgt_node_corr_indices"].cpu()[sel_g], out["src_node_corr_indices"].cpu()[sel_g])
+        r64 = fr.fine_stage_fp64(alpha, ref["tgt_point_feats"], ref["src_point_feats"], raux["tgt_node_knn_indices"],
+                                 raux["src_node_knn_indices"], raux["tgt_node_knn_masks"], raux["src_node_knn_masks"],
+                                 ref["tgt_node_corr_indices"][sel_r], ref["src_node_corr_indices"][sel_r])
+        rel = lambda a, b: float(((a.double() - b).abs() / (1 + b.abs()))[b > -1e5].max()) if a.numel() else 0.0
+        e_ms_o, e_ms_g = rel(ref["matching_scores"][sel_r], r64), rel(out["matching_scores"].cpu()[sel_g], g64)
+        add("matching_scores vs fp64 (oracle fp32)", "max |d|/(1+|x|), %d patches" % len(sel_r), e_ms_o, "info")
+        add("matching_scores vs fp64 (cuda)", "max |d|/(1+|x|), %d patches" % len(sel_g), e_ms_g, "info")
+        add("matching_scores vs fp64", "cuda err - max(1e-4, oracle err)", e_ms_g - max(1e-4, e_ms_o), "nonpos")
+        pos_g = torch.full((max(1, len(g_pairs)),), -1, dtype=torch.long); pos_g[sel_g] = torch.arange(len(sel_g))
+        pos_r = torch.full((max(1, len(r_pairs)),), -1, dtype=torch.long); pos_r[sel_r] = torch.arange(len(sel_r))
+        gp, gr_, gc = gflat >> 12, (gflat >> 6) & 63, gflat & 63
+        gm = pos_g[gp] >= 0 if gflat.numel() else torch.zeros(0, dtype=torch.bool)
+        e_cs_g = float((out["corr_scores"].cpu().double()[gm] - torch.exp(g64[pos_g[gp[gm]], gr_[gm], gc[gm]])).abs().max()) if gm.any() else 0.0
+        brc = raux["corr_brc"]
+        rm = pos_r[brc[:, 0]] >= 0 if brc.numel() else torch.zeros(0, dtype=torch.bool)
+        e_cs_o = float((ref["corr_scores"].double()[rm] - torch.exp(r64[pos_r[brc[rm, 0]], brc[rm, 1], brc[rm, 2]])).abs().max()) if rm.any() else 0.0
+        add("corr_scores vs fp64 (oracle fp32)", "maxabs", e_cs_o, "info")
+        add("corr_scores vs fp64 (cuda)", "maxabs", e_cs_g, "info")
+        add("corr_scores vs fp64", "cuda err - max(1e-4, oracle err)", e_cs_g - max(1e-4, e_cs_o), "nonpos")
+        # and the end-to-end statement: CUDA correspondence scores against the fp64 evaluation of the ORACLE's descriptors
+        r64k = {(r_pairs[int(b_)], int(r), int(c)): float(torch.exp(r64[pos_r[b_], r, c])) for (b_, r, c) in brc[rm].tolist()}
+        both = [k for k in set(gk) & set(rk) & set(r64k)]
+        e_lit_g = max([abs(gk[k] - r64k[k]) for k in both] or [0.0])
+        e_lit_o = max([abs(rk[k] - r64k[k]) for k in both] or [0.0])
+        add("corr_scores: cuda vs fp64(oracle feats)", "maxabs (common, %d)" % len(both), e_lit_g, "info")
+        add("corr_scores: oracle vs fp64(oracle feats)", "maxabs (common)", e_lit_o, "info")
+        add("corr_scores end to end", "cuda err - max(1e-4, oracle err)", e_lit_g - max(1e-4, e_lit_o), "nonpos")
     add("corr points consistent", "maxabs", _corr_points_check(out, aux, g_pairs), "exactf")
     return rows, out, ref
 
@@ -145,15 +209,20 @@ def _corr_points_check(out, aux, g_pairs):
     return float(max((t - out["tgt_corr_points"].cpu()).abs().max(), (s - out["src_corr_points"].cpu()).abs().max()))
 
 
-# f3e-4: log-assignment scores after 100 Sinkhorn iterations of inputs whose magnitude is O(100) (the x8 fine_proj of the
-# seeded weights); the exp'd correspondence scores ("final corr scores") are held to 2e-4 absolute: a score is
-# exp(z + u + v - norm) with |z|, |u|, |v| up to ~740 for these weights, where one fp32 ulp is 6e-5, so two correct fp32
-# evaluation orders of the same formula differ by a few 1e-5 .. 1.2e-4 (measured 4.5e-5 .. 1.16e-4 over kernel revisions
-# whose upstream features agree to 1e-6); the reference's own result carries the same rounding noise against exact math.
-# The 4DMatch head (factor 2) contracts 512-dim descriptors (log-scores of magnitude ~150-200): fp32 summation-order
-# differences scale with that magnitude, so its two score tolerances are 2x the 3DMatch ones.
-THRESH = {"f6e-4": 6e-4, "f2e-4": 2e-4, "f3e-4": 3e-4, "exact": 0, "exactf": 0.0, "ties": 1e-3, "f1e-5": 1e-5, "feat": 2e-4, "f1e-4": 1e-4, "f1e-3": 1e-3, "f1e-2": 1e-2,
-          "set": 0.05}
+# Tolerances. north_star: "outputs match the reference forward to a stated fp32 tolerance (bit-exact for kNN/FPS indices)
+# ... matching reference correspondences within 1e-4".
+#   feat     1e-4 absolute on every feature tensor (encoder / decoder levels, descriptors, geometric embedding)
+#   f1e-4    1e-4 on the exp'd coarse similarity and the log-assignment scores relative to (1+|x|)
+#   set0     0: coarse selection must be the identical set (3DMatch head: exact top-k)
+#   set4d    the 4DMatch head selects by THRESHOLD (similarity <= 0.75, modules.py:105-112): entries within fp32 noise of
+#            the threshold may flip; budget 0.5 % of P
+#   flipset  final correspondences: entries at the 0.05 confidence threshold / a top-k rank tie may flip (budget 0.3 %),
+#            and every flip must be AT such a boundary ("flips away from a decision boundary" is exact 0)
+#   tiefrac  fraction of partition rows whose 64-NN list is permuted among EXACTLY equal distances (torch.topk's order
+#            among ties is unspecified; the rows agree as sets, which is checked exactly)
+#   nonpos   value <= 0: "CUDA error - max(1e-4, the fp32 oracle's own error)" against the float64 evaluation
+THRESH = {"exact": 0, "exactf": 0.0, "f1e-5": 1e-5, "feat": 1e-4, "f1e-4": 1e-4, "f1e-3": 1e-3, "f1e-2": 1e-2,
+          "set0": 0.0, "set4d": 5e-3, "flipset": 3e-3, "tiefrac": 0.05, "nonpos": 0.0}
 
 
 def failures(rows):
@@ -164,6 +233,9 @@ def failures(rows):
         if kind == "true":
             if val != 1.0:
                 bad.append((stage, name, val))
+        elif kind == "nonpos":
+            if not (val <= 0.0):
+                bad.append((stage, name, val, "must be <= 0"))
         elif not (abs(val) <= THRESH[kind]):
             bad.append((stage, name, val, "limit %g" % THRESH[kind]))
     return bad
