@@ -334,6 +334,22 @@ int roitr_corr_gather(int capacity, int Ms, const int* flat, const int* count, c
 int roitr_weighted_procrustes(int batch, int n, const float* src, const float* tgt, const float* weights,
                               float weight_thresh, float eps, float* R, float* t, void* stream);
 
+/* Correspondence RANSAC: replaces ransac_pose_estimation_correspondences (registration/benchmark_utils.py:165-209, called
+ * from registration/evaluate_registration_c2f.py:88) = Open3D registration_ransac_based_on_correspondence with
+ * TransformationEstimationPointToPoint(False), ransac_n = 3, checkers EdgeLength(edge_similarity = 0.9) and
+ * Distance(distance_threshold), RANSACConvergenceCriteria(iterations = 50000, confidence clamped to 1 => no early exit).
+ * `pairs` problems in one launch: src / tgt (total, 3) f32 hold the matched points of every pair back to back (correspondence i
+ * = row i of both), offset (pairs,) int32 cumulative ends, max_corr >= the largest per-pair count (<= 8192).
+ * Hypothesis j of pair p samples rows hash(seed, p, 3 j + {0,1,2}) with replacement (deterministic; oracle/ransac_ref.py
+ * shares the hash). Outputs per pair: transform (4,4) f64 row-major mapping src onto tgt (identity when no hypothesis
+ * passes), fitness = inliers / n, rmse over the inliers, best_itr (-1 if none); ties go to the lower iteration.
+ * workspace: roitr_ransac_workspace_bytes(pairs, iterations) bytes. All arithmetic is fp64, like Open3D. */
+long long roitr_ransac_workspace_bytes(int pairs, int iterations);
+int roitr_ransac_correspondences(int pairs, int iterations, const float* src, const float* tgt, const int* offset,
+                                 int max_corr, double distance_threshold, double edge_similarity, unsigned seed,
+                                 void* workspace, double* transform, double* fitness, double* rmse, int* best_itr,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

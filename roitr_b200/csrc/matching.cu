@@ -415,11 +415,16 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
     // ---- 64 x 64 x C scores (rows = tgt patch points, cols = src patch points), threads 0..255 ----
     const bool mm = tid < 256;
     const int tx = tid & 15, ty = (tid >> 4) & 15;
-    float acc[4][4];
+    // The contraction runs over C = 256 / 512 terms whose sum reaches |z| sqrt(C) ~ 10^4 for peaky descriptors: one long fp32
+    // FMA chain then carries ~1e-4 of rounding noise into z (measured against a float64 evaluation, tests/parity.py - more
+    // than the reference's blocked sgemm does). Each 32-term chunk is therefore summed on its own (`part`) and added to a
+    // COMPENSATED running total (Knuth TwoSum: `acc` + the exact rounding errors collected in `comp`), which makes z
+    // correctly rounded to within an ulp for 7 extra FADDs per output per chunk.
+    float acc[4][4], comp[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; comp[i][j] = 0.f; }
     const int lrow = (tid >> 2) & 63, lk = (tid & 3) * 8;
     const int ti = t_idx[lrow], si = s_idx[lrow];
     for (int k0 = 0; k0 < P.C; k0 += 32) {
@@ -435,6 +440,11 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
         }
         __syncthreads();
         if (mm) {
+            float part[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 const float4 a = *reinterpret_cast<const float4*>(&At[k][ty * 4]);
@@ -443,10 +453,27 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                    for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {       // TwoSum(acc, part): sum + exact error, in round-to-nearest adds
+                    const float a0 = acc[i][j], b0 = part[i][j];
+                    const float sum = __fadd_rn(a0, b0);
+                    const float bb = __fsub_rn(sum, a0);
+                    const float err = __fadd_rn(__fsub_rn(a0, __fsub_rn(sum, bb)), __fsub_rn(b0, bb));
+                    acc[i][j] = sum;
+                    comp[i][j] = __fadd_rn(comp[i][j], err);
+                }
         }
         __syncthreads();
+    }
+    if (mm) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = __fadd_rn(acc[i][j], comp[i][j]);
     }
     // ---- padded, masked score matrix (modules.py:36-46) and marginals (:48-60) ----
     const float alpha = __ldg(P.alpha);
@@ -523,7 +550,11 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
                 float m = fmaxf(fmaxf(m0, m1), fmaxf(fmaxf(m2, m3), x[16]));
                 m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 1));
                 m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 2));
+                // nml = rn(-m log2 e) carries a rounding error eps = nml + m log2 e (up to 3e-5 for |m| ~ 500) that would scale
+                // every term by 2^eps, i.e. shift the logsumexp by eps ln 2: the FMA recovers eps exactly and it is taken out
+                // after the log (one FMA per logsumexp instead of a subtraction per term)
                 const float nml = -m * L2E;
+                const float eps = fmaf(m, L2E, nml);
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
@@ -534,13 +565,14 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
                 float sm = (s0 + s1) + (s2 + s3);
                 sm += __shfl_xor_sync(FULL_MASK, sm, 1);
                 sm += __shfl_xor_sync(FULL_MASK, sm, 2);
-                if (q == 0) dst[ri] = marg[ri] - fmaf(__log2f(sm), LN2, m);
+                if (q == 0) dst[ri] = marg[ri] - fmaf(__log2f(sm) - eps, LN2, m);
             } else {
                 const float x0 = z[0] + add[lane], x1 = z[1] + add[lane + 32], x2 = z[2] + add[64];
                 const float m = warp_max(fmaxf(fmaxf(x0, x1), x2));
                 const float nml = -m * L2E;
+                const float eps = fmaf(m, L2E, nml);
                 const float sm = warp_sum(fast_ex2(fmaf(x0, L2E, nml)) + fast_ex2(fmaf(x1, L2E, nml)) + fast_ex2(fmaf(x2, L2E, nml)));
-                if (lane == 0) dst[64] = marg[64] - fmaf(__log2f(sm), LN2, m);
+                if (lane == 0) dst[64] = marg[64] - fmaf(__log2f(sm) - eps, LN2, m);
             }
         };
         // Iterations 1 .. warm and the last one run in the log domain exactly as written in the reference. The ones in between

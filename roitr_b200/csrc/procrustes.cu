@@ -11,6 +11,7 @@
 // sign-ambiguous singular vectors themselves.
 #include "../../include/roitr_b200.h"
 #include "common.cuh"
+#include "horn.cuh"
 
 namespace {
 
@@ -59,39 +60,8 @@ __global__ void __launch_bounds__(PR_THREADS) procrustes_kernel(int n, const flo
     }
     for (int k = 0; k < 9; ++k) H[k] = block_sum(H[k], sh);
     if (tid != 0) return;
-    // Horn's 4x4 matrix of S = H (S_rc = sum w p_r q_c); its dominant eigenvector is the unit quaternion of R
-    const double Sxx = H[0], Sxy = H[1], Sxz = H[2], Syx = H[3], Syy = H[4], Syz = H[5], Szx = H[6], Szy = H[7], Szz = H[8];
-    double A[4][4] = {{Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
-                      {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
-                      {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
-                      {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
-    double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
-    for (int sweep = 0; sweep < 32; ++sweep) {
-        double off = 0.0;
-        for (int i = 0; i < 4; ++i)
-            for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
-        double diag = 0.0;
-        for (int i = 0; i < 4; ++i) diag += A[i][i] * A[i][i];
-        if (off <= 1e-32 * (diag + off) || off == 0.0) break;
-        for (int p = 0; p < 3; ++p)
-            for (int q = p + 1; q < 4; ++q) {
-                if (A[p][q] == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 4; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
-                for (int k = 0; k < 4; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
-                for (int k = 0; k < 4; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
-            }
-    }
-    int best = 0;
-    for (int i = 1; i < 4; ++i) if (A[i][i] > A[best][best]) best = i;
-    double qw = V[0][best], qx = V[1][best], qy = V[2][best], qz = V[3][best];
-    const double nq = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
-    qw /= nq; qx /= nq; qy /= nq; qz /= nq;
-    const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qw * qz), 2 * (qx * qz + qw * qy),
-                         2 * (qx * qy + qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qw * qx),
-                         2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx), 1 - 2 * (qx * qx + qy * qy)};
+    double R[9];
+    horn_rotation(H, R);
     for (int k = 0; k < 9; ++k) R_out[9 * (size_t)b + k] = (float)R[k];
     for (int r = 0; r < 3; ++r)
         t_out[3 * (size_t)b + r] = (float)(cq[r] - (R[3 * r] * cp[0] + R[3 * r + 1] * cp[1] + R[3 * r + 2] * cp[2]));

@@ -48,6 +48,9 @@ def main():
         o, no = i32([n]), i32([n // 4])
         idx = pointops.furthestsampling(levels[-1][0], o, no).long()
         levels.append((levels[-1][0][idx].contiguous(), levels[-1][1][idx].contiguous()))
+    print("# ours = libroitr_b200 (kNN FUSED with PPF where the op is knn_ppf); reference_kernel = the reference's own .cu compiled")
+    print("# unmodified for sm_100a (oracle/_ref: knnquery_cuda_kernel.cu:65-108 - kNN only, no PPF; sampling_cuda_kernel.cu:14-129).")
+    print("# One cloud per call (batch size 1, as the reference runs); median of 10, 256 MiB L2 flush between iterations.")
     print("op, n_ref, m_query, k, ours_ms, reference_kernel_ms")
     for (li, lq, k) in [(0, 0, 8), (0, 1, 16), (1, 1, 16), (1, 2, 16), (2, 2, 16), (2, 3, 16), (3, 3, 16)]:
         (x, xn), (q, qn) = levels[li], levels[lq]
@@ -64,7 +67,13 @@ def main():
         (x, _), (q, _) = levels[lc], levels[lf]
         o, no = i32([x.shape[0]]), i32([q.shape[0]])
         t = timeit(lambda: pointops.knnquery(3, x, q, o, no))
-        print("knn3, %d, %d, 3, %.4f, nan" % (x.shape[0], q.shape[0], t))
+        tr = float("nan")
+        if ref is not None:
+            m = q.shape[0]
+            idx = torch.zeros(m, 3, dtype=torch.int32, device=DEV)
+            d2 = torch.zeros(m, 3, device=DEV)
+            tr = timeit(lambda: ref.knnquery_cuda_launcher(m, 3, p(x), p(q), p(o), p(no), p(idx), p(d2)))
+        print("knn3, %d, %d, 3, %.4f, %.4f" % (x.shape[0], q.shape[0], t, tr))
     for li, n in enumerate((20000, 5000, 1250)):
         x = levels[li][0]
         o, no = i32([n]), i32([n // 4])

@@ -20,6 +20,32 @@ def test_forward_parity_3dmatch(n, index):
     assert not parity.failures(rows), parity.failures(rows)
 
 
+@pytest.mark.parametrize("name,cfg,factor", [("3dmatch_30k", CONFIG_3D, 1), ("4dmatch_8k", CONFIG_4D, 2)])
+def test_forward_parity_other_baseline_configs(name, cfg, factor):
+    """BASELINE.json configs 3 and 5 against the ORACLE (not against the CUDA path itself): 30 000 / 28 000 points with the
+    3DMatch head (468 / 437 superpoints) and the 8 000 / 7 000-point non-rigid pair with the factor-2 backbone and the
+    adaptive head, where P is data dependent (here every one of the 125 x 109 superpoint pairs passes the similarity
+    threshold: P = 13 625, the head's maximum)."""
+    from tests.helpers import baseline_pair
+    rows, out, ref = parity.run(baseline_pair(name), cfg, weights(factor))
+    print("\n" + parity.format_rows(rows))
+    assert out["matching_scores"].shape[0] == ref["matching_scores"].shape[0]
+    for k in out:
+        assert out[k].dtype == ref[k].dtype and out[k].shape[1:] == ref[k].shape[1:], k
+    assert not parity.failures(rows), parity.failures(rows)
+
+
+def test_forward_parity_unscaled_fine_proj():
+    """The seeded weights scale fine_proj x8 so that correspondences exist; with the un-scaled projection the log-scores are
+    O(10) instead of O(700) and every score agrees to fp32 round-off (measured 6e-7), which shows the 1e-4-level differences
+    of the scaled cases are the conditioning of the inputs, not the kernels."""
+    rows, out, ref = parity.run(synthetic_pair(1, 4096), CONFIG_3D, weights(1, fine_scale=1.0))
+    print("\n" + parity.format_rows(rows))
+    assert not parity.failures(rows), parity.failures(rows)
+    worst = max(v for s, n, v, k in rows if s == "final corr scores")
+    assert worst < 5e-6, worst
+
+
 def test_forward_ragged_sizes():
     # unequal clouds, sizes not multiples of 4/32
     pair = synthetic_pair(5, 3000)
