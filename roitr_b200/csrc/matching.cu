@@ -359,7 +359,7 @@ struct FineParams {
     const float* alpha;
     float* scores;               // (Pmax, 65, 65)
     unsigned char* flags;        // (Pmax, 64, 64)
-    int num_iter, topk, mutual, warmup;
+    int num_iter, topk, mutual;
     float threshold, sqrt_c;
 };
 
@@ -380,13 +380,6 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return y;
 }
 
-// Log-domain iterations before the scaling-form ones (fine_patch_kernel). Default: all of them, i.e. the reference's
-// iteration verbatim. roitr_debug_fine_warmup(20) switches 4/5 of the iterations to the scaling form: fine matching 3.0 ->
-// 2.5 ms per step (+2.4 % pairs/s), same correspondences, but log-scores of slowly converging (unbalanced) patches then
-// differ by up to 2.9e-4 (1+|x|) from the all-log-domain result - the fp32 rounding of either form is amplified along the
-// slow modes - which is at the edge of the parity tolerance, so it is opt-in.
-constexpr int FINE_WARMUP = 1 << 20;
-static int g_host_fine_warmup = FINE_WARMUP; // roitr_debug_fine_warmup: >= num_iter = every iteration in the log domain
 constexpr int FT = 288, FW = FT / 32;      // 8 warps own rows/columns 0..63 (4 threads each), warp 8 owns the dustbin row/column
 
 __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
@@ -507,7 +500,6 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
     }
     if (tid < FP1 + 3) { u[tid] = 0.f; v[tid] = 0.f; }
     __syncthreads();
-    float* rowsc = reinterpret_cast<float*>(rowf);          // 2 x (FP1 + 3) floats, free until the top-k phase
     // ---- log-domain Sinkhorn (modules.py:21-26) ----
     // 200 dependent logsumexp sweeps per patch pair; the kernel's time is the instruction count of this loop, so a
     // logsumexp is split over only FOUR threads: thread (i, q) of warps 0-7 holds elements 16q .. 16q+15 (+ the dustbin
@@ -575,106 +567,10 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
                 if (lane == 0) dst[64] = marg[64] - fmaf(__log2f(sm) - eps, LN2, m);
             }
         };
-        // Iterations 1 .. warm and the last one run in the log domain exactly as written in the reference. The ones in between
-        // are the SAME iteration in scaling form: with the potentials after the warm-up absorbed into
-        //     Kt_ij = exp(Z_ij + u0_i + v0_j)          (one exp per element, entries <= ~1),   u = u0 + log a,  v = v0 + log b,
-        // u <- log_mu - LSE_j(Z + v) becomes a_i = mu_i / sum_j Kt_ij b_j (and b_j = nu_j / sum_i Kt_ij a_i): a 17-term FMA
-        // chain per thread instead of 17 x (add, max, fma, ex2, add), ~3x fewer instructions for 4/5 of the iterations. Rows /
-        // columns that are masked out have Kt = 0 and mu = 0: their scale stays 0 and their potentials are recomputed by the
-        // final log-domain iteration from the other side's potentials, which is all they depend on.
-        const int warm = min(P.warmup, max(P.num_iter - 1, 0));
-        const int nscale = max(P.num_iter - 1 - warm, 0);
-        for (int it = 0; it < warm; ++it) {
+        for (int it = 0; it < P.num_iter; ++it) {
             sweep(zr, v, log_mu, u);      // u = log_mu - LSE_j(Z + v)
             __syncthreads();
             sweep(zc, u, log_nu, v);      // v = log_nu - LSE_i(Z + u)
-            __syncthreads();
-        }
-        if (nscale > 0) {
-            float* sa = rowsc;            // a (rows), b (columns): [FP1 + 3] each, float4-aligned
-            float* sb = rowsc + FP1 + 3;
-            float mu_r = 0.f, nu_r = 0.f; // this thread's marginals in the linear domain (q == 0 / lane 0 only)
-            if (warp < 8) { if (q == 0) { mu_r = __expf(log_mu[ri]); nu_r = __expf(log_nu[ri]); } }
-            else if (lane == 0) { mu_r = __expf(log_mu[64]); nu_r = __expf(log_nu[64]); }
-            auto load_z = [&]() {         // this thread's elements of Z (row and column view) from shared memory
-                if (warp < 8) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        zr[j] = Z[ri * FP1 + q * 16 + j];
-                        zc[j] = Z[(q * 16 + j) * FP1 + ri];
-                    }
-                    zr[16] = q == 3 ? Z[ri * FP1 + 64] : -CUDART_INF_F;
-                    zc[16] = q == 3 ? Z[64 * FP1 + ri] : -CUDART_INF_F;
-                } else {
-                    zr[0] = Z[64 * FP1 + lane]; zr[1] = Z[64 * FP1 + lane + 32]; zr[2] = lane == 0 ? Z[64 * FP1 + 64] : -CUDART_INF_F;
-                    zc[0] = Z[lane * FP1 + 64]; zc[1] = Z[(lane + 32) * FP1 + 64]; zc[2] = lane == 0 ? Z[64 * FP1 + 64] : -CUDART_INF_F;
-                }
-            };
-            auto absorb = [&]() {         // Kt = exp(Z + u + v) with the CURRENT potentials; scales reset to 1. Ends with a barrier.
-                if (warp < 8) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        zr[j] = __expf((zr[j] + u[ri]) + v[q * 16 + j]);
-                        zc[j] = __expf((zc[j] + u[q * 16 + j]) + v[ri]);
-                    }
-                    zr[16] = q == 3 ? __expf((zr[16] + u[ri]) + v[64]) : 0.f;
-                    zc[16] = q == 3 ? __expf((zc[16] + u[64]) + v[ri]) : 0.f;
-                } else {
-                    zr[0] = __expf((zr[0] + u[64]) + v[lane]); zr[1] = __expf((zr[1] + u[64]) + v[lane + 32]);
-                    zr[2] = lane == 0 ? __expf((zr[2] + u[64]) + v[64]) : 0.f;
-                    zc[0] = __expf((zc[0] + u[lane]) + v[64]); zc[1] = __expf((zc[1] + u[lane + 32]) + v[64]);
-                    zc[2] = lane == 0 ? __expf((zc[2] + u[64]) + v[64]) : 0.f;
-                }
-                if (tid < FP1 + 3) { sa[tid] = 1.f; sb[tid] = 1.f; }
-                __syncthreads();
-            };
-            auto fold = [&]() {           // u += log a, v += log b (a scale of 0 marks a masked row / column). Ends with a barrier.
-                if (tid < FP1) {
-                    const float a = sa[tid], b = sb[tid];
-                    if (a > 0.f) u[tid] += __logf(a);
-                    if (b > 0.f) v[tid] += __logf(b);
-                }
-                __syncthreads();
-            };
-            // returns (through the block-wide OR of the following barrier) whether a scale left [1e-15, 1e15]: fp32 cannot hold
-            // scales that drift by more than e^+-87, and entries of Kt that underflowed when it was formed must not become
-            // relevant later, so a drifting patch (unbalanced masks converge slowly) is re-absorbed: potentials updated, Kt
-            // rebuilt from Z. Well-conditioned patches never trigger it.
-            auto scale_sweep = [&](const float (&kt)[17], const float* __restrict__ other, float marg, float* __restrict__ dst) -> int {
-                float val = 1.f;
-                if (warp < 8) {
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 o = *reinterpret_cast<const float4*>(other + q * 16 + 4 * j4);
-                        s0 = fmaf(kt[4 * j4], o.x, s0); s1 = fmaf(kt[4 * j4 + 1], o.y, s1);
-                        s2 = fmaf(kt[4 * j4 + 2], o.z, s2); s3 = fmaf(kt[4 * j4 + 3], o.w, s3);
-                    }
-                    s0 = fmaf(kt[16], other[64], s0);
-                    float sm = (s0 + s1) + (s2 + s3);
-                    sm += __shfl_xor_sync(FULL_MASK, sm, 1);
-                    sm += __shfl_xor_sync(FULL_MASK, sm, 2);
-                    if (q == 0) { val = sm > 0.f ? __fdividef(marg, sm) : 0.f; dst[ri] = val; }
-                } else {
-                    const float sm = warp_sum(fmaf(kt[0], other[lane], fmaf(kt[1], other[lane + 32], kt[2] * other[64])));
-                    if (lane == 0) { val = sm > 0.f ? __fdividef(marg, sm) : 0.f; dst[64] = val; }
-                }
-                return (val != 0.f) && !(val >= 1e-15f && val <= 1e15f);
-            };
-            __syncthreads();              // (u, v) of the warm-up are final
-            absorb();
-            for (int it = 0; it < nscale; ++it) {
-                const int t1 = __syncthreads_or(scale_sweep(zr, sb, mu_r, sa));     // a = mu / (Kt b)
-                const int t2 = __syncthreads_or(scale_sweep(zc, sa, nu_r, sb));     // b = nu / (Kt^T a)
-                if ((t1 | t2) && it + 1 < nscale) { fold(); load_z(); absorb(); }
-            }
-            fold();
-            load_z();
-        }
-        if (P.num_iter > 0) {
-            sweep(zr, v, log_mu, u);
-            __syncthreads();
-            sweep(zc, u, log_nu, v);
             __syncthreads();
         }
     }
@@ -818,7 +714,6 @@ extern "C" int roitr_coarse_matching(int Mr, int Ms, int C, int k, int dual, con
     return ROITR_OK;
 }
 
-extern "C" int roitr_debug_fine_warmup(int n) { g_host_fine_warmup = n; return 0; }
 
 extern "C" int roitr_fine_matching(int Pmax, int Nt, int Ns, int C, const float* tgt_feat, const float* src_feat,
                                    const int* tgt_knn, const int* src_knn, const unsigned char* tgt_kmask,
@@ -832,7 +727,7 @@ extern "C" int roitr_fine_matching(int Pmax, int Nt, int Ns, int C, const float*
     FineParams P;
     P.tgt_feat = tgt_feat; P.src_feat = src_feat; P.Nt = Nt; P.Ns = Ns; P.C = C; P.tgt_knn = tgt_knn; P.src_knn = src_knn;
     P.tgt_kmask = tgt_kmask; P.src_kmask = src_kmask; P.corr_t = corr_t; P.corr_s = corr_s; P.corr_count = corr_count;
-    P.warmup = g_host_fine_warmup; P.alpha = alpha; P.scores = scores; P.flags = flags; P.num_iter = num_iter; P.topk = topk; P.mutual = mutual;
+    P.alpha = alpha; P.scores = scores; P.flags = flags; P.num_iter = num_iter; P.topk = topk; P.mutual = mutual;
     P.threshold = threshold; P.sqrt_c = sqrtf((float)C);
     cudaStream_t st = (cudaStream_t)stream;
     ROITR_CUDA(cudaMemsetAsync(flags, 0, (size_t)Pmax * FP * FP, st));

@@ -63,27 +63,3 @@ def test_forward_parity_4dmatch(n, index):
     for k in out:
         assert out[k].dtype == ref[k].dtype and out[k].shape[1:] == ref[k].shape[1:], k
     assert not parity.failures(rows), parity.failures(rows)
-
-
-def test_scaling_form_sinkhorn_option_agrees_with_log_domain():
-    """The opt-in scaling-form Sinkhorn (csrc/matching.cu, roitr_debug_fine_warmup) is the same iteration in exact
-    arithmetic: same correspondences, log-scores within the fp32 slow-mode noise of the all-log-domain default."""
-    import torch
-    from roitr_b200 import _lib, model
-    from roitr_b200.synthetic import forward_args, synthetic_pair
-    from tests.helpers import CONFIG_3D, weights
-    m = model.create_model(CONFIG_3D)
-    m.load_state_dict(weights(1))
-    m = m.cuda().eval()
-    args = forward_args(synthetic_pair(0, 4096), "cuda:0")
-    try:
-        _lib.lib().roitr_debug_fine_warmup(20)
-        fast = m(*args)
-    finally:
-        _lib.lib().roitr_debug_fine_warmup(1 << 20)
-    ref = m(*args)
-    live = ref["matching_scores"] > -1e5
-    d = (fast["matching_scores"] - ref["matching_scores"]).abs() / (1 + ref["matching_scores"].abs())
-    assert d[live].max().item() < 6e-4
-    assert fast["corr_scores"].shape == ref["corr_scores"].shape
-    assert (fast["corr_scores"] - ref["corr_scores"]).abs().max().item() < 2e-4
