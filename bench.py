@@ -281,12 +281,46 @@ def main():
         wall = time.perf_counter() - t0
         return sum(a.elapsed_time(b) for a, b in ev), wall, d2h, ncorr
 
-    run_loop(False, warmup)
+    depth = int(os.environ.get("ROITR_PIPELINE", "1"))
+    pipe = m.pipelined_runner(B, N_POINTS, N_POINTS, depth=depth, mid_level=int(os.environ.get("ROITR_MID_LEVEL", "1"))) if depth > 1 else None
+
+    def pipe_loop(e2e, n_steps):
+        """Pipelined steps (engine.PipelinedRunner): step i+1 starts beside the latency-bound back of step i, so per-step event
+        pairs would overlap; ONE event pair on the launching stream brackets the K steps (every step's work, the L2 flush and,
+        for e2e, every H2D / D2H copy lie inside it)."""
+        d2h, ncorr = 0, 0
+        _lib.reset_stats()
+        barrier()
+        t0 = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        prev = None
+        for i in range(n_steps):
+            slot = pipe.submit(collated[i % NB] if e2e else resident[i % NB], pre=flush.zero_)
+            if e2e and prev is not None:
+                pipe.wait(prev)
+                res = pipe.runner(prev).correspondences()
+                d2h = sum(t.numel() * t.element_size() for trip in res for t in trip) + 12 * B
+            prev = slot
+        if e2e:
+            pipe.wait(prev)
+            res = pipe.runner(prev).correspondences()
+            ncorr = sum(int(trip[2].shape[0]) for trip in res)
+        pipe.join()
+        b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        return a.elapsed_time(b), wall, d2h, ncorr
+
+    loop = pipe_loop if pipe is not None else run_loop
+    loop(False, warmup)
     with ClockSampler(local) as clk:
-        ms_dev, wall, _, _ = run_loop(False, steps)
-    counts = runner.results(full=False)
-    run_loop(True, 2)
-    ms_e2e, _, d2h_bytes, ncorr = run_loop(True, steps)
+        ms_dev, wall, _, _ = loop(False, steps)
+    counts = (pipe.runner((pipe.step - 1) % depth) if pipe is not None else runner).results(full=False)
+    loop(True, 2)
+    ms_e2e, _, d2h_bytes, ncorr = loop(True, steps)
+    if pipe is not None:
+        runner.load(resident[0]); runner.run(); torch.cuda.synchronize()     # the plain runner serves the record / replica legs below
 
     # e2e with the FULL record lib/tester.py:56-69 builds per pair (16 tensors incl. the (N,256) point descriptors)
     from roitr_b200 import results as results_mod
@@ -406,7 +440,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "parallelism": "independent pairs x%d" % world,
                        "l2": "256 MiB flush between steps (outside the timed events); %d distinct batches cycled" % NB,
-                       "mode": ("one CUDA graph per step" if not args.no_graph else "eager") + ", %d pairs in flight per GPU" % B},
+                       "mode": ("one CUDA graph per step" if not args.no_graph else "eager") + ", %d pairs per step per GPU" % B +
+                               (", %d steps in flight (software pipeline: step i+1 starts when step i is past its encoder level %d; "
+                                "K steps timed with one event pair)" % (depth, int(os.environ.get("ROITR_MID_LEVEL", "1")) + 1) if depth > 1 else "")},
             "e2e": {"value": world * B * steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
             "e2e_record": {"value": world * B * rec_steps / (ms_rec * 1e-3), "unit": "pairs/s", "d2h_bytes_per_step": rec_bytes,

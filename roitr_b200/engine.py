@@ -446,6 +446,11 @@ def encode(W, plan, pts, feats, nrm, on_nodes=None):
             x = block(W, "%s.%d" % (p, bi), x, g["idx"], g["ppf"], order)
         levels.append(dict(p=g["p"], n=g["n"], x=x, o=g["o"], idx=g["idx"], ppf=g["ppf"], down_idx=g["down_idx"], g=g,
                            order=order))
+        if getattr(plan, "mid_event", None) is not None and li == plan.mid_level:
+            # PipelinedRunner: the bandwidth-heavy front of the step (FPS chain, level-1/2 neighbour search and layers) is
+            # behind the main stream here; the next step may start beside the latency-bound rest (an EXTERNAL event: a
+            # record node in the captured graph that streams outside the graph can wait on)
+            plan.mid_event.record()
         if li + 1 < 4:
             issue_search(li + 1)
             if li + 2 < 4:
@@ -875,10 +880,11 @@ class BatchRunner:
 
     INPUT_KEYS = ("pts", "feats", "nrm", "src_pcd", "rot", "trans")
 
-    def __init__(self, W, cfg, B, n_src, n_tgt, device, graph=True, fps_cluster=0, serial=False):
+    def __init__(self, W, cfg, B, n_src, n_tgt, device, graph=True, fps_cluster=0, serial=False, mid_event=None, mid_level=1):
         self.W, self.cfg, self.B, self.Ns, self.Nt, self.device = W, cfg, B, n_src, n_tgt, device
         self.plan = Plan(n_src, n_tgt, B, device, fps_cluster)
         self.plan.serial = serial     # True: no side streams at all (bench.py's per-kernel timing replica)
+        self.plan.mid_event, self.plan.mid_level = mid_event, mid_level
         tot = B * (n_src + n_tgt)
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
         self.inp = dict(pts=f(tot, 3), feats=f(tot, 1), nrm=f(tot, 3), src_pcd=f(B * n_src, 3), rot=f(B, 3, 3), trans=f(B, 3, 1))
@@ -941,6 +947,10 @@ class BatchRunner:
         return riga_batch(self.W, self.cfg, self.plan, i["pts"], i["feats"], i["nrm"], i["src_pcd"], i["rot"], i["trans"])
 
     def run(self):
+        with torch.cuda.device(self.device):       # streams / events / launches of the runner's own device
+            self._run()
+
+    def _run(self):
         if self._want_graph and self.graph is None:
             # one eager pass first: lazily-set kernel attributes and allocator warm-up must not happen under capture
             self.outs, self.counts = self._body()
@@ -960,3 +970,69 @@ class BatchRunner:
         if not full:
             return counts
         return [finalize(self.outs[b], counts[b], self.Ns, self.Nt) for b in range(self.B)]
+
+
+class PipelinedRunner:
+    """Software pipeline over consecutive steps: ``depth`` BatchRunners (own static buffers, own CUDA graph, own stream)
+    take the steps round-robin, and step i+1 starts as soon as step i is past the front of its graph (the FPS chain and the
+    level-1/2 neighbour search and layers, which saturate the GPU) instead of after its last kernel. The back of a step -
+    levels 3-4, the global transformer, the decoder's small layers, the matching head - is a chain of latency-bound launches
+    on two streams that leaves most SMs idle (profiles/r01k_timeline.txt: 13 of 28 ms); the next step's front fills them.
+    Every step still runs the whole forward of its own B pairs; only the phase between steps changes. Results of step i are
+    read after ``wait(slot)``.
+
+        slot = pr.submit(collated_host_batch)        # H2D + graph launch on the slot's stream, returns immediately
+        ...
+        pr.wait(slot); pr.runner(slot).correspondences() / .results()
+    """
+
+    def __init__(self, W, cfg, B, n_src, n_tgt, device, depth=2, mid_level=1, fps_cluster=0):
+        self.depth, self.device = depth, device
+        self.mid = [torch.cuda.Event(external=True) for _ in range(depth)]
+        self.runners = [BatchRunner(W, cfg, B, n_src, n_tgt, device, graph=True, fps_cluster=fps_cluster, mid_event=self.mid[k],
+                                    mid_level=mid_level) for k in range(depth)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.step = 0
+        self._captured = False
+
+    def runner(self, slot):
+        return self.runners[slot]
+
+    def _capture(self, example):
+        # capture every slot's graph once, one after the other (a capture must not overlap other work of the process)
+        for k, r in enumerate(self.runners):
+            with torch.cuda.stream(self.streams[k]):
+                (r.load_batched if isinstance(example, dict) else r.load)(example)
+                r.run()
+            torch.cuda.synchronize(self.device)
+        self._captured = True
+
+    def submit(self, batch, pre=None):
+        """batch: a collated host dict (BatchRunner.collate) or a list of per-pair dicts of device tensors. ``pre``: optional
+        callable issued on the slot's stream before the load (bench.py's L2 flush). Returns the slot."""
+        if not self._captured:
+            self._capture(batch)
+        k = self.step % self.depth
+        st = self.streams[k]
+        st.wait_stream(torch.cuda.current_stream(self.device))          # whatever produced `batch` / the caller's start marker
+        if self.step > 0:
+            st.wait_event(self.mid[(self.step - 1) % self.depth])      # the previous step is past its heavy front
+        with torch.cuda.stream(st):
+            if pre is not None:
+                pre()
+            r = self.runners[k]
+            (r.load_batched if isinstance(batch, dict) else r.load)(batch)
+            r.run()
+            self.done[k].record(st)
+        self.step += 1
+        return k
+
+    def wait(self, slot):
+        self.done[slot].synchronize()
+
+    def join(self):
+        """The current stream waits for every submitted step (for an end-of-region event or a barrier)."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)

@@ -284,6 +284,17 @@ class RIGA_v2(nn.Module, _PackedMixin):
                                   serial=serial)
 
 
+    def pipelined_runner(self, batch_pairs, n_src, n_tgt, depth=2, mid_level=1, fps_cluster=0):
+        """engine.PipelinedRunner: ``depth`` batch runners whose steps overlap (the next step's bandwidth-heavy front runs
+        beside the current step's latency-bound back)."""
+        if self.training:
+            raise RuntimeError("inference only: call .eval()")
+        W = self._packed("", self.cfg["transformer_architecture"])
+        dev = next(self.parameters()).device
+        return engine.PipelinedRunner(W, self.cfg, batch_pairs, n_src, n_tgt, dev, depth=depth, mid_level=mid_level,
+                                      fps_cluster=fps_cluster)
+
+
 def create_model(config):
     """model/RIGA_v2.py:178-180."""
     return RIGA_v2(config)

@@ -78,3 +78,30 @@ def test_batch_runner_other_baseline_configs(name, n_src, n_tgt, B):
         for k in s:
             assert o[k].shape == s[k].shape and torch.equal(o[k], s[k]), k
     assert sum(int(s["corr_scores"].shape[0]) for s in singles) > 0
+
+
+def test_pipelined_runner_equals_single_pair_forward():
+    """engine.PipelinedRunner: consecutive steps overlap in time (two runners, two graphs, staggered by an external event
+    recorded inside the graph); every step must still return exactly the single-pair forward of its own pairs."""
+    from roitr_b200.engine import BatchRunner
+    N, B = 2048, 2
+    m = model.create_model(CONFIG_3D)
+    m.load_state_dict(weights(1))
+    m = m.to(DEV).eval()
+    batches = [[synthetic_pair(40 + 2 * s + i, N) for i in range(B)] for s in range(5)]
+    singles = [[m(*forward_args(p, DEV)) for p in batch] for batch in batches]
+    pr = m.pipelined_runner(B, N, N, depth=2, mid_level=1)
+    slots = []
+    got = [None] * len(batches)
+    for s, batch in enumerate(batches):
+        slots.append(pr.submit(BatchRunner.collate(batch)))
+        if s >= 1:                       # read step s-1 while step s runs (its slot is reused only at step s+1)
+            pr.wait(slots[s - 1])
+            got[s - 1] = pr.runner(slots[s - 1]).results()
+    pr.wait(slots[-1])
+    got[-1] = pr.runner(slots[-1]).results()
+    for outs, ref in zip(got, singles):
+        for o, r in zip(outs, ref):
+            assert set(o) == set(r)
+            for k in r:
+                assert o[k].shape == r[k].shape and torch.equal(o[k], r[k]), k
