@@ -201,9 +201,9 @@ def op_work(name, ints):
     if name == "roitr_geo_attention_batched":
         b, N, M, C = ints[:4]
         return b * (2.0 * N * M * C * 4 + 4.0 * N * C * 4), 0.0, "hbm"
-    if name == "roitr_fine_matching":
-        P, _, _, C = ints[:4]
-        return P * (2.0 * 64 * C * 4 + 65 * 65 * 4), 0.0, "hbm"
+    if name == "roitr_fine_matching_batched":
+        B, P, _, _, _, _, C = ints[:7]
+        return B * P * (2.0 * 64 * C * 4 + 65 * 65 * 4), 0.0, "hbm"
     return 0.0, 0.0, "hbm"
 
 
@@ -433,7 +433,7 @@ def main():
         named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid_q", "roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build"]),
                  "global_attention_qk_pv": roofline_of(["roitr_gemm_tc_batched"]),
                  "dense_layers": roofline_of(["roitr_linear_tc_packed", "roitr_linear_ln_tc_packed"]),
-                 "fine_matching": roofline_of(["roitr_fine_matching"])}
+                 "fine_matching": roofline_of(["roitr_fine_matching_batched"])}
         line = {
             "metric": METRIC, "value": world * B * steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",

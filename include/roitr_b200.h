@@ -262,47 +262,63 @@ int roitr_geo_attention_batched(int batch, int N, int M, int C, int heads, const
  * Matching head (lib/utils.py:428-471, model/modules.py:10-72,135-178,216-324, model/RIGA_v2.py:150-173).
  * ---------------------------------------------------------------------------------------------------------- */
 
-/* point_to_node_partition (lib/utils.py:448-463): owner (N) int32 = nearest node (matmul-form distance, clamp 1e-12),
- * per node the `limit` nearest of its own points ascending (ties: lower index); unfilled slots = N (pad row) with mask 0.
- * dmin (N) f32 and count (M) int32 are scratch outputs. Masks are bytes (0/1). */
-int roitr_point_to_node(int N, int M, int limit, const float* pts, const float* nodes, int* owner, float* dmin,
-                        int* count, int* knn_idx, unsigned char* knn_mask, unsigned char* node_mask, void* stream);
+/* Every entry point of the matching head takes a leading PAIR dimension B: `B` equally sized problems whose arrays lie
+ * back to back (pair-major, contiguous), served by ONE launch per kernel (blockIdx.y / .z = pair). B = 1 is the single-pair
+ * forward of lib/tester.py:53; the batched runner passes its 16 pairs at once. */
+
+/* point_to_node_partition (lib/utils.py:448-463) for B clouds: pts (B,N,3), nodes (B,M,3) -> owner (B,N) int32 = nearest node
+ * (matmul-form distance, clamp 1e-12, first minimum), dmin (B,N), count (B,M), and per node its `limit` nearest OWN points
+ * sorted by (distance, index): knn_idx (B,M,limit) int32 (pad = N), knn_mask (B,M,limit), node_mask (B,M) bytes. A counting
+ * sort by owner (buckets in `workspace`, roitr_point_to_node_workspace_bytes) lets a node touch only the points it owns. */
+long long roitr_point_to_node_workspace_bytes(int B, int N, int M);
+int roitr_point_to_node_batched(int B, int N, int M, int limit, const float* pts, const float* nodes, int* owner, float* dmin,
+                                int* count, void* workspace, int* knn_idx, unsigned char* knn_mask, unsigned char* node_mask,
+                                void* stream);
 
 /* torch.nonzero replacement: ascending flat indices of the non-zero bytes, at most `capacity` written, the true total in
- * *count (device). chunk_scratch needs roitr_compact_scratch_ints(n) ints. */
+ * *count (device). chunk_scratch needs roitr_compact_scratch_ints(n) ints. The batched form compacts B segments of n flags
+ * each: out (B, max(capacity,1)), count (B), chunk_scratch B * roitr_compact_scratch_ints(n) ints. */
 int roitr_compact_flags(long long n, const unsigned char* flags, int* chunk_scratch, int* out, int capacity, int* count,
                         void* stream);
+int roitr_compact_flags_batched(int B, long long n, const unsigned char* flags, int* chunk_scratch, int* out, int capacity,
+                                int* count, void* stream);
 long long roitr_compact_scratch_ints(long long n);
 
-/* CoarseMatching.forward (model/modules.py:141-178) on (Mr,C) x (Ms,C) L2-normalised descriptors with validity masks:
- * exp(-sqdist), dual normalisation, flat top-k (sorted descending). xy = ref @ src^T (Mr,Ms) is supplied by the caller
- * (roitr_linear). work: Mr*Ms + 2*(Mr+Ms) floats. Outputs padded to k; *out_count = min(k, #valid pairs). k <= 1024. */
-int roitr_coarse_matching(int Mr, int Ms, int C, int k, int dual, const float* ref_feats, const float* src_feats,
-                          const unsigned char* ref_mask, const unsigned char* src_mask, const float* xy, float* work,
-                          int* out_ref, int* out_src, float* out_score, int* out_count, void* stream);
+/* CoarseMatching.forward (model/modules.py:141-178) on (B,Mr,C) x (B,Ms,C) L2-normalised descriptors with validity masks
+ * (B,Mr) / (B,Ms): exp(-sqdist), dual normalisation (fused into the selection kernel), flat top-k (sorted descending, ties
+ * by ascending flat index). xy = ref @ src^T (B,Mr,Ms) is supplied by the caller. work: B * (Mr*Ms + 2*(Mr+Ms)) floats.
+ * Outputs (B,k) padded; out_count (B) = min(k, #valid pairs). k <= 1024. */
+int roitr_coarse_matching_batched(int B, int Mr, int Ms, int C, int k, int dual, const float* ref_feats, const float* src_feats,
+                                  const unsigned char* ref_mask, const unsigned char* src_mask, const float* xy, float* work,
+                                  int* out_ref, int* out_src, float* out_score, int* out_count, void* stream);
 
 /* AdaptiveSuperPointMatching.forward (model/modules.py:81-123, 4DMatch head): sim = sqrt(clamp(2 - 2 a.b, 1e-12)) on valid
  * superpoints; all pairs with sim <= threshold in row-major (torch.nonzero) order, or the min_num smallest (ascending) when
  * fewer than min(min_num, #valid pairs) qualify; scores exp(-sim). Both candidate lists are built on the device and
- * selected from the device-side counts (no host sync). xy = a @ b^T (Ma,Mb). work: 2*Ma*Mb floats + Ma*Mb bytes;
- * iwork: cap + 3*min_num + 4 + roitr_compact_scratch_ints(Ma*Mb) ints. Outputs padded to cap (<= Ma*Mb). min_num <= 1024. */
-int roitr_coarse_matching_adaptive(int Ma, int Mb, int min_num, float threshold, const unsigned char* a_mask,
-                                   const unsigned char* b_mask, const float* xy, float* work, int* iwork, int cap,
-                                   int* out_a, int* out_b, float* out_score, int* out_count, void* stream);
+ * selected from the device-side counts (no host sync). xy = a @ b^T (B,Ma,Mb). work: B * (2*Ma*Mb floats + Ma*Mb bytes
+ * rounded up to floats); iwork: B * (cap + 3*min_num + 4 + roitr_compact_scratch_ints(Ma*Mb)) ints. Outputs (B,cap) padded
+ * (cap <= Ma*Mb). min_num <= 1024. */
+int roitr_coarse_matching_adaptive_batched(int B, int Ma, int Mb, int min_num, float threshold, const unsigned char* a_mask,
+                                           const unsigned char* b_mask, const float* xy, float* work, int* iwork, int cap,
+                                           int* out_a, int* out_b, float* out_score, int* out_count, void* stream);
 
-/* One CTA per superpoint correspondence p < *corr_count: gather the two 64-point patches' descriptors, scores =
- * Ft Fs^T / sqrt(C) (RIGA_v2.py:150-152), LearnableLogOptimalTransport (modules.py:28-68, num_iter Sinkhorn iterations
- * in shared memory) -> scores (Pmax,65,65); then FineMatching.compute_correspondence_matrix (modules.py:242-274) ->
- * flags (Pmax,64,64) bytes. */
-int roitr_fine_matching(int Pmax, int Nt, int Ns, int C, const float* tgt_feat, const float* src_feat, const int* tgt_knn,
-                        const int* src_knn, const unsigned char* tgt_kmask, const unsigned char* src_kmask,
-                        const int* corr_t, const int* corr_s, const int* corr_count, const float* alpha, int num_iter,
-                        int topk, int mutual, float threshold, float* scores, unsigned char* flags, void* stream);
+/* One CTA per superpoint correspondence p < corr_count[pair]: gather the two 64-point patches' descriptors, scores =
+ * Ft Fs^T / sqrt(C) (RIGA_v2.py:150-152; 32-term chunks summed into a compensated total), LearnableLogOptimalTransport
+ * (modules.py:28-68, num_iter Sinkhorn iterations in registers / shared memory) -> scores (B,Pmax,65,65); then
+ * FineMatching.compute_correspondence_matrix (modules.py:242-274) -> flags (B,Pmax,64,64) bytes. tgt_feat (B,Nt,C),
+ * src_feat (B,Ns,C), tgt_knn / tgt_kmask (B,Mt,64), src_knn / src_kmask (B,Ms,64), corr_t / corr_s (B,Pmax), corr_count (B). */
+int roitr_fine_matching_batched(int B, int Pmax, int Mt, int Ms, int Nt, int Ns, int C, const float* tgt_feat,
+                                const float* src_feat, const int* tgt_knn, const int* src_knn, const unsigned char* tgt_kmask,
+                                const unsigned char* src_kmask, const int* corr_t, const int* corr_s, const int* corr_count,
+                                const float* alpha, int num_iter, int topk, int mutual, float threshold, float* scores,
+                                unsigned char* flags, void* stream);
 
-/* FineMatching.extract_correspondences (modules.py:276-283) from the compacted flat (p,row,col) indices. */
-int roitr_fine_gather(int capacity, const int* flat, const int* count, const float* scores, const int* corr_t,
-                      const int* corr_s, const int* tgt_knn, const int* src_knn, const float* tgt_pts,
-                      const float* src_pts, float* out_t, float* out_s, float* out_score, void* stream);
+/* FineMatching.extract_correspondences (modules.py:276-283) from the compacted flat (p,row,col) indices: flat (B,capacity),
+ * count (B), tgt_pts (B,Nt1,3) / src_pts (B,Ns1,3) -> out_t / out_s (B,capacity,3), out_score (B,capacity). */
+int roitr_fine_gather_batched(int B, int capacity, int Pmax, int Mt, int Ms, int Nt1, int Ns1, const int* flat, const int* count,
+                              const float* scores, const int* corr_t, const int* corr_s, const int* tgt_knn, const int* src_knn,
+                              const float* tgt_pts, const float* src_pts, float* out_t, float* out_s, float* out_score,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Ground-truth bookkeeping that RIGA_v2.forward runs in test mode too (lib/utils.py:474-614).
@@ -314,19 +330,20 @@ int roitr_pad_transform(int N, const float* pts, const float* rot, const float* 
 int roitr_pad_transform_batched(int B, int N, const float* pts, const float* rot, const float* trans, float* out,
                                 void* stream);
 
-/* get_node_occlusion_score tail (lib/utils.py:511-526) given the 1-NN distances of the padded clouds. */
-int roitr_node_occlusion(int M, int K, const int* knn, const unsigned char* kmask, const unsigned char* nmask,
-                         const float* nn_dist, float thr, float* occ, void* stream);
+/* get_node_occlusion_score tail (lib/utils.py:511-526) given the 1-NN distances of the padded clouds: knn / kmask (B,M,K),
+ * nmask (B,M), nn_dist (B,nn_stride) -> occ (B,M). */
+int roitr_node_occlusion_batched(int B, int M, int K, int nn_stride, const int* knn, const unsigned char* kmask,
+                                 const unsigned char* nmask, const float* nn_dist, float thr, float* occ, void* stream);
 
-/* get_node_correspondences (lib/utils.py:562-606): dense (Mr,Ms) overlap ratios and >0 flags (compact them with
- * roitr_compact_flags, then roitr_corr_gather). work: 4*(Mr+Ms) floats. K = 64. */
-int roitr_node_overlaps(int Mr, int Ms, int K, int Nr, int Nsrc, const float* ref_nodes, const float* src_nodes,
-                        const int* ref_knn, const int* src_knn, const unsigned char* ref_kmask,
-                        const unsigned char* src_kmask, const unsigned char* ref_mask, const unsigned char* src_mask,
-                        const float* ref_pts, const float* src_pts, const float* rot, const float* trans, float radius,
-                        float* work, float* overlap, unsigned char* flag, void* stream);
-int roitr_corr_gather(int capacity, int Ms, const int* flat, const int* count, const float* overlap, long long* out_idx,
-                      float* out_ov, void* stream);
+/* get_node_correspondences (lib/utils.py:562-606): dense (B,Mr,Ms) overlap ratios and >0 flags (compact them with
+ * roitr_compact_flags_batched, then roitr_corr_gather_batched). rot (B,3,3), trans (B,3). work: B * 4*(Mr+Ms) floats. K = 64. */
+int roitr_node_overlaps_batched(int B, int Mr, int Ms, int K, int Nr, int Nsrc, const float* ref_nodes, const float* src_nodes,
+                                const int* ref_knn, const int* src_knn, const unsigned char* ref_kmask,
+                                const unsigned char* src_kmask, const unsigned char* ref_mask, const unsigned char* src_mask,
+                                const float* ref_pts, const float* src_pts, const float* rot, const float* trans, float radius,
+                                float* work, float* overlap, unsigned char* flag, void* stream);
+int roitr_corr_gather_batched(int B, int capacity, int Mr, int Ms, const int* flat, const int* count, const float* overlap,
+                              long long* out_idx, float* out_ov, void* stream);
 
 /* Weighted Procrustes (lib/utils.py:159-218): per batch item the rigid transform (R (3,3) row-major, t (3)) that maps the
  * src points (batch, n, 3) onto the tgt points under the weights (batch, n) (NULL = all ones; weights below weight_thresh

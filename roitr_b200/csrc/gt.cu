@@ -46,10 +46,14 @@ __global__ void pad_transform_kernel(int N, const float* __restrict__ pts, const
 
 // occ[node] = node_mask * sum_j (nn_dist[knn[node,j]] < thr) * kmask / (sum_j kmask + 1e-10)     (lib/utils.py:511-526)
 __global__ void node_occ_kernel(int M, int K, const int* __restrict__ knn, const unsigned char* __restrict__ kmask,
-                                const unsigned char* __restrict__ nmask, const float* __restrict__ nn_dist, float thr,
-                                float* __restrict__ occ) {
+                                const unsigned char* __restrict__ nmask, const float* __restrict__ nn_dist, int nn_stride,
+                                float thr, float* __restrict__ occ) {
     const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (node >= M) return;
+    {   // blockIdx.y = pair: knn / kmask (B,M,K), nmask / occ (B,M), nn_dist (B, nn_stride)
+        const size_t b = blockIdx.y;
+        knn += b * M * K; kmask += b * M * K; nmask += b * M; occ += b * M; nn_dist += b * nn_stride;
+    }
     float hit = 0.f, cnt = 0.f;
     for (int j = lane; j < K; j += 32) {
         const float mk = kmask[(size_t)node * K + j] ? 1.f : 0.f;
@@ -68,6 +72,11 @@ __global__ void node_radius_kernel(int M, int K, int N, const float* __restrict_
                                    float* __restrict__ nodes_out, float* __restrict__ radius) {
     const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (node >= M) return;
+    {   // blockIdx.y = pair
+        const size_t b = blockIdx.y;
+        nodes += b * M * 3; knn += b * M * K; kmask += b * M * K; pts += b * N * 3; nodes_out += b * M * 3; radius += b * M;
+        if (rot) { rot += b * 9; trans += b * 3; }
+    }
     float R[9], t[3];
     if (rot) {
 #pragma unroll
@@ -113,6 +122,12 @@ __global__ void __launch_bounds__(64) node_overlap_kernel(int Mr, int Ms, int K,
                                                           float radius, float radius2, float* __restrict__ overlap,
                                                           unsigned char* __restrict__ flag) {
     const int i = blockIdx.y, j = blockIdx.x, tid = threadIdx.x;
+    {   // blockIdx.z = pair
+        const size_t b = blockIdx.z;
+        rnodes += b * Mr * 3; snodes_t += b * Ms * 3; rrad += b * Mr; srad += b * Ms; rmask += b * Mr; smask += b * Ms;
+        rknn += b * Mr * K; sknn += b * Ms * K; rkmask += b * Mr * K; skmask += b * Ms * K; rpts += b * Nr * 3; spts += b * Nsrc * 3;
+        rot += b * 9; trans += b * 3; overlap += b * Mr * Ms; flag += b * Mr * Ms;
+    }
     const size_t e = (size_t)i * Ms + j;
     bool go = rmask[i] && smask[j];
     if (go) {
@@ -161,10 +176,14 @@ __global__ void __launch_bounds__(64) node_overlap_kernel(int Mr, int Ms, int K,
     }
 }
 
-__global__ void corr_gather_kernel(const int* __restrict__ flat, const int* __restrict__ count, int capacity, int Ms,
+__global__ void corr_gather_kernel(const int* __restrict__ flat, const int* __restrict__ count, int capacity, int Ms, long long stride,
                                    const float* __restrict__ overlap, long long* __restrict__ out_idx,
                                    float* __restrict__ out_ov) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    {   // blockIdx.y = pair: flat / out (B, capacity), overlap (B, Mr*Ms = stride)
+        const size_t b = blockIdx.y;
+        flat += b * capacity; count += b; overlap += b * stride; out_idx += b * capacity * 2; out_ov += b * capacity;
+    }
     if (i >= min(__ldg(count), capacity)) return;
     const int f = __ldg(flat + i);
     out_idx[2 * (size_t)i] = f / Ms;
@@ -187,34 +206,36 @@ extern "C" int roitr_pad_transform(int N, const float* pts, const float* rot, co
     return roitr_pad_transform_batched(1, N, pts, rot, trans, out, stream);
 }
 
-extern "C" int roitr_node_occlusion(int M, int K, const int* knn, const unsigned char* kmask, const unsigned char* nmask,
-                                    const float* nn_dist, float thr, float* occ, void* stream) {
-    ROITR_CHECK_ARG(M >= 1 && K >= 1 && knn && kmask && nmask && nn_dist && occ, "node_occlusion: bad arguments");
-    node_occ_kernel<<<ceil_div(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(M, K, knn, kmask, nmask, nn_dist, thr, occ);
+extern "C" int roitr_node_occlusion_batched(int B, int M, int K, int nn_stride, const int* knn, const unsigned char* kmask,
+                                            const unsigned char* nmask, const float* nn_dist, float thr, float* occ,
+                                            void* stream) {
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && M >= 1 && K >= 1 && knn && kmask && nmask && nn_dist && occ, "node_occlusion: bad arguments");
+    node_occ_kernel<<<dim3(ceil_div(M * 32, 256), B), 256, 0, (cudaStream_t)stream>>>(M, K, knn, kmask, nmask, nn_dist, nn_stride, thr, occ);
     ROITR_CHECK_LAUNCH("node_occ_kernel");
     return ROITR_OK;
 }
 
-extern "C" int roitr_node_overlaps(int Mr, int Ms, int K, int Nr, int Nsrc, const float* ref_nodes,
-                                   const float* src_nodes, const int* ref_knn, const int* src_knn,
-                                   const unsigned char* ref_kmask, const unsigned char* src_kmask,
-                                   const unsigned char* ref_mask, const unsigned char* src_mask, const float* ref_pts,
-                                   const float* src_pts, const float* rot, const float* trans, float radius,
-                                   float* work, float* overlap, unsigned char* flag, void* stream) {
-    // work: 4*Ms + Mr + 3*Mr floats
+extern "C" int roitr_node_overlaps_batched(int B, int Mr, int Ms, int K, int Nr, int Nsrc, const float* ref_nodes,
+                                           const float* src_nodes, const int* ref_knn, const int* src_knn,
+                                           const unsigned char* ref_kmask, const unsigned char* src_kmask,
+                                           const unsigned char* ref_mask, const unsigned char* src_mask, const float* ref_pts,
+                                           const float* src_pts, const float* rot, const float* trans, float radius,
+                                           float* work, float* overlap, unsigned char* flag, void* stream) {
+    // work: B * (4*Ms + 4*Mr) floats
     ROITR_CHECK_ARG(K == 64, "node_overlaps: point_per_patch must be 64, got %d", K);
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && Mr <= 65535, "node_overlaps: bad sizes");
     ROITR_CHECK_ARG(ref_nodes && src_nodes && ref_knn && src_knn && rot && trans && work && overlap && flag, "node_overlaps: null");
     cudaStream_t st = (cudaStream_t)stream;
     float* snodes_t = work;
-    float* srad = snodes_t + 3 * (size_t)Ms;
-    float* rnodes_c = srad + Ms;
-    float* rrad = rnodes_c + 3 * (size_t)Mr;
-    node_radius_kernel<<<ceil_div(Mr * 32, 256), 256, 0, st>>>(Mr, K, Nr, ref_nodes, ref_knn, ref_kmask, ref_pts, nullptr,
-                                                              nullptr, rnodes_c, rrad);
-    node_radius_kernel<<<ceil_div(Ms * 32, 256), 256, 0, st>>>(Ms, K, Nsrc, src_nodes, src_knn, src_kmask, src_pts, rot,
-                                                              trans, snodes_t, srad);
+    float* srad = snodes_t + 3 * (size_t)B * Ms;
+    float* rnodes_c = srad + (size_t)B * Ms;
+    float* rrad = rnodes_c + 3 * (size_t)B * Mr;
+    node_radius_kernel<<<dim3(ceil_div(Mr * 32, 256), B), 256, 0, st>>>(Mr, K, Nr, ref_nodes, ref_knn, ref_kmask, ref_pts, nullptr,
+                                                                        nullptr, rnodes_c, rrad);
+    node_radius_kernel<<<dim3(ceil_div(Ms * 32, 256), B), 256, 0, st>>>(Ms, K, Nsrc, src_nodes, src_knn, src_kmask, src_pts, rot,
+                                                                        trans, snodes_t, srad);
     const double r2 = (double)radius * (double)radius;  // pos_radius ** 2 in double, then cast (lib/utils.py:597)
-    dim3 grid(Ms, Mr);
+    dim3 grid(Ms, Mr, B);
     node_overlap_kernel<<<grid, 64, 0, st>>>(Mr, Ms, K, Nr, Nsrc, rnodes_c, snodes_t, rrad, srad, ref_mask, src_mask,
                                              ref_knn, src_knn, ref_kmask, src_kmask, ref_pts, src_pts, rot, trans,
                                              radius, (float)r2, overlap, flag);
@@ -222,11 +243,12 @@ extern "C" int roitr_node_overlaps(int Mr, int Ms, int K, int Nr, int Nsrc, cons
     return ROITR_OK;
 }
 
-extern "C" int roitr_corr_gather(int capacity, int Ms, const int* flat, const int* count, const float* overlap,
-                                 long long* out_idx, float* out_ov, void* stream) {
+extern "C" int roitr_corr_gather_batched(int B, int capacity, int Mr, int Ms, const int* flat, const int* count,
+                                         const float* overlap, long long* out_idx, float* out_ov, void* stream) {
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && capacity >= 0, "corr_gather: bad sizes");
     if (capacity == 0) return ROITR_OK;
-    corr_gather_kernel<<<ceil_div(capacity, 256), 256, 0, (cudaStream_t)stream>>>(flat, count, capacity, Ms, overlap,
-                                                                                  out_idx, out_ov);
+    corr_gather_kernel<<<dim3(ceil_div(capacity, 256), B), 256, 0, (cudaStream_t)stream>>>(flat, count, capacity, Ms, (long long)Mr * Ms,
+                                                                                           overlap, out_idx, out_ov);
     ROITR_CHECK_LAUNCH("corr_gather_kernel");
     return ROITR_OK;
 }

@@ -20,10 +20,15 @@ __device__ __forceinline__ float sumsq3(float x, float y, float z) {
 }
 
 // ------------------------------------------------------------------------------------------------ partition
+// All kernels of the head take a leading PAIR (cloud) dimension: blockIdx.y (or .z) selects one of `B` equally sized
+// problems whose arrays lie back to back, so one launch serves every pair of a batch (B = 1: the single-pair forward).
+//
 // owner[p] = argmin_nodes d(node, p) (first minimum), dmin[p] = that distance, count[node]++.
 __global__ void point_owner_kernel(int N, int M, const float* __restrict__ pts, const float* __restrict__ nodes,
                                    int* __restrict__ owner, float* __restrict__ dmin, int* __restrict__ count) {
     extern __shared__ float sn[];  // M x 4: x, y, z, |n|^2
+    const size_t cloud = blockIdx.y;
+    pts += cloud * N * 3; nodes += cloud * M * 3; owner += cloud * N; dmin += cloud * N; count += cloud * M;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         const float x = __ldg(nodes + 3 * i), y = __ldg(nodes + 3 * i + 1), z = __ldg(nodes + 3 * i + 2);
         sn[4 * i] = x; sn[4 * i + 1] = y; sn[4 * i + 2] = z; sn[4 * i + 3] = sumsq3(x, y, z);
@@ -46,6 +51,45 @@ __global__ void point_owner_kernel(int N, int M, const float* __restrict__ pts, 
     atomicAdd(count + bi, 1);
 }
 
+// start[node] = exclusive prefix sum of count over the nodes of one cloud (one CTA per cloud; M is a few hundred)
+__global__ void __launch_bounds__(1024) node_start_kernel(int M, const int* __restrict__ count, int* __restrict__ start) {
+    __shared__ int buf[1024];
+    __shared__ int carry;
+    const size_t cloud = blockIdx.x;
+    count += cloud * M; start += cloud * M;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < M; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < M ? count[i] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < M) start[i] = carry + buf[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += buf[1023];
+        __syncthreads();
+    }
+}
+
+// counting-sort scatter: every point drops its (distance bits, index) key into its owner's bucket (slot order inside a
+// bucket is arbitrary; the per-node sort below orders it)
+__global__ void node_bucket_kernel(int N, int M, const int* __restrict__ owner, const float* __restrict__ dmin,
+                                   const int* __restrict__ start, int* __restrict__ cursor,
+                                   unsigned long long* __restrict__ bucket) {
+    const size_t cloud = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int o = __ldg(owner + cloud * N + p);
+    const int slot = __ldg(start + cloud * M + o) + atomicAdd(cursor + cloud * M + o, 1);
+    bucket[cloud * N + slot] = ((unsigned long long)__float_as_uint(__ldg(dmin + cloud * N + p)) << 32) | (unsigned)p;
+}
+
 __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* a, int n, int tid, int nthreads) {
     for (int k = 2; k <= n; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -61,35 +105,33 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* a, int n, i
         }
 }
 
-// per node: its own points sorted by (distance, index), first `limit` kept (topk(k=limit, largest=False), :459);
-// remaining slots = N (the pad row) with mask false.
+// per node: its own points (its bucket) sorted by (distance, index), first `limit` kept (topk(k=limit, largest=False),
+// :459); remaining slots = N (the pad row) with mask false. The reference scans a masked (M,N) matrix per node; here a
+// node touches only the ~N/M points it owns.
 constexpr int PART_CAP = 4096;
-__global__ void __launch_bounds__(256) node_knn_kernel(int N, int M, int limit, const int* __restrict__ owner,
-                                                       const float* __restrict__ dmin, const int* __restrict__ count,
+__global__ void __launch_bounds__(256) node_knn_kernel(int N, int M, int limit, const int* __restrict__ count,
+                                                       const int* __restrict__ start,
+                                                       const unsigned long long* __restrict__ bucket,
                                                        int* __restrict__ knn_idx, unsigned char* __restrict__ knn_mask,
                                                        unsigned char* __restrict__ node_mask) {
     __shared__ unsigned long long keys[PART_CAP];
-    __shared__ int s_n;
+    const size_t cloud = blockIdx.y;
     const int node = blockIdx.x, tid = threadIdx.x;
-    const int cnt = __ldg(count + node);
-    if (tid == 0) { s_n = 0; node_mask[node] = cnt > 0; }
-    __syncthreads();
+    const int cnt = __ldg(count + cloud * M + node);
+    const unsigned long long* mine = bucket + cloud * N + __ldg(start + cloud * M + node);
+    knn_idx += (cloud * M + node) * (size_t)limit;
+    knn_mask += (cloud * M + node) * (size_t)limit;
+    if (tid == 0) node_mask[cloud * M + node] = cnt > 0;
     if (cnt <= PART_CAP) {
-        for (int p = tid; p < N; p += blockDim.x)
-            if (__ldg(owner + p) == node) {
-                const int slot = atomicAdd(&s_n, 1);
-                keys[slot] = ((unsigned long long)__float_as_uint(__ldg(dmin + p)) << 32) | (unsigned)p;
-            }
-        __syncthreads();
         int n2 = 64;
         while (n2 < cnt) n2 <<= 1;
-        for (int i = cnt + tid; i < n2; i += blockDim.x) keys[i] = ~0ull;
+        for (int i = tid; i < n2; i += blockDim.x) keys[i] = i < cnt ? mine[i] : ~0ull;
         __syncthreads();
         bitonic_sort_u64(keys, n2, tid, blockDim.x);
         for (int j = tid; j < limit; j += blockDim.x) {
             const bool ok = j < cnt;
-            knn_idx[(size_t)node * limit + j] = ok ? (int)(keys[j] & 0xffffffffu) : N;
-            knn_mask[(size_t)node * limit + j] = ok;
+            knn_idx[j] = ok ? (int)(keys[j] & 0xffffffffu) : N;
+            knn_mask[j] = ok;
         }
     } else {
         // pathological node owning more than PART_CAP points: `limit` rounds of "smallest key greater than the last"
@@ -98,24 +140,20 @@ __global__ void __launch_bounds__(256) node_knn_kernel(int N, int M, int limit, 
         bool first = true;
         for (int j = 0; j < limit; ++j) {
             unsigned long long best = ~0ull;
-            for (int p = tid; p < N; p += blockDim.x)
-                if (__ldg(owner + p) == node) {
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(__ldg(dmin + p)) << 32) | (unsigned)p;
-                    if ((first || key > last) && key < best) best = key;
-                }
+            for (int i = tid; i < cnt; i += blockDim.x) {
+                const unsigned long long key = mine[i];
+                if ((first || key > last) && key < best) best = key;
+            }
             red[tid] = best;
             __syncthreads();
-            for (int s = 128; s > 0; s >>= 1) {
-                if (tid < s && red[tid + s] < red[tid]) red[tid] = red[tid + s];
+            for (int s2 = 128; s2 > 0; s2 >>= 1) {
+                if (tid < s2 && red[tid + s2] < red[tid]) red[tid] = red[tid + s2];
                 __syncthreads();
             }
             last = red[0];
             first = false;
             __syncthreads();
-            if (tid == 0) {
-                knn_idx[(size_t)node * limit + j] = (int)(last & 0xffffffffu);
-                knn_mask[(size_t)node * limit + j] = 1;
-            }
+            if (tid == 0) { knn_idx[j] = (int)(last & 0xffffffffu); knn_mask[j] = 1; }
         }
     }
 }
@@ -123,7 +161,10 @@ __global__ void __launch_bounds__(256) node_knn_kernel(int N, int M, int limit, 
 // ------------------------------------------------------------------------------------------------ ordered compaction
 // out = flat indices of the non-zero flags in ascending order (torch.nonzero order). Three passes.
 constexpr int CMP_CHUNK = 2048;
+// blockIdx.y = segment: `n` flags per segment, ceil(n / CMP_CHUNK) chunk counters per segment, `capacity` outputs per segment
 __global__ void compact_count_kernel(long long n, const unsigned char* __restrict__ flags, int* __restrict__ chunk_count) {
+    flags += (size_t)blockIdx.y * n;
+    chunk_count += (size_t)blockIdx.y * gridDim.x;
     const long long base = (long long)blockIdx.x * CMP_CHUNK;
     int c = 0;
     for (int i = threadIdx.x; i < CMP_CHUNK; i += blockDim.x)
@@ -139,7 +180,8 @@ __global__ void compact_count_kernel(long long n, const unsigned char* __restric
     }
 }
 __global__ void compact_scan_kernel(int nchunks, int* __restrict__ chunk_count, int* __restrict__ total) {
-    // single CTA exclusive scan (nchunks is small: n / 2048)
+    // one CTA per segment: exclusive scan (nchunks is small: n / 2048)
+    chunk_count += (size_t)blockIdx.x * nchunks;
     __shared__ int carry;
     __shared__ int buf[1024];
     if (threadIdx.x == 0) carry = 0;
@@ -160,11 +202,14 @@ __global__ void compact_scan_kernel(int nchunks, int* __restrict__ chunk_count, 
         if (threadIdx.x == 0) carry += buf[1023];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (threadIdx.x == 0) total[blockIdx.x] = carry;
 }
 __global__ void compact_write_kernel(long long n, const unsigned char* __restrict__ flags,
                                      const int* __restrict__ chunk_offset, int* __restrict__ out, int capacity) {
     // 256 threads, each owns 8 consecutive flags of the chunk -> order preserved
+    flags += (size_t)blockIdx.y * n;
+    chunk_offset += (size_t)blockIdx.y * gridDim.x;
+    out += (size_t)blockIdx.y * (capacity > 0 ? capacity : 1);
     const long long base = (long long)blockIdx.x * CMP_CHUNK + threadIdx.x * 8;
     int c = 0;
     unsigned bits = 0;
@@ -198,12 +243,14 @@ __global__ void row_sqnorm_kernel(int M, int C, const float* __restrict__ f, flo
     s = warp_sum(s);
     if (lane == 0) out[row] = s;
 }
-// s_ij = exp(-sqdist) on valid (i,j), else 0; one CTA per row, also the row sum (modules.py:163)
+// s_ij = exp(-sqdist) on valid (i,j), else 0; one CTA per row (blockIdx.y = pair), also the row sum (modules.py:163)
 __global__ void coarse_exp_kernel(int Mr, int Ms, const float* __restrict__ xy, const float* __restrict__ r2,
                                   const float* __restrict__ s2, const unsigned char* __restrict__ rmask,
                                   const unsigned char* __restrict__ smask, float* __restrict__ S,
                                   float* __restrict__ rowsum) {
     const int i = blockIdx.x;
+    const size_t b = blockIdx.y;
+    xy += b * Mr * Ms; S += b * Mr * Ms; r2 += b * Mr; s2 += b * Ms; rmask += b * Mr; smask += b * Ms; rowsum += b * Mr;
     __shared__ float red[8];
     float acc = 0.f;
     const bool rv = rmask[i];
@@ -225,28 +272,39 @@ __global__ void coarse_exp_kernel(int Mr, int Ms, const float* __restrict__ xy, 
 __global__ void col_sum_kernel(int Mr, int Ms, const float* __restrict__ S, float* __restrict__ colsum) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Ms) return;
+    S += (size_t)blockIdx.y * Mr * Ms;
     float t = 0.f;
     for (int i = 0; i < Mr; ++i) t += __ldg(S + (size_t)i * Ms + j);
-    colsum[j] = t;
-}
-// dual normalisation (modules.py:166-169); invalid entries get -1 so they are never selected
-__global__ void coarse_dualnorm_kernel(int Mr, int Ms, float* __restrict__ S, const float* __restrict__ rowsum,
-                                       const float* __restrict__ colsum, const unsigned char* __restrict__ rmask,
-                                       const unsigned char* __restrict__ smask, int dual) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long long)Mr * Ms) return;
-    const int i = (int)(e / Ms), j = (int)(e % Ms);
-    if (!(rmask[i] && smask[j])) { S[e] = -1.f; return; }
-    const float s = S[e];
-    if (dual) S[e] = __fmul_rn(__fdiv_rn(s, __fadd_rn(rowsum[i], 1e-8f)), __fdiv_rn(s, __fadd_rn(colsum[j], 1e-8f)));
+    colsum[(size_t)blockIdx.y * Ms + j] = t;
 }
 
-// Flat top-k (largest, sorted descending; ties by ascending flat index) of n floats >= 0 (entries < 0 are excluded),
-// single CTA of 1024 threads: 4 x 8-bit radix-select passes for the k-th value, collect, bitonic sort.
+// Flat top-k (largest, sorted descending; ties by ascending flat index) of n floats >= 0 (entries < 0 are excluded), one
+// CTA of 1024 threads per pair (blockIdx.x): 4 x 8-bit radix-select passes for the k-th value, collect, bitonic sort.
+// With `dn` the kernel first applies the dual normalisation of modules.py:166-169 in place (row / column sums from
+// coarse_exp / col_sum; invalid entries become -1 so they are never selected), which used to be a launch of its own.
+struct DualNorm {
+    const float* rowsum; const float* colsum; const unsigned char* rmask; const unsigned char* smask;
+    int Mr, Ms, dual;
+};
 constexpr int TOPK_MAX = 1024;
-__global__ void __launch_bounds__(1024) flat_topk_kernel(int n, int k, const float* __restrict__ v, int row_len,
+__global__ void __launch_bounds__(1024) flat_topk_kernel(int n, int k, float* __restrict__ v, int row_len,
                                                          int* __restrict__ out_row, int* __restrict__ out_col,
-                                                         float* __restrict__ out_val, int* __restrict__ out_count) {
+                                                         float* __restrict__ out_val, int* __restrict__ out_count,
+                                                         int out_stride, DualNorm dn) {
+    {
+        const size_t b = blockIdx.x;
+        v += b * n; out_row += b * out_stride; out_col += b * out_stride; out_val += b * out_stride; out_count += b;
+        if (dn.rowsum) { dn.rowsum += b * dn.Mr; dn.colsum += b * dn.Ms; dn.rmask += b * dn.Mr; dn.smask += b * dn.Ms; }
+    }
+    if (dn.rowsum) {
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int i = e / dn.Ms, j = e % dn.Ms;
+            if (!(dn.rmask[i] && dn.smask[j])) { v[e] = -1.f; continue; }
+            const float sv = v[e];
+            if (dn.dual) v[e] = __fmul_rn(__fdiv_rn(sv, __fadd_rn(dn.rowsum[i], 1e-8f)), __fdiv_rn(sv, __fadd_rn(dn.colsum[j], 1e-8f)));
+        }
+        __syncthreads();
+    }
     __shared__ unsigned hist[256];
     __shared__ unsigned s_prefix, s_remaining;
     __shared__ int s_valid, s_cnt;
@@ -256,7 +314,7 @@ __global__ void __launch_bounds__(1024) flat_topk_kernel(int n, int k, const flo
     if (tid == 0) { s_valid = 0; s_cnt = 0; }
     __syncthreads();
     int c = 0;
-    for (int i = tid; i < n; i += blockDim.x) c += (__ldg(v + i) >= 0.f);
+    for (int i = tid; i < n; i += blockDim.x) c += (v[i] >= 0.f);
     atomicAdd(&s_valid, c);
     __syncthreads();
     const int kk = min(k, s_valid);
@@ -270,7 +328,7 @@ __global__ void __launch_bounds__(1024) flat_topk_kernel(int n, int k, const flo
         const unsigned prefix = s_prefix;
         const unsigned himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
         for (int i = tid; i < n; i += blockDim.x) {
-            const float f = __ldg(v + i);
+            const float f = v[i];
             if (f < 0.f) continue;
             const unsigned b = __float_as_uint(f);
             if ((b & himask) == (prefix & himask)) atomicAdd(&hist[(b >> shift) & 255u], 1u);
@@ -292,7 +350,7 @@ __global__ void __launch_bounds__(1024) flat_topk_kernel(int n, int k, const flo
     const unsigned need_eq = s_remaining; // how many entries equal to the pivot are taken (lowest flat index first)
     // entries strictly greater than the pivot
     for (int i = tid; i < n; i += blockDim.x) {
-        const float f = __ldg(v + i);
+        const float f = v[i];
         if (f >= 0.f && __float_as_uint(f) > pivot) {
             const int s = atomicAdd(&s_cnt, 1);
             keys[s] = ((unsigned long long)(~__float_as_uint(f)) << 32) | (unsigned)i;  // ascending sort == descending value
@@ -305,7 +363,7 @@ __global__ void __launch_bounds__(1024) flat_topk_kernel(int n, int k, const flo
     if (tid == 0) s_eq = 0;
     __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) {
-        const float f = __ldg(v + i);
+        const float f = v[i];
         if (f >= 0.f && __float_as_uint(f) == pivot) {
             const int s = atomicAdd(&s_eq, 1);
             if (s < TOPK_MAX) eq_idx[s] = (unsigned)i;
@@ -326,7 +384,7 @@ __global__ void __launch_bounds__(1024) flat_topk_kernel(int n, int k, const flo
     } else if (tid == 0) {  // massive ties (e.g. constant scores): sequential walk in index order
         unsigned taken = 0;
         for (int i = 0; i < n && taken < need_eq; ++i)
-            if (__ldg(v + i) >= 0.f && __float_as_uint(__ldg(v + i)) == pivot) {
+            if (v[i] >= 0.f && __float_as_uint(v[i]) == pivot) {
                 keys[base_cnt + taken] = ((unsigned long long)(~pivot) << 32) | (unsigned)i;
                 ++taken;
             }
@@ -361,6 +419,7 @@ struct FineParams {
     unsigned char* flags;        // (Pmax, 64, 64)
     int num_iter, topk, mutual;
     float threshold, sqrt_c;
+    int Pmax, Mt, Ms;            // batched launch (blockIdx.y = pair): per-pair strides of every array above
 };
 
 constexpr int FP = 64, FP1 = 65;
@@ -382,7 +441,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 
 constexpr int FT = 288, FW = FT / 32;      // 8 warps own rows/columns 0..63 (4 threads each), warp 8 owns the dustbin row/column
 
-__global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
+__global__ void __launch_bounds__(FT, 3) fine_patch_kernel(FineParams P) {
     __shared__ float Z[FP1 * FP1];
     __shared__ __align__(16) float At[32][FP + 4];
     __shared__ __align__(16) float Bs[32][FP + 4];
@@ -394,6 +453,13 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
     __shared__ float s_norm;
 
     const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {   // blockIdx.y = pair of the batch: every per-pair array advances by its own size
+        const size_t b = blockIdx.y;
+        P.corr_count += b; P.corr_t += b * P.Pmax; P.corr_s += b * P.Pmax;
+        P.tgt_knn += b * P.Mt * FP; P.src_knn += b * P.Ms * FP; P.tgt_kmask += b * P.Mt * FP; P.src_kmask += b * P.Ms * FP;
+        P.tgt_feat += b * P.Nt * P.C; P.src_feat += b * P.Ns * P.C;
+        P.scores += b * P.Pmax * FP1 * FP1; P.flags += b * P.Pmax * FP * FP;
+    }
     if (p >= __ldg(P.corr_count)) return;
     const int nt = __ldg(P.corr_t + p), ns = __ldg(P.corr_s + p);
     if (tid < FP) {
@@ -632,13 +698,20 @@ __global__ void __launch_bounds__(FT, 3) fine_patch_kernel(const FineParams P) {
     }
 }
 
-// gather the final correspondences from the compacted flat indices (modules.py:276-283)
+// gather the final correspondences from the compacted flat indices (modules.py:276-283); blockIdx.y = pair
+struct FineGatherStrides { int Pmax, Mt, Ms, Nt1, Ns1; };     // Nt1 / Ns1: rows of the per-pair (padded) point arrays
 __global__ void fine_gather_kernel(const int* __restrict__ flat, const int* __restrict__ count, int capacity,
                                    const float* __restrict__ scores, const int* __restrict__ corr_t,
                                    const int* __restrict__ corr_s, const int* __restrict__ tgt_knn,
                                    const int* __restrict__ src_knn, const float* __restrict__ tgt_pts,
                                    const float* __restrict__ src_pts, float* __restrict__ out_t,
-                                   float* __restrict__ out_s, float* __restrict__ out_score) {
+                                   float* __restrict__ out_s, float* __restrict__ out_score, FineGatherStrides S) {
+    {
+        const size_t b = blockIdx.y;
+        flat += b * capacity; count += b; scores += b * S.Pmax * FP1 * FP1; corr_t += b * S.Pmax; corr_s += b * S.Pmax;
+        tgt_knn += b * S.Mt * FP; src_knn += b * S.Ms * FP; tgt_pts += b * S.Nt1 * 3; src_pts += b * S.Ns1 * 3;
+        out_t += b * capacity * 3; out_s += b * capacity * 3; out_score += b * capacity;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(__ldg(count), capacity);
     if (i >= n) return;
@@ -656,95 +729,117 @@ __global__ void fine_gather_kernel(const int* __restrict__ flat, const int* __re
 
 }  // namespace
 
-extern "C" int roitr_point_to_node(int N, int M, int limit, const float* pts, const float* nodes, int* owner,
-                                   float* dmin, int* count, int* knn_idx, unsigned char* knn_mask,
-                                   unsigned char* node_mask, void* stream) {
-    ROITR_CHECK_ARG(N >= 1 && M >= 1 && limit >= 1 && limit <= PART_CAP, "point_to_node: bad sizes");
-    ROITR_CHECK_ARG(pts && nodes && owner && dmin && count && knn_idx && knn_mask && node_mask, "point_to_node: null");
+extern "C" long long roitr_point_to_node_workspace_bytes(int B, int N, int M) {
+    return (long long)B * N * 8 + (long long)B * M * 8;      // buckets (u64 per point) + start / cursor (int per node each)
+}
+
+extern "C" int roitr_point_to_node_batched(int B, int N, int M, int limit, const float* pts, const float* nodes, int* owner,
+                                           float* dmin, int* count, void* workspace, int* knn_idx, unsigned char* knn_mask,
+                                           unsigned char* node_mask, void* stream) {
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && N >= 1 && M >= 1 && limit >= 1 && limit <= PART_CAP, "point_to_node: bad sizes");
+    ROITR_CHECK_ARG(pts && nodes && owner && dmin && count && workspace && knn_idx && knn_mask && node_mask, "point_to_node: null");
     ROITR_CHECK_ARG((size_t)M * 16 <= 200 * 1024, "point_to_node: too many nodes (%d)", M);
     cudaStream_t st = (cudaStream_t)stream;
-    ROITR_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * M, st));
+    unsigned long long* bucket = (unsigned long long*)workspace;
+    int* start = (int*)(bucket + (size_t)B * N);
+    int* cursor = start + (size_t)B * M;
+    ROITR_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)B * M, st));
+    ROITR_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)B * M, st));
     const size_t smem = (size_t)M * 16;
-    if (smem > 48 * 1024)
+    static size_t configured_dev[ROITR_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[roitr_cur_device()];
+    if (smem > 48 * 1024 && smem > configured) {
         ROITR_CUDA(cudaFuncSetAttribute(point_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    point_owner_kernel<<<ceil_div(N, 256), 256, smem, st>>>(N, M, pts, nodes, owner, dmin, count);
+        configured = smem;
+    }
+    point_owner_kernel<<<dim3(ceil_div(N, 256), B), 256, smem, st>>>(N, M, pts, nodes, owner, dmin, count);
     ROITR_CHECK_LAUNCH("point_owner_kernel");
-    node_knn_kernel<<<M, 256, 0, st>>>(N, M, limit, owner, dmin, count, knn_idx, knn_mask, node_mask);
+    node_start_kernel<<<B, 1024, 0, st>>>(M, count, start);
+    node_bucket_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(N, M, owner, dmin, start, cursor, bucket);
+    node_knn_kernel<<<dim3(M, B), 256, 0, st>>>(N, M, limit, count, start, bucket, knn_idx, knn_mask, node_mask);
     ROITR_CHECK_LAUNCH("node_knn_kernel");
+    return ROITR_OK;
+}
+
+extern "C" int roitr_compact_flags_batched(int B, long long n, const unsigned char* flags, int* chunk_scratch, int* out,
+                                           int capacity, int* count, void* stream) {
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && n >= 0 && flags && chunk_scratch && out && count, "compact_flags: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nchunks = (int)ceil_div_ll(n, CMP_CHUNK);
+    if (nchunks == 0) { ROITR_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * B, st)); return ROITR_OK; }
+    compact_count_kernel<<<dim3(nchunks, B), 256, 0, st>>>(n, flags, chunk_scratch);
+    compact_scan_kernel<<<B, 1024, 0, st>>>(nchunks, chunk_scratch, count);
+    compact_write_kernel<<<dim3(nchunks, B), 256, 0, st>>>(n, flags, chunk_scratch, out, capacity);
+    ROITR_CHECK_LAUNCH("compact_flags");
     return ROITR_OK;
 }
 
 extern "C" int roitr_compact_flags(long long n, const unsigned char* flags, int* chunk_scratch, int* out, int capacity,
                                    int* count, void* stream) {
-    ROITR_CHECK_ARG(n >= 0 && flags && chunk_scratch && out && count, "compact_flags: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int nchunks = (int)ceil_div_ll(n, CMP_CHUNK);
-    if (nchunks == 0) { ROITR_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st)); return ROITR_OK; }
-    compact_count_kernel<<<nchunks, 256, 0, st>>>(n, flags, chunk_scratch);
-    compact_scan_kernel<<<1, 1024, 0, st>>>(nchunks, chunk_scratch, count);
-    compact_write_kernel<<<nchunks, 256, 0, st>>>(n, flags, chunk_scratch, out, capacity);
-    ROITR_CHECK_LAUNCH("compact_flags");
-    return ROITR_OK;
+    return roitr_compact_flags_batched(1, n, flags, chunk_scratch, out, capacity, count, stream);
 }
 
 extern "C" long long roitr_compact_scratch_ints(long long n) { return ceil_div_ll(n, CMP_CHUNK) + 1; }
 
-extern "C" int roitr_coarse_matching(int Mr, int Ms, int C, int k, int dual, const float* ref_feats,
-                                     const float* src_feats, const unsigned char* ref_mask,
-                                     const unsigned char* src_mask, const float* xy, float* work, int* out_ref,
-                                     int* out_src, float* out_score, int* out_count, void* stream) {
-    // xy = ref_feats @ src_feats^T (Mr x Ms) computed by the caller with roitr_linear; work: Mr*Ms + 2*(Mr+Ms) floats
-    ROITR_CHECK_ARG(Mr >= 1 && Ms >= 1 && k >= 1 && k <= TOPK_MAX, "coarse_matching: bad sizes (k <= %d)", TOPK_MAX);
+extern "C" int roitr_coarse_matching_batched(int B, int Mr, int Ms, int C, int k, int dual, const float* ref_feats,
+                                             const float* src_feats, const unsigned char* ref_mask,
+                                             const unsigned char* src_mask, const float* xy, float* work, int* out_ref,
+                                             int* out_src, float* out_score, int* out_count, void* stream) {
+    // xy = ref_feats @ src_feats^T per pair (B, Mr, Ms), computed by the caller; work: B * (Mr*Ms + 2*(Mr+Ms)) floats
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && Mr >= 1 && Ms >= 1 && k >= 1 && k <= TOPK_MAX, "coarse_matching: bad sizes (k <= %d)", TOPK_MAX);
     ROITR_CHECK_ARG(ref_feats && src_feats && ref_mask && src_mask && xy && work && out_ref && out_src && out_score && out_count,
                     "coarse_matching: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     float* S = work;
-    float* r2 = S + (size_t)Mr * Ms;
-    float* s2 = r2 + Mr;
-    float* rowsum = s2 + Ms;
-    float* colsum = rowsum + Mr;
-    row_sqnorm_kernel<<<ceil_div(Mr * 32, 256), 256, 0, st>>>(Mr, C, ref_feats, r2);
-    row_sqnorm_kernel<<<ceil_div(Ms * 32, 256), 256, 0, st>>>(Ms, C, src_feats, s2);
-    coarse_exp_kernel<<<Mr, 256, 0, st>>>(Mr, Ms, xy, r2, s2, ref_mask, src_mask, S, rowsum);
-    col_sum_kernel<<<ceil_div(Ms, 128), 128, 0, st>>>(Mr, Ms, S, colsum);
-    coarse_dualnorm_kernel<<<(unsigned)ceil_div_ll((long long)Mr * Ms, 256), 256, 0, st>>>(Mr, Ms, S, rowsum, colsum,
-                                                                                           ref_mask, src_mask, dual);
-    flat_topk_kernel<<<1, 1024, 0, st>>>(Mr * Ms, k, S, Ms, out_ref, out_src, out_score, out_count);
+    float* r2 = S + (size_t)B * Mr * Ms;
+    float* s2 = r2 + (size_t)B * Mr;
+    float* rowsum = s2 + (size_t)B * Ms;
+    float* colsum = rowsum + (size_t)B * Mr;
+    row_sqnorm_kernel<<<ceil_div(B * Mr * 32, 256), 256, 0, st>>>(B * Mr, C, ref_feats, r2);
+    row_sqnorm_kernel<<<ceil_div(B * Ms * 32, 256), 256, 0, st>>>(B * Ms, C, src_feats, s2);
+    coarse_exp_kernel<<<dim3(Mr, B), 256, 0, st>>>(Mr, Ms, xy, r2, s2, ref_mask, src_mask, S, rowsum);
+    col_sum_kernel<<<dim3(ceil_div(Ms, 128), B), 128, 0, st>>>(Mr, Ms, S, colsum);
+    DualNorm dn;
+    dn.rowsum = rowsum; dn.colsum = colsum; dn.rmask = ref_mask; dn.smask = src_mask; dn.Mr = Mr; dn.Ms = Ms; dn.dual = dual;
+    flat_topk_kernel<<<B, 1024, 0, st>>>(Mr * Ms, k, S, Ms, out_ref, out_src, out_score, out_count, k, dn);
     ROITR_CHECK_LAUNCH("coarse_matching");
     return ROITR_OK;
 }
 
-
-extern "C" int roitr_fine_matching(int Pmax, int Nt, int Ns, int C, const float* tgt_feat, const float* src_feat,
-                                   const int* tgt_knn, const int* src_knn, const unsigned char* tgt_kmask,
-                                   const unsigned char* src_kmask, const int* corr_t, const int* corr_s,
-                                   const int* corr_count, const float* alpha, int num_iter, int topk, int mutual,
-                                   float threshold, float* scores, unsigned char* flags, void* stream) {
-    ROITR_CHECK_ARG(Pmax >= 1 && C % 32 == 0 && topk >= 1 && topk <= 32, "fine_matching: bad sizes");
+extern "C" int roitr_fine_matching_batched(int B, int Pmax, int Mt, int Ms, int Nt, int Ns, int C, const float* tgt_feat,
+                                           const float* src_feat, const int* tgt_knn, const int* src_knn,
+                                           const unsigned char* tgt_kmask, const unsigned char* src_kmask, const int* corr_t,
+                                           const int* corr_s, const int* corr_count, const float* alpha, int num_iter, int topk,
+                                           int mutual, float threshold, float* scores, unsigned char* flags, void* stream) {
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && Pmax >= 1 && C % 32 == 0 && topk >= 1 && topk <= 32, "fine_matching: bad sizes");
     ROITR_CHECK_ARG(tgt_feat && src_feat && tgt_knn && src_knn && tgt_kmask && src_kmask && corr_t && corr_s &&
                     corr_count && alpha && scores && flags, "fine_matching: null pointer");
-    ROITR_CHECK_ARG(((uintptr_t)tgt_feat | (uintptr_t)src_feat) % 16 == 0, "fine_matching: alignment");
+    ROITR_CHECK_ARG(((uintptr_t)tgt_feat | (uintptr_t)src_feat) % 16 == 0 && ((size_t)Nt * C) % 4 == 0 && ((size_t)Ns * C) % 4 == 0,
+                    "fine_matching: alignment");
     FineParams P;
     P.tgt_feat = tgt_feat; P.src_feat = src_feat; P.Nt = Nt; P.Ns = Ns; P.C = C; P.tgt_knn = tgt_knn; P.src_knn = src_knn;
     P.tgt_kmask = tgt_kmask; P.src_kmask = src_kmask; P.corr_t = corr_t; P.corr_s = corr_s; P.corr_count = corr_count;
     P.alpha = alpha; P.scores = scores; P.flags = flags; P.num_iter = num_iter; P.topk = topk; P.mutual = mutual;
-    P.threshold = threshold; P.sqrt_c = sqrtf((float)C);
+    P.threshold = threshold; P.sqrt_c = sqrtf((float)C); P.Pmax = Pmax; P.Mt = Mt; P.Ms = Ms;
     cudaStream_t st = (cudaStream_t)stream;
-    ROITR_CUDA(cudaMemsetAsync(flags, 0, (size_t)Pmax * FP * FP, st));
-    fine_patch_kernel<<<Pmax, FT, 0, st>>>(P);
+    ROITR_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * Pmax * FP * FP, st));
+    fine_patch_kernel<<<dim3(Pmax, B), FT, 0, st>>>(P);
     ROITR_CHECK_LAUNCH("fine_patch_kernel");
     return ROITR_OK;
 }
 
-extern "C" int roitr_fine_gather(int capacity, const int* flat, const int* count, const float* scores,
-                                 const int* corr_t, const int* corr_s, const int* tgt_knn, const int* src_knn,
-                                 const float* tgt_pts_padded, const float* src_pts_padded, float* out_t, float* out_s,
-                                 float* out_score, void* stream) {
-    ROITR_CHECK_ARG(capacity >= 0 && flat && count && scores && out_t && out_s && out_score, "fine_gather: bad arguments");
+extern "C" int roitr_fine_gather_batched(int B, int capacity, int Pmax, int Mt, int Ms, int Nt1, int Ns1, const int* flat,
+                                         const int* count, const float* scores, const int* corr_t, const int* corr_s,
+                                         const int* tgt_knn, const int* src_knn, const float* tgt_pts_padded,
+                                         const float* src_pts_padded, float* out_t, float* out_s, float* out_score,
+                                         void* stream) {
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && capacity >= 0 && flat && count && scores && out_t && out_s && out_score, "fine_gather: bad arguments");
     if (capacity == 0) return ROITR_OK;
-    fine_gather_kernel<<<ceil_div(capacity, 256), 256, 0, (cudaStream_t)stream>>>(
+    FineGatherStrides S;
+    S.Pmax = Pmax; S.Mt = Mt; S.Ms = Ms; S.Nt1 = Nt1; S.Ns1 = Ns1;
+    fine_gather_kernel<<<dim3(ceil_div(capacity, 256), B), 256, 0, (cudaStream_t)stream>>>(
         flat, count, capacity, scores, corr_t, corr_s, tgt_knn, src_knn, tgt_pts_padded, src_pts_padded, out_t, out_s,
-        out_score);
+        out_score, S);
     ROITR_CHECK_LAUNCH("fine_gather_kernel");
     return ROITR_OK;
 }
@@ -760,7 +855,10 @@ __global__ void adaptive_sim_kernel(int Ma, int Mb, const float* __restrict__ xy
                                     const unsigned char* __restrict__ bmask, float thr, float* __restrict__ sim,
                                     float* __restrict__ key, unsigned char* __restrict__ flag) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long long)Ma * Mb) return;
+    const long long n = (long long)Ma * Mb;
+    if (e >= n) return;
+    const size_t b = blockIdx.y;
+    xy += b * n; sim += b * n; key += b * n; flag += b * n; amask += b * Ma; bmask += b * Mb;
     const int i = (int)(e / Mb), j = (int)(e % Mb);
     if (!(amask[i] && bmask[j])) { sim[e] = CUDART_INF_F; key[e] = -1.f; flag[e] = 0; return; }
     // square_distance(normalized=True): 2 - 2 xy, clamp 1e-12 (lib/utils.py:149,155); then sqrt (modules.py:101)
@@ -770,11 +868,16 @@ __global__ void adaptive_sim_kernel(int Ma, int Mb, const float* __restrict__ xy
     flag[e] = d <= thr;
 }
 
-__global__ void adaptive_select_kernel(int Mb, int cap, const int* __restrict__ count_c, const int* __restrict__ flat_c,
-                                       const int* __restrict__ count_k, const int* __restrict__ row_k,
-                                       const int* __restrict__ col_k, const float* __restrict__ sim,
-                                       int* __restrict__ out_a, int* __restrict__ out_b, float* __restrict__ out_score,
-                                       int* __restrict__ out_count) {
+__global__ void adaptive_select_kernel(int Ma, int Mb, int cap, int min_num, const int* __restrict__ count_c,
+                                       const int* __restrict__ flat_c, const int* __restrict__ count_k,
+                                       const int* __restrict__ row_k, const int* __restrict__ col_k,
+                                       const float* __restrict__ sim, int* __restrict__ out_a, int* __restrict__ out_b,
+                                       float* __restrict__ out_score, int* __restrict__ out_count) {
+    {
+        const size_t b = blockIdx.y;
+        count_c += b; count_k += b; flat_c += b * cap; row_k += b * min_num; col_k += b * min_num;
+        sim += b * Ma * Mb; out_a += b * cap; out_b += b * cap; out_score += b * cap; out_count += b;
+    }
     const int nc = __ldg(count_c), nk = __ldg(count_k);
     const bool use_topk = nc < nk;                                  // masks.sum() < min_num (modules.py:105)
     const int n = use_topk ? nk : min(nc, cap);
@@ -790,34 +893,37 @@ __global__ void adaptive_select_kernel(int Mb, int cap, const int* __restrict__ 
 
 }  // namespace
 
-extern "C" int roitr_coarse_matching_adaptive(int Ma, int Mb, int min_num, float threshold, const unsigned char* a_mask,
-                                              const unsigned char* b_mask, const float* xy, float* work, int* iwork,
-                                              int cap, int* out_a, int* out_b, float* out_score, int* out_count,
-                                              void* stream) {
-    // xy = a_feats @ b_feats^T (Ma x Mb) from roitr_linear. work: 2*Ma*Mb floats + Ma*Mb bytes (rounded up to floats).
-    // iwork: cap + 3*min_num + 4 + roitr_compact_scratch_ints(Ma*Mb) ints.
-    ROITR_CHECK_ARG(Ma >= 1 && Mb >= 1 && min_num >= 1 && min_num <= TOPK_MAX && cap >= min_num, "coarse_matching_adaptive: bad sizes");
+extern "C" int roitr_coarse_matching_adaptive_batched(int B, int Ma, int Mb, int min_num, float threshold,
+                                                      const unsigned char* a_mask, const unsigned char* b_mask, const float* xy,
+                                                      float* work, int* iwork, int cap, int* out_a, int* out_b,
+                                                      float* out_score, int* out_count, void* stream) {
+    // xy = a_feats @ b_feats^T per pair (B, Ma, Mb). work: B * (2*Ma*Mb floats + Ma*Mb bytes rounded up to floats).
+    // iwork: B * (cap + 3*min_num + 4 + roitr_compact_scratch_ints(Ma*Mb)) ints.
+    ROITR_CHECK_ARG(B >= 1 && B <= 65535 && Ma >= 1 && Mb >= 1 && min_num >= 1 && min_num <= TOPK_MAX && cap >= min_num,
+                    "coarse_matching_adaptive: bad sizes");
     ROITR_CHECK_ARG(a_mask && b_mask && xy && work && iwork && out_a && out_b && out_score && out_count, "coarse_matching_adaptive: null");
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = (long long)Ma * Mb;
-    float* sim = work;
-    float* key = sim + n;
-    unsigned char* flag = reinterpret_cast<unsigned char*>(key + n);
-    int* flat_c = iwork;
-    int* row_k = flat_c + cap;
-    int* col_k = row_k + min_num;
-    float* val_k = reinterpret_cast<float*>(col_k + min_num);
-    int* count_c = reinterpret_cast<int*>(val_k + min_num);
-    int* count_k = count_c + 1;
-    int* scratch = count_k + 3;
-    adaptive_sim_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(Ma, Mb, xy, a_mask, b_mask, threshold, sim, key, flag);
     const int nchunks = (int)ceil_div_ll(n, CMP_CHUNK);
-    compact_count_kernel<<<nchunks, 256, 0, st>>>(n, flag, scratch);
-    compact_scan_kernel<<<1, 1024, 0, st>>>(nchunks, scratch, count_c);
-    compact_write_kernel<<<nchunks, 256, 0, st>>>(n, flag, scratch, flat_c, cap);
-    flat_topk_kernel<<<1, 1024, 0, st>>>((int)n, min_num, key, Mb, row_k, col_k, val_k, count_k);
-    adaptive_select_kernel<<<ceil_div(cap, 256) > 1024 ? 1024 : ceil_div(cap, 256), 256, 0, st>>>(Mb, cap, count_c, flat_c, count_k, row_k, col_k, sim,
-                                                                                                   out_a, out_b, out_score, out_count);
+    float* sim = work;
+    float* key = sim + (size_t)B * n;
+    unsigned char* flag = reinterpret_cast<unsigned char*>(key + (size_t)B * n);
+    int* flat_c = iwork;
+    int* row_k = flat_c + (size_t)B * cap;
+    int* col_k = row_k + (size_t)B * min_num;
+    float* val_k = reinterpret_cast<float*>(col_k + (size_t)B * min_num);
+    int* count_c = reinterpret_cast<int*>(val_k + (size_t)B * min_num);
+    int* count_k = count_c + B;
+    int* scratch = count_k + B;
+    adaptive_sim_kernel<<<dim3((unsigned)ceil_div_ll(n, 256), B), 256, 0, st>>>(Ma, Mb, xy, a_mask, b_mask, threshold, sim, key, flag);
+    compact_count_kernel<<<dim3(nchunks, B), 256, 0, st>>>(n, flag, scratch);
+    compact_scan_kernel<<<B, 1024, 0, st>>>(nchunks, scratch, count_c);
+    compact_write_kernel<<<dim3(nchunks, B), 256, 0, st>>>(n, flag, scratch, flat_c, cap);
+    DualNorm none;
+    none.rowsum = nullptr; none.colsum = nullptr; none.rmask = nullptr; none.smask = nullptr; none.Mr = 0; none.Ms = 0; none.dual = 0;
+    flat_topk_kernel<<<B, 1024, 0, st>>>((int)n, min_num, key, Mb, row_k, col_k, val_k, count_k, min_num, none);
+    adaptive_select_kernel<<<dim3(ceil_div(cap, 256) > 1024 ? 1024 : ceil_div(cap, 256), B), 256, 0, st>>>(
+        Ma, Mb, cap, min_num, count_c, flat_c, count_k, row_k, col_k, sim, out_a, out_b, out_score, out_count);
     ROITR_CHECK_LAUNCH("coarse_matching_adaptive");
     return ROITR_OK;
 }

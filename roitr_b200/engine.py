@@ -615,7 +615,8 @@ def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=Non
         # node coordinates come from the (possibly deformed) source cloud: src_deformed is the batch of src clouds only
         s_nodes_all = ops.gather_rows(src_deformed, d4[:split])
         nodes.update(d4=d4, src=[s_nodes_all[plan.starts(3, b)[0]:plan.starts(3, b)[1]] for b in range(B)],
-                     tgt=[p4[plan.starts(3, B + b)[0]:plan.starts(3, B + b)[1]] for b in range(B)])
+                     tgt=[p4[plan.starts(3, B + b)[0]:plan.starts(3, B + b)[1]] for b in range(B)],
+                     src_all=s_nodes_all, tgt_all=p4[split:])
         if on_nodes is not None:
             on_nodes(nodes)
         # the geometric structure embedding needs the superpoint coordinates only: it is issued here, on the sampling
@@ -691,13 +692,13 @@ class _Fork:
                 fn(b)
 
     def run_one(self, fn):
-        """fn() on the first side stream (after everything issued so far on the main stream); returns an event that
+        """fn() on the first side stream (after everything issued so far on the CURRENT stream); returns an event that
         marks its completion, or None when running inline."""
         if not self.streams:
             fn()
             return None
         st = self.streams[0]
-        st.wait_event(self.main.record_event())
+        st.wait_event(torch.cuda.current_stream().record_event())     # the issuing stream: main, or the lane that produced the inputs
         with torch.cuda.stream(st):
             fn()
             return st.record_event()
@@ -707,20 +708,16 @@ class _Fork:
             self.main.wait_stream(st)
 
 
-HEAD_STREAMS = 16
-
-
 def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
     """RIGA_v2.forward (eval) for the B pairs of ``plan``. Inputs are the concatenated clouds
     [src_raw_0..src_raw_{B-1}, tgt_0..tgt_{B-1}] (pts/feats/nrm), the concatenated (deformed) source clouds ``src_pcd``
     and rot (B,3,3) / trans (B,3,1). No host sync. Returns a list of per-pair dicts of PADDED tensors plus a (B,3) int32
     device tensor of counts [P, n_gt, n_corr].
 
-    The per-pair matching head is a chain of latency-bound, low-occupancy kernels (single-CTA top-k / scans, one CTA per
-    patch pair for the Sinkhorn iterations) and pairs are independent, so it runs on side streams in three stages, each
-    forked as early as its inputs exist: (1) partition + ground-truth bookkeeping after the last FPS (overlaps the level-4
-    encoder, the global transformer and the decoder), (2) coarse matching after the global transformer (overlaps the
-    decoder), (3) fine matching after the decoder."""
+    The matching head is batched over the pairs (one launch per kernel, the pair is a grid dimension) and runs in three
+    stages, each issued as early as its inputs exist: (1) partition + ground-truth bookkeeping after the last FPS, on a side
+    stream (overlaps the level-4 encoder, the global transformer and the decoder), (2) coarse matching behind the global
+    transformer on its lane (overlaps the decoder), (3) fine matching after the decoder."""
     four_d = cfg["benchmark"] not in ("3DMatch", "3DLoMatch")
     B, Ns, Nt = plan.B, plan.n_src, plan.n_tgt
     K = int(cfg["point_per_patch"])
@@ -734,10 +731,11 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
                          "reference config uses 64), got %d" % K)
     # mutual: at most topk matches per row; non-mutual = the UNION of the row-wise and column-wise top-k (modules.py:283-287)
     cap = Pmax * K * topk * (1 if bool(cfg["fine_matching_mutual"]) else 2)
-    fork = _Fork(plan.side_streams(min(HEAD_STREAMS, B)) if B > 1 else [])
-    st = [dict() for _ in range(B)]          # per-pair state handed from stage to stage (same side stream per pair)
-    src_of = lambda b: src_pcd[b * Ns:(b + 1) * Ns]
-    tgt_of = lambda b: pts[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
+    # The head is batched over the pairs (every kernel takes the pair as a grid dimension), so its three stages are three short
+    # chains of launches, each forked onto ONE side stream as early as its inputs exist.
+    fork = _Fork(plan.side_streams(1) if B > 1 else [])
+    hd = {}                                   # batched head state handed from stage to stage
+    tgt_all = pts[B * Ns:]                    # (B*Nt, 3): the B target clouds
 
     # 0. occlusion 1-NN of the zero-padded clouds (lib/utils.py:505-509): depends on the inputs only, so it is issued first
     # and for all pairs at once (one segment per pair)
@@ -745,7 +743,7 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
 
     def occlusion_nn():
         o_s, o_t = plan.pad_offsets(Ns + 1), plan.pad_offsets(Nt + 1)
-        t_pad = ops.pad_transform_batched(B, Nt, pts[B * Ns:])
+        t_pad = ops.pad_transform_batched(B, Nt, tgt_all)
         s_pad_t = ops.pad_transform_batched(B, Ns, src_pcd, rot, trans)
         g_s = ops.knn_grid_build(s_pad_t, o_s) if Ns + 1 >= ops.GRID_MIN_SEGMENT else None
         g_t = ops.knn_grid_build(t_pad, o_t) if Nt + 1 >= ops.GRID_MIN_SEGMENT else None
@@ -757,65 +755,69 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
     occ_done = fork.run_one(occlusion_nn)
 
     def on_nodes(nodes):
-        def gt(b):   # 2. partition + ground-truth bookkeeping
-            q = st[b]
-            src_pts, tgt_pts, src_nodes, tgt_nodes = src_of(b), tgt_of(b), nodes["src"][b], nodes["tgt"][b]
-            _, s_nm, s_ki, s_km = ops.point_to_node(src_pts, src_nodes, K)
-            _, t_nm, t_ki, t_km = ops.point_to_node(tgt_pts, tgt_nodes, K)
-            Ms, Mt = src_nodes.shape[0], tgt_nodes.shape[0]
-            ov, ov_flag = ops.node_overlaps(tgt_nodes, src_nodes, t_ki, s_ki, t_km, s_km, t_nm, s_nm, tgt_pts, src_pts,
-                                            rot[b], trans[b], float(cfg["matching_radius"]))
-            gt_flat, gt_count = ops.compact_flags(ov_flag, Mt * Ms)
-            gt_idx, gt_ov = ops.corr_gather(Mt * Ms, Ms, gt_flat, gt_count, ov)
+        def gt():   # 2. partition + ground-truth bookkeeping, all pairs per launch
+            s_nodes, t_nodes = nodes["src_all"], nodes["tgt_all"]
+            _, s_nm, s_ki, s_km = ops.point_to_node_batched(B, src_pcd, s_nodes, K)
+            _, t_nm, t_ki, t_km = ops.point_to_node_batched(B, tgt_all, t_nodes, K)
+            ov, ov_flag = ops.node_overlaps_batched(B, t_nodes, s_nodes, t_ki, s_ki, t_km, s_km, t_nm, s_nm, tgt_all, src_pcd,
+                                                    rot, trans, float(cfg["matching_radius"]))
+            gt_flat, gt_count = ops.compact_flags_batched(B, ov_flag, M4t * M4s)
+            gt_idx, gt_ov = ops.corr_gather_batched(B, M4t * M4s, M4t, M4s, gt_flat, gt_count, ov)
             if occ_done is not None:
                 torch.cuda.current_stream().wait_event(occ_done)
-            q.update(src_points=src_pts, tgt_points=tgt_pts, src_nodes=src_nodes, tgt_nodes=tgt_nodes, s_nm=s_nm, s_ki=s_ki,
-                     s_km=s_km, t_nm=t_nm, t_ki=t_ki, t_km=t_km, gt_idx=gt_idx, gt_ov=gt_ov, gt_count=gt_count,
-                     gt_tgt_node_occ=ops.node_occlusion(t_ki, t_km, t_nm, occ["t_nn"][b]),
-                     gt_src_node_occ=ops.node_occlusion(s_ki, s_km, s_nm, occ["s_nn"][b]))
-        fork.run(B, gt)
+            hd.update(s_nm=s_nm, s_ki=s_ki, s_km=s_km, t_nm=t_nm, t_ki=t_ki, t_km=t_km, gt_idx=gt_idx, gt_ov=gt_ov,
+                      gt_count=gt_count, t_occ=ops.node_occlusion_batched(B, t_ki, t_km, t_nm, occ["t_nn"]),
+                      s_occ=ops.node_occlusion_batched(B, s_ki, s_km, s_nm, occ["s_nn"]), keep=(ov, ov_flag, gt_flat))
+        hd["ev_gt"] = fork.run_one(gt)
 
     def on_global(per_pair, s_g_all, t_g_all):
         # coarse_proj + L2 normalisation for every superpoint of the batch at once (RIGA_v2.py:64-65)
         s_nf_all = ops.row_epilogue(_lin(W, "coarse_proj", s_g_all), mode=ops.MODE_L2NORM)
         t_nf_all = ops.row_epilogue(_lin(W, "coarse_proj", t_g_all), mode=ops.MODE_L2NORM)
-
         # tgt . src^T of every pair in one batched tensor-core launch (the per-pair feature-similarity matrices)
         C = s_nf_all.shape[1]
         xy_all = torch.empty(B, M4t, M4s, dtype=torch.float32, device=s_nf_all.device)
         ops.gemm_tc_batched(B, 1, M4t, M4s, C, t_nf_all, C, (M4t * C, 0), s_nf_all, C, (M4s * C, 0), xy_all, M4s, (M4t * M4s, 0))
-
-        def coarse(b):   # 3. coarse matching   (called as (tgt, src), model/RIGA_v2.py:121)
-            q = st[b]
-            src_nf, tgt_nf = s_nf_all[b * M4s:(b + 1) * M4s], t_nf_all[b * M4t:(b + 1) * M4t]
-            if four_d:
-                t_ci, s_ci, node_sc, p_count = ops.coarse_matching_adaptive(tgt_nf, src_nf, q["t_nm"], q["s_nm"],
-                                                                            int(cfg["num_est_coarse_corr"]), 0.75, Pmax, xy=xy_all[b])
-            else:
-                t_ci, s_ci, node_sc, p_count = ops.coarse_matching(tgt_nf, src_nf, q["t_nm"], q["s_nm"], Pmax, dual=True,
-                                                                   xy=xy_all[b])
-            q.update(src_node_feats=src_nf, tgt_node_feats=tgt_nf, t_ci=t_ci, s_ci=s_ci, node_sc=node_sc, p_count=p_count)
-        fork.run(B, coarse)
+        _wait(hd["ev_gt"])      # the node masks of the partition
+        # 3. coarse matching (called as (tgt, src), model/RIGA_v2.py:121), all pairs per launch
+        if four_d:
+            t_ci, s_ci, node_sc, p_count = ops.coarse_matching_adaptive_batched(B, t_nf_all, s_nf_all, hd["t_nm"], hd["s_nm"],
+                                                                                int(cfg["num_est_coarse_corr"]), 0.75, Pmax, xy=xy_all)
+        else:
+            t_ci, s_ci, node_sc, p_count = ops.coarse_matching_batched(B, t_nf_all, s_nf_all, hd["t_nm"], hd["s_nm"], Pmax,
+                                                                       dual=True, xy=xy_all)
+        hd.update(s_nf=s_nf_all, t_nf=t_nf_all, t_ci=t_ci, s_ci=s_ci, node_sc=node_sc, p_count=p_count, keep2=xy_all)
 
     L, dec, per_pair = backbone_batch(W, cfg["transformer_architecture"], plan, pts, feats, nrm, src_pcd, aux,
                                       on_nodes=on_nodes, on_global=on_global, join=False)
     pf_all = _lin(W, "fine_proj", dec[0])                                # all points of all clouds at once
-
-    def fine(b):   # 4-6. fine scoring + OT + fine matching
-        q = st[b]
-        src_pf, tgt_pf = pf_all[b * Ns:(b + 1) * Ns], pf_all[B * Ns + b * Nt: B * Ns + (b + 1) * Nt]
-        scores, flags = ops.fine_matching(tgt_pf, src_pf, q["t_ki"], q["s_ki"], q["t_km"], q["s_km"], q["t_ci"], q["s_ci"],
-                                          q["p_count"], W["optimal_transport.alpha"].view(1), 100, topk,
-                                          bool(cfg["fine_matching_mutual"]), float(cfg["fine_matching_confidence_threshold"]))
-        c_flat, c_count = ops.compact_flags(flags, cap)
-        t_cp, s_cp, c_sc = ops.fine_gather(cap, c_flat, c_count, scores, q["t_ci"], q["s_ci"], q["t_ki"], q["s_ki"],
-                                           q["tgt_points"], q["src_points"])
-        q.update(src_point_feats=src_pf, tgt_point_feats=tgt_pf, matching_scores=scores, t_cp=t_cp, s_cp=s_cp, c_sc=c_sc,
-                 c_flat=c_flat, cap=cap, counts=torch.cat([q["p_count"], q["gt_count"], c_count]))
-    fork.run(B, fine)
+    join_lanes(plan)                                                     # the global lane carried the coarse stage
     fork.join()
-    join_lanes(plan)
-    return st, torch.stack([q["counts"] for q in st])
+    # 4-6. fine scoring + OT + fine matching, all pairs per launch (grid = (patch pair, pair))
+    src_pf, tgt_pf = pf_all[:B * Ns], pf_all[B * Ns:]
+    scores, flags = ops.fine_matching_batched(B, tgt_pf, src_pf, hd["t_ki"], hd["s_ki"], hd["t_km"], hd["s_km"], hd["t_ci"],
+                                              hd["s_ci"], hd["p_count"], W["optimal_transport.alpha"].view(1), 100, topk,
+                                              bool(cfg["fine_matching_mutual"]), float(cfg["fine_matching_confidence_threshold"]))
+    c_flat, c_count = ops.compact_flags_batched(B, flags, cap)
+    t_cp, s_cp, c_sc = ops.fine_gather_batched(B, cap, c_flat, c_count, scores, hd["t_ci"], hd["s_ci"], hd["t_ki"], hd["s_ki"],
+                                               tgt_all, src_pcd)
+    counts = torch.stack([hd["p_count"], hd["gt_count"], c_count], dim=1)
+    st = []
+    for b in range(B):      # per-pair VIEWS of the batched tensors, in the layout finalize() trims
+        st.append(dict(src_points=src_pcd[b * Ns:(b + 1) * Ns], tgt_points=tgt_all[b * Nt:(b + 1) * Nt],
+                       src_nodes=nodes_of(per_pair, b, "src_nodes"), tgt_nodes=nodes_of(per_pair, b, "tgt_nodes"),
+                       s_nm=hd["s_nm"][b], s_ki=hd["s_ki"][b], s_km=hd["s_km"][b], t_nm=hd["t_nm"][b], t_ki=hd["t_ki"][b],
+                       t_km=hd["t_km"][b], gt_idx=hd["gt_idx"][b], gt_ov=hd["gt_ov"][b], gt_tgt_node_occ=hd["t_occ"][b],
+                       gt_src_node_occ=hd["s_occ"][b], src_node_feats=hd["s_nf"][b * M4s:(b + 1) * M4s],
+                       tgt_node_feats=hd["t_nf"][b * M4t:(b + 1) * M4t], t_ci=hd["t_ci"][b], s_ci=hd["s_ci"][b],
+                       node_sc=hd["node_sc"][b], src_point_feats=src_pf[b * Ns:(b + 1) * Ns],
+                       tgt_point_feats=tgt_pf[b * Nt:(b + 1) * Nt], matching_scores=scores[b], t_cp=t_cp[b], s_cp=s_cp[b],
+                       c_sc=c_sc[b], c_flat=c_flat[b], cap=cap))
+    return st, counts
+
+
+def nodes_of(per_pair, b, key):
+    return per_pair[b][key]
 
 
 def finalize(o, counts, Ns, Nt, aux=None):

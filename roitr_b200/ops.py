@@ -303,92 +303,146 @@ def attention_tc(batch, N, M, C, q, k, v, heads=4, E=None, gq=None, bp=None):
     return (hidden, G) if E is not None else hidden
 
 
-def point_to_node(pts, nodes, limit):
-    N, M = pts.shape[0], nodes.shape[0]
+# ---- matching head: every op takes B equally sized problems laid back to back and issues ONE launch per kernel ----
+def point_to_node_batched(B, pts, nodes, limit):
+    """pts (B*N,3), nodes (B*M,3) -> owner (B,N), node_mask (B,M) u8, knn_idx (B,M,limit) int32 (pad = N), knn_mask (B,M,limit) u8."""
+    N, M = pts.shape[0] // B, nodes.shape[0] // B
     dev = pts.device
-    owner = torch.empty(N, dtype=torch.int32, device=dev)
-    dmin = torch.empty(N, dtype=torch.float32, device=dev)
-    count = torch.empty(M, dtype=torch.int32, device=dev)
-    knn_idx = torch.empty(M, limit, dtype=torch.int32, device=dev)
-    knn_mask = torch.empty(M, limit, dtype=torch.uint8, device=dev)
-    node_mask = torch.empty(M, dtype=torch.uint8, device=dev)
-    _lib.call("roitr_point_to_node", c_int(N), c_int(M), c_int(limit), f32(pts), f32(nodes), i32(owner), f32(dmin),
-              i32(count), i32(knn_idx), _u8(knn_mask), _u8(node_mask), stream_ptr())
+    owner = torch.empty(B, N, dtype=torch.int32, device=dev)
+    dmin = torch.empty(B, N, dtype=torch.float32, device=dev)
+    count = torch.empty(B, M, dtype=torch.int32, device=dev)
+    knn_idx = torch.empty(B, M, limit, dtype=torch.int32, device=dev)
+    knn_mask = torch.empty(B, M, limit, dtype=torch.uint8, device=dev)
+    node_mask = torch.empty(B, M, dtype=torch.uint8, device=dev)
+    fn = _lib.lib().roitr_point_to_node_workspace_bytes
+    fn.restype = c_ll
+    ws = torch.empty(int(fn(c_int(B), c_int(N), c_int(M))), dtype=torch.uint8, device=dev)
+    _lib.call("roitr_point_to_node_batched", c_int(B), c_int(N), c_int(M), c_int(limit), f32(pts), f32(nodes), i32(owner),
+              f32(dmin), i32(count), ptr(ws), i32(knn_idx), _u8(knn_mask), _u8(node_mask), stream_ptr())
     return owner, node_mask, knn_idx, knn_mask
 
 
-def compact_flags(flags, capacity):
-    """Ascending flat indices of the non-zero bytes (torch.nonzero order), padded to ``capacity``; device count."""
-    n = flags.numel()
+def point_to_node(pts, nodes, limit):
+    owner, node_mask, knn_idx, knn_mask = point_to_node_batched(1, pts, nodes, limit)
+    return owner[0], node_mask[0], knn_idx[0], knn_mask[0]
+
+
+def compact_flags_batched(B, flags, capacity):
+    """flags: B equal segments of bytes. Ascending flat indices (within the segment) of the non-zero bytes, (B, max(capacity,1))
+    int32 padded, and the true totals (B,) int32 on the device (torch.nonzero order per segment)."""
+    n = flags.numel() // B
     fn = _lib.lib().roitr_compact_scratch_ints
     fn.restype = c_ll
-    scratch = torch.empty(int(fn(c_ll(n))), dtype=torch.int32, device=flags.device)
-    out = torch.empty(max(capacity, 1), dtype=torch.int32, device=flags.device)
-    count = torch.empty(1, dtype=torch.int32, device=flags.device)
-    _lib.call("roitr_compact_flags", c_ll(n), _u8(flags), i32(scratch), i32(out), c_int(capacity), i32(count),
+    scratch = torch.empty(B * int(fn(c_ll(n))), dtype=torch.int32, device=flags.device)
+    out = torch.empty(B, max(capacity, 1), dtype=torch.int32, device=flags.device)
+    count = torch.empty(B, dtype=torch.int32, device=flags.device)
+    _lib.call("roitr_compact_flags_batched", c_int(B), c_ll(n), _u8(flags), i32(scratch), i32(out), c_int(capacity), i32(count),
               stream_ptr())
     return out, count
 
 
-def coarse_matching(ref_feats, src_feats, ref_mask, src_mask, k, dual=True, xy=None):
-    Mr, Ms, C = ref_feats.shape[0], src_feats.shape[0], ref_feats.shape[1]
+def compact_flags(flags, capacity):
+    """Ascending flat indices of the non-zero bytes (torch.nonzero order), padded to ``capacity``; device count."""
+    out, count = compact_flags_batched(1, flags, capacity)
+    return out[0], count
+
+
+def coarse_matching_batched(B, ref_feats, src_feats, ref_mask, src_mask, k, dual=True, xy=None):
+    """ref_feats (B*Mr,C), src_feats (B*Ms,C), masks (B,Mr) / (B,Ms) u8, xy (B,Mr,Ms) -> (B,k) ref idx, src idx, scores; (B,) counts."""
+    Mr, Ms, C = ref_feats.shape[0] // B, src_feats.shape[0] // B, ref_feats.shape[1]
     dev = ref_feats.device
     if xy is None:
-        xy = linear(ref_feats, src_feats)                   # (Mr, Ms) = ref @ src^T
-    work = torch.empty(Mr * Ms + 2 * (Mr + Ms), dtype=torch.float32, device=dev)
-    out_ref = torch.zeros(k, dtype=torch.int32, device=dev)
-    out_src = torch.zeros(k, dtype=torch.int32, device=dev)
-    out_score = torch.zeros(k, dtype=torch.float32, device=dev)
-    count = torch.empty(1, dtype=torch.int32, device=dev)
-    _lib.call("roitr_coarse_matching", c_int(Mr), c_int(Ms), c_int(C), c_int(k), c_int(1 if dual else 0), f32(ref_feats),
-              f32(src_feats), _u8(ref_mask), _u8(src_mask), f32(xy), f32(work), i32(out_ref), i32(out_src),
+        xy = torch.empty(B, Mr, Ms, dtype=torch.float32, device=dev)
+        for b in range(B):
+            linear(ref_feats[b * Mr:(b + 1) * Mr], src_feats[b * Ms:(b + 1) * Ms], out=xy[b])     # ref @ src^T
+    work = torch.empty(B * (Mr * Ms + 2 * (Mr + Ms)), dtype=torch.float32, device=dev)
+    out_ref = torch.zeros(B, k, dtype=torch.int32, device=dev)
+    out_src = torch.zeros(B, k, dtype=torch.int32, device=dev)
+    out_score = torch.zeros(B, k, dtype=torch.float32, device=dev)
+    count = torch.empty(B, dtype=torch.int32, device=dev)
+    _lib.call("roitr_coarse_matching_batched", c_int(B), c_int(Mr), c_int(Ms), c_int(C), c_int(k), c_int(1 if dual else 0),
+              f32(ref_feats), f32(src_feats), _u8(ref_mask), _u8(src_mask), f32(xy), f32(work), i32(out_ref), i32(out_src),
               f32(out_score), i32(count), stream_ptr())
     return out_ref, out_src, out_score, count
 
 
-def coarse_matching_adaptive(a_feats, b_feats, a_mask, b_mask, min_num, threshold, cap, xy=None):
-    Ma, Mb = a_feats.shape[0], b_feats.shape[0]
+def coarse_matching(ref_feats, src_feats, ref_mask, src_mask, k, dual=True, xy=None):
+    r, s_, sc, c = coarse_matching_batched(1, ref_feats, src_feats, ref_mask, src_mask, k, dual, None if xy is None else xy[None])
+    return r[0], s_[0], sc[0], c
+
+
+def coarse_matching_adaptive_batched(B, a_feats, b_feats, a_mask, b_mask, min_num, threshold, cap, xy=None):
+    Ma, Mb = a_feats.shape[0] // B, b_feats.shape[0] // B
     dev = a_feats.device
     if xy is None:
-        xy = linear(a_feats, b_feats)
+        xy = torch.empty(B, Ma, Mb, dtype=torch.float32, device=dev)
+        for b in range(B):
+            linear(a_feats[b * Ma:(b + 1) * Ma], b_feats[b * Mb:(b + 1) * Mb], out=xy[b])
     n = Ma * Mb
-    work = torch.empty(2 * n + (n + 3) // 4, dtype=torch.float32, device=dev)
+    work = torch.empty(B * (2 * n + (n + 3) // 4), dtype=torch.float32, device=dev)
     fn = _lib.lib().roitr_compact_scratch_ints
     fn.restype = c_ll
-    iwork = torch.empty(cap + 3 * min_num + 4 + int(fn(c_ll(n))), dtype=torch.int32, device=dev)
-    out_a = torch.zeros(cap, dtype=torch.int32, device=dev)
-    out_b = torch.zeros(cap, dtype=torch.int32, device=dev)
-    out_score = torch.zeros(cap, dtype=torch.float32, device=dev)
-    count = torch.empty(1, dtype=torch.int32, device=dev)
-    _lib.call("roitr_coarse_matching_adaptive", c_int(Ma), c_int(Mb), c_int(min_num), c_float(threshold), _u8(a_mask),
-              _u8(b_mask), f32(xy), f32(work), i32(iwork), c_int(cap), i32(out_a), i32(out_b), f32(out_score), i32(count),
-              stream_ptr())
+    iwork = torch.empty(B * (cap + 3 * min_num + 4 + int(fn(c_ll(n)))), dtype=torch.int32, device=dev)
+    out_a = torch.zeros(B, cap, dtype=torch.int32, device=dev)
+    out_b = torch.zeros(B, cap, dtype=torch.int32, device=dev)
+    out_score = torch.zeros(B, cap, dtype=torch.float32, device=dev)
+    count = torch.empty(B, dtype=torch.int32, device=dev)
+    _lib.call("roitr_coarse_matching_adaptive_batched", c_int(B), c_int(Ma), c_int(Mb), c_int(min_num), c_float(threshold),
+              _u8(a_mask), _u8(b_mask), f32(xy), f32(work), i32(iwork), c_int(cap), i32(out_a), i32(out_b), f32(out_score),
+              i32(count), stream_ptr())
     return out_a, out_b, out_score, count
+
+
+def coarse_matching_adaptive(a_feats, b_feats, a_mask, b_mask, min_num, threshold, cap, xy=None):
+    a, b, sc, c = coarse_matching_adaptive_batched(1, a_feats, b_feats, a_mask, b_mask, min_num, threshold, cap,
+                                                   None if xy is None else xy[None])
+    return a[0], b[0], sc[0], c
+
+
+def fine_matching_batched(B, tgt_feat, src_feat, tgt_knn, src_knn, tgt_kmask, src_kmask, corr_t, corr_s, corr_count, alpha,
+                          num_iter, topk, mutual, threshold):
+    """tgt_feat (B*Nt,C), src_feat (B*Ns,C), knn / kmask (B,M,64), corr_t / corr_s (B,Pmax), corr_count (B) ->
+    scores (B,Pmax,65,65), flags (B,Pmax,64,64) u8."""
+    Pmax = corr_t.shape[1]
+    Nt, Ns, C = tgt_feat.shape[0] // B, src_feat.shape[0] // B, tgt_feat.shape[1]
+    Mt, Ms = tgt_knn.shape[1], src_knn.shape[1]
+    dev = tgt_feat.device
+    if tgt_knn.shape[2] != 64 or src_knn.shape[2] != 64:
+        raise _lib.RoitrError("fine_matching: patches must hold 64 points (got %d / %d)" % (tgt_knn.shape[2], src_knn.shape[2]))
+    scores = torch.zeros(B, Pmax, 65, 65, dtype=torch.float32, device=dev)
+    flags = torch.empty(B, Pmax, 64, 64, dtype=torch.uint8, device=dev)
+    _lib.call("roitr_fine_matching_batched", c_int(B), c_int(Pmax), c_int(Mt), c_int(Ms), c_int(Nt), c_int(Ns), c_int(C),
+              f32(tgt_feat), f32(src_feat), i32(tgt_knn), i32(src_knn), _u8(tgt_kmask), _u8(src_kmask), i32(corr_t), i32(corr_s),
+              i32(corr_count), f32(alpha), c_int(num_iter), c_int(topk), c_int(1 if mutual else 0), c_float(threshold),
+              f32(scores), _u8(flags), stream_ptr())
+    return scores, flags
 
 
 def fine_matching(tgt_feat, src_feat, tgt_knn, src_knn, tgt_kmask, src_kmask, corr_t, corr_s, corr_count, alpha,
                   num_iter, topk, mutual, threshold):
-    Pmax = corr_t.shape[0]
-    dev = tgt_feat.device
-    if tgt_knn.shape[1] != 64 or src_knn.shape[1] != 64:
-        raise _lib.RoitrError("fine_matching: patches must hold 64 points (got %d / %d)" % (tgt_knn.shape[1], src_knn.shape[1]))
-    scores = torch.zeros(Pmax, 65, 65, dtype=torch.float32, device=dev)
-    flags = torch.empty(Pmax, 64, 64, dtype=torch.uint8, device=dev)
-    _lib.call("roitr_fine_matching", c_int(Pmax), c_int(tgt_feat.shape[0]), c_int(src_feat.shape[0]),
-              c_int(tgt_feat.shape[1]), f32(tgt_feat), f32(src_feat), i32(tgt_knn), i32(src_knn), _u8(tgt_kmask),
-              _u8(src_kmask), i32(corr_t), i32(corr_s), i32(corr_count), f32(alpha), c_int(num_iter), c_int(topk),
-              c_int(1 if mutual else 0), c_float(threshold), f32(scores), _u8(flags), stream_ptr())
-    return scores, flags
+    sc, fl = fine_matching_batched(1, tgt_feat, src_feat, tgt_knn[None], src_knn[None], tgt_kmask[None], src_kmask[None],
+                                   corr_t[None], corr_s[None], corr_count.view(1), alpha, num_iter, topk, mutual, threshold)
+    return sc[0], fl[0]
+
+
+def fine_gather_batched(B, capacity, flat, count, scores, corr_t, corr_s, tgt_knn, src_knn, tgt_pts, src_pts):
+    """flat (B,capacity), count (B), tgt_pts (B*Nt1,3), src_pts (B*Ns1,3) -> (B,capacity,3) x2 and (B,capacity) scores."""
+    dev = scores.device
+    cap = max(capacity, 1)
+    out_t = torch.empty(B, cap, 3, dtype=torch.float32, device=dev)
+    out_s = torch.empty(B, cap, 3, dtype=torch.float32, device=dev)
+    out_sc = torch.empty(B, cap, dtype=torch.float32, device=dev)
+    _lib.call("roitr_fine_gather_batched", c_int(B), c_int(cap), c_int(corr_t.shape[1]), c_int(tgt_knn.shape[1]),
+              c_int(src_knn.shape[1]), c_int(tgt_pts.shape[0] // B), c_int(src_pts.shape[0] // B), i32(flat), i32(count), f32(scores),
+              i32(corr_t), i32(corr_s), i32(tgt_knn), i32(src_knn), f32(tgt_pts), f32(src_pts), f32(out_t), f32(out_s), f32(out_sc),
+              stream_ptr())
+    return out_t, out_s, out_sc
 
 
 def fine_gather(capacity, flat, count, scores, corr_t, corr_s, tgt_knn, src_knn, tgt_pts, src_pts):
-    dev = scores.device
-    out_t = torch.empty(capacity, 3, dtype=torch.float32, device=dev)
-    out_s = torch.empty(capacity, 3, dtype=torch.float32, device=dev)
-    out_sc = torch.empty(capacity, dtype=torch.float32, device=dev)
-    _lib.call("roitr_fine_gather", c_int(capacity), i32(flat), i32(count), f32(scores), i32(corr_t), i32(corr_s),
-              i32(tgt_knn), i32(src_knn), f32(tgt_pts), f32(src_pts), f32(out_t), f32(out_s), f32(out_sc), stream_ptr())
-    return out_t, out_s, out_sc
+    t, s_, sc = fine_gather_batched(1, capacity, flat.view(1, -1), count.view(1), scores[None], corr_t[None], corr_s[None],
+                                    tgt_knn[None], src_knn[None], tgt_pts, src_pts)
+    return t[0], s_[0], sc[0]
 
 
 def pad_transform(pts, rot=None, trans=None):
@@ -405,32 +459,53 @@ def pad_transform_batched(B, N, pts, rot=None, trans=None):
     return out
 
 
-def node_occlusion(knn, kmask, nmask, nn_dist, thr=0.0375):
-    M, K = knn.shape
-    occ = torch.empty(M, dtype=torch.float32, device=knn.device)
-    _lib.call("roitr_node_occlusion", c_int(M), c_int(K), i32(knn), _u8(kmask), _u8(nmask), f32(nn_dist), c_float(thr),
-              f32(occ), stream_ptr())
+def node_occlusion_batched(B, knn, kmask, nmask, nn_dist, thr=0.0375):
+    """knn / kmask (B,M,K), nmask (B,M), nn_dist (B,N+1) -> occ (B,M)."""
+    M, K = knn.shape[1], knn.shape[2]
+    occ = torch.empty(B, M, dtype=torch.float32, device=knn.device)
+    _lib.call("roitr_node_occlusion_batched", c_int(B), c_int(M), c_int(K), c_int(nn_dist.shape[1]), i32(knn), _u8(kmask),
+              _u8(nmask), f32(nn_dist), c_float(thr), f32(occ), stream_ptr())
     return occ
+
+
+def node_occlusion(knn, kmask, nmask, nn_dist, thr=0.0375):
+    return node_occlusion_batched(1, knn[None], kmask[None], nmask[None], nn_dist.view(1, -1), thr)[0]
+
+
+def node_overlaps_batched(B, ref_nodes, src_nodes, ref_knn, src_knn, ref_kmask, src_kmask, ref_mask, src_mask, ref_pts, src_pts,
+                          rot, trans, radius):
+    """ref_nodes (B*Mr,3), src_nodes (B*Ms,3), knn / kmask (B,M,64), masks (B,M), pts (B*N,3), rot (B,3,3), trans (B,3[,1]) ->
+    overlap (B,Mr,Ms) f32, flag (B,Mr,Ms) u8."""
+    Mr, Ms, K = ref_nodes.shape[0] // B, src_nodes.shape[0] // B, ref_knn.shape[2]
+    dev = ref_nodes.device
+    work = torch.empty(B * (4 * Ms + 4 * Mr), dtype=torch.float32, device=dev)
+    overlap = torch.empty(B, Mr, Ms, dtype=torch.float32, device=dev)
+    flag = torch.empty(B, Mr, Ms, dtype=torch.uint8, device=dev)
+    _lib.call("roitr_node_overlaps_batched", c_int(B), c_int(Mr), c_int(Ms), c_int(K), c_int(ref_pts.shape[0] // B),
+              c_int(src_pts.shape[0] // B), f32(ref_nodes), f32(src_nodes), i32(ref_knn), i32(src_knn), _u8(ref_kmask),
+              _u8(src_kmask), _u8(ref_mask), _u8(src_mask), f32(ref_pts), f32(src_pts), f32(rot), f32(trans), c_float(radius),
+              f32(work), f32(overlap), _u8(flag), stream_ptr())
+    return overlap, flag
 
 
 def node_overlaps(ref_nodes, src_nodes, ref_knn, src_knn, ref_kmask, src_kmask, ref_mask, src_mask, ref_pts, src_pts,
                   rot, trans, radius):
-    Mr, Ms, K = ref_nodes.shape[0], src_nodes.shape[0], ref_knn.shape[1]
-    dev = ref_nodes.device
-    work = torch.empty(4 * Ms + 4 * Mr, dtype=torch.float32, device=dev)
-    overlap = torch.empty(Mr, Ms, dtype=torch.float32, device=dev)
-    flag = torch.empty(Mr, Ms, dtype=torch.uint8, device=dev)
-    _lib.call("roitr_node_overlaps", c_int(Mr), c_int(Ms), c_int(K), c_int(ref_pts.shape[0]), c_int(src_pts.shape[0]),
-              f32(ref_nodes), f32(src_nodes), i32(ref_knn), i32(src_knn), _u8(ref_kmask), _u8(src_kmask), _u8(ref_mask),
-              _u8(src_mask), f32(ref_pts), f32(src_pts), f32(rot), f32(trans), c_float(radius), f32(work), f32(overlap),
-              _u8(flag), stream_ptr())
-    return overlap, flag
+    ov, fl = node_overlaps_batched(1, ref_nodes, src_nodes, ref_knn[None], src_knn[None], ref_kmask[None], src_kmask[None],
+                                   ref_mask[None], src_mask[None], ref_pts, src_pts, rot.reshape(1, 3, 3), trans.reshape(1, 3), radius)
+    return ov[0], fl[0]
+
+
+def corr_gather_batched(B, capacity, Mr, Ms, flat, count, overlap):
+    dev = overlap.device
+    cap = max(capacity, 1)
+    out_idx = torch.empty(B, cap, 2, dtype=torch.int64, device=dev)
+    out_ov = torch.empty(B, cap, dtype=torch.float32, device=dev)
+    _lib.call("roitr_corr_gather_batched", c_int(B), c_int(cap), c_int(Mr), c_int(Ms), i32(flat), i32(count), f32(overlap),
+              ptr(out_idx), f32(out_ov), stream_ptr())
+    return out_idx, out_ov
 
 
 def corr_gather(capacity, Ms, flat, count, overlap):
-    dev = overlap.device
-    out_idx = torch.empty(capacity, 2, dtype=torch.int64, device=dev)
-    out_ov = torch.empty(capacity, dtype=torch.float32, device=dev)
-    _lib.call("roitr_corr_gather", c_int(capacity), c_int(Ms), i32(flat), i32(count), f32(overlap), ptr(out_idx),
-              f32(out_ov), stream_ptr())
-    return out_idx, out_ov
+    Mr = overlap.shape[0]
+    i, o = corr_gather_batched(1, capacity, Mr, Ms, flat.view(1, -1), count.view(1), overlap[None])
+    return i[0], o[0]

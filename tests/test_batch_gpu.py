@@ -93,13 +93,14 @@ def test_pipelined_runner_equals_single_pair_forward():
     pr = m.pipelined_runner(B, N, N, depth=2, mid_level=1)
     slots = []
     got = [None] * len(batches)
+    clone = lambda outs: [{k: v.clone() for k, v in o.items()} for o in outs]     # outputs are views of buffers the slot reuses
     for s, batch in enumerate(batches):
         slots.append(pr.submit(BatchRunner.collate(batch)))
         if s >= 1:                       # read step s-1 while step s runs (its slot is reused only at step s+1)
             pr.wait(slots[s - 1])
-            got[s - 1] = pr.runner(slots[s - 1]).results()
+            got[s - 1] = clone(pr.runner(slots[s - 1]).results())
     pr.wait(slots[-1])
-    got[-1] = pr.runner(slots[-1]).results()
+    got[-1] = clone(pr.runner(slots[-1]).results())
     for outs, ref in zip(got, singles):
         for o, r in zip(outs, ref):
             assert set(o) == set(r)
