@@ -281,8 +281,8 @@ def main():
         wall = time.perf_counter() - t0
         return sum(a.elapsed_time(b) for a, b in ev), wall, d2h, ncorr
 
-    depth = int(os.environ.get("ROITR_PIPELINE", "1"))
-    pipe = m.pipelined_runner(B, N_POINTS, N_POINTS, depth=depth, mid_level=int(os.environ.get("ROITR_MID_LEVEL", "1"))) if depth > 1 else None
+    depth = int(os.environ.get("ROITR_PIPELINE", "2"))        # steps in flight (1 = one step at a time)
+    pipe = m.pipelined_runner(B, N_POINTS, N_POINTS, depth=depth, mid_level=int(os.environ.get("ROITR_MID_LEVEL", "0"))) if depth > 1 else None
 
     def pipe_loop(e2e, n_steps):
         """Pipelined steps (engine.PipelinedRunner): step i+1 starts beside the latency-bound back of step i, so per-step event
@@ -442,7 +442,7 @@ def main():
                        "l2": "256 MiB flush between steps (outside the timed events); %d distinct batches cycled" % NB,
                        "mode": ("one CUDA graph per step" if not args.no_graph else "eager") + ", %d pairs per step per GPU" % B +
                                (", %d steps in flight (software pipeline: step i+1 starts when step i is past its encoder level %d; "
-                                "K steps timed with one event pair)" % (depth, int(os.environ.get("ROITR_MID_LEVEL", "1")) + 1) if depth > 1 else "")},
+                                "K steps timed with one event pair)" % (depth, int(os.environ.get("ROITR_MID_LEVEL", "0")) + 1) if depth > 1 else "")},
             "e2e": {"value": world * B * steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
             "e2e_record": {"value": world * B * rec_steps / (ms_rec * 1e-3), "unit": "pairs/s", "d2h_bytes_per_step": rec_bytes,

@@ -24,9 +24,11 @@ STRIDES = (1, 4, 4, 4)
 NSAMPLE = (8, 16, 16, 16)
 BLOCKS = (2, 3, 3, 3)
 HEADS = 4
-# EXPERIMENTAL, off: LayerNorm of the 256-channel layers (levels 3-4, global transformer) fused into a 256-column dense-layer
-# tile (csrc/gemm_tc2.cu launch_tc3<256,1,4,8,1>). Compiles; NOT yet run on a GPU (tests/test_experimental.py, opt-in).
-LN256 = False
+# LayerNorm of the 256-channel layers (levels 3-4, global transformer) fused into a 256-column dense-layer tile
+# (csrc/gemm_tc2.cu launch_tc3<256,1,4,8,1>; tests/test_gemm_gpu.py::test_fused_layernorm_256_column_tile). ROITR_LN256=0 restores
+# linear + row_epilogue.
+import os as _os
+LN256 = _os.environ.get("ROITR_LN256", "1") != "0"
 FPS_AFTER_KNN = False        # measured: the level-1 layers start 3 ms earlier but crawl next to the FPS clusters; 563 vs 569 pairs/s
 LIGHT_VARIANT = 3          # streaming dense-layer configuration used while the FPS clusters are resident (0 = none)
 
@@ -77,6 +79,17 @@ def pack_linear_tc(Wm, bn=None):
             out[:, :, :, j, ar ^ j, :] = T[:, :, :, j, :, :]
         return out.reshape(Np // bn, Kp // 32, bn * 32)
     return torch.stack([tile(hi), tile(lo)], dim=2).contiguous(), bn
+
+
+def ws_tile_rows(N, K):
+    """Tile rows of the packing the weight-stationary dense-layer kernel takes for an (N, K) weight, or None when the layer
+    stays on the streaming kernel: the whole row in one tile (64 / 128 / 192 / 256 columns) and the packed weight (hi + lo,
+    rows x K x 8 bytes) resident in shared memory next to two 32 KB operand stages (csrc/gemm_tc2.cu ws_fits)."""
+    bn = 64 if N <= 64 else 128 if N <= 128 else 192 if N <= 192 else 256 if N <= 256 else None
+    if bn is None:
+        return None
+    nkc = -(-K // 32)
+    return bn if nkc * 2 * bn * 128 + 2 * 32768 + 1024 <= 200 * 1024 else None
 
 
 def build_geo_tables(Wd, bd, Wa, ba, div_term, sigma_a=15.0, t_d_max=512.0):
@@ -212,6 +225,9 @@ def _pack_weights(state_dict, device, architecture):
         for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("#Wkv") or k.endswith("#Wfq") or k.endswith("#Wqkvg") or k.endswith("#Wposf") or k.endswith("Big")) and W[k].dim() == 2
                   and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
+            bn_ws = ws_tile_rows(W[k].shape[0], W[k].shape[1])
+            if bn_ws is not None and bn_ws != W[k + "#tc"][1]:       # 192 / 256-row tile: only the weight-stationary kernel takes it
+                W[k + "#ws"] = pack_linear_tc(W[k], bn_ws)
             if LN256 and W[k].shape[0] == 256 and W[k].shape[1] % 32 == 0 and k.endswith(".weight"):
                 W[k + "#tc256"] = pack_linear_tc(W[k], 256)
     finally:
@@ -224,8 +240,15 @@ ATTENTION_TC = True          # global attention: Q K^T / P V on tcgen05 + one st
 LINEAR_TC = True             # dense layers on tcgen05 (csrc/gemm_tc2.cu) when a packed weight exists; False = fp32 FFMA
 
 
+def _pk(W, key):
+    """The packed forms of weight ``key`` as ops.linear keyword arguments."""
+    if not LINEAR_TC:
+        return {}
+    return dict(wpack=W.get(key + "#tc"), wpack_ws=W.get(key + "#ws"))
+
+
 def _lin(W, p, x, **kw):
-    return ops.linear(x, W[p + ".weight"], W[p + ".bias"], wpack=W.get(p + ".weight#tc") if LINEAR_TC else None, **kw)
+    return ops.linear(x, W[p + ".weight"], W[p + ".bias"], **_pk(W, p + ".weight"), **kw)
 
 
 def _ln(W, p, x, **kw):
@@ -235,7 +258,8 @@ def _ln(W, p, x, **kw):
 def _lin_ln(W, p, n, x, **kw):
     """Linear p followed by LayerNorm n (+ residuals / ReLU), fused into the dense layer's epilogue where it fits."""
     return ops.linear_ln(x, W[p + ".weight"], W[p + ".bias"], W.get(p + ".weight#tc") if LINEAR_TC else None,
-                         W[n + ".weight"], W[n + ".bias"], wpack_wide=W.get(p + ".weight#tc256") if LINEAR_TC else None, **kw)
+                         W[n + ".weight"], W[n + ".bias"], wpack_wide=W.get(p + ".weight#tc256") if LINEAR_TC else None,
+                         wpack_ws=W.get(p + ".weight#ws") if LINEAR_TC else None, **kw)
 
 
 def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None, post=None):
@@ -243,18 +267,18 @@ def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None, pos
     ``post`` = (LayerNorm prefix, res_post, relu): a row epilogue applied to the output (the block's bn2 + identity + ReLU)."""
     C = W[p + ".in_proj.weight"].shape[0]
     if LINEAR_TC and node_idx is not None and (p + "#Wkv#tc") in W:
-        kv = ops.linear(feats, W[p + "#Wkv"], W[p + "#bkv"], wpack=W[p + "#Wkv#tc"])                       # (n, 2C) all rows
-        fq = ops.linear(feats, W[p + "#Wfq"], W[p + "#bfq"], wpack=W[p + "#Wfq#tc"], a_index=node_idx)     # (m, 2C) sampled rows
+        kv = ops.linear(feats, W[p + "#Wkv"], W[p + "#bkv"], **_pk(W, p + "#Wkv"))                       # (n, 2C) all rows
+        fq = ops.linear(feats, W[p + "#Wfq"], W[p + "#bfq"], a_index=node_idx, **_pk(W, p + "#Wfq"))     # (m, 2C) sampled rows
         h = ops.local_attention((fq[:, C:], kv[:, :C], kv[:, C:]), C, None, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"],
                                 W[p + "#Avp"], W[p + "#cvp"], order=order)
         f, node_idx = fq[:, :C], None
     else:
         if LINEAR_TC and (p + "#W4#tc") in W:
-            fq = ops.linear(feats, W[p + "#W4"], W[p + "#b4"], wpack=W[p + "#W4#tc"])      # (n, 4C) = [f | q | k | v]
+            fq = ops.linear(feats, W[p + "#W4"], W[p + "#b4"], **_pk(W, p + "#W4"))      # (n, 4C) = [f | q | k | v]
             f, qkv = fq[:, :C], fq[:, C:]
         else:
             f = _lin(W, p + ".in_proj", feats)
-            qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], wpack=W.get(p + "#Wqkv#tc") if LINEAR_TC else None)
+            qkv = ops.linear(f, W[p + "#Wqkv"], W[p + "#bqkv"], **_pk(W, p + "#Wqkv"))
         h = ops.local_attention(qkv, C, node_idx, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"], W[p + "#Avp"], W[p + "#cvp"],
                                 order=order)
     y = _lin_ln(W, p + ".transformer.linear", p + ".transformer.norm", h, res_pre=f, res_pre_index=node_idx)

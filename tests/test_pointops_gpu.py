@@ -195,3 +195,51 @@ def test_grid_knn_lattice_ties_and_degenerate_clouds():
     a = ops.knn_ppf(5, flat, None, flat, None, off, off, drop_first=0, want_ppf=False, want_dist=True)
     b = ops.knn_ppf(5, flat, None, flat, None, off, off, drop_first=0, want_ppf=False, want_dist=True, grid=ops.knn_grid_build(flat, off))
     assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+
+
+def test_dropin_is_called_the_way_the_reference_op_layer_calls_it():
+    """INTEGRATION.md level 1: ``sys.modules['pointops_cuda'] = roitr_b200.pointops_cuda`` under the UNMODIFIED reference
+    op layer. /root/reference does not exist on the GPU box, so the two call sequences the forward path uses are restated
+    here statement by statement from cpp_wrappers/pointops/functions/pointops.py (FurthestSampling.forward :17-25,
+    KNNQuery.forward :37-43): legacy ``torch.cuda.IntTensor`` / ``FloatTensor`` constructors for the outputs, ``n_max``
+    arriving as a 0-d CUDA tensor produced by ``max()`` over offset differences, ``m`` / ``nsample`` as Python ints."""
+    import sys
+    import types
+    saved = sys.modules.get("pointops_cuda")
+    sys.modules["pointops_cuda"] = pointops_cuda
+    try:
+        import pointops_cuda as ext                                  # what `import pointops_cuda` (pointops.py:7) resolves to
+        assert isinstance(ext, types.ModuleType) and ext is pointops_cuda
+        xyz_h, _ = _cloud(9000, 6)
+        xyz = xyz_h.to(DEV)
+        offset, new_offset = _i32([5000, 6000, 9000]).to(DEV), _i32([1250, 1500, 2250]).to(DEV)
+        # ---- FurthestSampling.forward, pointops.py:17-25 ----
+        assert xyz.is_contiguous()
+        n, b, n_max = xyz.shape[0], offset.shape[0], offset[0]
+        for i in range(1, b):
+            n_max = max(offset[i] - offset[i - 1], n_max)
+        assert torch.is_tensor(n_max) and n_max.dim() == 0 and n_max.is_cuda        # the 0-d tensor the binding must accept
+        idx = torch.cuda.IntTensor(new_offset[b - 1].item()).zero_()
+        tmp = torch.cuda.FloatTensor(n).fill_(1e10)
+        ext.furthestsampling_cuda(b, n_max, xyz, offset, new_offset, tmp, idx)
+        del tmp
+        assert torch.equal(idx.cpu(), native.fps(xyz_h, offset.cpu(), new_offset.cpu()))
+        # ---- KNNQuery.forward, pointops.py:37-43 (new_xyz = the sampled points) ----
+        nsample = 17
+        new_xyz = xyz[idx.long()].contiguous()
+        assert xyz.is_contiguous() and new_xyz.is_contiguous()
+        m = new_xyz.shape[0]
+        kidx = torch.cuda.IntTensor(m, nsample).zero_()
+        dist2 = torch.cuda.FloatTensor(m, nsample).zero_()
+        ext.knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, kidx, dist2)
+        idx_o, d2_o = native.knn(nsample, xyz_h, new_xyz.cpu(), offset.cpu(), new_offset.cpu())
+        assert torch.equal(kidx.cpu(), idx_o) and torch.equal(dist2.cpu(), d2_o)
+        assert kidx.dtype == torch.int32 and torch.sqrt(dist2).dtype == torch.float32   # what :43 returns
+        # the out-of-path entry points exist (pointops_api.cpp:15-22) and say so when called
+        with pytest.raises(NotImplementedError):
+            ext.grouping_forward_cuda(1, 1, 1, 1, None, None, None)
+    finally:
+        if saved is None:
+            del sys.modules["pointops_cuda"]
+        else:
+            sys.modules["pointops_cuda"] = saved
