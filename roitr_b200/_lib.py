@@ -28,6 +28,8 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.roitr_last_error.restype = ctypes.c_char_p
         _lib.roitr_abi_version.restype = c_int
+        if os.environ.get("ROITR_SELF_V3"):             # A/B timing of the barrier-free self-attention pass (csrc/geo_attn2.cu)
+            _lib.roitr_debug_geo_self_v3(int(os.environ["ROITR_SELF_V3"]))
         if os.environ.get("ROITR_LINEAR_VARIANT"):      # tuning knob (scripts/): streaming dense-layer kernel configuration
             _lib.roitr_debug_linear_variant(int(os.environ["ROITR_LINEAR_VARIANT"]))
     return _lib

@@ -34,9 +34,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 struct Tc2Params {
     int M, N, K;
@@ -589,185 +586,12 @@ int launch_tc2(const Tc2Params& P, cudaStream_t st) {
     return ROITR_OK;
 }
 
-// ---- weight-stationary variant -----------------------------------------------------------------------------------------
-// ncu on the streaming kernel at the level-1 shapes (profiles/r02_linear_tc3_l2.txt): every 128-row tile re-fetches its
-// weight tiles from L2 with TMA - 32 KB per (tile, K chunk) - which for (M,N,K) = (640000, 256, 64) is 655 MB of L2->SM
-// traffic next to 164 MB of activations and 655 MB of output, and for N > 128 the activation chunk is loaded and split once
-// per 128-column tile. Where the whole packed weight (hi + lo, N x K x 8 bytes <= 128 KB: every K = 64 layer and the
-// 128 x 128 ones) fits in shared memory it is loaded ONCE per persistent CTA and stays there:
-//
-//   warps 0-3    EPILOGUE   as in the streaming kernel (tile_epilogue), one n-tile = the whole row (BN = 64 / 128 / 192 / 256)
-//   warps 4-11   A LOADERS  register-staged: each thread keeps the 16-byte pieces of the next two K chunks in flight
-//                           (ld.global.cs, 8 lanes per 128-byte row segment), then splits into the AST-deep operand ring
-//   warp 12      lane 0: one bulk TMA copy of the packed weight at start, then the MMA issuer: 4 K-steps x 3
-//                           tcgen05.mma.kind::tf32 of shape 128 x BN per chunk, two TMEM accumulators of BN columns
-//
-// L2->SM traffic per tile is the activation tile alone; the split runs once per chunk whatever N is.
-template <int BN, int AST>
-__global__ void __launch_bounds__(416, 1) linear_ws_kernel(const Tc2Params P) {
-    constexpr int WS_LOADERS = 256;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr int B_HALF = BN * 128;
-    constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    __shared__ __align__(8) uint64_t full_bar[AST], empty_bar[AST], tmem_full[2], tmem_empty[2], w_bar;
-    __shared__ uint32_t s_tmem;
-    __shared__ __align__(16) float s_pad[4][32 * PAD_STRIDE];
-    __shared__ __align__(16) float s_ln[3][BN];        // bias, gamma, beta of the fused LayerNorm epilogue
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nkc = P.nkc;
-    unsigned char* w_smem = smem;                                   // nkc x [hi BN x 128 B | lo BN x 128 B]
-    unsigned char* a_smem = smem + (size_t)nkc * 2 * B_HALF;        // AST x [hi 16 KB | lo 16 KB]
-    if (tid == 0) {
-        for (int i = 0; i < AST; ++i) { mbar_init(&full_bar[i], WS_LOADERS); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
-        mbar_init(&w_bar, 1);
-        mbar_fence_init();
-    }
-    if (warp == 0) tmem_alloc(&s_tmem, TMEM_COLS);
-    if (P.ln && tid < 128) {
-        for (int i = tid; i < BN; i += 128) {
-            const bool in = i < P.N;
-            s_ln[0][i] = (in && P.bias) ? __ldg(P.bias + i) : 0.f;
-            s_ln[1][i] = in ? __ldg(P.ln_gamma + i) : 0.f;
-            s_ln[2][i] = in ? __ldg(P.ln_beta + i) : 0.f;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = s_tmem;
-    const int total_tiles = P.tiles_m;                              // one n-tile
-    const int my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const uint32_t my_chunks = (uint32_t)my_tiles * (uint32_t)nkc;
-
-    if (warp >= 4 && warp < 12) {
-        // ================================================= A loaders =================================================
-        const int t = tid - 128;
-        const int c = t & 7, r0 = t >> 3;                           // 16-byte piece c of rows r0, r0 + 32, r0 + 64, r0 + 96
-        auto load = [&](float4 (&b)[4], uint32_t idx) {
-            if (idx >= my_chunks) return;
-            const int tile = (int)blockIdx.x + (int)(idx / nkc) * (int)gridDim.x;
-            const int k = (int)(idx % nkc) * T2_BK + 4 * c;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int am = tile * T2_BM + r0 + 32 * j;
-                b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (am < P.M && k < P.K) {
-                    const long long row = P.a_index ? (long long)__ldg(P.a_index + am) : (long long)am;
-                    b[j] = __ldcs(reinterpret_cast<const float4*>(P.A + row * P.lda + k));
-                }
-            }
-        };
-        auto consume = [&](const float4 (&b)[4], uint32_t idx) {
-            if (idx >= my_chunks) return;
-            const int st = idx % AST;
-            mbar_wait(&empty_bar[st], ((idx / AST) & 1) ^ 1);       // the MMAs that read this stage have retired
-            unsigned char* a_hi = a_smem + (size_t)st * 2 * A_HALF;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) split_store(a_hi, a_hi + A_HALF, r0 + 32 * j, c, b[j]);
-            fence_proxy_async_smem();
-            mbar_arrive(&full_bar[st]);
-        };
-        float4 b0[4], b1[4], b2[4];
-        load(b0, 0);
-        load(b1, 1);
-        for (uint32_t it = 0; it < my_chunks; it += 3) {            // three register buffers rotate: two chunks always in flight
-            load(b2, it + 2); consume(b0, it);
-            load(b0, it + 3); consume(b1, it + 1);
-            load(b1, it + 4); consume(b2, it + 2);
-        }
-    } else if (warp == 12) {
-        if (lane == 0) {
-            // ============================================ weights once, then the MMA issuer ==========================
-            const uint32_t wbytes = (uint32_t)nkc * 2 * B_HALF;
-            mbar_expect_tx(&w_bar, wbytes);
-            for (int kc = 0; kc < nkc; ++kc)
-                tma_load_1d(w_smem + (size_t)kc * 2 * B_HALF, P.wpack + (size_t)kc * (2 * B_HALF / 4), 2 * B_HALF, &w_bar);
-            mbar_wait(&w_bar, 0);
-            constexpr uint32_t idesc = make_idesc_tf32(T2_BM, BN);
-            uint32_t it = 0;
-            for (int tcount = 0; tcount < my_tiles; ++tcount) {
-                const int acc = tcount & 1;
-                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem + (uint32_t)(acc * BN);
-                for (int kc = 0; kc < nkc; ++kc, ++it) {
-                    const int st = it % AST;
-                    mbar_wait(&full_bar[st], (it / AST) & 1);
-                    tc_fence_after();
-                    const uint32_t ah = smem_u32(a_smem + (size_t)st * 2 * A_HALF), al = ah + A_HALF;
-                    const uint32_t bh = smem_u32(w_smem + (size_t)kc * 2 * B_HALF), bl = bh + B_HALF;
-#pragma unroll
-                    for (int ks = 0; ks < T2_BK / 8; ++ks) {
-                        const uint64_t dah = make_desc_sw128(ah + ks * 32), dal = make_desc_sw128(al + ks * 32);
-                        const uint64_t dbh = make_desc_sw128(bh + ks * 32), dbl = make_desc_sw128(bl + ks * 32);
-                        umma_tf32(d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                        umma_tf32(d, dah, dbl, idesc, 1u);
-                        umma_tf32(d, dah, dbh, idesc, 1u);
-                    }
-                    umma_commit(&empty_bar[st]);
-                }
-                umma_commit(&tmem_full[acc]);
-            }
-        }
-    } else if (warp < 4) {
-        // ================================================= epilogue (warps 0-3) ======================================
-        float* pad = s_pad[warp];
-        for (int tcount = 0; tcount < my_tiles; ++tcount) {
-            const int tile = (int)blockIdx.x + tcount * (int)gridDim.x;
-            const int acc = tcount & 1;
-            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
-            tc_fence_after();
-            tile_epilogue<BN>(P, pad, s_ln, warp, lane, tile, 0, tcount + 1 < my_tiles ? tile + (int)gridDim.x : -1,
-                              tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN));
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
-}
-
-// largest operand ring that fits next to the resident weight (nkc x 2 x BN x 128 bytes) in ~200 KB of dynamic shared memory
-constexpr int WS_SMEM_BUDGET = 200 * 1024;
-static inline bool ws_fits(int bn, int nkc) { return (long long)nkc * 2 * bn * 128 + 2 * 2 * A_HALF + 1024 <= WS_SMEM_BUDGET; }
-
-template <int BN, int AST>
-int launch_ws(const Tc2Params& P, cudaStream_t st) {
-    const int smem = P.nkc * 2 * BN * 128 + AST * 2 * A_HALF + 1024;
-    static int configured_dev[ROITR_MAX_DEVICES] = {};
-    static int num_sms_dev[ROITR_MAX_DEVICES] = {};
-    const int dv = roitr_cur_device();
-    if (!num_sms_dev[dv]) ROITR_CUDA(cudaDeviceGetAttribute(&num_sms_dev[dv], cudaDevAttrMultiProcessorCount, dv));
-    if (smem > configured_dev[dv]) {
-        ROITR_CUDA(cudaFuncSetAttribute(linear_ws_kernel<BN, AST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured_dev[dv] = smem;
-    }
-    const int grid = P.tiles_m < num_sms_dev[dv] ? P.tiles_m : num_sms_dev[dv];
-    linear_ws_kernel<BN, AST><<<grid, 416, smem, st>>>(P);
-    ROITR_CHECK_LAUNCH("linear_ws_kernel");
-    return ROITR_OK;
-}
-
-template <int BN>
-int launch_ws_bn(const Tc2Params& P, cudaStream_t st) {
-    const long long w = (long long)P.nkc * 2 * BN * 128;
-    if (w + 4 * 2 * A_HALF + 1024 <= WS_SMEM_BUDGET) return launch_ws<BN, 4>(P, st);
-    if (w + 3 * 2 * A_HALF + 1024 <= WS_SMEM_BUDGET) return launch_ws<BN, 3>(P, st);
-    return launch_ws<BN, 2>(P, st);
-}
-
 }  // namespace
 
 static int g_ablate = 0;
 extern "C" int roitr_debug_linear_ablate(int mask) { g_ablate = mask; return 0; }
 static int g_tc3_variant = 0;  // set per launch by the engine (roitr_debug_linear_variant): streaming-kernel configuration (0: deep rings, one CTA per SM; 3: light footprint, shares an SM with other kernels)
 extern "C" int roitr_debug_linear_variant(int v) { g_tc3_variant = v; return 0; }
-static int g_ws_enabled = 1;  // roitr_debug_linear_ws(0): route around the weight-stationary kernel (A/B timing, scripts/bench_gemm.py)
-extern "C" int roitr_debug_linear_ws(int on) { g_ws_enabled = on; return 0; }
 static int g_force_tc2 = 0;   // debug only: route everything through the coupled-ring kernel (A/B timing)
 extern "C" int roitr_debug_force_linear_tc2(int on) { g_force_tc2 = on; return 0; }
 
@@ -777,8 +601,7 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
                                  const float* res_post, int ldr, void* stream) {
     ROITR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && A && wpack && C, "linear_tc_packed: bad arguments M=%d N=%d K=%d", M, N, K);
     ROITR_CHECK_ARG(lda >= K && ldc >= N, "linear_tc_packed: bad leading dimensions");
-    ROITR_CHECK_ARG(bn == 64 || bn == 128 || bn == 192 || bn == 256,
-                    "linear_tc_packed: weights must be packed with 64-, 128-, 192- or 256-row tiles, got %d", bn);
+    ROITR_CHECK_ARG(bn == 64 || bn == 128, "linear_tc_packed: weights must be packed with 64- or 128-row tiles, got %d", bn);
     ROITR_CHECK_ARG((uintptr_t)wpack % 16 == 0, "linear_tc_packed: wpack must be 16-byte aligned");
     if (M == 0) return ROITR_OK;
     Tc2Params P;
@@ -789,31 +612,20 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
     P.tiles_m = ceil_div(M, T2_BM); P.tiles_n = ceil_div(N, bn); P.nkc = ceil_div(K, T2_BK);
     cudaStream_t st = (cudaStream_t)stream;
     const bool stream_ok = !a_add && !a_index && lda % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0;
-    // weight-stationary kernel: the whole row in one tile and the packed weight resident in shared memory (row gathers are fine)
-    const bool ws_ok = !a_add && lda % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0 && P.tiles_n == 1 && ws_fits(bn, P.nkc) &&
-                       g_tc3_variant != 3 && !g_force_tc2 && !(P.ln && a_index);
     if (P.ln)
         ROITR_CHECK_ARG(stream_ok && P.tiles_n == 1 && N % 32 == 0 && ln_beta && ldr >= N && ldr % 4 == 0 &&
                             ((uintptr_t)res_pre | (uintptr_t)res_post) % 16 == 0,
                         "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile (N=%d, tile %d)", N, bn);
-    if (ws_ok && g_ws_enabled) {
-        if (bn == 64) return launch_ws_bn<64>(P, st);
-        if (bn == 128) return launch_ws_bn<128>(P, st);
-        if (bn == 192) return launch_ws_bn<192>(P, st);
-        return launch_ws_bn<256>(P, st);
-    }
-    ROITR_CHECK_ARG(bn == 64 || bn == 128 || (bn == 256 && P.ln),
-                    "linear_tc_packed: a %d-row packing needs the weight-stationary kernel (plain 16-byte aligned input, N <= %d, "
-                    "weight resident in shared memory)", bn, bn);
     if (P.ln) {
-        // 256-column tile (EXPERIMENTAL, not used by the engine by default, see engine.LN256): the whole row of a 256-channel
-        // layer in one tile - one operand stage of 96 KB, four raw stages, both TMEM accumulators = all 512 columns
-        if (bn == 256) return launch_tc3<256, 1, 4, 8, 1>(P, st);
         if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
+        if (g_tc3_variant == 4 && bn == 64) return launch_tc3<64, 2, 6, 8, 1>(P, st);
+        if (g_tc3_variant == 5) return bn == 64 ? launch_tc3<64, 2, 6, 8, 1>(P, st) : launch_tc3<128, 1, 8, 8, 1>(P, st);
         return bn == 64 ? launch_tc3<64, 3, 3, 8, 1>(P, st) : launch_tc3<128, 2, 4, 8, 1>(P, st);
     }
     if (stream_ok && !g_force_tc2) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
+        if (g_tc3_variant == 4 && bn == 64) return launch_tc3<64, 2, 6, 8, 1>(P, st);
+        if (g_tc3_variant == 5) return bn == 64 ? launch_tc3<64, 2, 6, 8, 1>(P, st) : launch_tc3<128, 1, 8, 8, 1>(P, st);
         return bn == 128 ? launch_tc3<128, 2, 4, 8, 1>(P, st) : launch_tc3<64, 3, 3, 8, 1>(P, st);
     }
     if (bn == 64) return launch_tc2<64, 4>(P, st);

@@ -212,6 +212,167 @@ __global__ void __launch_bounds__(GA_THREADS, (C <= 256 ? 3 : 2)) geo_self_score
     }
 }
 
+// ---- C = 256: barrier-free variant ------------------------------------------------------------------------------------
+// ncu on the kernel above (profiles/r01j_geo_self_scores_kernel_*): 52 % issue slots, 36 % of the warp slots active and 3.1 TB/s
+// of E - the three phases per chunk are separated by CTA barriers, phase B runs on 4 of the 8 warps, and E is read from
+// shared memory twice (scores, then accumulation). Here every WARP owns a subset of the keys and carries its own online
+// softmax: for a key it loads the row once (8 channels per lane), forms the four per-head dot products, folds them so that
+// lane group g (8 lanes) holds head g's score, updates that head's running (max, denominator), broadcasts the four weights
+// and accumulates G[4][8] from the registers that still hold the row. No barrier, no second pass over the chunk; a stage of
+// the three-stage TMA ring is released by one mbarrier arrival per warp. The eight partial (max, denominator, G) states
+// are merged once per row through shared memory.
+constexpr int GV_STAGES = 3;
+constexpr int GV_CHK = 32;      // keys per stage (32 KB at C = 256)
+
+__global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_v3_kernel(const SelfParams P) {
+    constexpr int C = 256, H = GA_H, CPL = 8, WARPS = GA_THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);              // GV_STAGES x [GV_CHK][C]; reused as the merge buffer
+    float* S = ring + GV_STAGES * GV_CHK * C;                      // [H][M] raw q.k on entry, final scores on exit
+    __shared__ __align__(8) uint64_t full[GV_STAGES], empty[GV_STAGES];
+    __shared__ float s_mx[WARPS][H], s_den[WARPS][H];
+
+    const int n = blockIdx.x, b = blockIdx.y;
+    const int N = P.N, M = P.M;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* Erow = P.E + ((size_t)b * N + n) * (size_t)M * C;
+    const size_t rowid = (size_t)b * N + n;
+    const int nch = (M + GV_CHK - 1) / GV_CHK;
+
+    if (tid == 0) {
+        for (int i = 0; i < GV_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int c) {   // thread 0: chunk c -> stage c % GV_STAGES
+        const int rows = min(GV_CHK, M - c * GV_CHK);
+        const uint32_t bytes = (uint32_t)rows * C * 4;
+        const int st = c % GV_STAGES;
+        mbar_expect_tx(&full[st], bytes);
+        tma_load_1d(ring + (size_t)st * GV_CHK * C, Erow + (size_t)c * GV_CHK * C, bytes, &full[st]);
+    };
+    if (tid == 0)
+        for (int c = 0; c < GV_STAGES && c < nch; ++c) issue(c);
+
+    // raw q.k of the row (tcgen05 GEMM output) -> S, coalesced
+    const float* qk_row = P.qk + (((size_t)b * H) * N + n) * M;
+    for (int i = tid; i < H * M; i += GA_THREADS) S[i] = __ldg(qk_row + (size_t)(i / M) * N * M + (i % M));
+
+    const int c0 = lane * CPL;
+    float gq[H][CPL];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(P.gq + rowid * (size_t)P.ldgq + h * C + c0));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(P.gq + rowid * (size_t)P.ldgq + h * C + c0) + 1);
+        gq[h][0] = a.x; gq[h][1] = a.y; gq[h][2] = a.z; gq[h][3] = a.w; gq[h][4] = d.x; gq[h][5] = d.y; gq[h][6] = d.z; gq[h][7] = d.w;
+    }
+    float qb = 0.f;
+    {
+        const float* q = P.q + (size_t)b * P.q_bs + (size_t)n * P.ldq;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) qb = fmaf(__ldg(q + c0 + i), __ldg(P.bp + c0 + i), qb);
+        qb += __shfl_xor_sync(FULL_MASK, qb, 1); qb += __shfl_xor_sync(FULL_MASK, qb, 2); qb += __shfl_xor_sync(FULL_MASK, qb, 4);
+    }
+    const int myh = lane >> 3;                                      // the head whose total reduce4_to_head leaves in this lane
+    const float qb_h = qb;                                          // lanes 8h .. 8h+7 hold channels of head h: qb IS q_h . b_p,h
+    float G[H][CPL];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) G[h][i] = 0.f;
+    float mx = -CUDART_INF_F, den = 0.f;                            // running state of head myh (diagonal-free softmax)
+    __syncthreads();                                                // S is in place
+
+    for (int c = 0; c < nch; ++c) {
+        const int st = c % GV_STAGES;
+        const int m0 = c * GV_CHK, rows = min(GV_CHK, M - m0);
+        const float* Ec = ring + (size_t)st * GV_CHK * C;
+        mbar_wait(&full[st], (c / GV_STAGES) & 1);
+        for (int r = warp; r < rows; r += WARPS) {
+            const int m = m0 + r;
+            const float4 ea = *reinterpret_cast<const float4*>(Ec + (size_t)r * C + c0);
+            const float4 eb = *reinterpret_cast<const float4*>(Ec + (size_t)r * C + c0 + 4);
+            const float e[CPL] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+            float a[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                a[h] = gq[h][0] * e[0];
+#pragma unroll
+                for (int i = 1; i < CPL; ++i) a[h] = fmaf(gq[h][i], e[i], a[h]);
+            }
+            const float sp = reduce4_to_head(a[0], a[1], a[2], a[3], lane);
+            const float sc = __fdiv_rn(S[myh * M + m] + (sp + qb_h), P.sqrt_c);
+            if ((lane & 7) == 0) S[myh * M + m] = sc;
+            if (m == n) continue;                                   // the position branch excludes the diagonal (warp-uniform)
+            const float nm = fmaxf(mx, sc);
+            const bool grew = nm > mx;
+            const float w = expf(sc - nm);
+            if (__any_sync(FULL_MASK, grew)) {                      // some head's running maximum moved: rescale (rare after the first keys)
+                const float f = grew ? (mx == -CUDART_INF_F ? 0.f : expf(mx - nm)) : 1.f;
+                den *= f;
+                const float f0 = __shfl_sync(FULL_MASK, f, 0), f1 = __shfl_sync(FULL_MASK, f, 8);
+                const float f2 = __shfl_sync(FULL_MASK, f, 16), f3 = __shfl_sync(FULL_MASK, f, 24);
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) { G[0][i] *= f0; G[1][i] *= f1; G[2][i] *= f2; G[3][i] *= f3; }
+                mx = nm;
+            }
+            den += w;
+            const float w0 = __shfl_sync(FULL_MASK, w, 0), w1 = __shfl_sync(FULL_MASK, w, 8);
+            const float w2 = __shfl_sync(FULL_MASK, w, 16), w3 = __shfl_sync(FULL_MASK, w, 24);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                G[0][i] = fmaf(w0, e[i], G[0][i]); G[1][i] = fmaf(w1, e[i], G[1][i]);
+                G[2][i] = fmaf(w2, e[i], G[2][i]); G[3][i] = fmaf(w3, e[i], G[3][i]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);                     // this warp is done with the stage
+        if (tid == 0 && c + GV_STAGES < nch) {                      // refill it once every warp is
+            mbar_wait(&empty[st], (c / GV_STAGES) & 1);
+            issue(c + GV_STAGES);
+        }
+    }
+    // ---- merge the eight warps' states: G = sum_w G_w exp(mx_w - mx*) / sum_w den_w exp(mx_w - mx*) ----
+    if ((lane & 7) == 0) { s_mx[warp][myh] = mx; s_den[warp][myh] = den; }
+    __syncthreads();                                                // also: every warp is past its last read of the ring
+    float gmx = -CUDART_INF_F;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) gmx = fmaxf(gmx, s_mx[w][myh]);
+    float gden = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) gden += s_mx[w][myh] == -CUDART_INF_F ? 0.f : s_den[w][myh] * expf(s_mx[w][myh] - gmx);
+    const float fm = mx == -CUDART_INF_F ? 0.f : expf(mx - gmx);    // this warp's factor for head myh
+    const float f0 = __shfl_sync(FULL_MASK, fm, 0), f1 = __shfl_sync(FULL_MASK, fm, 8);
+    const float f2 = __shfl_sync(FULL_MASK, fm, 16), f3 = __shfl_sync(FULL_MASK, fm, 24);
+    float* mg = ring + (size_t)warp * H * C;                        // [warp][H][C]
+#pragma unroll
+    for (int i = 0; i < CPL; i += 4) {
+        *reinterpret_cast<float4*>(mg + 0 * C + c0 + i) = make_float4(G[0][i] * f0, G[0][i + 1] * f0, G[0][i + 2] * f0, G[0][i + 3] * f0);
+        *reinterpret_cast<float4*>(mg + 1 * C + c0 + i) = make_float4(G[1][i] * f1, G[1][i + 1] * f1, G[1][i + 2] * f1, G[1][i + 3] * f1);
+        *reinterpret_cast<float4*>(mg + 2 * C + c0 + i) = make_float4(G[2][i] * f2, G[2][i + 1] * f2, G[2][i + 2] * f2, G[2][i + 3] * f2);
+        *reinterpret_cast<float4*>(mg + 3 * C + c0 + i) = make_float4(G[3][i] * f3, G[3][i + 1] * f3, G[3][i + 2] * f3, G[3][i + 3] * f3);
+    }
+    if ((lane & 7) == 0 && warp == 0) s_den[0][myh] = gden;          // every warp computed the same gden; publish one copy
+    __syncthreads();
+    for (int o = tid; o < H * C; o += GA_THREADS) {                  // o = h * C + channel
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) acc += ring[(size_t)w * H * C + o];
+        P.G[rowid * H * C + o] = acc / s_den[0][o / C];
+    }
+    // ---- full softmax (with the diagonal) of the row's scores -> P (warp h < 4 owns head h) ----
+    if (warp < H) {
+        const int h = warp;
+        float m2 = -CUDART_INF_F, d2 = 0.f;
+        for (int m = lane; m < M; m += 32) m2 = fmaxf(m2, S[h * M + m]);
+        m2 = warp_max(m2);
+        for (int m = lane; m < M; m += 32) d2 += expf(S[h * M + m] - m2);
+        d2 = warp_sum(d2);
+        float* out = P.P + (((size_t)b * H + h) * N + n) * M;
+        for (int m = lane; m < M; m += 32) out[m] = expf(S[h * M + m] - m2) / d2;
+    }
+}
+
 // cross attention: P[row,:] = softmax(QK[row,:] / sqrt(c)); one warp per row of M scores, in place allowed
 __global__ void softmax_rows_kernel(long long rows, int M, const float* __restrict__ qk, float sqrt_c, float* __restrict__ out) {
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -245,6 +406,9 @@ int launch_self(const SelfParams& P, int batch, cudaStream_t st) {
 
 }  // namespace
 
+static int g_self_v3 = 1;     // roitr_debug_geo_self_v3(0): the chunk-synchronous kernel for C = 256 too (A/B timing; C = 512 always uses it)
+extern "C" int roitr_debug_geo_self_v3(int on) { g_self_v3 = on; return 0; }
+
 extern "C" int roitr_geo_self_scores_ld(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq,
                                      long long q_bs, const float* E, const float* gq, int ldgq, const float* bp, float* P, float* G,
                                      void* stream) {
@@ -255,6 +419,19 @@ extern "C" int roitr_geo_self_scores_ld(int batch, int N, int C, int heads, cons
     S.qk = qk; S.q = q; S.ldq = ldq; S.q_bs = q_bs; S.E = E; S.gq = gq; S.ldgq = ldgq; S.bp = bp; S.P = P; S.G = G; S.N = N; S.M = N;
     S.sqrt_c = sqrtf((float)(C / heads));
     cudaStream_t st = (cudaStream_t)stream;
+    if (C == 256 && g_self_v3) {
+        const size_t smem = (size_t)GV_STAGES * GV_CHK * 256 * 4 + (size_t)GA_H * S.M * 4;
+        ROITR_CHECK_ARG(smem <= 226 * 1024 && (ldgq % 4) == 0 && (uintptr_t)gq % 16 == 0, "geo_self_scores: %d keys do not fit / gq alignment", S.M);
+        static size_t configured_dev[ROITR_MAX_DEVICES] = {};
+        size_t& configured = configured_dev[roitr_cur_device()];
+        if (smem > configured) {
+            ROITR_CUDA(cudaFuncSetAttribute(geo_self_scores_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        geo_self_scores_v3_kernel<<<dim3(S.N, batch), GA_THREADS, smem, st>>>(S);
+        ROITR_CHECK_LAUNCH("geo_self_scores_v3_kernel");
+        return ROITR_OK;
+    }
     if (C == 256) return launch_self<256>(S, batch, st);
     return launch_self<512>(S, batch, st);
 }

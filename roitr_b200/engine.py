@@ -24,11 +24,6 @@ STRIDES = (1, 4, 4, 4)
 NSAMPLE = (8, 16, 16, 16)
 BLOCKS = (2, 3, 3, 3)
 HEADS = 4
-# LayerNorm of the 256-channel layers (levels 3-4, global transformer) fused into a 256-column dense-layer tile
-# (csrc/gemm_tc2.cu launch_tc3<256,1,4,8,1>; tests/test_gemm_gpu.py::test_fused_layernorm_256_column_tile). ROITR_LN256=0 restores
-# linear + row_epilogue.
-import os as _os
-LN256 = _os.environ.get("ROITR_LN256", "1") != "0"
 FPS_AFTER_KNN = False        # measured: the level-1 layers start 3 ms earlier but crawl next to the FPS clusters; 563 vs 569 pairs/s
 LIGHT_VARIANT = 3          # streaming dense-layer configuration used while the FPS clusters are resident (0 = none)
 
@@ -79,17 +74,6 @@ def pack_linear_tc(Wm, bn=None):
             out[:, :, :, j, ar ^ j, :] = T[:, :, :, j, :, :]
         return out.reshape(Np // bn, Kp // 32, bn * 32)
     return torch.stack([tile(hi), tile(lo)], dim=2).contiguous(), bn
-
-
-def ws_tile_rows(N, K):
-    """Tile rows of the packing the weight-stationary dense-layer kernel takes for an (N, K) weight, or None when the layer
-    stays on the streaming kernel: the whole row in one tile (64 / 128 / 192 / 256 columns) and the packed weight (hi + lo,
-    rows x K x 8 bytes) resident in shared memory next to two 32 KB operand stages (csrc/gemm_tc2.cu ws_fits)."""
-    bn = 64 if N <= 64 else 128 if N <= 128 else 192 if N <= 192 else 256 if N <= 256 else None
-    if bn is None:
-        return None
-    nkc = -(-K // 32)
-    return bn if nkc * 2 * bn * 128 + 2 * 32768 + 1024 <= 200 * 1024 else None
 
 
 def build_geo_tables(Wd, bd, Wa, ba, div_term, sigma_a=15.0, t_d_max=512.0):
@@ -225,11 +209,6 @@ def _pack_weights(state_dict, device, architecture):
         for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("#Wkv") or k.endswith("#Wfq") or k.endswith("#Wqkvg") or k.endswith("#Wposf") or k.endswith("Big")) and W[k].dim() == 2
                   and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
-            bn_ws = ws_tile_rows(W[k].shape[0], W[k].shape[1])
-            if bn_ws is not None and bn_ws != W[k + "#tc"][1]:       # 192 / 256-row tile: only the weight-stationary kernel takes it
-                W[k + "#ws"] = pack_linear_tc(W[k], bn_ws)
-            if LN256 and W[k].shape[0] == 256 and W[k].shape[1] % 32 == 0 and k.endswith(".weight"):
-                W[k + "#tc256"] = pack_linear_tc(W[k], 256)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = hp
     return W
@@ -244,7 +223,7 @@ def _pk(W, key):
     """The packed forms of weight ``key`` as ops.linear keyword arguments."""
     if not LINEAR_TC:
         return {}
-    return dict(wpack=W.get(key + "#tc"), wpack_ws=W.get(key + "#ws"))
+    return dict(wpack=W.get(key + "#tc"))
 
 
 def _lin(W, p, x, **kw):
@@ -258,8 +237,7 @@ def _ln(W, p, x, **kw):
 def _lin_ln(W, p, n, x, **kw):
     """Linear p followed by LayerNorm n (+ residuals / ReLU), fused into the dense layer's epilogue where it fits."""
     return ops.linear_ln(x, W[p + ".weight"], W[p + ".bias"], W.get(p + ".weight#tc") if LINEAR_TC else None,
-                         W[n + ".weight"], W[n + ".bias"], wpack_wide=W.get(p + ".weight#tc256") if LINEAR_TC else None,
-                         wpack_ws=W.get(p + ".weight#ws") if LINEAR_TC else None, **kw)
+                         W[n + ".weight"], W[n + ".bias"], **kw)
 
 
 def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None, post=None):
@@ -505,8 +483,6 @@ def decode(W, L):
 # ------------------------------------------------------------------------------------------------ global transformer
 def _ffn(W, p, x):
     h = _lin(W, p + ".expand", x, relu=True)
-    if LN256:
-        return _lin_ln(W, p + ".squeeze", p + ".norm", h, res_pre=x)
     return _ln(W, p + ".norm", _lin(W, p + ".squeeze", h), res_pre=x, mode=ops.MODE_LN)
 
 
@@ -535,10 +511,7 @@ def _self_layer_batch(W, lp, x, E, nb, N):
         for h in range(HEADS):
             ops.linear(G2[:, h * C:(h + 1) * C], Wvp[h * c:(h + 1) * c], bvp[h * c:(h + 1) * c], out=pos[:, h * c:(h + 1) * c],
                        M=R, K=C)
-    if LN256:
-        y = _lin_ln(W, lp + ".attention.linear", lp + ".attention.norm", hidden, res_pre=x)
-    else:
-        y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
+    y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     pos = _ln(W, lp + ".attention.pos_norm", pos if LINEAR_TC else _lin(W, lp + ".attention.pos_linear", pos), mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
 
@@ -551,10 +524,7 @@ def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, wpack=tcw("k"))
     v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], wpack=tcw("v"))
     hidden = (ops.attention_tc if ATTENTION_TC else ops.geo_attention_batched_compat)(nb, N, M, C, q, k, v)
-    if LN256:
-        z = _lin_ln(W, lp + ".attention.linear", lp + ".attention.norm", hidden, res_pre=x)
-    else:
-        z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
+    z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", z)
 
 

@@ -22,19 +22,8 @@ def empty(*shape, dtype=torch.float32, like=None, device=None):
 USE_TENSOR_CORES = False    # roitr_linear_tc (tcgen05, 3xTF32) is correct but, being thread-loaded and 2-stage, slower than FFMA on these skinny GEMMs (scripts/bench_gemm.py); opt in per call with tc=True
 
 
-_LINEAR_VARIANT = 0
-
-
-def _pick_pack(wpack, wpack_ws, a_add=None):
-    """The wide (192 / 256-row) packing serves the weight-stationary kernel only; the light configuration that shares an SM
-    with the FPS clusters, and inputs with a second addend, take the 64 / 128-row packing of the streaming kernel."""
-    if wpack_ws is not None and _LINEAR_VARIANT != 3 and a_add is None:
-        return wpack_ws
-    return wpack
-
-
 def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=None, K=None, lda=None, ldw=None,
-           ldc=None, tc=None, wpack=None, wpack_ws=None):
+           ldc=None, tc=None, wpack=None):
     """out[M,N] = (a [+ a_add])[rows, :K] @ w[:N, :K]^T + bias. ``a``/``out`` may be column slices of wider buffers
     (pass lda/ldc); ``a_index`` gathers rows of ``a``."""
     N = w.shape[0]
@@ -46,7 +35,6 @@ def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=No
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     ldc = out.stride(0) if ldc is None else ldc
-    wpack = _pick_pack(wpack, wpack_ws, a_add)
     if wpack is not None:       # (packed weight, tile rows) from engine.pack_linear_tc: persistent tcgen05 kernel
         _lib.call("roitr_linear_tc_packed", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
                   f32(wpack[0]), c_int(wpack[1]), c_void(bias), c_void(out), c_int(ldc), c_int(1 if relu else 0), stream_ptr())
@@ -57,15 +45,11 @@ def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=No
     return out
 
 
-def linear_ln(a, w, bias, wpack, gamma, beta, res_pre=None, res_pre_index=None, res_post=None, relu=False, wpack_wide=None,
-              wpack_ws=None):
+def linear_ln(a, w, bias, wpack, gamma, beta, res_pre=None, res_pre_index=None, res_post=None, relu=False):
     """act(LN(a @ w^T + bias + res_pre[res_pre_index]) * gamma + beta + res_post) in ONE kernel when the layer fits the fused
     epilogue (N a multiple of 32 within one weight tile, plain aligned input); otherwise linear + row_epilogue."""
     M, K = a.shape
     N = w.shape[0]
-    wpack = _pick_pack(wpack, wpack_ws)
-    if wpack_wide is not None and N <= wpack_wide[1] and (wpack is None or N > wpack[1]):   # a 256-row packing whose tile spans the whole row
-        wpack = wpack_wide
     fused = (wpack is not None and N % 32 == 0 and N <= wpack[1] and a.stride(0) % 4 == 0 and K % 4 == 0 and
              a.data_ptr() % 16 == 0 and a.stride(1) == 1 and
              (res_pre is None or res_post is None or res_pre.stride(0) == res_post.stride(0)))      # one residual pitch
@@ -86,8 +70,6 @@ def linear_ln(a, w, bias, wpack, gamma, beta, res_pre=None, res_pre_index=None, 
 def set_linear_variant(v):
     """Configuration of the streaming dense-layer kernel for the launches issued from now on (baked into a graph at capture):
     0 = deep rings, one CTA per SM; 3 = light footprint that shares an SM with other kernels' CTAs."""
-    global _LINEAR_VARIANT
-    _LINEAR_VARIANT = int(v)
     _lib.lib().roitr_debug_linear_variant(c_int(int(v)))
 
 

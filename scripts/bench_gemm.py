@@ -18,7 +18,7 @@ def timeit(fn, iters=7):
 out = open(os.path.join(ROOT, "gpurun_out", "bench_gemm.txt"), "w")
 def log(s):
     print(s); out.write(s + "\n"); out.flush()
-log("M,N,K, tc2_ms, tc3_ms (streaming), ws_ms (weight-stationary, nan = does not apply), best GB/s(A+C), frac of measured HBM 6532 GB/s, max|tc3-tc2|")
+log("M,N,K, tc2_ms, tc3_ms (streaming), GB/s(A+C+W), frac of measured HBM 6532 GB/s, max|tc3-tc2|")
 SHAPES = [(640000, 64, 64), (640000, 192, 64), (640000, 128, 64), (640000, 256, 64), (640000, 384, 128), (160000, 128, 128),
           (160000, 384, 128), (160000, 256, 128), (160000, 768, 256), (40000, 256, 256), (40000, 768, 256), (9984, 256, 256),
           (9984, 768, 256), (4992, 256, 256), (4992, 512, 256), (4992, 256, 512), (4992, 768, 256), (4992, 1024, 256), (4992, 256, 1024)]
@@ -29,19 +29,16 @@ for (M, N, K) in SHAPES:
     _lib.lib().roitr_debug_force_linear_tc2(1)
     t2 = timeit(lambda: ops.linear(a, w, b, out=o2, wpack=wp))
     _lib.lib().roitr_debug_force_linear_tc2(0)
-    _lib.lib().roitr_debug_linear_ws(0)
     t3 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp))
-    _lib.lib().roitr_debug_linear_ws(1)
-    bn = engine.ws_tile_rows(N, K)
-    tw = float("nan")
-    if bn is not None:
-        wpw = engine.pack_linear_tc(w, bn)
-        ow = torch.empty(M, N, device=DEV)
-        tw = timeit(lambda: ops.linear(a, w, b, out=ow, wpack=wp, wpack_ws=wpw))
-        assert torch.equal(ow, o3)
-    best = min(t3, tw) if tw == tw else t3
+    best = t3
+    extra = []
+    for v in (4, 5):            # deeper raw rings (more bytes in flight per SM)
+        ops.set_linear_variant(v)
+        extra.append(timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp)))
+    ops.set_linear_variant(0)
+    print("   variants 4/5 (raw ring 6 / 8 deep): %.4f %.4f" % tuple(extra))
     gbs = (M * K + M * N + N * K) * 4 / best / 1e6
-    log("%d,%d,%d, %.4f, %.4f, %.4f, %.0f, %.3f, %.2e" % (M, N, K, t2, t3, tw, gbs, gbs / 6532.5, (o3 - o2).abs().max().item()))
+    log("%d,%d,%d, %.4f, %.4f, %.0f, %.3f, %.2e" % (M, N, K, t2, t3, gbs, gbs / 6532.5, (o3 - o2).abs().max().item()))
 
 log("fused LayerNorm epilogue: M,N,K, plain_ms, row_epilogue_ms, fused_ms (res_pre), fused_ms (res_post+relu)")
 for (M, N, K) in [(640000, 64, 64), (160000, 128, 128)]:

@@ -211,56 +211,3 @@ def test_linear_ln_fused_matches_fp64(M, N, K, pre, gather, post, relu):
     two = ops.row_epilogue(t32, res_pre=res_pre, res_pre_index=idx, gamma=gamma, beta=beta, res_post=res_post,
                            mode=ops.MODE_LN | (ops.MODE_RELU if relu else 0))
     assert (y - two).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
-
-
-@pytest.mark.parametrize("M,K,pre,post,relu", [(9984, 256, True, False, False), (4992, 512, True, False, False), (40000, 256, False, True, True)])
-def test_fused_layernorm_256_column_tile(M, K, pre, post, relu):
-    """engine.LN256 (on by default): LayerNorm of a 256-channel layer in the epilogue of a 256-column tile == linear + row_epilogue."""
-    from roitr_b200 import engine, ops
-    g = torch.Generator().manual_seed(M + K)
-    a = torch.randn(M, K, generator=g).cuda()
-    w = (torch.randn(256, K, generator=g) / K ** 0.5).cuda()
-    b = torch.randn(256, generator=g).cuda()
-    gamma, beta = (1 + 0.1 * torch.randn(256, generator=g)).cuda(), (0.1 * torch.randn(256, generator=g)).cuda()
-    res = torch.randn(M, 256, generator=g).cuda()
-    y = ops.linear_ln(a, w, b, engine.pack_linear_tc(w), gamma, beta, res_pre=res if pre else None, res_post=res if post else None,
-                      relu=relu, wpack_wide=engine.pack_linear_tc(w, 256))
-    t = ops.linear(a, w, b, wpack=engine.pack_linear_tc(w))
-    two = ops.row_epilogue(t, res_pre=res if pre else None, gamma=gamma, beta=beta, res_post=res if post else None,
-                           mode=ops.MODE_LN | (ops.MODE_RELU if relu else 0))
-    assert (y - two).abs().max().item() <= 1e-5 * max(1.0, two.abs().max().item())
-
-
-@pytest.mark.parametrize("M,N,K,gather", [(20000, 192, 64, False), (20000, 256, 64, False), (640000, 256, 64, False), (5000, 256, 64, True),
-                                          (5000, 128, 128, False), (3000, 64, 256, False), (777, 150, 40, False), (129, 192, 96, True),
-                                          (127, 256, 64, False), (160000, 128, 128, False)])
-def test_weight_stationary_kernel_matches_fp64_and_streaming_kernel(M, N, K, gather):
-    """linear_ws_kernel (csrc/gemm_tc2.cu: packed weight resident in shared memory, the whole row in one 64..256-column tile)
-    against fp64, and bit for bit against the streaming kernel on the same operands (same split, same MMA order per row)."""
-    from roitr_b200 import _lib, engine
-    g = torch.Generator().manual_seed(M + 5 * N + 11 * K)
-    R = 2 * M if gather else M
-    a = torch.randn(R, K, generator=g).to(DEV)
-    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
-    b = torch.randn(N, generator=g).to(DEV)
-    idx = torch.randint(0, R, (M,), generator=g).int().to(DEV) if gather else None
-    bn = engine.ws_tile_rows(N, K)
-    assert bn is not None
-    y = ops.linear(a, w, b, relu=True, a_index=idx, wpack=engine.pack_linear_tc(w), wpack_ws=engine.pack_linear_tc(w, bn))
-    ref = _ref(a[idx.long()] if gather else a, w, b, True)
-    assert (y.double() - ref).abs().max().item() <= 6e-6 * ref.abs().max().item() * max(1.0, (K / 256) ** 0.5)
-    try:
-        _lib.lib().roitr_debug_linear_ws(0)
-        y2 = ops.linear(a, w, b, relu=True, a_index=idx, wpack=engine.pack_linear_tc(w))
-    finally:
-        _lib.lib().roitr_debug_linear_ws(1)
-    assert torch.equal(y, y2)
-
-
-def test_weight_stationary_kernel_rejects_what_it_cannot_take():
-    from roitr_b200 import _lib, engine
-    assert engine.ws_tile_rows(256, 128) is None and engine.ws_tile_rows(512, 64) is None and engine.ws_tile_rows(256, 64) == 256
-    a = torch.randn(300, 64, device=DEV)
-    w = torch.randn(256, 64, device=DEV)
-    with pytest.raises(_lib.RoitrError):          # a 256-row packing with an unaligned input cannot fall back to the streaming kernel
-        ops.linear(a[:, 1:], w[:, 1:].contiguous(), None, K=63, wpack=engine.pack_linear_tc(w[:, 1:].contiguous(), 256))
