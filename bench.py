@@ -386,6 +386,12 @@ def main():
     eager_ms = sum(v["ms"] for v in shares.values())
 
     ms_dev, ms_e2e, ms_rec = sharding.max_over_ranks([ms_dev, ms_e2e, ms_rec], dist, dev)   # device-timed, max over ranks
+    # the result gather (outside the timed regions): every rank's correspondences of its last batch, variable length per pair,
+    # to rank 0 - the one data-bearing collective of a sharded run
+    runner.load(resident[0]); runner.run()
+    own_last = sharding.owned_pairs(rank, world, B, NB)[0]
+    local_corr = [(g, torch.cat([t, s_, c[:, None]], 1)) for g, (t, s_, c) in zip(own_last, runner.correspondences())]
+    gathered = sharding.gather_correspondences(local_corr, dist, dev)
     total_corr = sum(sharding.gather_counts(sum(x[2] for x in counts), dist, dev))   # the (trivial) result gather
 
     if rank == 0:
@@ -453,7 +459,8 @@ def main():
             "gpu_launches": launches_per_step * steps, "clocks": clk.summary(), "roofline": roof,
             "north_star_rooflines": named, "serial_replica_ms": round(eager_ms, 3),
             "kernel_shares_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])},
-            "result_check": {"correspondences_per_pair": total_corr / (world * B), "e2e_correspondences_last_step": ncorr},
+            "result_check": {"correspondences_per_pair": total_corr / (world * B), "e2e_correspondences_last_step": ncorr,
+                             "gathered_on_rank0": {"pairs": len(gathered), "correspondences": int(sum(t.shape[0] for t in gathered.values()))}},
             "wall_s_between_barriers": wall,
         }
         if not args.no_cpu_baseline and world == 1:

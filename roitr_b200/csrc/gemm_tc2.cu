@@ -618,14 +618,10 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
                         "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile (N=%d, tile %d)", N, bn);
     if (P.ln) {
         if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
-        if (g_tc3_variant == 4 && bn == 64) return launch_tc3<64, 2, 6, 8, 1>(P, st);
-        if (g_tc3_variant == 5) return bn == 64 ? launch_tc3<64, 2, 6, 8, 1>(P, st) : launch_tc3<128, 1, 8, 8, 1>(P, st);
         return bn == 64 ? launch_tc3<64, 3, 3, 8, 1>(P, st) : launch_tc3<128, 2, 4, 8, 1>(P, st);
     }
     if (stream_ok && !g_force_tc2) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
-        if (g_tc3_variant == 4 && bn == 64) return launch_tc3<64, 2, 6, 8, 1>(P, st);
-        if (g_tc3_variant == 5) return bn == 64 ? launch_tc3<64, 2, 6, 8, 1>(P, st) : launch_tc3<128, 1, 8, 8, 1>(P, st);
         return bn == 128 ? launch_tc3<128, 2, 4, 8, 1>(P, st) : launch_tc3<64, 3, 3, 8, 1>(P, st);
     }
     if (bn == 64) return launch_tc2<64, 4>(P, st);

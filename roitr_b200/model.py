@@ -127,6 +127,7 @@ class _PackedMixin:
 
     def _apply(self, fn, *a, **kw):            # .to() / .cuda() / .float(): new storage
         self._pack_key = None
+        self.__dict__.pop("_graph_cache", None)
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):
@@ -143,6 +144,7 @@ class _PackedMixin:
             sd = {prefix + k: v for k, v in self.state_dict().items()}
             self._pack = engine.pack_weights(sd, params[0].device, architecture)
             self._pack_key = key
+            self.__dict__.pop("_graph_cache", None)      # captured graphs hold the old packed weights
         return self._pack
 
 
@@ -270,7 +272,43 @@ class RIGA_v2(nn.Module, _PackedMixin):
             W = self._packed("", self.cfg["transformer_architecture"])
             args = [t.contiguous().float() for t in (src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, tgt_normals, rot,
                                                      trans, src_raw_pcd)]
+            if _aux is None and self.graph_cache_size > 0:
+                out = self._forward_cached_graph(W, args)
+                if out is not None:
+                    return out
             return engine.riga_forward(W, self.cfg, *args, aux=_aux)
+
+    # lib/tester.py:53 calls forward once per pair (batch_size 1): ~700 kernel launches whose HOST cost (~38 ms through ctypes)
+    # exceeds their device time (~12 ms at 2 x 20 000 points). Cloud sizes that REPEAT - fixed-size inference, benchmarks,
+    # voxel-capped datasets - are served from a per-shape CUDA graph instead: the second forward with a given (n_src, n_tgt)
+    # captures a one-pair engine.BatchRunner, later ones replay it (inputs copied into its static buffers, outputs cloned out
+    # of them, so results stay valid after the next call). Results are bit-identical to the eager path (same kernels).
+    # ``graph_cache_size = 0`` disables it; least-recently-used shapes are dropped beyond the limit.
+    graph_cache_size = 4
+
+    def _forward_cached_graph(self, W, args):
+        src_pcd, tgt_pcd, src_feats, tgt_feats, src_normals, tgt_normals, rot, trans, src_raw_pcd = args
+        key = (int(src_raw_pcd.shape[0]), int(tgt_pcd.shape[0]), src_pcd.device, id(W))
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        seen = self.__dict__.setdefault("_graph_seen", {})
+        r = cache.get(key)
+        if r is None:
+            seen[key] = seen.get(key, 0) + 1
+            if seen[key] < 2:                 # first sight of a shape: eager (a capture costs several forwards)
+                if len(seen) > 64:
+                    seen.clear()
+                return None
+            r = engine.BatchRunner(W, self.cfg, 1, key[0], key[1], src_pcd.device, graph=True)
+            cache[key] = r
+            while len(cache) > self.graph_cache_size:
+                cache.pop(next(iter(cache)))
+        else:
+            cache[key] = cache.pop(key)        # most recently used last
+        r.load([dict(src_pcd=src_pcd, tgt_pcd=tgt_pcd, src_feats=src_feats, tgt_feats=tgt_feats, src_normals=src_normals,
+                     tgt_normals=tgt_normals, rot=rot, trans=trans.reshape(3, 1), src_raw_pcd=src_raw_pcd)])
+        r.run()
+        out = r.results()[0]                   # the one host sync (counts)
+        return {k: v.clone() for k, v in out.items()}
 
 
     def batch_runner(self, batch_pairs, n_src, n_tgt, graph=True, fps_cluster=0, serial=False):

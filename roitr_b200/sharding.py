@@ -39,6 +39,45 @@ def gather_counts(count, dist=None, device="cpu"):
     return [int(c)]
 
 
+def gather_correspondences(local, dist=None, device="cpu", dst=0):
+    """The result gather of a sharded run: ``local`` = this rank's list of (global_pair_index, tensor (c_i, 7)) - per pair the
+    rows [tgt_xyz | src_xyz | score] of its correspondences, c_i data dependent. Returns on rank ``dst`` a dict
+    {global_pair_index: tensor (c_i, 7)} holding every rank's pairs, and None on the other ranks. Two collectives: an
+    all_gather of the per-rank (pair index, count) tables (padded to the longest), then one all_gather of the payloads padded
+    to the largest per-rank total - a gatherv expressed with the collectives both nccl and gloo implement."""
+    idx = torch.tensor([[int(g), int(t.shape[0])] for g, t in local], dtype=torch.int64, device=device).reshape(-1, 2)
+    payload = torch.cat([t.reshape(-1, 7).to(device=device, dtype=torch.float32) for _, t in local]) if local else \
+        torch.zeros(0, 7, dtype=torch.float32, device=device)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        out, o = {}, 0
+        for g, c in idx.tolist():
+            out[g] = payload[o:o + c]
+            o += c
+        return out
+    world = dist.get_world_size()
+    sizes = torch.tensor([idx.shape[0], payload.shape[0]], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    max_pairs, max_rows = max(int(s[0]) for s in all_sizes), max(int(s[1]) for s in all_sizes)
+    idx_pad = torch.zeros(max(max_pairs, 1), 2, dtype=torch.int64, device=device)
+    idx_pad[:idx.shape[0]] = idx
+    pay_pad = torch.zeros(max(max_rows, 1), 7, dtype=torch.float32, device=device)
+    pay_pad[:payload.shape[0]] = payload
+    all_idx = [torch.zeros_like(idx_pad) for _ in range(world)]
+    all_pay = [torch.zeros_like(pay_pad) for _ in range(world)]
+    dist.all_gather(all_idx, idx_pad)
+    dist.all_gather(all_pay, pay_pad)
+    if dist.get_rank() != dst:
+        return None
+    out = {}
+    for r in range(world):
+        o = 0
+        for g, c in all_idx[r][:int(all_sizes[r][0])].tolist():
+            out[g] = all_pay[r][o:o + c]
+            o += c
+    return out
+
+
 def job_throughput(pairs_per_step_per_rank, world, steps, ms_max):
     """Whole-job pairs/s: units all ranks processed / the max-over-ranks device time."""
     return world * pairs_per_step_per_rank * steps / (ms_max * 1e-3)

@@ -31,12 +31,6 @@ for (M, N, K) in SHAPES:
     _lib.lib().roitr_debug_force_linear_tc2(0)
     t3 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp))
     best = t3
-    extra = []
-    for v in (4, 5):            # deeper raw rings (more bytes in flight per SM)
-        ops.set_linear_variant(v)
-        extra.append(timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp)))
-    ops.set_linear_variant(0)
-    print("   variants 4/5 (raw ring 6 / 8 deep): %.4f %.4f" % tuple(extra))
     gbs = (M * K + M * N + N * K) * 4 / best / 1e6
     log("%d,%d,%d, %.4f, %.4f, %.0f, %.3f, %.2e" % (M, N, K, t2, t3, gbs, gbs / 6532.5, (o3 - o2).abs().max().item()))
 

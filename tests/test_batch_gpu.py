@@ -106,3 +106,27 @@ def test_pipelined_runner_equals_single_pair_forward():
             assert set(o) == set(r)
             for k in r:
                 assert o[k].shape == r[k].shape and torch.equal(o[k], r[k]), k
+
+
+def test_single_pair_forward_graph_cache_is_transparent():
+    """RIGA_v2.forward serves a REPEATED cloud shape from a per-shape CUDA graph (model.graph_cache_size): same dict, same
+    values bit for bit as the eager forward, outputs stay valid after later calls, other shapes still work."""
+    N = 2048
+    m = model.create_model(CONFIG_3D)
+    m.load_state_dict(weights(1))
+    m = m.to(DEV).eval()
+    pairs = [synthetic_pair(60 + i, N) for i in range(4)]
+    m.graph_cache_size = 0
+    eager = [m(*forward_args(p, DEV)) for p in pairs]
+    m.graph_cache_size = 4
+    outs = [m(*forward_args(p, DEV)) for p in pairs]          # 1st eager, 2nd captures, 3rd / 4th replay
+    assert len(m._graph_cache) == 1
+    other = m(*forward_args(synthetic_pair(70, 1500), DEV))    # a different shape in between (eager: first sight)
+    again = m(*forward_args(pairs[0], DEV))                    # replay with the first pair's data
+    for o, e in zip(outs + [again], eager + [eager[0]]):
+        assert set(o) == set(e)
+        for k in e:
+            assert o[k].shape == e[k].shape and o[k].dtype == e[k].dtype and torch.equal(o[k], e[k]), k
+    assert other["src_points"].shape[0] == 1500
+    m.float()                                                  # _apply drops the captured graphs (they hold the old weights)
+    assert "_graph_cache" not in m.__dict__

@@ -36,6 +36,8 @@ def test_weak_scaling_throughput_formula():
 def test_single_process_paths_need_no_process_group():
     assert sharding.max_over_ranks([3.0, 4.0]) == [3.0, 4.0]
     assert sharding.gather_counts(7) == [7]
+    one = sharding.gather_correspondences([(3, torch.ones(2, 7)), (5, torch.zeros(0, 7))])
+    assert sorted(one) == [3, 5] and one[3].shape == (2, 7) and one[5].shape == (0, 7)
 
 
 def _free_port():
@@ -58,8 +60,12 @@ def _worker(rank, world, port, out):
         flat = torch.tensor([g for o in own for g in o], dtype=torch.int64)
         allidx = [torch.zeros_like(flat) for _ in range(world)]
         dist.all_gather(allidx, flat)
+        # variable-length result gather: pair g contributes (g % 5) + rank rows whose first column encodes (g, row)
+        local = [(g, torch.arange((g % 5) + rank, dtype=torch.float32)[:, None].repeat(1, 7) + 100.0 * g) for o in own for g in o]
+        gathered = sharding.gather_correspondences(local, dist)
         dist.barrier()
-        out.put((rank, ms, counts, [t.tolist() for t in allidx], own[0][0], checksum))
+        summary = None if gathered is None else {g: (t.shape[0], float(t.sum())) for g, t in gathered.items()}
+        out.put((rank, ms, counts, [t.tolist() for t in allidx], own[0][0], checksum, summary))
     finally:
         dist.destroy_process_group()
 
@@ -75,7 +81,15 @@ def test_two_gloo_ranks_shard_reduce_gather():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ms, counts, allidx, g0, checksum in got:
+    for rank, ms, counts, allidx, g0, checksum, summary in got:
+        if rank == 0:      # rank 0 holds every pair's correspondences, each with its own length
+            assert sorted(summary) == list(range(8))
+            for g, (rows, total) in summary.items():
+                r_own, _ = sharding.owner_of(g, world)
+                n = (g % 5) + r_own
+                assert rows == n and total == pytest.approx(7 * (n * (n - 1) / 2 + 100.0 * g * n))
+        else:
+            assert summary is None
         assert ms == [11.0, 20.0]
         assert counts == [100, 101]
         assert sorted(i for l in allidx for i in l) == list(range(8))          # disjoint and complete across ranks
