@@ -136,18 +136,20 @@ int roitr_gather_rows(long long rows, int c, const void* index, int index_is_i64
 int roitr_linear(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index, const float* W,
                  int ldw, const float* bias, float* C, int ldc, int relu, void* stream);
 
-/* Same contract as roitr_linear, computed on the tensor cores: tcgen05.mma kind::tf32 with 3xTF32 split precision
- * (x = hi + lo exactly; hi*hi + hi*lo + lo*hi accumulated in fp32 TMEM; relative error ~2^-21, fp32-grade). One CTA per
- * 128 x {64,128,256} output tile, operands split on the fly into 128B-swizzled shared memory, 2-stage pipeline. */
-int roitr_linear_tc(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index, const float* W,
-                    int ldw, const float* bias, float* C, int ldc, int relu, void* stream);
-
-/* The production tensor-core dense layer: persistent, warp-specialised (A loader warps, bulk-TMA weight producer, single-
+/* The tensor-core dense layer: tcgen05.mma kind::tf32 with 3xTF32 split precision (x = hi + lo exactly; hi*hi + hi*lo + lo*hi
+ * accumulated in fp32 TMEM; relative error ~2^-21, fp32-grade); persistent, warp-specialised (A loader warps, bulk-TMA weight producer, single-
  * thread tcgen05 MMA issuer, epilogue warps; two TMEM accumulators so the epilogue of a tile overlaps the next tile).
  * wpack = the weight pre-split into TF32 hi/lo and pre-swizzled by roitr_b200.engine.pack_linear_tc:
  * [ceil(N/bn)][ceil(K/32)][hi|lo][bn*32] floats, zero padded, bn in {64,128}. Same contract as roitr_linear otherwise. */
 int roitr_linear_tc_packed(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
                            const float* wpack, int bn, const float* bias, float* C, int ldc, int relu, void* stream);
+
+/* Launch configuration of the streaming dense-layer kernel for the calls issued from now on (a process-wide host-side mode;
+ * baked into a CUDA graph at capture): 0 = deep rings, one CTA per SM (215 KB shared memory, 57 K registers); 3 = light
+ * footprint (one operand stage, two raw stages, <= 64 registers: ~115 KB, 20 K registers) that shares an SM with the CTAs of
+ * other streams' kernels - the engine sets it around the level-1 layers it issues while the FPS clusters are resident.
+ * Results are identical in both. */
+int roitr_set_linear_config(int config);
 /* Dense layer with the row epilogue fused (one kernel instead of roitr_linear_tc_packed + roitr_row_epilogue):
  *   C = act( LayerNorm_N( A W^T + bias + res_pre[res_pre_index] ) * gamma + beta + res_post ),  act = ReLU if relu
  * (LocalRPEAttentionLayer output: attention.py:317-319; RIPointTransformerBlock: model/model.py:139-141; TransitionUp:
@@ -195,12 +197,10 @@ int roitr_geo_knn(int N, int k, const float* pts, int* nn, void* stream);
 int roitr_geo_knn_batched(int batch, int N, int k, const float* pts, int* nn, void* stream);
 
 /* E (N,N,C) = proj_d(sinusoid(dist/sigma_d)) + max_{r<3} proj_a(sinusoid(angle_r * 180/(sigma_a*pi)))
- * (GeometricStructureEmbedding.forward, :139-154); sinusoids are generated in-kernel. C multiple of 128. */
-int roitr_geo_embedding(int N, int C, const float* pts, const int* nn3, const float* Wd, const float* bd,
-                        const float* Wa, const float* ba, const float* div_term, float sigma_d, float sigma_a, float* E,
-                        void* stream);
-
-/* Same result on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split precision, four accumulators per tile in TMEM).
+ * (GeometricStructureEmbedding.forward, :139-154) as the GEMM the reference runs, on the tensor cores (tcgen05.mma
+ * kind::tf32, 3xTF32 split precision, sinusoid A operand generated in-kernel, four accumulators per tile in TMEM). This is
+ * the FALLBACK of roitr_geo_embedding_table: the engine takes it when the table's interpolation error bound cannot be met
+ * for the loaded weights (roitr_b200.engine.build_geo_tables). C multiple of 128.
  * wpack: W_d and W_a pre-split into TF32 hi/lo and pre-swizzled into 32 KB SWIZZLE_128B blocks,
  * layout [mat(d,a)][C/128][C/32][hi|lo][4096] floats (roitr_b200.engine.pack_tf32_sw128); fetched by bulk TMA. */
 int roitr_geo_embedding_tc(int N, int C, const float* pts, const int* nn3, const float* wpack, const float* bd,
@@ -214,15 +214,14 @@ int roitr_geo_embedding_tc_batched(int batch, int N, int C, const float* pts, co
  * they are sampled once per weight load on a uniform grid of step h = 1/inv_h (a power of two) in fp64
  * (roitr_b200.engine.build_geo_tables) and evaluated per (n,m) scalar by 4-point Lagrange interpolation (error bound
  * (3/128) h^4 max|d4F/dt4|, chosen <= 2.5e-7 at pack time). tab_a [C/64][rows_a][64], tab_d [C/64][rows_d][64], row r
- * holds t = (r - 1) h. Scalars beyond the tables are evaluated directly from Wd / Wa (same contract as
- * roitr_geo_embedding). pts (batch*N,3), nn3 (batch*N,3) cloud-local, E (batch,N,N,C). C multiple of 64. */
+ * holds t = (r - 1) h. Scalars beyond the tables (and NaN / Inf) are evaluated directly from Wd / Wa. pts (batch*N,3), nn3 (batch*N,3) cloud-local, E (batch,N,N,C). C multiple of 64. */
 long long roitr_geo_table_smem_rows(void);
 int roitr_geo_embedding_table(int batch, int N, int C, const float* pts, const int* nn3, const float* tab_a, int rows_a,
                               const float* tab_d, int rows_d, float inv_h, const float* Wd, const float* bd,
                               const float* Wa, const float* ba, const float* div_term, float sigma_d, float sigma_a,
                               float* E, void* stream);
 
-/* Batched dense contraction on the tensor cores (tcgen05 3xTF32, the thread-loaded kernel of roitr_linear_tc) for
+/* Batched dense contraction on the tensor cores (tcgen05 3xTF32, one CTA per 128 x {64,128,256} tile, operands split on the fly) for
  * operands that are activations: for every (o, i) in batch_outer x batch_inner
  *     C_oi[M,N] = A_oi[M,K] W_oi[N,K]^T,   X_oi = X + o * sX_o + i * sX_i  (element strides)
  * w_transposed != 0: W_oi is given as (K, >= N) row-major with leading dimension ldw (W_oi[n][k] = Wt[k * ldw + n]).
@@ -244,19 +243,6 @@ int roitr_geo_self_scores_ld(int batch, int N, int C, int heads, const float* qk
 
 /* out[row,:] = softmax(qk[row,:] / scale_div) over M entries per row (MultiHeadAttention, geoattention.py:50-60). */
 int roitr_softmax_rows(long long rows, int M, const float* qk, float scale_div, float* out, void* stream);
-
-/* First-generation attention core (one SIMT kernel; kept as the reference implementation of the path above). E == NULL: MultiHeadAttention (geoattention.py:50-64) hidden = softmax(q k^T / sqrt(c)) v.
- * E != NULL (N == M): RPEMultiHeadAttention (geoattention.py:107-134) with gq (N,4,C) = folded positional queries
- * (gq[n,h,:] = W_p[h*c:(h+1)*c,:]^T q[n,h*c:(h+1)*c]) and bp = proj_p.bias; also G (N,4,C) = sum_m A-_nm E_nm where A- is
- * the softmax with the diagonal removed (the caller maps G through proj_vp per head). heads = 4, C in {256,512}. */
-int roitr_geo_attention(int N, int M, int C, int heads, const float* q, int ldq, const float* k, int ldk, const float* v,
-                        int ldv, const float* E, const float* gq, const float* bp, float* hidden, float* G, void* stream);
-
-/* `batch` independent clouds per launch (blockIdx.y): q/k/v advance by q_bs/k_bs/v_bs elements per cloud; E (batch,N,M,C),
- * gq, G (batch,N,4,C) and hidden (batch,N,C) are contiguous per cloud. */
-int roitr_geo_attention_batched(int batch, int N, int M, int C, int heads, const float* q, int ldq, long long q_bs,
-                                const float* k, int ldk, long long k_bs, const float* v, int ldv, long long v_bs,
-                                const float* E, const float* gq, const float* bp, float* hidden, float* G, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Matching head (lib/utils.py:428-471, model/modules.py:10-72,135-178,216-324, model/RIGA_v2.py:150-173).

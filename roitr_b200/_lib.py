@@ -28,10 +28,6 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.roitr_last_error.restype = ctypes.c_char_p
         _lib.roitr_abi_version.restype = c_int
-        if os.environ.get("ROITR_SELF_V3"):             # A/B timing of the barrier-free self-attention pass (csrc/geo_attn2.cu)
-            _lib.roitr_debug_geo_self_v3(int(os.environ["ROITR_SELF_V3"]))
-        if os.environ.get("ROITR_LINEAR_VARIANT"):      # tuning knob (scripts/): streaming dense-layer kernel configuration
-            _lib.roitr_debug_linear_variant(int(os.environ["ROITR_LINEAR_VARIANT"]))
     return _lib
 
 
@@ -74,9 +70,9 @@ def i32(t):
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim; memsets not counted)
 KERNELS_PER_CALL = {
     "roitr_knnquery_n": 2, "roitr_knn_ppf_n": 2, "roitr_knn_ppf_grid": 2, "roitr_knn_ppf_grid_q": 2, "roitr_knn_grid_build": 4, "roitr_furthestsampling_cfg": 1, "roitr_interpolate": 1,
-    "roitr_gather_rows": 1, "roitr_linear": 1, "roitr_linear_tc": 1, "roitr_linear_tc_packed": 1, "roitr_linear_ln_tc_packed": 1, "roitr_row_epilogue": 1, "roitr_segment_mean": 1,
-    "roitr_concat_segment": 1, "roitr_local_attention": 1, "roitr_local_attention_ordered": 1, "roitr_geo_knn": 1, "roitr_geo_embedding": 1, "roitr_geo_embedding_tc": 1, "roitr_geo_embedding_tc_batched": 1, "roitr_geo_knn_batched": 1, "roitr_geo_embedding_table": 1, "roitr_gemm_tc_batched": 1, "roitr_geo_self_scores": 1, "roitr_geo_self_scores_ld": 1, "roitr_softmax_rows": 1,
-    "roitr_geo_attention": 1, "roitr_geo_attention_batched": 1, "roitr_point_to_node_batched": 4, "roitr_compact_flags": 3, "roitr_compact_flags_batched": 3, "roitr_coarse_matching_batched": 5, "roitr_coarse_matching_adaptive_batched": 6,
+    "roitr_gather_rows": 1, "roitr_linear": 1, "roitr_linear_tc_packed": 1, "roitr_linear_ln_tc_packed": 1, "roitr_row_epilogue": 1, "roitr_segment_mean": 1,
+    "roitr_concat_segment": 1, "roitr_local_attention": 1, "roitr_local_attention_ordered": 1, "roitr_geo_knn": 1, "roitr_geo_embedding_tc": 1, "roitr_geo_embedding_tc_batched": 1, "roitr_geo_knn_batched": 1, "roitr_geo_embedding_table": 1, "roitr_gemm_tc_batched": 1, "roitr_geo_self_scores": 1, "roitr_geo_self_scores_ld": 1, "roitr_softmax_rows": 1,
+    "roitr_point_to_node_batched": 4, "roitr_compact_flags": 3, "roitr_compact_flags_batched": 3, "roitr_coarse_matching_batched": 5, "roitr_coarse_matching_adaptive_batched": 6,
     "roitr_fine_matching_batched": 1, "roitr_fine_gather_batched": 1, "roitr_pad_transform": 1, "roitr_pad_transform_batched": 1, "roitr_node_occlusion_batched": 1,
     "roitr_node_overlaps_batched": 3, "roitr_corr_gather_batched": 1, "roitr_ransac_correspondences": 2, "roitr_weighted_procrustes": 1, "roitr_estimate_normals": 1,
 }

@@ -215,21 +215,6 @@ int launch_tc(const TcParams& P, cudaStream_t st, int batch = 1) {
 
 }  // namespace
 
-extern "C" int roitr_linear_tc(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
-                               const float* W, int ldw, const float* bias, float* C, int ldc, int relu, void* stream) {
-    ROITR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && A && W && C, "linear_tc: bad arguments M=%d N=%d K=%d", M, N, K);
-    ROITR_CHECK_ARG(lda >= K && ldc >= N && ldw >= K, "linear_tc: bad leading dimensions");
-    if (M == 0) return ROITR_OK;
-    TcParams P;
-    P.M = M; P.N = N; P.K = K; P.A = A; P.A2 = a_add; P.lda = lda; P.a_index = a_index; P.W = W; P.ldw = ldw; P.bias = bias;
-    P.C = C; P.ldc = ldc; P.relu = relu;
-    P.inner = 1; P.sA_o = P.sA_i = P.sW_o = P.sW_i = P.sC_o = P.sC_i = 0; P.w_transposed = 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 64) return launch_tc<64>(P, st);
-    if (N <= 128) return launch_tc<128>(P, st);
-    return launch_tc<256>(P, st);
-}
-
 extern "C" int roitr_gemm_tc_batched(int batch_outer, int batch_inner, int M, int N, int K, const float* A, int lda,
                                      long long sA_o, long long sA_i, const float* W, int ldw, long long sW_o, long long sW_i,
                                      int w_transposed, float* C, int ldc, long long sC_o, long long sC_i, void* stream) {

@@ -45,7 +45,6 @@ struct Tc2Params {
     // fused row epilogue (streaming kernel, N <= one tile): out = act(LN(acc + bias + res_pre[idx]) * gamma + beta + res_post)
     const float* ln_gamma; const float* ln_beta; const float* res_pre; const int* res_pre_index; const float* res_post;
     int ln, ldr;            // ln != 0: LayerNorm over the N columns (eps 1e-5); ldr = row pitch of res_pre / res_post
-    int ablate;             // debug only (roitr_debug_linear_ablate): 1 no C stores, 2 W fetched once, 4 no MMA, 8 no split, 16 no A loads
 };
 
 // Epilogue of one 32x32 accumulator block held as "thread = row, v[j] = column j" (the tcgen05.ld 32x32b layout): bias,
@@ -62,7 +61,7 @@ __device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, co
     __syncwarp();
     if (vec) {
         const int sub = lane >> 3, n = ncol0 + 4 * (lane & 7);
-        if (n < P.N && !(P.ablate & 1)) {
+        if (n < P.N) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + n));
             float* dst = P.C + (long long)(row0 + sub) * P.ldc + n;
@@ -85,7 +84,7 @@ __device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, co
         }
     } else {
         const int n = ncol0 + lane;
-        if (n < P.N && !(P.ablate & 1)) {
+        if (n < P.N) {
             const float bv = bias ? __ldg(bias + n) : 0.f;
             for (int i = 0; i < 32; ++i) {
                 if (row0 + i >= P.M) break;
@@ -443,7 +442,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
                 for (int j = 0; j < NPIECE; ++j) {
                     const int am = am0 + RSTEP * j;
                     const bool ok = am < P.M && k < P.K;
-                    if (!(P.ablate & 16)) cp_async16(dst + j * RSTEP * 128, P.A + (ok ? (long long)am * P.lda + k : 0ll), ok ? 16u : 0u);
+                    cp_async16(dst + j * RSTEP * 128, P.A + (ok ? (long long)am * P.lda + k : 0ll), ok ? 16u : 0u);
                 }
                 ++i_it;
                 if (++i_kc == nkc) { i_kc = 0; i_tile += gridDim.x; }
@@ -464,10 +463,8 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
                 const int st = it % OPS;
                 mbar_wait(&empty_bar[st], ((it / OPS) & 1) ^ 1);        // MMAs of chunk it - OPS have retired
                 unsigned char* a_hi = smem + st * STAGE_BYTES;
-                if (!(P.ablate & 8)) {
 #pragma unroll
-                    for (int j = 0; j < NPIECE; ++j) split_store(a_hi, a_hi + A_HALF, r0 + RSTEP * j, c, v[j]);
-                }
+                for (int j = 0; j < NPIECE; ++j) split_store(a_hi, a_hi + A_HALF, r0 + RSTEP * j, c, v[j]);
                 fence_proxy_async_smem();
                 mbar_arrive(&full_bar[st]);
             }
@@ -482,7 +479,6 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const int st = it % OPS;
                     mbar_wait(&empty_bar[st], ((it / OPS) & 1) ^ 1);
-                    if ((P.ablate & 2) && it >= OPS) { mbar_arrive(&full_bar[st]); continue; }
                     mbar_expect_tx(&full_bar[st], 2 * B_HALF);
                     tma_load_1d(smem + st * STAGE_BYTES + 2 * A_HALF, P.wpack + ((size_t)tn * nkc + kc) * (2 * B_HALF / 4),
                                 2 * B_HALF, &full_bar[st]);
@@ -504,15 +500,13 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
                     mbar_wait(&full_bar[st], (it / OPS) & 1);
                     tc_fence_after();
                     const uint32_t ah = smem_u32(smem + st * STAGE_BYTES), al = ah + A_HALF, bh = ah + 2 * A_HALF, bl = bh + B_HALF;
-                    if (!(P.ablate & 4)) {
 #pragma unroll
-                        for (int ks = 0; ks < T2_BK / 8; ++ks) {
-                            const uint64_t dah = make_desc_sw128(ah + ks * 32), dal = make_desc_sw128(al + ks * 32);
-                            const uint64_t dbh = make_desc_sw128(bh + ks * 32), dbl = make_desc_sw128(bl + ks * 32);
-                            umma_tf32(d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                            umma_tf32(d, dah, dbl, idesc, 1u);
-                            umma_tf32(d, dah, dbh, idesc, 1u);
-                        }
+                    for (int ks = 0; ks < T2_BK / 8; ++ks) {
+                        const uint64_t dah = make_desc_sw128(ah + ks * 32), dal = make_desc_sw128(al + ks * 32);
+                        const uint64_t dbh = make_desc_sw128(bh + ks * 32), dbl = make_desc_sw128(bl + ks * 32);
+                        umma_tf32(d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(d, dah, dbl, idesc, 1u);
+                        umma_tf32(d, dah, dbh, idesc, 1u);
                     }
                     umma_commit(&empty_bar[st]);
                 }
@@ -588,12 +582,12 @@ int launch_tc2(const Tc2Params& P, cudaStream_t st) {
 
 }  // namespace
 
-static int g_ablate = 0;
-extern "C" int roitr_debug_linear_ablate(int mask) { g_ablate = mask; return 0; }
-static int g_tc3_variant = 0;  // set per launch by the engine (roitr_debug_linear_variant): streaming-kernel configuration (0: deep rings, one CTA per SM; 3: light footprint, shares an SM with other kernels)
-extern "C" int roitr_debug_linear_variant(int v) { g_tc3_variant = v; return 0; }
-static int g_force_tc2 = 0;   // debug only: route everything through the coupled-ring kernel (A/B timing)
-extern "C" int roitr_debug_force_linear_tc2(int on) { g_force_tc2 = on; return 0; }
+// Configuration of the streaming kernel for the launches issued from now on (a host-side mode the engine sets around the
+// level-1 layers it issues while the FPS clusters hold most SMs): 0 = deep rings, one CTA per SM (215 KB, 57 K registers);
+// 3 = light footprint (one operand stage, two raw stages, 4 loader warps, <= 64 registers: ~115 KB, 20 K registers) that
+// shares an SM with the CTAs of other streams' kernels. Same arithmetic, same results.
+static int g_tc3_variant = 0;
+extern "C" int roitr_set_linear_config(int v) { g_tc3_variant = (v == 3) ? 3 : 0; return 0; }
 
 static int linear_tc_packed_impl(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
                                  const float* wpack, int bn, const float* bias, float* C, int ldc, int relu,
@@ -606,7 +600,7 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
     if (M == 0) return ROITR_OK;
     Tc2Params P;
     P.M = M; P.N = N; P.K = K; P.A = A; P.A2 = a_add; P.lda = lda; P.a_index = a_index; P.wpack = wpack; P.bias = bias; P.C = C;
-    P.ldc = ldc; P.relu = relu; P.ablate = g_ablate;
+    P.ldc = ldc; P.relu = relu;
     P.ln = ln_gamma != nullptr; P.ln_gamma = ln_gamma; P.ln_beta = ln_beta; P.res_pre = res_pre; P.res_pre_index = res_pre_index;
     P.res_post = res_post; P.ldr = ldr;
     P.tiles_m = ceil_div(M, T2_BM); P.tiles_n = ceil_div(N, bn); P.nkc = ceil_div(K, T2_BK);
@@ -620,7 +614,7 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
         if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
         return bn == 64 ? launch_tc3<64, 3, 3, 8, 1>(P, st) : launch_tc3<128, 2, 4, 8, 1>(P, st);
     }
-    if (stream_ok && !g_force_tc2) {
+    if (stream_ok) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
         return bn == 128 ? launch_tc3<128, 2, 4, 8, 1>(P, st) : launch_tc3<64, 3, 3, 8, 1>(P, st);
     }

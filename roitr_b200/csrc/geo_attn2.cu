@@ -428,9 +428,6 @@ int launch_self(const SelfParams& P, int batch, cudaStream_t st) {
 
 }  // namespace
 
-static int g_self_v3 = 1;     // roitr_debug_geo_self_v3(0): the chunk-synchronous kernel for C = 256 too (A/B timing; C = 512 always uses it)
-extern "C" int roitr_debug_geo_self_v3(int on) { g_self_v3 = on; return 0; }
-
 extern "C" int roitr_geo_self_scores_ld(int batch, int N, int C, int heads, const float* qk, const float* q, int ldq,
                                      long long q_bs, const float* E, const float* gq, int ldgq, const float* bp, float* P, float* G,
                                      void* stream) {
@@ -441,7 +438,7 @@ extern "C" int roitr_geo_self_scores_ld(int batch, int N, int C, int heads, cons
     S.qk = qk; S.q = q; S.ldq = ldq; S.q_bs = q_bs; S.E = E; S.gq = gq; S.ldgq = ldgq; S.bp = bp; S.P = P; S.G = G; S.N = N; S.M = N;
     S.sqrt_c = sqrtf((float)(C / heads));
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 256 && g_self_v3) {
+    if (C == 256) {      // barrier-free kernel; C = 512 (factor-2 backbone) needs twice the registers per lane and keeps the chunk-synchronous one
         const size_t smem = (size_t)GV_STAGES * GV_CHK * 256 * 4 + (size_t)GA_H * S.M * 4;
         ROITR_CHECK_ARG(smem <= 226 * 1024 && (ldgq % 4) == 0 && (uintptr_t)gq % 16 == 0, "geo_self_scores: %d keys do not fit / gq alignment", S.M);
         static size_t configured_dev[ROITR_MAX_DEVICES] = {};
@@ -454,7 +451,6 @@ extern "C" int roitr_geo_self_scores_ld(int batch, int N, int C, int heads, cons
         ROITR_CHECK_LAUNCH("geo_self_scores_v3_kernel");
         return ROITR_OK;
     }
-    if (C == 256) return launch_self<256>(S, batch, st);
     return launch_self<512>(S, batch, st);
 }
 

@@ -671,10 +671,8 @@ __global__ void __launch_bounds__(KT_THREADS) normals_kernel(int b, int n, const
     normals[3 * (size_t)q + 2] = (float)(sgn * nrm[2]);
 }
 
-int g_knn_thread = 1;         // debug only (roitr_debug_knn_thread_per_query): 0 = warp-per-query grid kernel everywhere, 1 = thread-per-query
                               // for k <= 9 slots (measured: 2-4x faster there, slower for 17 slots), 2 = thread-per-query everywhere
-float g_grid_target = 1.0f;   // average points per grid cell over the bounding box (roitr_debug_set_knn_grid_target)
-int g_skip_fixup = 0;  // debug only (roitr_debug_skip_knn_fixup): leave the -1 markers in place to count flagged queries
+constexpr float GRID_TARGET = 1.0f;   // average points per grid cell over the bounding box (tuned on B200: scripts history)
 
 int launch_knn(const KnnParams& P, cudaStream_t st) {
     if (P.m == 0) return ROITR_OK;
@@ -699,7 +697,6 @@ int launch_knn(const KnnParams& P, cudaStream_t st) {
         knn_ppf_kernel<1><<<ceil_div(P.m, KNN_WARPS), KNN_THREADS, smem, st>>>(P);
     }
     ROITR_CHECK_LAUNCH("knn_ppf_kernel");
-    if (g_skip_fixup) return ROITR_OK;
     knn_tie_fixup_kernel<<<ceil_div(P.m, FIX_WARPS * 32), FIX_WARPS * 32, 0, st>>>(P);
     ROITR_CHECK_LAUNCH("knn_tie_fixup_kernel");
     return ROITR_OK;
@@ -728,8 +725,6 @@ static int knn_common(int b, int m, int nslots, int drop, const float* xyz, cons
     return launch_knn(P, (cudaStream_t)stream);
 }
 
-extern "C" int roitr_debug_skip_knn_fixup(int skip) { g_skip_fixup = skip; return 0; }
-extern "C" int roitr_debug_set_knn_grid_target(float per_cell) { if (per_cell > 0.f) g_grid_target = per_cell; return 0; }
 
 extern "C" int roitr_knnquery_n(int b, int m, int nsample, int n_total, const float* xyz, const float* new_xyz,
                                 const int* offset, const int* new_offset, int* idx, float* dist2, void* stream) {
@@ -787,7 +782,7 @@ extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* o
     int* cursor = (int*)(w + grid_hdr_bytes(b) + grid_cells_bytes(b));
     float4* sorted = (float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b));
     ROITR_CUDA(cudaMemsetAsync(cursor, 0, grid_cells_bytes(b), st));
-    knngrid::grid_header_kernel<<<b, 256, 0, st>>>(b, xyz, offset, hdr, g_grid_target);
+    knngrid::grid_header_kernel<<<b, 256, 0, st>>>(b, xyz, offset, hdr, GRID_TARGET);
     if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 0);
     knngrid::grid_scan_kernel<<<b, 1024, 0, st>>>(hdr, cursor, cell_start);
     if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 1);
@@ -795,7 +790,6 @@ extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* o
     return ROITR_OK;
 }
 
-extern "C" int roitr_debug_knn_thread_per_query(int on) { g_knn_thread = on; return 0; }
 
 extern "C" int roitr_knn_ppf_grid_q(int b, int m, int k_out, int drop_first, int n_total, const float* xyz,
                                     const float* normals, const float* new_xyz, const float* new_normals, const int* offset,
@@ -820,16 +814,15 @@ extern "C" int roitr_knn_ppf_grid_q(int b, int m, int k_out, int drop_first, int
     if (!qw && new_xyz == xyz && m == n_total) qw = w;
     const float4* qorder = qw ? (const float4*)(qw + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b)) : nullptr;
     const int grid = ceil_div(m, KT_THREADS);
+    // thread-per-query (sorted list in registers) for 1 / 3 / 9 slots; at 17 slots the unrolled insertion diverges and the
+    // warp-per-query kernel (top-k spread over the lanes) measured faster, as it is for any other slot count
     bool done = true;
-    if (!g_knn_thread) done = false;
-    else if (nslots == 1) knn_grid_thread_kernel<1><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
+    if (nslots == 1) knn_grid_thread_kernel<1><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else if (nslots == 3) knn_grid_thread_kernel<3><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else if (nslots == 9) knn_grid_thread_kernel<9><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
-    else if (nslots == 17 && g_knn_thread > 1) knn_grid_thread_kernel<17><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else done = false;
     if (!done) knn_grid_kernel<<<ceil_div(m, KNN_WARPS), KNN_THREADS, 0, st>>>(P, hdr, cell_start, sorted);
     ROITR_CHECK_LAUNCH("knn_grid_kernel");
-    if (g_skip_fixup) return ROITR_OK;
     knn_tie_fixup_kernel<<<ceil_div(m, FIX_WARPS * 32), FIX_WARPS * 32, 0, st>>>(P);
     ROITR_CHECK_LAUNCH("knn_tie_fixup_kernel");
     return ROITR_OK;

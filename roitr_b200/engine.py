@@ -17,8 +17,8 @@ import torch
 
 from . import ops
 
-GEO_EMBEDDING_TC = True      # tcgen05 3xTF32 kernel (csrc/geo_tc.cu); False = fp32 FFMA kernel (csrc/geo.cu)
-GEO_EMBEDDING_TABLE = True   # batched path: weight-derived tables + cubic interpolation (csrc/geo_table.cu) instead of the GEMM
+GEO_EMBEDDING_TABLE = True   # weight-derived tables + cubic interpolation (csrc/geo_table.cu); when the error bound cannot be met
+                             # for the loaded weights (or with False) the embedding GEMM runs on tcgen05 (csrc/geo_tc.cu)
 GEO_TABLE_TOL = 2.5e-7       # interpolation error bound the table step is chosen for (one fp32 rounding of an O(1) value)
 STRIDES = (1, 4, 4, 4)
 NSAMPLE = (8, 16, 16, 16)
@@ -91,8 +91,7 @@ def build_geo_tables(Wd, bd, Wa, ba, div_term, sigma_a=15.0, t_d_max=512.0):
         k += 1
     bound = (3.0 / 128.0) * (2.0 ** (-4 * k)) * m4
     if bound > 4 * GEO_TABLE_TOL:
-        raise ValueError("geometric-embedding weights too large for the tabulated evaluation (error bound %.2e); set "
-                         "engine.GEO_EMBEDDING_TABLE = False to use the tensor-core GEMM" % bound)
+        raise ValueError("geometric-embedding weights too large for the tabulated evaluation (error bound %.2e)" % bound)
     h = 2.0 ** (-k)
     t_a_max = 180.0 / sigma_a + 0.25                                        # angle index <= 180 / sigma_a (:99)
 
@@ -173,9 +172,12 @@ def _pack_weights(state_dict, device, architecture):
         W[g + ".embedding#wpack"] = torch.stack([pack_tf32_sw128(W[g + ".embedding.proj_d.weight"]),
                                                  pack_tf32_sw128(W[g + ".embedding.proj_a.weight"])], 0).contiguous()
         if GEO_EMBEDDING_TABLE and C % 64 == 0:
-            W[g + ".embedding#tables"] = build_geo_tables(W[g + ".embedding.proj_d.weight"], W[g + ".embedding.proj_d.bias"],
-                                                          W[g + ".embedding.proj_a.weight"], W[g + ".embedding.proj_a.bias"],
-                                                          W[g + ".embedding.embedding.div_term"])
+            try:
+                W[g + ".embedding#tables"] = build_geo_tables(W[g + ".embedding.proj_d.weight"], W[g + ".embedding.proj_d.bias"],
+                                                              W[g + ".embedding.proj_a.weight"], W[g + ".embedding.proj_a.bias"],
+                                                              W[g + ".embedding.embedding.div_term"])
+            except ValueError:
+                pass       # the interpolation error bound cannot be met for these weights: geo_embedding_tc_batched (the GEMM) is used
         for i, kind in enumerate(architecture):
             a = "%s.transformer.layers.%d.attention.attention" % (g, i)
             if kind == "self":
@@ -183,7 +185,6 @@ def _pack_weights(state_dict, device, architecture):
                 W[a + "#bqkv"] = torch.cat([W[a + ".proj_%s.bias" % t] for t in "qkv"], 0).contiguous()
                 Wp = W[a + ".proj_p.weight"]                                       # (C, C): p = Wp e + bp
                 # gq[n,h,:] = sum_{k in head h} q[n, h*c+k] * Wp[h*c+k, :]  ->  per head a (C x c) matrix, K = c
-                W[a + "#WpT"] = torch.stack([Wp[h * c:(h + 1) * c, :].t().contiguous() for h in range(HEADS)], 0).contiguous()
                 # the same per-head maps as ONE dense layer each (block-structured weights, exact zeros elsewhere), so that
                 # the batched path issues two tensor-core launches instead of eight skinny FFMA ones:
                 #   gq (R, H*C) = q (R, C) WpBig^T,  WpBig[h*C + j, h*c + k] = Wp[h*c + k, j]
@@ -215,14 +216,8 @@ def _pack_weights(state_dict, device, architecture):
 
 
 # ------------------------------------------------------------------------------------------------ local layers
-ATTENTION_TC = True          # global attention: Q K^T / P V on tcgen05 + one streaming pass over E (csrc/geo_attn2.cu)
-LINEAR_TC = True             # dense layers on tcgen05 (csrc/gemm_tc2.cu) when a packed weight exists; False = fp32 FFMA
-
-
 def _pk(W, key):
     """The packed forms of weight ``key`` as ops.linear keyword arguments."""
-    if not LINEAR_TC:
-        return {}
     return dict(wpack=W.get(key + "#tc"))
 
 
@@ -236,7 +231,7 @@ def _ln(W, p, x, **kw):
 
 def _lin_ln(W, p, n, x, **kw):
     """Linear p followed by LayerNorm n (+ residuals / ReLU), fused into the dense layer's epilogue where it fits."""
-    return ops.linear_ln(x, W[p + ".weight"], W[p + ".bias"], W.get(p + ".weight#tc") if LINEAR_TC else None,
+    return ops.linear_ln(x, W[p + ".weight"], W[p + ".bias"], W.get(p + ".weight#tc"),
                          W[n + ".weight"], W[n + ".bias"], **kw)
 
 
@@ -244,14 +239,14 @@ def local_ppf_transformer(W, p, feats, node_idx, group_idx, ppf, order=None, pos
     """LocalPPFTransformer.forward (ppftransformer.py:243-253): (n,Cin) -> (m,Cout). ``order``: see ops.local_attention.
     ``post`` = (LayerNorm prefix, res_post, relu): a row epilogue applied to the output (the block's bn2 + identity + ReLU)."""
     C = W[p + ".in_proj.weight"].shape[0]
-    if LINEAR_TC and node_idx is not None and (p + "#Wkv#tc") in W:
+    if node_idx is not None and (p + "#Wkv#tc") in W:
         kv = ops.linear(feats, W[p + "#Wkv"], W[p + "#bkv"], **_pk(W, p + "#Wkv"))                       # (n, 2C) all rows
         fq = ops.linear(feats, W[p + "#Wfq"], W[p + "#bfq"], a_index=node_idx, **_pk(W, p + "#Wfq"))     # (m, 2C) sampled rows
         h = ops.local_attention((fq[:, C:], kv[:, :C], kv[:, C:]), C, None, group_idx, ppf, W[p + "#Ap"], W[p + "#cp"],
                                 W[p + "#Avp"], W[p + "#cvp"], order=order)
         f, node_idx = fq[:, :C], None
     else:
-        if LINEAR_TC and (p + "#W4#tc") in W:
+        if (p + "#W4#tc") in W:
             fq = ops.linear(feats, W[p + "#W4"], W[p + "#b4"], **_pk(W, p + "#W4"))      # (n, 4C) = [f | q | k | v]
             f, qkv = fq[:, :C], fq[:, C:]
         else:
@@ -492,38 +487,23 @@ def _self_layer_batch(W, lp, x, E, nb, N):
     C = x.shape[1]
     c = C // HEADS
     R = x.shape[0]
-    if LINEAR_TC:
-        qkvg = ops.linear(x, W[a + "#Wqkvg"], W[a + "#bqkvg"], wpack=W[a + "#Wqkvg#tc"])     # (R, 3C + H*C)
-        qkv, gq = qkvg[:, :3 * C], qkvg[:, 3 * C:]
-    else:
-        qkv = ops.linear(x, W[a + "#Wqkv"], W[a + "#bqkv"])
-        gq = torch.empty(R, HEADS * C, dtype=torch.float32, device=x.device)
-        for h in range(HEADS):
-            ops.linear(qkv[:, h * c:(h + 1) * c], W[a + "#WpT"][h], None, out=gq[:, h * C:(h + 1) * C], M=R, K=c)
-    attn = ops.attention_tc if ATTENTION_TC else ops.geo_attention_batched_compat
-    hidden, G = attn(nb, N, N, C, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], E=E, gq=gq, bp=W[a + ".proj_p.bias"])
-    Wvp, bvp = W[a + ".proj_vp.weight"], W[a + ".proj_vp.bias"]
-    G2 = G.view(R, HEADS * C)
-    if LINEAR_TC:
-        pos = ops.linear(G2, W[a + "#Wposf"], W[a + "#bposf"], wpack=W[a + "#Wposf#tc"])      # pos_linear already applied
-    else:
-        pos = torch.empty(R, C, dtype=torch.float32, device=x.device)
-        for h in range(HEADS):
-            ops.linear(G2[:, h * C:(h + 1) * C], Wvp[h * c:(h + 1) * c], bvp[h * c:(h + 1) * c], out=pos[:, h * c:(h + 1) * c],
-                       M=R, K=C)
+    qkvg = ops.linear(x, W[a + "#Wqkvg"], W[a + "#bqkvg"], wpack=W[a + "#Wqkvg#tc"])     # (R, 3C + H*C)
+    qkv, gq = qkvg[:, :3 * C], qkvg[:, 3 * C:]
+    hidden, G = ops.attention_tc(nb, N, N, C, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], E=E, gq=gq, bp=W[a + ".proj_p.bias"])
+    pos = ops.linear(G.view(R, HEADS * C), W[a + "#Wposf"], W[a + "#bposf"], wpack=W[a + "#Wposf#tc"])   # pos_linear already applied
     y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
-    pos = _ln(W, lp + ".attention.pos_norm", pos if LINEAR_TC else _lin(W, lp + ".attention.pos_linear", pos), mode=ops.MODE_LN)
+    pos = _ln(W, lp + ".attention.pos_norm", pos, mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
 
 
 def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     a = lp + ".attention.attention"
     C = x.shape[1]
-    tcw = (lambda n: W.get(a + ".proj_%s.weight#tc" % n)) if LINEAR_TC else (lambda n: None)
+    tcw = lambda n: W.get(a + ".proj_%s.weight#tc" % n)
     q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x, wpack=tcw("q"))
     k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, wpack=tcw("k"))
     v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], wpack=tcw("v"))
-    hidden = (ops.attention_tc if ATTENTION_TC else ops.geo_attention_batched_compat)(nb, N, M, C, q, k, v)
+    hidden = ops.attention_tc(nb, N, M, C, q, k, v)
     z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", z)
 
@@ -544,15 +524,8 @@ def geometric_embedding_batch(W, B, pts, split, sigma_d=0.2, sigma_a=15.0):
             return ops.geo_embedding_table(nb, N, p_, nn3, W[e + "#tables"], W[e + ".proj_d.weight"], W[e + ".proj_d.bias"],
                                            W[e + ".proj_a.weight"], W[e + ".proj_a.bias"], W[e + ".embedding.div_term"],
                                            sigma_d, sigma_a)
-        if GEO_EMBEDDING_TC:
-            return ops.geo_embedding_tc_batched(nb, N, p_, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
-                                                W[e + ".embedding.div_term"], sigma_d, sigma_a)
-        E = torch.empty(nb, N, N, C, dtype=torch.float32, device=p_.device)
-        for b in range(nb):
-            ops.geo_embedding(p_[b * N:(b + 1) * N], nn3[b * N:(b + 1) * N], W[e + ".proj_d.weight"], W[e + ".proj_d.bias"],
-                              W[e + ".proj_a.weight"], W[e + ".proj_a.bias"], W[e + ".embedding.div_term"], sigma_d, sigma_a,
-                              out=E[b])
-        return E
+        return ops.geo_embedding_tc_batched(nb, N, p_, nn3, W[e + "#wpack"], W[e + ".proj_d.bias"], W[e + ".proj_a.bias"],
+                                            W[e + ".embedding.div_term"], sigma_d, sigma_a)
     if N0 == N1:
         E_all = embed(pts, 2 * B, N0)
         return E_all, (E_all[:B], E_all[B:])

@@ -19,11 +19,8 @@ def empty(*shape, dtype=torch.float32, like=None, device=None):
     return torch.empty(*shape, dtype=dtype, device=like.device if like is not None else device)
 
 
-USE_TENSOR_CORES = False    # roitr_linear_tc (tcgen05, 3xTF32) is correct but, being thread-loaded and 2-stage, slower than FFMA on these skinny GEMMs (scripts/bench_gemm.py); opt in per call with tc=True
-
-
 def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=None, K=None, lda=None, ldw=None,
-           ldc=None, tc=None, wpack=None):
+           ldc=None, wpack=None):
     """out[M,N] = (a [+ a_add])[rows, :K] @ w[:N, :K]^T + bias. ``a``/``out`` may be column slices of wider buffers
     (pass lda/ldc); ``a_index`` gathers rows of ``a``."""
     N = w.shape[0]
@@ -39,8 +36,7 @@ def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=No
         _lib.call("roitr_linear_tc_packed", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
                   f32(wpack[0]), c_int(wpack[1]), c_void(bias), c_void(out), c_int(ldc), c_int(1 if relu else 0), stream_ptr())
         return out
-    use_tc = (USE_TENSOR_CORES if tc is None else tc) and K >= 16
-    _lib.call("roitr_linear_tc" if use_tc else "roitr_linear", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
+    _lib.call("roitr_linear", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
               c_void(w), c_int(ldw), c_void(bias), c_void(out), c_int(ldc), c_int(1 if relu else 0), stream_ptr())
     return out
 
@@ -70,7 +66,7 @@ def linear_ln(a, w, bias, wpack, gamma, beta, res_pre=None, res_pre_index=None, 
 def set_linear_variant(v):
     """Configuration of the streaming dense-layer kernel for the launches issued from now on (baked into a graph at capture):
     0 = deep rings, one CTA per SM; 3 = light footprint that shares an SM with other kernels' CTAs."""
-    _lib.lib().roitr_debug_linear_variant(c_int(int(v)))
+    _lib.lib().roitr_set_linear_config(c_int(int(v)))
 
 
 def c_void(t):
@@ -224,47 +220,12 @@ def geo_embedding_table(batch, N, pts, nn3, tables, Wd, bd, Wa, ba, div_term, si
     return E
 
 
-def geo_embedding(pts, nn3, Wd, bd, Wa, ba, div_term, sigma_d, sigma_a, out=None):
-    N, C = pts.shape[0], Wd.shape[0]
-    E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device) if out is None else out
-    _lib.call("roitr_geo_embedding", c_int(N), c_int(C), f32(pts), i32(nn3), f32(Wd), f32(bd), f32(Wa), f32(ba),
-              f32(div_term), c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
-    return E
-
-
 def geo_embedding_tc(pts, nn3, wpack, bd, ba, div_term, sigma_d, sigma_a, out=None):
     N, C = pts.shape[0], bd.shape[0]
     E = torch.empty(N, N, C, dtype=torch.float32, device=pts.device) if out is None else out
     _lib.call("roitr_geo_embedding_tc", c_int(N), c_int(C), f32(pts), i32(nn3), f32(wpack), f32(bd), f32(ba), f32(div_term),
               c_float(sigma_d), c_float(sigma_a), f32(E), stream_ptr())
     return E
-
-
-def geo_attention(q, k, v, C, E=None, gq=None, bp=None):
-    """q (N, >=C view), k, v (M, >=C views) with explicit strides. Returns hidden (N,C) [, G (N,4,C)]."""
-    N, M = q.shape[0], k.shape[0]
-    hidden = torch.empty(N, C, dtype=torch.float32, device=q.device)
-    G = torch.empty(N, 4, C, dtype=torch.float32, device=q.device) if E is not None else None
-    _lib.call("roitr_geo_attention", c_int(N), c_int(M), c_int(C), c_int(4), c_void(q), c_int(q.stride(0)), c_void(k),
-              c_int(k.stride(0)), c_void(v), c_int(v.stride(0)), f32(E), f32(gq), f32(bp), f32(hidden), f32(G),
-              stream_ptr())
-    return (hidden, G) if E is not None else hidden
-
-
-def geo_attention_batched(batch, N, M, q, k, v, C, E=None, gq=None, bp=None):
-    """q: rows of `batch` clouds of N queries each (stride N rows), k/v: `batch` clouds of M keys. Views with explicit
-    leading dims. Returns hidden (batch*N, C) [, G (batch*N, 4, C)]."""
-    hidden = torch.empty(batch * N, C, dtype=torch.float32, device=q.device)
-    G = torch.empty(batch * N, 4, C, dtype=torch.float32, device=q.device) if E is not None else None
-    _lib.call("roitr_geo_attention_batched", c_int(batch), c_int(N), c_int(M), c_int(C), c_int(4), c_void(q),
-              c_int(q.stride(0)), c_ll(N * q.stride(0)), c_void(k), c_int(k.stride(0)), c_ll(M * k.stride(0)), c_void(v),
-              c_int(v.stride(0)), c_ll(M * v.stride(0)), f32(E), f32(gq), f32(bp), f32(hidden), f32(G), stream_ptr())
-    return (hidden, G) if E is not None else hidden
-
-
-def geo_attention_batched_compat(batch, N, M, C, q, k, v, heads=4, E=None, gq=None, bp=None):
-    """First-generation SIMT attention core with the argument order of attention_tc."""
-    return geo_attention_batched(batch, N, M, q, k, v, C, E=E, gq=gq, bp=bp)
 
 
 def gemm_tc_batched(outer, inner, M, N, K, A, lda, sA, W, ldw, sW, C, ldc, sC, w_transposed=False):
