@@ -434,12 +434,29 @@ def main():
                                           "source": cap["source"]}
         except Exception:
             pass
+        try:        # north_star asks for the kNN+PPF DRAM traffic and its FP32-issue fraction next to the compulsory-byte figure
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            tj = {}
         roof["how"] = ("CUDA events around every entry-point call in a single-stream eager replica of the timed step (the timed "
                        "step itself is one multi-stream CUDA graph); algorithmic work per DESIGN.md §4 / SURVEY.md §8d")
         named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid_q", "roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build"]),
                  "global_attention_qk_pv": roofline_of(["roitr_gemm_tc_batched"]),
                  "dense_layers": roofline_of(["roitr_linear_tc_packed", "roitr_linear_ln_tc_packed"]),
+                 "global_attention_e_pass": roofline_of(["roitr_geo_self_scores_ld"]),
+                 "geo_embedding": roofline_of(["roitr_geo_embedding_table"]),
                  "fine_matching": roofline_of(["roitr_fine_matching_batched"])}
+        if named.get("knn_ppf") and tj.get("knn_ppf"):
+            k = tj["knn_ppf"]
+            named["knn_ppf"].update({"traffic": k["dram_bytes"], "fp32_issue_frac": k["issue_active_pct"] / 100.0,
+                                     "fp32_pipe_active_frac": k["fp32_pipe_active_pct"] / 100.0,
+                                     "traffic_detail": {"launch": "knn_grid_thread_kernel<1>, 320016 queries (occlusion 1-NN), %.1f us" % k["gpu_time_us"],
+                                                        "source": k["source"]},
+                                     "note": "exact kNN is bound by dependent cell->point loads and FP32 issue, not by HBM: the compulsory-byte "
+                                             "fraction is ~0.01 by construction (SURVEY.md 8d: 21 MB per pair), issue slots are the roofline that applies"})
+        for nm, key in (("fine_matching", "roitr_fine_matching_batched"),):
+            if named.get(nm) and tj.get(key):
+                named[nm].update({"traffic": tj[key]["dram_bytes"], "issue_active_frac": tj[key]["issue_active_pct"] / 100.0})
         line = {
             "metric": METRIC, "value": world * B * steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",

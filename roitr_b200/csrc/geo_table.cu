@@ -130,40 +130,38 @@ __global__ void __launch_bounds__(GTB_THREADS, 1) geo_embedding_table_kernel(con
     const long long npairs = (long long)N * N;
     const long long blocks_per_cloud = (npairs + GTB_THREADS - 1) / GTB_THREADS;   // a work item = 32 pairs per warp
     const long long items = blocks_per_cloud * P.batch;
-    const int ch = group * GTB_GROUP + 2 * lane;
+    // A half-warp covers the 64 channels of the group (4 per lane, 16-byte table reads and stores), so one pass of the loop
+    // below evaluates TWO pairs: the per-pair scalar work (shuffle, cell index, Lagrange weights) is issued once for both.
+    const int half = lane >> 4, l16 = lane & 15;
+    const int ch = group * GTB_GROUP + 4 * l16;
     const int rows_a = P.rows_a, rows_ds = P.rows_d_smem, rows_d = P.rows_d;
-
     for (long long item = slot; item < items; item += P.ctas_per_group) {
         const int cloud = (int)(item / blocks_per_cloud);
         const long long p0 = (item % blocks_per_cloud) * GTB_THREADS + warp * 32;
         const float* pts = P.pts + (size_t)cloud * N * 3;
         const int* nn3 = P.nn3 + (size_t)cloud * N * 3;
         float* E = P.E + (size_t)cloud * npairs * C;
-        // ---- lane = pair: geometry, cell index and fraction of the four scalars ----
+        // ---- lane = pair: geometry of the four scalars ----
         float t[4] = {0.f, 0.f, 0.f, 0.f};
         const long long mine = p0 + lane;
         if (mine < npairs) pair_scalars(pts, nn3, (int)(mine / N), (int)(mine % N), P.sigma_d, P.factor_a, t);
-        int ci[4];
-        float cu[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float x = t[k] * P.inv_h;                                // exact: inv_h is a power of two
-            const float fl = floorf(x);
-            cu[k] = x - fl;                                                // exact (Sterbenz / same binade)
-            // out of table (huge, negative, NaN / Inf): a sentinel that cannot overflow in `i + 3` below -> direct evaluation,
-            // which propagates NaN like the reference instead of reading outside the table
-            ci[k] = (x >= 0.0f && x < 1.0e9f) ? (int)fl : 0x3fffffff;
-        }
         const int npw = (int)max((long long)0, min((long long)32, npairs - p0));
-        for (int p = 0; p < npw; ++p) {
-            float2 acc[4];
+        for (int j = 0; j < 16; ++j) {
+            const int src = 2 * j + half;                                  // the pair this half-warp evaluates
+            const bool live = src < npw;
+            float4 acc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int i = __shfl_sync(FULL_MASK, ci[k], p);
-                const float u = __shfl_sync(FULL_MASK, cu[k], p);
+                const float tv = __shfl_sync(FULL_MASK, t[k], src);
+                const float x = tv * P.inv_h;                              // exact: inv_h is a power of two
+                const float fl = floorf(x);
+                const float u = x - fl;                                    // exact (Sterbenz / same binade)
+                // out of table (huge, negative, NaN / Inf): a sentinel that cannot overflow in `i + 3` below -> direct
+                // evaluation, which propagates NaN like the reference instead of reading outside the table
+                const int i = (x >= 0.0f && x < 1.0e9f) ? (int)fl : 0x3fffffff;
                 float w[4];
                 lagrange4(u, w);
-                const float* tab;
+                const float* tab = s_a;
                 bool ok = true;
                 if (k == 0) {
                     if (i + 3 < rows_ds) tab = s_d + (size_t)i * GTB_GROUP;
@@ -171,26 +169,35 @@ __global__ void __launch_bounds__(GTB_THREADS, 1) geo_embedding_table_kernel(con
                     else ok = false;
                 } else {
                     ok = i + 3 < rows_a;
-                    tab = s_a + (size_t)i * GTB_GROUP;
+                    tab = s_a + (size_t)(ok ? i : 0) * GTB_GROUP;
                 }
+                acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!live) continue;
                 if (ok) {
-                    const float2 v0 = *reinterpret_cast<const float2*>(tab + 2 * lane);
-                    const float2 v1 = *reinterpret_cast<const float2*>(tab + GTB_GROUP + 2 * lane);
-                    const float2 v2 = *reinterpret_cast<const float2*>(tab + 2 * GTB_GROUP + 2 * lane);
-                    const float2 v3 = *reinterpret_cast<const float2*>(tab + 3 * GTB_GROUP + 2 * lane);
+                    const float4 v0 = *reinterpret_cast<const float4*>(tab + 4 * l16);
+                    const float4 v1 = *reinterpret_cast<const float4*>(tab + GTB_GROUP + 4 * l16);
+                    const float4 v2 = *reinterpret_cast<const float4*>(tab + 2 * GTB_GROUP + 4 * l16);
+                    const float4 v3 = *reinterpret_cast<const float4*>(tab + 3 * GTB_GROUP + 4 * l16);
                     // inner nodes first (largest weights), outer corrections last
                     acc[k].x = fmaf(w[3], v3.x, fmaf(w[0], v0.x, fmaf(w[2], v2.x, w[1] * v1.x)));
                     acc[k].y = fmaf(w[3], v3.y, fmaf(w[0], v0.y, fmaf(w[2], v2.y, w[1] * v1.y)));
-                } else {   // beyond every table (warp-uniform branch): evaluate from the weights
-                    const float tv = __shfl_sync(FULL_MASK, t[k], p);
-                    acc[k] = (k == 0) ? direct_eval(P.Wd, P.bd, P.div_term, C, ch, tv)
-                                      : direct_eval(P.Wa, P.ba, P.div_term, C, ch, tv);
+                    acc[k].z = fmaf(w[3], v3.z, fmaf(w[0], v0.z, fmaf(w[2], v2.z, w[1] * v1.z)));
+                    acc[k].w = fmaf(w[3], v3.w, fmaf(w[0], v0.w, fmaf(w[2], v2.w, w[1] * v1.w)));
+                } else {   // beyond every table: evaluate from the weights
+                    const float2 lo2 = (k == 0) ? direct_eval(P.Wd, P.bd, P.div_term, C, ch, tv) : direct_eval(P.Wa, P.ba, P.div_term, C, ch, tv);
+                    const float2 hi2 = (k == 0) ? direct_eval(P.Wd, P.bd, P.div_term, C, ch + 2, tv)
+                                                : direct_eval(P.Wa, P.ba, P.div_term, C, ch + 2, tv);
+                    acc[k] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
                 }
             }
-            float2 o;
-            o.x = acc[0].x + fmaxf(fmaxf(acc[1].x, acc[2].x), acc[3].x);
-            o.y = acc[0].y + fmaxf(fmaxf(acc[1].y, acc[2].y), acc[3].y);
-            *reinterpret_cast<float2*>(E + (size_t)(p0 + p) * C + ch) = o;
+            if (live) {
+                float4 o;
+                o.x = acc[0].x + fmaxf(fmaxf(acc[1].x, acc[2].x), acc[3].x);
+                o.y = acc[0].y + fmaxf(fmaxf(acc[1].y, acc[2].y), acc[3].y);
+                o.z = acc[0].z + fmaxf(fmaxf(acc[1].z, acc[2].z), acc[3].z);
+                o.w = acc[0].w + fmaxf(fmaxf(acc[1].w, acc[2].w), acc[3].w);
+                *reinterpret_cast<float4*>(E + (size_t)(p0 + src) * C + ch) = o;
+            }
         }
     }
 }

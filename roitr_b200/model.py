@@ -148,7 +148,7 @@ class _PackedMixin:
         return self._pack
 
 
-class RIPointTransformer(nn.Module, _PackedMixin):
+class RIPointTransformer(_PackedMixin, nn.Module):
     """model/model.py:145-237: same constructor, same forward(s_pxon, t_pxon, src_deformed_pcd) -> 8-tuple."""
 
     def __init__(self, blocks=[2, 3, 3, 3], block=RIPointTransformerBlock, c=1, transformer_architecture=None,
@@ -224,7 +224,7 @@ class FineMatching(nn.Module):
         self.correspondence_threshold = correspondence_threshold
 
 
-class RIGA_v2(nn.Module, _PackedMixin):
+class RIGA_v2(_PackedMixin, nn.Module):
     """model/RIGA_v2.py:10-175: the RoITr pipeline. ``config`` needs the 17 keys RIGA_v2.__init__ reads (attribute or
     item access). forward(...) -> dict with the reference's 22 keys."""
 
