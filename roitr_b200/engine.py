@@ -210,6 +210,8 @@ def _pack_weights(state_dict, device, architecture):
         for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("#Wkv") or k.endswith("#Wfq") or k.endswith("#Wqkvg") or k.endswith("#Wposf") or k.endswith("Big")) and W[k].dim() == 2
                   and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
+            if W[k + "#tc"][1] == 128:
+                W[k + "#tc64"] = pack_linear_tc(W[k], 64)      # for launches with fewer 128-column tiles than SMs (ops._pick_pack)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = hp
     return W
@@ -218,7 +220,7 @@ def _pack_weights(state_dict, device, architecture):
 # ------------------------------------------------------------------------------------------------ local layers
 def _pk(W, key):
     """The packed forms of weight ``key`` as ops.linear keyword arguments."""
-    return dict(wpack=W.get(key + "#tc"))
+    return dict(wpack=W.get(key + "#tc"), wpack64=W.get(key + "#tc64"))
 
 
 def _lin(W, p, x, **kw):
@@ -487,10 +489,10 @@ def _self_layer_batch(W, lp, x, E, nb, N):
     C = x.shape[1]
     c = C // HEADS
     R = x.shape[0]
-    qkvg = ops.linear(x, W[a + "#Wqkvg"], W[a + "#bqkvg"], wpack=W[a + "#Wqkvg#tc"])     # (R, 3C + H*C)
+    qkvg = ops.linear(x, W[a + "#Wqkvg"], W[a + "#bqkvg"], **_pk(W, a + "#Wqkvg"))     # (R, 3C + H*C)
     qkv, gq = qkvg[:, :3 * C], qkvg[:, 3 * C:]
     hidden, G = ops.attention_tc(nb, N, N, C, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], E=E, gq=gq, bp=W[a + ".proj_p.bias"])
-    pos = ops.linear(G.view(R, HEADS * C), W[a + "#Wposf"], W[a + "#bposf"], wpack=W[a + "#Wposf#tc"])   # pos_linear already applied
+    pos = ops.linear(G.view(R, HEADS * C), W[a + "#Wposf"], W[a + "#bposf"], **_pk(W, a + "#Wposf"))   # pos_linear already applied
     y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     pos = _ln(W, lp + ".attention.pos_norm", pos, mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
@@ -499,10 +501,9 @@ def _self_layer_batch(W, lp, x, E, nb, N):
 def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     a = lp + ".attention.attention"
     C = x.shape[1]
-    tcw = lambda n: W.get(a + ".proj_%s.weight#tc" % n)
-    q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x, wpack=tcw("q"))
-    k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, wpack=tcw("k"))
-    v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], wpack=tcw("v"))
+    q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x, **_pk(W, a + ".proj_q.weight"))
+    k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, **_pk(W, a + ".proj_k.weight"))
+    v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], **_pk(W, a + ".proj_v.weight"))
     hidden = ops.attention_tc(nb, N, M, C, q, k, v)
     z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
     return _ffn(W, lp + ".output", z)

@@ -206,14 +206,14 @@ def test_linear_ln_fused_matches_fp64(M, N, K, pre, gather, post, relu):
 
 
 def test_geo_embedding_falls_back_to_the_gemm_when_the_table_bound_fails():
-    """engine.pack_weights: weights whose 4th-derivative bound defeats the table (here proj_d scaled x 1e4) take the tcgen05
+    """engine.pack_weights: weights whose 4th-derivative bound defeats the table (here proj_d scaled x 1e6) take the tcgen05
     GEMM (csrc/geo_tc.cu) without any flag; the forward still agrees with the oracle on the embedding."""
     from oracle import forward_ref as fr
     from roitr_b200 import engine
     from tests.helpers import CONFIG_3D, weights
     sd = dict(weights(1))
     e = "backbone.global_transformer.embedding"
-    sd[e + ".proj_d.weight"] = sd[e + ".proj_d.weight"] * 1.0e4
+    sd[e + ".proj_d.weight"] = sd[e + ".proj_d.weight"] * 1.0e6
     W = engine.pack_weights(sd, torch.device(DEV), CONFIG_3D["transformer_architecture"])
     assert (e + "#tables") not in W and (e + "#wpack") in W
     W_ok = engine.pack_weights(weights(1), torch.device(DEV), CONFIG_3D["transformer_architecture"])
