@@ -210,8 +210,6 @@ def _pack_weights(state_dict, device, architecture):
         for k in [k for k in W if (k.endswith(".weight") or k.endswith("#Wqkv") or k.endswith("#W4") or k.endswith("#Wkv") or k.endswith("#Wfq") or k.endswith("#Wqkvg") or k.endswith("#Wposf") or k.endswith("Big")) and W[k].dim() == 2
                   and W[k].shape[1] >= 16]:
             W[k + "#tc"] = pack_linear_tc(W[k])
-            if W[k + "#tc"][1] == 128:
-                W[k + "#tc64"] = pack_linear_tc(W[k], 64)      # for launches with fewer 128-column tiles than SMs (ops._pick_pack)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = hp
     return W
@@ -220,7 +218,7 @@ def _pack_weights(state_dict, device, architecture):
 # ------------------------------------------------------------------------------------------------ local layers
 def _pk(W, key):
     """The packed forms of weight ``key`` as ops.linear keyword arguments."""
-    return dict(wpack=W.get(key + "#tc"), wpack64=W.get(key + "#tc64"))
+    return dict(wpack=W.get(key + "#tc"))
 
 
 def _lin(W, p, x, **kw):

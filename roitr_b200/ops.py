@@ -19,20 +19,8 @@ def empty(*shape, dtype=torch.float32, like=None, device=None):
     return torch.empty(*shape, dtype=dtype, device=like.device if like is not None else device)
 
 
-SM_COUNT = 148      # B200
-
-
-def _pick_pack(wpack, wpack64, M, N):
-    """Few row tiles (the 5-10 k-row layers of levels 3-4 and the global transformer): with 128-column tiles the launch has
-    fewer tiles than the GPU has SMs and every CTA's single tile is a serial chain of K/32 chunks x 12 MMAs; the 64-column
-    packing of the same weight gives twice the tiles at half the MMA time each (measured: scripts/bench_gemm.py)."""
-    if wpack64 is not None and wpack is not None and wpack[1] == 128 and -(-M // 128) * -(-N // 128) < SM_COUNT:
-        return wpack64
-    return wpack
-
-
 def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=None, K=None, lda=None, ldw=None,
-           ldc=None, wpack=None, wpack64=None):
+           ldc=None, wpack=None):
     """out[M,N] = (a [+ a_add])[rows, :K] @ w[:N, :K]^T + bias. ``a``/``out`` may be column slices of wider buffers
     (pass lda/ldc); ``a_index`` gathers rows of ``a``."""
     N = w.shape[0]
@@ -44,7 +32,6 @@ def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=No
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     ldc = out.stride(0) if ldc is None else ldc
-    wpack = _pick_pack(wpack, wpack64, M, N)
     if wpack is not None:       # (packed weight, tile rows) from engine.pack_linear_tc: persistent tcgen05 kernel
         _lib.call("roitr_linear_tc_packed", c_int(M), c_int(N), c_int(K), c_void(a), c_void(a_add), c_int(lda), i32(a_index),
                   f32(wpack[0]), c_int(wpack[1]), c_void(bias), c_void(out), c_int(ldc), c_int(1 if relu else 0), stream_ptr())

@@ -26,15 +26,9 @@ for (M, N, K) in SHAPES:
     a = torch.randn(M, K, device=DEV); w = torch.randn(N, K, device=DEV) / K ** 0.5; b = torch.randn(N, device=DEV)
     o3 = torch.empty(M, N, device=DEV)
     wp = engine.pack_linear_tc(w)
-    t3 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp))       # wpack64 not passed: always the default packing
+    t3 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp))
     idx = torch.randperm(M, device=DEV).int()
     t2 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp, a_index=idx))      # gathered rows: the coupled-ring kernel (linear_tc2)
-    if wp[1] == 128 and -(-M // 128) * -(-N // 128) < 148:       # few tiles: the 64-column packing (ops._pick_pack)
-        wp64 = engine.pack_linear_tc(w, 64)
-        t64 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp, wpack64=wp64))
-        print("   64-column tiles: %.4f ms (128-column: %.4f)" % (t64, t3))
-        out.write("   64-column tiles: %.4f ms (128-column: %.4f)\n" % (t64, t3))
-        t3 = min(t3, t64)
     gbs = (M * K + M * N + N * K) * 4 / t3 / 1e6
     log("%d,%d,%d, %.4f, %.4f, %.0f, %.3f" % (M, N, K, t3, t2, gbs, gbs / 6532.5))
 

@@ -224,7 +224,8 @@ def test_geo_embedding_falls_back_to_the_gemm_when_the_table_bound_fails():
     E_all, _ = engine.geometric_embedding_batch(W, B, pts.to(DEV), B * N)
     ref = fr.geometric_embedding(sd, e, pts[None, :N])[0]
     off = ~torch.eye(N, dtype=torch.bool)
-    assert ((E_all[0].cpu() - ref)[off].abs() / (1 + ref[off].abs())).max().item() < 1e-4
+    # fp32-grade against the scale of the (x 1e6) embedding: entries are sums of terms of that size
+    assert (E_all[0].cpu() - ref)[off].abs().max().item() < 2e-5 * ref[off].abs().max().item()
 
 
 def test_geo_embedding_table_propagates_nan_instead_of_reading_out_of_bounds():
