@@ -69,7 +69,7 @@ def i32(t):
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim; memsets not counted)
 KERNELS_PER_CALL = {
-    "roitr_knnquery_n": 2, "roitr_knn_ppf_n": 2, "roitr_knn_ppf_grid": 2, "roitr_knn_ppf_grid_q": 2, "roitr_knn_grid_build": 4, "roitr_furthestsampling_cfg": 1, "roitr_interpolate": 1,
+    "roitr_knnquery_n": 2, "roitr_knn_ppf_n": 2, "roitr_knn_ppf_grid": 2, "roitr_knn_ppf_grid_q": 2, "roitr_knn_grid_build": 4, "roitr_knn_grid_build_target": 4, "roitr_furthestsampling_cfg": 1, "roitr_interpolate": 1,
     "roitr_gather_rows": 1, "roitr_linear": 1, "roitr_linear_tc_packed": 1, "roitr_linear_ln_tc_packed": 1, "roitr_row_epilogue": 1, "roitr_segment_mean": 1,
     "roitr_concat_segment": 1, "roitr_local_attention": 1, "roitr_local_attention_ordered": 1, "roitr_geo_knn": 1, "roitr_geo_embedding_tc": 1, "roitr_geo_embedding_tc_batched": 1, "roitr_geo_knn_batched": 1, "roitr_geo_embedding_table": 1, "roitr_gemm_tc_batched": 1, "roitr_geo_self_scores": 1, "roitr_geo_self_scores_ld": 1, "roitr_softmax_rows": 1,
     "roitr_point_to_node_batched": 4, "roitr_compact_flags": 3, "roitr_compact_flags_batched": 3, "roitr_coarse_matching_batched": 5, "roitr_coarse_matching_adaptive_batched": 6,

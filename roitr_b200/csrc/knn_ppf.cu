@@ -772,8 +772,9 @@ extern "C" long long roitr_knn_grid_workspace_bytes(int b, int n) {
 /* byte offset, inside a grid workspace of b segments, of the cell-sorted (x, y, z, index) float4 array */
 extern "C" long long roitr_knn_grid_sorted_offset(int b) { return (long long)(grid_hdr_bytes(b) + 2 * grid_cells_bytes(b)); }
 
-extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* offset, void* workspace, void* stream) {
-    ROITR_CHECK_ARG(b >= 1 && n >= 0 && xyz && offset && workspace, "knn_grid_build: bad arguments");
+extern "C" int roitr_knn_grid_build_target(int b, int n, const float* xyz, const int* offset, float target_per_cell, void* workspace,
+                                           void* stream) {
+    ROITR_CHECK_ARG(b >= 1 && n >= 0 && xyz && offset && workspace && target_per_cell > 0.f, "knn_grid_build: bad arguments");
     ROITR_CHECK_ARG((uintptr_t)workspace % 256 == 0, "knn_grid_build: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* w = (unsigned char*)workspace;
@@ -782,7 +783,7 @@ extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* o
     int* cursor = (int*)(w + grid_hdr_bytes(b) + grid_cells_bytes(b));
     float4* sorted = (float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b));
     ROITR_CUDA(cudaMemsetAsync(cursor, 0, grid_cells_bytes(b), st));
-    knngrid::grid_header_kernel<<<b, 256, 0, st>>>(b, xyz, offset, hdr, GRID_TARGET);
+    knngrid::grid_header_kernel<<<b, 256, 0, st>>>(b, xyz, offset, hdr, target_per_cell);
     if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 0);
     knngrid::grid_scan_kernel<<<b, 1024, 0, st>>>(hdr, cursor, cell_start);
     if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 1);
@@ -790,6 +791,9 @@ extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* o
     return ROITR_OK;
 }
 
+extern "C" int roitr_knn_grid_build(int b, int n, const float* xyz, const int* offset, void* workspace, void* stream) {
+    return roitr_knn_grid_build_target(b, n, xyz, offset, GRID_TARGET, workspace, stream);
+}
 
 extern "C" int roitr_knn_ppf_grid_q(int b, int m, int k_out, int drop_first, int n_total, const float* xyz,
                                     const float* normals, const float* new_xyz, const float* new_normals, const int* offset,
