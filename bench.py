@@ -331,11 +331,25 @@ def main():
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(n_steps):
-            runner.load_batched(collated[i % NB])
-            runner.run()
-            recs = results_mod.tester_records(host[i % NB], runner.results(), cfg["benchmark"])
-            nbytes = sum(t.numel() * t.element_size() for r in recs for t in r.values() if torch.is_tensor(t))
+        def fetch(r, i):
+            recs = results_mod.tester_records(host[i % NB], r.results(), cfg["benchmark"])
+            return sum(t.numel() * t.element_size() for rec in recs for t in rec.values() if torch.is_tensor(t))
+        if pipe is None:
+            for i in range(n_steps):
+                runner.load_batched(collated[i % NB])
+                runner.run()
+                nbytes = fetch(runner, i)
+        else:        # the record of step i crosses PCIe while step i+1 computes
+            prev = None
+            for i in range(n_steps):
+                slot = pipe.submit(collated[i % NB])
+                if prev is not None:
+                    pipe.wait(prev[0])
+                    nbytes = fetch(pipe.runner(prev[0]), prev[1])
+                prev = (slot, i)
+            pipe.wait(prev[0])
+            nbytes = fetch(pipe.runner(prev[0]), prev[1])
+            pipe.join()
         b.record()
         barrier()
         return a.elapsed_time(b), nbytes
@@ -470,7 +484,8 @@ def main():
                     "d2h_bytes_per_step": d2h_bytes},
             "e2e_record": {"value": world * B * rec_steps / (ms_rec * 1e-3), "unit": "pairs/s", "d2h_bytes_per_step": rec_bytes,
                            "steps": rec_steps, "what": "e2e with the full 16-key record of lib/tester.py:56-69 for every pair "
-                           "(roitr_b200.results.tester_records: one staged D2H copy per dtype per step)"},
+                           "(roitr_b200.results.tester_records: one staged D2H copy per dtype per step; with the pipelined runner the copy of step i "
+                           "overlaps the compute of step i+1)"},
             "single_pair_forward_ms": {"value": single_ms, "pairs_per_s": 1000.0 / single_ms,
                                        "what": "model.forward on one pair (lib/tester.py:53, batch_size 1), wall clock incl. its host sync, mean of 10"},
             "gpu_launches": launches_per_step * steps, "clocks": clk.summary(), "roofline": roof,

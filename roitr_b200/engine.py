@@ -324,8 +324,16 @@ class Plan:
         e = self.levels[li]["ends"]
         return (0 if cloud == 0 else e[cloud - 1]), e[cloud]
 
-    def side_streams(self, n):
+    def multistream(self):
+        """Whether the forward is issued on several streams (lanes): batches always, a single pair only when it is being
+        captured into a CUDA graph (``multi`` set by BatchRunner) - issued eagerly, one pair gains nothing from lanes because
+        the host cannot launch fast enough to keep even one stream busy."""
         if getattr(self, "serial", False):
+            return False
+        return self.B > 1 or getattr(self, "multi", False)
+
+    def side_streams(self, n):
+        if not self.multistream():
             return []
         if len(getattr(self, "_streams", [])) < n:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n)]
@@ -333,7 +341,7 @@ class Plan:
 
     def global_lane(self):
         """The stream that carries the global transformer next to the decoder (inline for single pairs / serial plans)."""
-        if self.B <= 1 or getattr(self, "serial", False):
+        if not self.multistream():
             return _Lane(None)
         if not hasattr(self, "_glane"):
             # high priority: its ~170 small launches are the critical path to coarse / fine matching; without it each of
@@ -344,7 +352,7 @@ class Plan:
     def lanes(self):
         """(sampling lane, neighbour-search lane): the two streams that carry the coordinate-only work of the backbone
         (FPS chain; grids + kNN/PPF), or (None, None) when the plan runs everything inline on the current stream."""
-        if self.B <= 1 or getattr(self, "serial", False):
+        if not self.multistream():
             return _Lane(None), _Lane(None)
         if not hasattr(self, "_lanes"):
             self._lanes = [torch.cuda.Stream(device=self.device) for _ in range(2)]
@@ -431,7 +439,8 @@ def encode(W, plan, pts, feats, nrm, on_nodes=None):
         # Level 1 is issued while the FPS clusters (44 K registers + 61 KB shared memory on 128 of the 148 SMs for ~3.5 ms) are
         # resident: the 215 KB / 57 K-register dense-layer CTAs cannot share an SM with them and would wait for the chain to
         # finish, the "light" configuration (64 registers, 320 threads, ~115 KB) can.
-        ops.set_linear_variant(LIGHT_VARIANT if (li == 0 and fps_lane.stream is not None) else 0)
+        # (only when the FPS clusters - 4 CTAs per cloud - actually hold at least half of the 148 SMs)
+        ops.set_linear_variant(LIGHT_VARIANT if (li == 0 and fps_lane.stream is not None and 8 * plan.B >= 74) else 0)
         if li > 0:
             _wait(g["ev_down"])
             x = local_ppf_transformer(W, p + ".0.transformer", x, g["down_idx"], g["gidx"], g["gppf"], order)
@@ -588,7 +597,7 @@ def backbone_batch(W, architecture, plan, pts, feats, nrm, src_deformed, aux=Non
         # the geometric structure embedding needs the superpoint coordinates only: it is issued here, on the sampling
         # lane, and overlaps the encoder instead of sitting between the encoder and the global transformer
         nodes["emb"] = geometric_embedding_batch(W, B, p4, split)
-        nodes["ev_emb"] = torch.cuda.current_stream().record_event() if B > 1 and not getattr(plan, "serial", False) else None
+        nodes["ev_emb"] = torch.cuda.current_stream().record_event() if plan.multistream() else None
 
     L, lanes = encode(W, plan, pts, feats, nrm, on_nodes=_nodes)
     per_pair = []
@@ -699,7 +708,7 @@ def riga_batch(W, cfg, plan, pts, feats, nrm, src_pcd, rot, trans, aux=None):
     cap = Pmax * K * topk * (1 if bool(cfg["fine_matching_mutual"]) else 2)
     # The head is batched over the pairs (every kernel takes the pair as a grid dimension), so its three stages are three short
     # chains of launches, each forked onto ONE side stream as early as its inputs exist.
-    fork = _Fork(plan.side_streams(1) if B > 1 else [])
+    fork = _Fork(plan.side_streams(1))
     hd = {}                                   # batched head state handed from stage to stage
     tgt_all = pts[B * Ns:]                    # (B*Nt, 3): the B target clouds
 
@@ -852,6 +861,7 @@ class BatchRunner:
         self.W, self.cfg, self.B, self.Ns, self.Nt, self.device = W, cfg, B, n_src, n_tgt, device
         self.plan = Plan(n_src, n_tgt, B, device, fps_cluster)
         self.plan.serial = serial     # True: no side streams at all (bench.py's per-kernel timing replica)
+        self.plan.multi = bool(graph)  # a captured step runs its lanes concurrently even for one pair
         self.plan.mid_event, self.plan.mid_level = mid_event, mid_level
         tot = B * (n_src + n_tgt)
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
