@@ -454,7 +454,7 @@ def main():
             tj = {}
         roof["how"] = ("CUDA events around every entry-point call in a single-stream eager replica of the timed step (the timed "
                        "step itself is one multi-stream CUDA graph); algorithmic work per DESIGN.md §4 / SURVEY.md §8d")
-        named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid_q", "roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build"]),
+        named = {"knn_ppf": roofline_of(["roitr_knn_ppf_grid_q", "roitr_knn_ppf_grid", "roitr_knn_ppf_n", "roitr_knn_grid_build", "roitr_knn_grid_build_target"]),
                  "global_attention_qk_pv": roofline_of(["roitr_gemm_tc_batched"]),
                  "dense_layers": roofline_of(["roitr_linear_tc_packed", "roitr_linear_ln_tc_packed"]),
                  "global_attention_e_pass": roofline_of(["roitr_geo_self_scores_ld"]),
