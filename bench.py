@@ -5,16 +5,19 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithm on the host CPU cores
 
 A step = RIGA_v2.forward over a batch of B (default 16) independent synthetic pairs of BASELINE.json configs[1]
-(2 x 20 000 points each, Gaussian blobs, seeded weights), issued as one CUDA graph. N > 1 (torchrun, one rank per GPU): pairs are independent units, rank r processes its own
-pairs (weak scaling), NCCL is used only for the barrier, the max-over-ranks time and the gather of per-pair result
-counts. `value` = pairs/s with inputs resident in HBM; `e2e` = the same metric through the batched public API
+(2 x 20 000 points each, Gaussian blobs, seeded weights), issued as one CUDA graph; by default two steps are
+in flight (engine.PipelinedRunner, ROITR_PIPELINE=2: step i+1 starts beside the latency-bound back of step i; every step runs
+the whole forward of its own B pairs; ROITR_PIPELINE=1 = one step at a time). N > 1 (torchrun, one rank per GPU): pairs are
+independent units, rank r processes its own pairs (weak scaling), NCCL is used only for the barrier, the max-over-ranks
+time and the result gather (per-rank counts; every rank's variable-length correspondences to rank 0, outside the timed region). `value` = pairs/s with inputs resident in HBM; `e2e` = the same metric through the batched public API
 (`BatchRunner.load_batched` / `run` / `correspondences`) with pinned HOST buffers: H2D of the 9 inputs of every pair and D2H
 of every pair's correspondences inside the timed region. `e2e_record` = the same with the FULL result record of
 lib/tester.py:56-69 (descriptors included, ~45 MB per pair) copied to the host; `single_pair_forward_ms` = the call
 lib/tester.py:53 makes (model.forward on ONE pair, batch_size 1, host sync at the end); `reference_gpu` = the reference's
 algorithm in eager PyTorch with the reference's OWN kNN / FPS kernels (oracle/_ref) on this GPU (information only).
-Timing: CUDA events on the launch stream; >= 3 warm-up steps; an L2 flush (256 MiB memset) between steps, outside the
-timed events; clocks sampled with nvidia-smi during the timed region.
+Timing: CUDA events on the launch stream, max over ranks; >= 3 warm-up steps; an L2 flush (256 MiB memset) before every step
+(pipelined: on the step's stream, inside the ONE event pair that brackets the K overlapping steps; unpipelined: between the
+per-step event pairs); clocks sampled with nvidia-smi during the timed region.
 """
 import argparse
 import json
@@ -476,7 +479,9 @@ def main():
             "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "parallelism": "independent pairs x%d" % world,
-                       "l2": "256 MiB flush between steps (outside the timed events); %d distinct batches cycled" % NB,
+                       "l2": ("256 MiB flush before every step (%s); %d distinct batches cycled; the step's working set (3.2 GB of "
+                              "embeddings, 0.16-0.65 GB activations per layer) exceeds the 126 MB L2 anyway"
+                              % ("issued on the step's stream inside the timed region" if depth > 1 else "outside the timed events", NB)),
                        "mode": ("one CUDA graph per step" if not args.no_graph else "eager") + ", %d pairs per step per GPU" % B +
                                (", %d steps in flight (software pipeline: step i+1 starts when step i is past its encoder level %d; "
                                 "K steps timed with one event pair)" % (depth, int(os.environ.get("ROITR_MID_LEVEL", "0")) + 1) if depth > 1 else "")},
