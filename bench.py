@@ -250,6 +250,7 @@ def main():
     resident = [[{k: v.to(dev) for k, v in p.items()} for p in batch] for batch in pinned]
     from roitr_b200.engine import BatchRunner
     collated = [BatchRunner.collate(batch) for batch in host]           # what a DataLoader's collate_fn hands over (pinned)
+    collated_dev = [{k: v.to(dev) for k, v in c.items()} for c in collated]   # the same batches resident in HBM (`value`)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     h2d_bytes = sum(t.numel() * t.element_size() for p in pinned[0] for t in p.values())        # = bytes of collated[0]
     runner = m.batch_runner(B, N_POINTS, N_POINTS, graph=not args.no_graph)
@@ -276,7 +277,7 @@ def main():
                 d2h = sum(t.numel() * t.element_size() for trip in res for t in trip) + 12 * B
                 ncorr = sum(int(trip[2].shape[0]) for trip in res)
             else:
-                r.load(resident[i % NB])                     # device-to-device: inputs already resident in HBM
+                r.load_batched(collated_dev[i % NB])          # device-to-device: inputs already resident in HBM
                 r.run()
             b.record()
             ev.append((a, b))
@@ -299,7 +300,7 @@ def main():
         a.record()
         prev = None
         for i in range(n_steps):
-            slot = pipe.submit(collated[i % NB] if e2e else resident[i % NB], pre=flush.zero_)
+            slot = pipe.submit(collated[i % NB] if e2e else collated_dev[i % NB], pre=flush.zero_)
             if e2e and prev is not None:
                 pipe.wait(prev)
                 res = pipe.runner(prev).correspondences()
