@@ -536,6 +536,146 @@ __global__ void __launch_bounds__(KT_THREADS) knn_grid_thread_kernel(const KnnPa
     }
 }
 
+// ---- one thread per query, k best in a shared-memory MAX-HEAP (17 slots) -------------------------------------------------
+// The register list above costs K-1 compare-exchange steps per admission (128 instructions at K = 17, and a warp pays them
+// whenever ANY of its 32 queries admits a candidate), which is why 17-slot queries used to run on the warp-per-query kernel
+// (5.2 ns per query against 1.6 ns for the 9-slot thread kernel). Here the k best live in a binary max-heap keyed by
+// (distance, index) in shared memory (column `tid` of a [K][KT_THREADS] array: conflict-free): an admission replaces the
+// root and sifts down at most 4 levels; the root IS the admission bound tau. A heap sort at the end yields the ascending
+// list. Same candidates, same lexicographic admission rule, same tie flags as the register kernel -> bit-identical results.
+template <int K>
+__global__ void __launch_bounds__(KT_THREADS) knn_grid_thread_heap_kernel(const KnnParams P, const knngrid::SegHeader* __restrict__ hdr,
+                                                                           const int* __restrict__ cell_start,
+                                                                           const float4* __restrict__ sorted,
+                                                                           const float4* __restrict__ qorder) {
+    __shared__ float s_d[K * KT_THREADS];       // [slot][thread]
+    __shared__ int s_i[K * KT_THREADS];
+    __shared__ int s_q[KT_THREADS];
+    __shared__ float s_qp[KT_THREADS * 3];
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * KT_THREADS + tid;
+    float* hd = s_d + tid;
+    int* hi = s_i + tid;
+    constexpr int S = KT_THREADS;
+    int q = -1;
+    bool tie = false;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    // (d1, i1) > (d2, i2) lexicographically
+    auto gt = [](float d1, int i1, float d2, int i2) { return d1 > d2 || (d1 == d2 && i1 > i2); };
+    // put (cd, ci) at the root of the heap of `n` elements and restore the heap property
+    auto sift_root = [&](float cd, int ci, int n) {
+        int pos = 0;
+        while (true) {
+            const int l = 2 * pos + 1;
+            if (l >= n) break;
+            int c = l;
+            float dc = hd[l * S];
+            int ic = hi[l * S];
+            if (l + 1 < n) {
+                const float dr = hd[(l + 1) * S];
+                const int ir = hi[(l + 1) * S];
+                if (gt(dr, ir, dc, ic)) { c = l + 1; dc = dr; ic = ir; }
+            }
+            if (!gt(dc, ic, cd, ci)) break;
+            hd[pos * S] = dc; hi[pos * S] = ic;
+            pos = c;
+        }
+        hd[pos * S] = cd; hi[pos * S] = ci;
+    };
+    if (t < P.m) {
+        const int sgm = find_segment(t, P.new_offset, P.b);
+        if (qorder) {
+            const float4 v = __ldg(qorder + t);
+            q = __float_as_int(v.w); qx = v.x; qy = v.y; qz = v.z;
+        } else {
+            q = t;
+            qx = __ldg(P.qxyz + 3 * (size_t)q); qy = __ldg(P.qxyz + 3 * (size_t)q + 1); qz = __ldg(P.qxyz + 3 * (size_t)q + 2);
+        }
+        const int qs = sgm == 0 ? 0 : __ldg(P.offset + sgm - 1);
+        const knngrid::SegHeader H = hdr[sgm];
+        const int* cs = cell_start + H.cell_base;
+        const float4* pts = sorted + qs;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { hd[j * S] = 1e10f; hi[j * S] = qs; }
+        float tau = 1e10f;
+        int tau_i = qs;
+        const int cx = knngrid::cell_coord(qx, H.ox, H.inv_h, H.nx), cy = knngrid::cell_coord(qy, H.oy, H.inv_h, H.ny),
+                  cz = knngrid::cell_coord(qz, H.oz, H.inv_h, H.nz);
+        auto scan_range = [&](int beg, int end) {
+            for (int p = beg; p < end; ++p) {
+                const float4 v = __ldg(pts + p);
+                const float cd = sqdist_ref(qx - v.x, qy - v.y, qz - v.z);
+                if (cd <= tau) {
+                    const int ci = __float_as_int(v.w);
+                    if (cd == tau && tau != 1e10f) tie = true;     // boundary tie: the reference's choice depends on its heap
+                    if (cd < tau || ci < tau_i) {
+                        sift_root(cd, ci, K);
+                        const float tau_old = tau;
+                        tau = hd[0]; tau_i = hi[0];
+                        if (tau == tau_old && tau_old != 1e10f) tie = true;
+                    }
+                }
+            }
+        };
+        for (int r = 0;; ++r) {          // the cube walk of grid_search_thread
+            const int x0 = max(cx - r, 0), x1 = min(cx + r, H.nx - 1);
+            for (int dz = -r; dz <= r; ++dz) {
+                const int z = cz + dz;
+                if (z < 0 || z >= H.nz) continue;
+                for (int dy = -r; dy <= r; ++dy) {
+                    const int y = cy + dy;
+                    if (y < 0 || y >= H.ny) continue;
+                    const int row = (z * H.ny + y) * H.nx;
+                    if (abs(dz) == r || abs(dy) == r) {
+                        scan_range(__ldg(cs + row + x0), __ldg(cs + row + x1 + 1));
+                    } else {
+                        if (cx - r >= 0) scan_range(__ldg(cs + row + cx - r), __ldg(cs + row + cx - r + 1));
+                        if (cx + r < H.nx) scan_range(__ldg(cs + row + cx + r), __ldg(cs + row + cx + r + 1));
+                    }
+                }
+            }
+            const bool all = (cx - r <= 0) && (cx + r >= H.nx - 1) && (cy - r <= 0) && (cy + r >= H.ny - 1) && (cz - r <= 0) &&
+                             (cz + r >= H.nz - 1);
+            if (all) break;
+            float bound = CUDART_INF_F;
+            if (cx - r > 0) bound = fminf(bound, qx - (H.ox + (float)(cx - r) * H.h));
+            if (cx + r < H.nx - 1) bound = fminf(bound, (H.ox + (float)(cx + r + 1) * H.h) - qx);
+            if (cy - r > 0) bound = fminf(bound, qy - (H.oy + (float)(cy - r) * H.h));
+            if (cy + r < H.ny - 1) bound = fminf(bound, (H.oy + (float)(cy + r + 1) * H.h) - qy);
+            if (cz - r > 0) bound = fminf(bound, qz - (H.oz + (float)(cz - r) * H.h));
+            if (cz + r < H.nz - 1) bound = fminf(bound, (H.oz + (float)(cz + r + 1) * H.h) - qz);
+            bound -= 1e-4f * H.h;
+            if (tau < 1e10f && bound > 0.f && tau < bound * bound * 0.99999f) break;
+        }
+        // heap sort: ascending (distance, index) in slots 0 .. K-1
+        for (int n = K - 1; n > 0; --n) {
+            const float rd = hd[0], ld = hd[n * S];
+            const int ri = hi[0], li = hi[n * S];
+            hd[n * S] = rd; hi[n * S] = ri;
+            sift_root(ld, li, n);
+        }
+        // equal distances inside the final list: the reference's order among them is its heap's
+        for (int j = 0; j + 1 < K; ++j)
+            if (hd[j * S] == hd[(j + 1) * S] && hd[j * S] != 1e10f) tie = true;
+    }
+    // ---- emit cooperatively (one (query, slot) per thread: contiguous index / PPF rows) ----
+    s_q[tid] = tie ? (-2 - q) : q;
+    s_qp[3 * tid] = qx; s_qp[3 * tid + 1] = qy; s_qp[3 * tid + 2] = qz;
+    __syncthreads();
+    const int kout = K - P.drop;
+    for (int e = tid; e < KT_THREADS * kout; e += KT_THREADS) {
+        const int ql = e / kout, slot = e - ql * kout;
+        const int qq = s_q[ql];
+        if (qq == -1) continue;
+        if (qq <= -2) {
+            if (slot == 0) P.idx[(size_t)(-2 - qq) * kout] = -1;      // marker consumed by knn_tie_fixup_kernel
+            continue;
+        }
+        emit_result(P, qq, slot, kout, s_i[(slot + P.drop) * S + ql], s_d[(slot + P.drop) * S + ql], s_qp[3 * ql], s_qp[3 * ql + 1],
+                    s_qp[3 * ql + 2]);
+    }
+}
+
 // ---- surface normals: kNN + covariance + smallest-eigenvalue eigenvector, one thread per point ---------------------------
 // The step before the hot path: Open3D's estimate_normals(KDTreeSearchParamKNN(knn)) followed by
 // dataset/common.py:312-320 normal_redirect, as called in dataset/tdmatch.py:120-127. Per point: the knn nearest points of
@@ -818,12 +958,13 @@ extern "C" int roitr_knn_ppf_grid_q(int b, int m, int k_out, int drop_first, int
     if (!qw && new_xyz == xyz && m == n_total) qw = w;
     const float4* qorder = qw ? (const float4*)(qw + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b)) : nullptr;
     const int grid = ceil_div(m, KT_THREADS);
-    // thread-per-query (sorted list in registers) for 1 / 3 / 9 slots; at 17 slots the unrolled insertion diverges and the
-    // warp-per-query kernel (top-k spread over the lanes) measured faster, as it is for any other slot count
+    // thread-per-query: sorted list in registers for 1 / 3 / 9 slots, a shared-memory max-heap for 17 (the unrolled insertion
+    // of a 17-entry register list diverges too much); any other slot count: the warp-per-query kernel (top-k over the lanes)
     bool done = true;
     if (nslots == 1) knn_grid_thread_kernel<1><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else if (nslots == 3) knn_grid_thread_kernel<3><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else if (nslots == 9) knn_grid_thread_kernel<9><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
+    else if (nslots == 17) knn_grid_thread_heap_kernel<17><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else done = false;
     if (!done) knn_grid_kernel<<<ceil_div(m, KNN_WARPS), KNN_THREADS, 0, st>>>(P, hdr, cell_start, sorted);
     ROITR_CHECK_LAUNCH("knn_grid_kernel");
