@@ -72,8 +72,8 @@ int roitr_knn_ppf_n(int b, int m, int k_out, int drop_first, int n_total, const 
  *   roitr_knn_ppf_grid(...)               as roitr_knn_ppf_n, with the workspace (256-byte aligned)
  */
 long long roitr_knn_grid_workspace_bytes(int b, int n);
-/* roitr_knn_grid_build with an explicit average number of points per grid cell over the bounding box (default build: 1.0;
- * larger cells suit queries with more neighbours - fewer cell-range lookups per candidate - smaller ones 1-NN queries). */
+/* roitr_knn_grid_build with an explicit average number of points per grid cell over the bounding box (default build: 0.5,
+ * measured best for every query type of the forward on B200, scripts/tune_grid.py). */
 int roitr_knn_grid_build_target(int b, int n, const float* xyz, const int* offset, float target_per_cell, void* workspace,
                                 void* stream);
 /* Surface normals of a (segmented) cloud: per point the `knn` (9, 17 or 33) nearest points of its own segment, itself

@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(KT_THREADS) normals_kernel(int b, int n, const
 }
 
                               // for k <= 9 slots (measured: 2-4x faster there, slower for 17 slots), 2 = thread-per-query everywhere
-constexpr float GRID_TARGET = 1.0f;   // average points per grid cell over the bounding box (tuned on B200: scripts history)
+constexpr float GRID_TARGET = 0.5f;   // average points per grid cell over the bounding box (scripts/tune_grid.py on B200: best for every query type of the forward)
 
 int launch_knn(const KnnParams& P, cudaStream_t st) {
     if (P.m == 0) return ROITR_OK;
@@ -963,7 +963,7 @@ extern "C" int roitr_knn_ppf_grid_q(int b, int m, int k_out, int drop_first, int
     bool done = true;
     if (nslots == 1) knn_grid_thread_kernel<1><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else if (nslots == 3) knn_grid_thread_kernel<3><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
-    else if (nslots == 9) knn_grid_thread_kernel<9><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
+    else if (nslots == 9) knn_grid_thread_heap_kernel<9><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else if (nslots == 17) knn_grid_thread_heap_kernel<17><<<grid, KT_THREADS, 0, st>>>(P, hdr, cell_start, sorted, qorder);
     else done = false;
     if (!done) knn_grid_kernel<<<ceil_div(m, KNN_WARPS), KNN_THREADS, 0, st>>>(P, hdr, cell_start, sorted);

@@ -106,14 +106,17 @@ def concat_segment(x, g, offset):
 GRID_MIN_SEGMENT = 1024     # reference sets with at least this many points per segment get the grid-accelerated kNN
 
 
-def knn_grid_build(xyz, offset, target=1.0):
+def knn_grid_build(xyz, offset, target=None):
     """Uniform-grid acceleration structure over a (segmented) reference set; reusable by every query against it.
-    ``target`` = average points per cell over the bounding box."""
+    ``target`` = average points per cell over the bounding box (None: the library default, 0.5)."""
     b, n = offset.shape[0], xyz.shape[0]
     fn = _lib.lib().roitr_knn_grid_workspace_bytes
     fn.restype = c_ll
     ws = torch.empty(int(fn(c_int(b), c_int(n))), dtype=torch.uint8, device=xyz.device)
-    _lib.call("roitr_knn_grid_build_target", c_int(b), c_int(n), f32(xyz), i32(offset), c_float(float(target)), ptr(ws), stream_ptr())
+    if target is None:
+        _lib.call("roitr_knn_grid_build", c_int(b), c_int(n), f32(xyz), i32(offset), ptr(ws), stream_ptr())
+    else:
+        _lib.call("roitr_knn_grid_build_target", c_int(b), c_int(n), f32(xyz), i32(offset), c_float(float(target)), ptr(ws), stream_ptr())
     return ws
 
 

@@ -24,13 +24,13 @@ for li in range(1, 4):
     prev = L[-1]; sz = prev["sz"] // 4
     idx, p_ = ops.fps(prev["p"], prev["o"], offs(sz), prev["sz"], sz * 2 * B)
     L.append(dict(p=p_, n=ops.gather_rows(prev["n"], idx), o=offs(sz), sz=sz))
-targets = (0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0)
+targets = (0.2, 0.3, 0.4, 0.5, 0.7, 1.0, 1.5)
 print("query (refs <- queries, k)            " + "  ".join("t=%.1f" % t for t in targets))
 def row(name, ref, qry, k, drop, ppf):
     out = []
     for t in targets:
         g = ops.knn_grid_build(ref["p"], ref["o"], t)
-        qg = g if qry is ref else ops.knn_grid_build(qry["p"], qry["o"], 1.0)
+        qg = g if qry is ref else ops.knn_grid_build(qry["p"], qry["o"])
         out.append(timeit(lambda: ops.knn_ppf(k, ref["p"], ref["n"] if ppf else None, qry["p"], qry["n"] if ppf else None, ref["o"], qry["o"],
                                               drop_first=drop, want_ppf=ppf, want_dist=not ppf, grid=g, qgrid=qg)))
     print("%-38s" % name + "  ".join("%5.3f" % v for v in out))
@@ -44,3 +44,5 @@ row("L2 queries in L3 refs, 3-NN", L[2], L[1], 3, 0, False)
 row("L1 self 1-NN (occlusion-like)", L[0], L[0], 1, 0, False)
 for t in targets:
     print("grid build L1 t=%.1f: %.3f ms" % (t, timeit(lambda: ops.knn_grid_build(L[0]["p"], L[0]["o"], t))))
+row("L3 queries in L4 refs, 3-NN", L[3], L[2], 3, 0, False)
+row("L4 <- L3 refs, k=16", L[2], L[3], 16, 1, True)
