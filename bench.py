@@ -286,7 +286,8 @@ def main():
         return sum(a.elapsed_time(b) for a, b in ev), wall, d2h, ncorr
 
     depth = int(os.environ.get("ROITR_PIPELINE", "2"))        # steps in flight (1 = one step at a time)
-    pipe = m.pipelined_runner(B, N_POINTS, N_POINTS, depth=depth, mid_level=int(os.environ.get("ROITR_MID_LEVEL", "0"))) if depth > 1 else None
+    pipe = m.pipelined_runner(B, N_POINTS, N_POINTS, depth=depth, mid_level=int(os.environ.get("ROITR_MID_LEVEL", "0")),
+                              fps_cluster=int(os.environ.get("ROITR_FPS_CLUSTER", "0"))) if depth > 1 else None
 
     def pipe_loop(e2e, n_steps):
         """Pipelined steps (engine.PipelinedRunner): step i+1 starts beside the latency-bound back of step i, so per-step event
