@@ -24,8 +24,9 @@ STRIDES = (1, 4, 4, 4)
 NSAMPLE = (8, 16, 16, 16)
 BLOCKS = (2, 3, 3, 3)
 HEADS = 4
-FPS_AFTER_KNN = False        # measured: the level-1 layers start 3 ms earlier but crawl next to the FPS clusters; 563 vs 569 pairs/s
-LIGHT_VARIANT = 3          # streaming dense-layer configuration used while the FPS clusters are resident (0 = none)
+import os as _os
+FPS_AFTER_KNN = _os.environ.get("ROITR_FPS_AFTER_KNN", "0") == "1"   # measured: the level-1 layers start 3 ms earlier but crawl next to the FPS clusters; 563 vs 569 pairs/s
+LIGHT_VARIANT = int(_os.environ.get("ROITR_LIGHT_VARIANT", "3"))    # streaming dense-layer configuration used while the FPS clusters are resident (0 = none)
 
 
 # ------------------------------------------------------------------------------------------------ weight packing
