@@ -248,3 +248,35 @@ def test_geo_embedding_table_propagates_nan_instead_of_reading_out_of_bounds():
     assert torch.isnan(E[0, 7, 3]).any() and torch.isnan(E[0, 3, 7]).any()
     clean = [i for i in range(N) if i not in (7, 11) and 7 not in nn3[i].tolist() and 11 not in nn3[i].tolist()]
     assert torch.isfinite(E[0][clean][:, clean]).all()
+
+
+@pytest.mark.parametrize("m,n,C,K,gather,ordered", [(1000, 1000, 64, 8, False, False), (1001, 4000, 64, 16, True, False),
+                                                    (777, 777, 128, 16, False, True), (500, 2000, 128, 8, True, False),
+                                                    (313, 313, 256, 16, False, False), (125, 500, 512, 16, True, False), (1, 40, 64, 8, True, False)])
+def test_local_attention_matches_fp64(m, n, C, K, gather, ordered):
+    """csrc/local_attn.cu (two queries per warp at C <= 128, one at C >= 256) against a float64 evaluation of the folded form
+    of attention.py:166-200: S = (q.k_j + (Ap^T q).ppf_j + q.cp) / sqrt(c), A = softmax_j S, out = sum_j A_j v_j + Avp (sum_j A_j ppf_j) + cvp."""
+    g = torch.Generator().manual_seed(m + C + K)
+    H, c = 4, C // 4
+    qkv = torch.randn(n, 3 * C, generator=g).to(DEV)
+    node_idx = torch.randint(0, n, (m,), generator=g).int().to(DEV) if gather else None
+    group = torch.randint(0, n, (m, K), generator=g).int().to(DEV)
+    ppf = torch.rand(m, K, 4, generator=g).to(DEV)
+    Ap, Avp = (torch.randn(C, 4, generator=g) * 0.3).to(DEV), (torch.randn(C, 4, generator=g) * 0.3).to(DEV)
+    cp, cvp = (torch.randn(C, generator=g) * 0.1).to(DEV), (torch.randn(C, generator=g) * 0.1).to(DEV)
+    order = None
+    if ordered:      # the queries' own grid as visiting order (any permutation must give the same rows)
+        pts = torch.rand(m, 3, generator=g).to(DEV)
+        off = torch.tensor([m], dtype=torch.int32, device=DEV)
+        order = (ops.knn_grid_build(pts, off), 1)
+    out = ops.local_attention(qkv, C, node_idx, group, ppf, Ap, cp, Avp, cvp, order=order)
+    q = qkv[:, :C].double()[node_idx.long() if gather else torch.arange(m, device=DEV)].view(m, H, c)
+    k = qkv[:, C:2 * C].double()[group.long()].view(m, K, H, c)
+    v = qkv[:, 2 * C:].double()[group.long()].view(m, K, H, c)
+    qa = torch.einsum("mhc,hcf->mhf", q, Ap.double().view(H, c, 4))
+    qb = (q * cp.double().view(1, H, c)).sum(-1)
+    S = (torch.einsum("mhc,mkhc->mhk", q, k) + torch.einsum("mhf,mkf->mhk", qa, ppf.double()) + qb[..., None]) / c ** 0.5
+    A = torch.softmax(S, -1)
+    w = torch.einsum("mhk,mkf->mhf", A, ppf.double())
+    ref = torch.einsum("mhk,mkhc->mhc", A, v) + torch.einsum("hcf,mhf->mhc", Avp.double().view(H, c, 4), w) + cvp.double().view(1, H, c)
+    assert (out.double() - ref.reshape(m, C)).abs().max().item() < 2e-5
