@@ -13,10 +13,9 @@
 // which removes the two (m k) x C x C GEMMs and the four (m,k,C) tensors the reference materialises; the kernel is a
 // pure gather of K and V rows.
 //
-// One WARP per query at C >= 256 (lane l owns C/32 channels, a head is 8 lanes); TWO queries per warp at C <= 128 (16 lanes
-// per query, C/16 channels per lane, a head is 4 lanes): the per-head dot products are 2-3-step shuffle reductions. K/V rows
-// are contiguous C*4 bytes: every gather is a fully coalesced 256 B..2 KB read, served from L1 / L2 (K,V of a level fit in
-// the 126 MB L2).
+// One WARP per query. Lane l owns channels [l*CPL, (l+1)*CPL), CPL = C/32, so a head (c = C/4 channels) is 8 lanes and
+// the per-head dot products are 3-step shuffle reductions. K/V rows are contiguous C*4 bytes: every gather is a fully
+// coalesced 256 B..2 KB warp read, served from L2 (K,V of a level fit in the 126 MB L2).
 #include "../../include/roitr_b200.h"
 #include "common.cuh"
 
@@ -36,11 +35,10 @@ __device__ __forceinline__ void load_row(const float* __restrict__ p, float (&r)
     }
 }
 
-template <int LPH>
-__device__ __forceinline__ float head_sum(float v) {  // reduce over the LPH (8 or 4) lanes of a head
+__device__ __forceinline__ float head_sum(float v) {  // reduce over the 8 lanes of a head
     v += __shfl_xor_sync(FULL_MASK, v, 1);
     v += __shfl_xor_sync(FULL_MASK, v, 2);
-    if constexpr (LPH == 8) v += __shfl_xor_sync(FULL_MASK, v, 4);
+    v += __shfl_xor_sync(FULL_MASK, v, 4);
     return v;
 }
 
@@ -59,26 +57,17 @@ struct LocalAttnParams {
     float sqrt_c;
 };
 
-// LPQ = lanes per query: 32 (one query per warp) or 16 (TWO queries per warp, for C <= 128: a lane then holds C/16 channels,
-// rows are read with 16-byte loads and every shuffle / scalar instruction serves two queries). A head is LPH = LPQ/4 lanes.
-template <int C, int KNB, int LPQ>
+template <int C, int KNB>
 __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P) {
-    constexpr int CPL = C / LPQ;           // channels per lane
-    constexpr int LPH = LPQ / 4;           // lanes per head
-    constexpr int QPW = 32 / LPQ;          // queries per warp
-    static_assert(KNB <= LPQ && KNB % LPH == 0 && CPL % 2 == 0, "local_attn_kernel: unsupported shape");
+    constexpr int CPL = C / 32;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int sub = lane / LPQ, l = lane % LPQ;        // query slot inside the warp, lane inside the query
-    if (warp * QPW >= P.m) return;
-    const int slot = min(warp * QPW + sub, P.m - 1);   // an odd tail repeats the last query (its store is predicated off)
-    const bool live = warp * QPW + sub < P.m;
+    if (warp >= P.m) return;
     // visiting order: with the cell-sorted order of the query set's grid the queries resident on an SM are spatial
     // neighbours, their k-neighbourhoods overlap and most K/V row gathers hit L1 instead of L2
-    const int qi = P.order ? __float_as_int(__ldg(P.order + slot).w) : slot;
+    const int qi = P.order ? __float_as_int(__ldg(P.order + warp).w) : warp;
     const int node = P.node_idx ? __ldg(P.node_idx + qi) : qi;
-    const int c0 = l * CPL;
-    const int qbase = sub * LPQ;                       // first lane of this query
+    const int c0 = lane * CPL;
 
     float q[CPL];
     load_row<CPL>(P.q + (size_t)node * P.ldq + c0, q);
@@ -91,26 +80,26 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P
         qa0 = fmaf(q[i], a.x, qa0); qa1 = fmaf(q[i], a.y, qa1); qa2 = fmaf(q[i], a.z, qa2); qa3 = fmaf(q[i], a.w, qa3);
         qb = fmaf(q[i], __ldg(P.cp + c0 + i), qb);
     }
-    qa0 = head_sum<LPH>(qa0); qa1 = head_sum<LPH>(qa1); qa2 = head_sum<LPH>(qa2); qa3 = head_sum<LPH>(qa3); qb = head_sum<LPH>(qb);
+    qa0 = head_sum(qa0); qa1 = head_sum(qa1); qa2 = head_sum(qa2); qa3 = head_sum(qa3); qb = head_sum(qb);
 
     const int* gi = P.group_idx + (size_t)qi * KNB;
     const float4* pf = reinterpret_cast<const float4*>(P.ppf) + (size_t)qi * KNB;
-    const int my_nb = (l < KNB) ? __ldg(gi + l) : 0;
+    const int my_nb = (lane < KNB) ? __ldg(gi + lane) : 0;
 
     // ---- scores ----
     // Lane l of a head computes the partial dot products of its CPL channels for all KNB neighbours; a halving butterfly
-    // over the LPH lanes of the head (exchange half of the values with lane^(LPH/2), ..., lane^1) leaves lane li with the
-    // COMPLETE dot product of neighbours li + LPH r: LPH-1 shuffles per LPH neighbours instead of LPH log2(LPH), and the
-    // per-neighbour scalar work (positional term, division, exp) is done once per neighbour instead of once per lane.
-    constexpr int R = KNB / LPH;
-    const int li = l % LPH;
+    // over the 8 lanes of the head (exchange half of the values with lane^4, then lane^2, lane^1) leaves lane li with the
+    // COMPLETE dot product of neighbours li (and li + 8): 7 shuffles per 8 neighbours instead of 24, and the per-neighbour
+    // scalar work (positional term, division, exp) is done once per neighbour instead of once per lane.
+    constexpr int R = KNB / 8;
+    const int li = lane & 7;
     float d[KNB];
 #pragma unroll
     for (int j0 = 0; j0 < KNB; j0 += 4) {
         float kr[4][CPL];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int nb = __shfl_sync(FULL_MASK, my_nb, qbase + j0 + u);
+            const int nb = __shfl_sync(FULL_MASK, my_nb, j0 + u);
             load_row<CPL>(P.k + (size_t)nb * P.ldk + c0, kr[u]);
         }
 #pragma unroll
@@ -121,39 +110,49 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P
             d[j0 + u] = t;
         }
     }
+    {
+        const bool b2 = li & 4, b1 = li & 2, b0 = li & 1;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        float* e = d + LPH * r;
+        for (int r = 0; r < R; ++r) {
+            float* e = d + 8 * r;
 #pragma unroll
-        for (int h = LPH / 2; h >= 1; h >>= 1) {
-            const bool bit = li & h;
+            for (int t = 0; t < 4; ++t) {
+                const float send = b2 ? e[t] : e[t + 4];
+                const float keep = b2 ? e[t + 4] : e[t];
+                e[t] = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+            }
 #pragma unroll
-            for (int t = 0; t < h; ++t) {
-                const float send = bit ? e[t] : e[t + h];
-                const float keep = bit ? e[t + h] : e[t];
-                e[t] = keep + __shfl_xor_sync(FULL_MASK, send, h);
+            for (int t = 0; t < 2; ++t) {
+                const float send = b1 ? e[t] : e[t + 2];
+                const float keep = b1 ? e[t + 2] : e[t];
+                e[t] = keep + __shfl_xor_sync(FULL_MASK, send, 2);
+            }
+            {
+                const float send = b0 ? e[0] : e[1];
+                const float keep = b0 ? e[1] : e[0];
+                e[0] = keep + __shfl_xor_sync(FULL_MASK, send, 1);
             }
         }
     }
-    // lane li now owns neighbours li + LPH r: score, softmax over the head's KNB values, positional weights
+    // lane li now owns neighbours li + 8 r: score, softmax over the head's KNB values, positional weights
     float sc[R];
     float4 fr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        fr[r] = __ldg(pf + li + LPH * r);
+        fr[r] = __ldg(pf + li + 8 * r);
         const float sp = fmaf(qa3, fr[r].w, fmaf(qa2, fr[r].z, fmaf(qa1, fr[r].y, fmaf(qa0, fr[r].x, qb))));
-        sc[r] = __fdiv_rn(d[LPH * r] + sp, P.sqrt_c);  // attention.py:187: (e + p) / c ** 0.5
+        sc[r] = __fdiv_rn(d[8 * r] + sp, P.sqrt_c);  // attention.py:187: (e + p) / c ** 0.5
     }
     float mx = sc[0];
 #pragma unroll
     for (int r = 1; r < R; ++r) mx = fmaxf(mx, sc[r]);
     mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, 2));
-    if constexpr (LPH == 8) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, 4));
+    mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, 4));
     float den = 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) { sc[r] = expf(sc[r] - mx); den += sc[r]; }
-    den = head_sum<LPH>(den);
+    den = head_sum(den);
     const float inv = 1.0f / den;
     float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;  // sum_j A_j ppf_j (per head)
 #pragma unroll
@@ -161,31 +160,29 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P
         sc[r] *= inv;
         w0 = fmaf(sc[r], fr[r].x, w0); w1 = fmaf(sc[r], fr[r].y, w1); w2 = fmaf(sc[r], fr[r].z, w2); w3 = fmaf(sc[r], fr[r].w, w3);
     }
-    w0 = head_sum<LPH>(w0); w1 = head_sum<LPH>(w1); w2 = head_sum<LPH>(w2); w3 = head_sum<LPH>(w3);
+    w0 = head_sum(w0); w1 = head_sum(w1); w2 = head_sum(w2); w3 = head_sum(w3);
 
     // ---- value aggregate ----
     float acc[CPL];
 #pragma unroll
     for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
-    const int head_base = lane & ~(LPH - 1);
+    const int head_base = lane & 24;
 #pragma unroll
     for (int j0 = 0; j0 < KNB; j0 += 4) {
         float vr[4][CPL];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int nb = __shfl_sync(FULL_MASK, my_nb, qbase + j0 + u);
+            const int nb = __shfl_sync(FULL_MASK, my_nb, j0 + u);
             load_row<CPL>(P.v + (size_t)nb * P.ldv + c0, vr[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u;
-            // the weight of neighbour j lives in lane (head, j % LPH), register j / LPH (a compile-time index)
-            const float a = __shfl_sync(FULL_MASK, sc[j / LPH], head_base | (j % LPH));
+            const float a = __shfl_sync(FULL_MASK, sc[j >> 3], head_base | (j & 7));   // the weight lives in lane (head, j % 8)
 #pragma unroll
             for (int i = 0; i < CPL; ++i) acc[i] = fmaf(a, vr[u][i], acc[i]);
         }
     }
-    if (!live) return;
     float* o = P.out + (size_t)qi * C + c0;
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
@@ -196,10 +193,8 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LocalAttnParams P
 
 template <int C, int KNB>
 int launch(const LocalAttnParams& P, cudaStream_t st) {
-    constexpr int LPQ = (C <= 128) ? 16 : 32;       // two queries per warp where a lane can hold C/16 channels
-    constexpr int QPW = 32 / LPQ;
     const int warps_per_cta = 8;
-    local_attn_kernel<C, KNB, LPQ><<<ceil_div(ceil_div(P.m, QPW), warps_per_cta), warps_per_cta * 32, 0, st>>>(P);
+    local_attn_kernel<C, KNB><<<ceil_div(P.m, warps_per_cta), warps_per_cta * 32, 0, st>>>(P);
     ROITR_CHECK_LAUNCH("local_attn_kernel");
     return ROITR_OK;
 }

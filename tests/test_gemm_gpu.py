@@ -254,7 +254,7 @@ def test_geo_embedding_table_propagates_nan_instead_of_reading_out_of_bounds():
                                                     (777, 777, 128, 16, False, True), (500, 2000, 128, 8, True, False),
                                                     (313, 313, 256, 16, False, False), (125, 500, 512, 16, True, False), (1, 40, 64, 8, True, False)])
 def test_local_attention_matches_fp64(m, n, C, K, gather, ordered):
-    """csrc/local_attn.cu (two queries per warp at C <= 128, one at C >= 256) against a float64 evaluation of the folded form
+    """csrc/local_attn.cu against a float64 evaluation of the folded form
     of attention.py:166-200: S = (q.k_j + (Ap^T q).ppf_j + q.cp) / sqrt(c), A = softmax_j S, out = sum_j A_j v_j + Avp (sum_j A_j ppf_j) + cvp."""
     g = torch.Generator().manual_seed(m + C + K)
     H, c = 4, C // 4
