@@ -101,38 +101,6 @@ __device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, co
     store_block32(P, pad, v, lane, row0, ncol0, P.bias, nullptr);
 }
 
-// Plain epilogue of one 32x32 block through the BULK-COPY engine: bias / ReLU in registers (thread = row), the row goes to
-// this thread's 128-byte slot of the pad and ONE cp.async.bulk per thread writes it to global memory - no shared-memory
-// read-back, no per-segment store loop, and the stores drain asynchronously while the warp fetches the next block from
-// TMEM. (The round-1 ablation, profiles/r01g_ablate_gemm.txt, shows the epilogue - not the loads, the split or the MMAs - is
-// what bounds the wide layers: 0.247 ms with the stores, 0.117 ms without at (640000, 192, 64).) `pad` alternates between
-// two buffers per warp; at most one bulk group may still be reading the other one.
-__device__ __forceinline__ void store_block32_bulk(const Tc2Params& P, float* pad, float (&v)[32], int lane, int row0, int ncol0) {
-    if (P.bias) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + ncol0) + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-        }
-    }
-    if (P.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the group that read THIS pad two blocks ago is done
-    float* mine = pad + lane * PAD_STRIDE;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(mine + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    fence_proxy_async_smem();                                            // my generic-proxy writes -> visible to the bulk engine
-    const int row = row0 + lane;
-    if (row < P.M) {
-        float* dst = P.C + (long long)row * P.ldc + ncol0;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(dst), "r"(smem_u32(mine)) : "memory");
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Params P) {
     extern __shared__ unsigned char smem_raw[];
@@ -332,9 +300,9 @@ constexpr int RAW_BYTES = T2_BM * 128;
 // Epilogue of one finished accumulator tile (rows tm*128 .. +127, columns tn*BN .. ) held in TMEM at `tbase` (this warp's 32
 // lanes): plain bias / ReLU store, or the fused row epilogue. `next_tm` = the row tile this CTA processes next (-1: none),
 // whose residual rows are prefetched into L2. Shared by the streaming (linear_tc3) and weight-stationary (linear_ws) kernels.
-template <int BN, bool BULK>
+template <int BN>
 __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, const float (*s_ln)[BN], int warp, int lane, int tm,
-                                              int tn, int next_tm, uint32_t tbase, uint32_t& bulk_count) {
+                                              int tn, int next_tm, uint32_t tbase) {
     const int row0 = tm * T2_BM + warp * 32;
     const int n0 = tn * BN;
     if (P.ln) {
@@ -411,20 +379,12 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
             store_block32(P, pad, v, lane, row0, c0, nullptr, P.res_post);
         }
     } else {
-        // whole 32-column blocks of 16-byte aligned rows go through the bulk-copy engine (two pads per warp, alternating)
-        const bool bulk_ok = BULK && (P.ldc % 4 == 0) && ((uintptr_t)P.C % 16 == 0) && (!P.bias || (uintptr_t)P.bias % 16 == 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             if (n0 + c0 >= P.N) break;
             float v[32];
             tmem_ld32(tbase + c0, v);
-            if (bulk_ok && n0 + c0 + 32 <= P.N) {
-                store_block32_bulk(P, pad + (bulk_count & 1) * (32 * PAD_STRIDE), v, lane, row0, n0 + c0);
-                ++bulk_count;
-            } else {
-                if (BULK) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the direct path reuses the first pad
-                store_block32(P, pad, v, lane, row0, n0 + c0);
-            }
+            store_block32(P, pad, v, lane, row0, n0 + c0);
         }
     }
 }
@@ -438,8 +398,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
     constexpr int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
     __shared__ __align__(8) uint64_t full_bar[OPS], empty_bar[OPS], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem;
-    constexpr bool BULK = (MINB == 1);                 // the light configurations keep one pad per warp and the direct stores
-    __shared__ __align__(16) float s_pad[4][(BULK ? 2 : 1) * 32 * PAD_STRIDE];
+    __shared__ __align__(16) float s_pad[4][32 * PAD_STRIDE];
     __shared__ __align__(16) float s_ln[3][BN];        // bias, gamma, beta of the fused LayerNorm epilogue
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -557,18 +516,17 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
     } else if (warp < 4) {
         // ================================================= epilogue (warps 0-3) ======================================
         float* pad = s_pad[warp];
-        uint32_t tcount = 0, bulk_count = 0;
+        uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const int tm = tile / P.tiles_n, tn = tile % P.tiles_n;
             const int acc = tcount & 1;
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             tc_fence_after();
-            tile_epilogue<BN, BULK>(P, pad, s_ln, warp, lane, tm, tn, (tile + (int)gridDim.x < total_tiles) ? (tile + (int)gridDim.x) / P.tiles_n : -1,
-                                    tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN), bulk_count);
+            tile_epilogue<BN>(P, pad, s_ln, warp, lane, tm, tn, (tile + (int)gridDim.x < total_tiles) ? (tile + (int)gridDim.x) / P.tiles_n : -1,
+                              tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN));
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }
-        if (BULK) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // every bulk store of this thread has completed
     }
     tc_fence_before();
     __syncthreads();
@@ -654,11 +612,11 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
                         "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile (N=%d, tile %d)", N, bn);
     if (P.ln) {
         if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
-        return bn == 64 ? launch_tc3<64, 2, 4, 8, 1>(P, st) : launch_tc3<128, 2, 3, 8, 1>(P, st);
+        return bn == 64 ? launch_tc3<64, 3, 3, 8, 1>(P, st) : launch_tc3<128, 2, 4, 8, 1>(P, st);
     }
     if (stream_ok) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
-        return bn == 128 ? launch_tc3<128, 2, 3, 8, 1>(P, st) : launch_tc3<64, 2, 4, 8, 1>(P, st);
+        return bn == 128 ? launch_tc3<128, 2, 4, 8, 1>(P, st) : launch_tc3<64, 3, 3, 8, 1>(P, st);
     }
     if (bn == 64) return launch_tc2<64, 4>(P, st);
     return launch_tc2<128, 3>(P, st);
