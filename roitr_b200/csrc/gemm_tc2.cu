@@ -302,7 +302,9 @@ constexpr int RAW_BYTES = T2_BM * 128;
 // whose residual rows are prefetched into L2. Shared by the streaming (linear_tc3) and weight-stationary (linear_ws) kernels.
 template <int BN>
 __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, const float (*s_ln)[BN], int warp, int lane, int tm,
-                                              int tn, int next_tm, uint32_t tbase) {
+                                              int tn, int next_tm, uint32_t tbase, int cb0 = 0, int cbstep = 1) {
+    // `warp` = the TMEM lane quadrant (rows 32 warp .. +31 of the tile); in the plain epilogue this warp stores the 32-column
+    // blocks cb0, cb0 + cbstep, ... (two warps per quadrant split the blocks even / odd)
     const int row0 = tm * T2_BM + warp * 32;
     const int n0 = tn * BN;
     if (P.ln) {
@@ -380,7 +382,7 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
         }
     } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 32 * cb0; c0 < BN; c0 += 32 * cbstep) {
             if (n0 + c0 >= P.N) break;
             float v[32];
             tmem_ld32(tbase + c0, v);
@@ -390,7 +392,13 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
 }
 
 template <int BN, int OPS, int RAW, int LW, int MINB>
-__global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(const Tc2Params P) {
+__global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MINB) linear_tc3_kernel(const Tc2Params P) {
+    // EW epilogue warps: the deep configuration (one CTA per SM) runs EIGHT - the round-1 ablation (profiles/r01g_ablate_gemm.txt)
+    // shows the C stores and the main loop adding up instead of overlapping (0.247 ms = 0.117 + 0.130 at (640000, 192, 64)):
+    // four warps walking 32x32 blocks one after the other (tcgen05.ld -> wait -> transpose -> stores) are the longest chain of
+    // the tile. Warps w and w + 4 (counted among the epilogue warps) share TMEM lane quadrant w % 4 and take the even / odd
+    // 32-column blocks. The fused LayerNorm epilogue needs a whole row per thread and stays on the first four.
+    constexpr int EW = (MINB == 1) ? 8 : 4;
     constexpr int T3_LOADERS = LW * 32;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -398,13 +406,13 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
     constexpr int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
     __shared__ __align__(8) uint64_t full_bar[OPS], empty_bar[OPS], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(16) float s_pad[4][32 * PAD_STRIDE];
+    __shared__ __align__(16) float s_pad[EW][32 * PAD_STRIDE];
     __shared__ __align__(16) float s_ln[3][BN];        // bias, gamma, beta of the fused LayerNorm epilogue
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < OPS; ++i) { mbar_init(&full_bar[i], T3_LOADERS + 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW * 32); }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&s_tmem, 2 * BN);
@@ -513,17 +521,21 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
                 umma_commit(&tmem_full[acc]);
             }
         }
-    } else if (warp < 4) {
-        // ================================================= epilogue (warps 0-3) ======================================
-        float* pad = s_pad[warp];
+    } else if (warp < 4 || warp > W_MMA) {
+        // ================================================= epilogue (warps 0-3 and, with EW = 8, the last four) ========
+        const int ew = warp < 4 ? warp : 4 + (warp - W_MMA - 1);     // index among the epilogue warps
+        const int quad = warp & 3;                                   // TMEM lanes 32 quad .. +31 are the ones this warp may read
+        const bool second = ew >= 4;
+        float* pad = s_pad[ew];
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const int tm = tile / P.tiles_n, tn = tile % P.tiles_n;
             const int acc = tcount & 1;
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             tc_fence_after();
-            tile_epilogue<BN>(P, pad, s_ln, warp, lane, tm, tn, (tile + (int)gridDim.x < total_tiles) ? (tile + (int)gridDim.x) / P.tiles_n : -1,
-                              tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN));
+            if (!(P.ln && second))
+                tile_epilogue<BN>(P, pad, s_ln, quad, lane, tm, tn, (tile + (int)gridDim.x < total_tiles) ? (tile + (int)gridDim.x) / P.tiles_n : -1,
+                                  tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN), (EW == 8 && second) ? 1 : 0, EW == 8 ? 2 : 1);
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }
@@ -535,7 +547,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64, MINB) linear_tc3_kernel(co
 
 template <int BN, int OPS, int RAW, int LW, int MINB>
 int launch_tc3(const Tc2Params& P, cudaStream_t st) {
-    constexpr int T3_THREADS = 128 + LW * 32 + 64;
+    constexpr int T3_THREADS = 128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0);
     constexpr int smem = OPS * (2 * A_HALF + 2 * BN * 128) + RAW * RAW_BYTES + 1024;
     static bool attr_dev[ROITR_MAX_DEVICES] = {};
     static int num_sms_dev[ROITR_MAX_DEVICES] = {}, per_sm_dev[ROITR_MAX_DEVICES] = {};
@@ -612,11 +624,11 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
                         "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile (N=%d, tile %d)", N, bn);
     if (P.ln) {
         if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
-        return bn == 64 ? launch_tc3<64, 3, 3, 8, 1>(P, st) : launch_tc3<128, 2, 4, 8, 1>(P, st);
+        return bn == 64 ? launch_tc3<64, 2, 4, 8, 1>(P, st) : launch_tc3<128, 2, 3, 8, 1>(P, st);
     }
     if (stream_ok) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
-        return bn == 128 ? launch_tc3<128, 2, 4, 8, 1>(P, st) : launch_tc3<64, 3, 3, 8, 1>(P, st);
+        return bn == 128 ? launch_tc3<128, 2, 3, 8, 1>(P, st) : launch_tc3<64, 2, 4, 8, 1>(P, st);
     }
     if (bn == 64) return launch_tc2<64, 4>(P, st);
     return launch_tc2<128, 3>(P, st);
