@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libroitr_b200.so")
+LIB_PATH = os.environ.get("ROITR_B200_LIB") or os.path.join(_HERE, "lib", "libroitr_b200.so")   # override: A/B runs of a variant build
 _lib = None
 
 c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p

@@ -24,6 +24,24 @@ def _newer(target, deps):
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
+def build_variant(name, defines):
+    """A second library with extra -D flags (scripts/gpu_ab.sh: A/B runs of compile-time choices via ROITR_B200_LIB)."""
+    vdir = os.path.join(LIBDIR, "variants")
+    odir = os.path.join(vdir, "obj_" + name)
+    os.makedirs(odir, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+    def one(s):
+        o = os.path.join(odir, os.path.basename(s)[:-3] + ".o")
+        subprocess.check_call([NVCC] + ARCH + FLAGS + ["-D" + d for d in defines] + ["-c", s, "-o", o])
+        return o
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, srcs))
+    so = os.path.join(vdir, "libroitr_b200_%s.so" % name)
+    subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", so] + objs + ["-lcudart"])
+    return so
+
+
 def build(force=False, verbose=False, ptxas_info=False):
     os.makedirs(OBJDIR, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))

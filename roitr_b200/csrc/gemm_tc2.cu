@@ -302,7 +302,8 @@ constexpr int RAW_BYTES = T2_BM * 128;
 // whose residual rows are prefetched into L2. Shared by the streaming (linear_tc3) and weight-stationary (linear_ws) kernels.
 template <int BN>
 __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, const float (*s_ln)[BN], int warp, int lane, int tm,
-                                              int tn, int next_tm, uint32_t tbase, int cb0 = 0, int cbstep = 1) {
+                                              int tn, int next_tm, uint32_t tbase, int cb0 = 0, int cbstep = 1,
+                                              float2* stat = nullptr) {
     // `warp` = the TMEM lane quadrant (rows 32 warp .. +31 of the tile); in the plain epilogue this warp stores the 32-column
     // blocks cb0, cb0 + cbstep, ... (two warps per quadrant split the blocks even / odd)
     const int row0 = tm * T2_BM + warp * 32;
@@ -333,9 +334,11 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
             pre = P.res_pre + (P.res_pre_index ? (long long)__ldg(P.res_pre_index + row) : (long long)row) * P.ldr;
         // one pass for both moments, shifted by the row's first value so that the subtraction sum2/N - (sum1/N)^2
         // never cancels (|mean - shift| is of the order of the standard deviation)
+        // With `stat` (two warps per quadrant, cbstep == 2) each warp owns every other 32-column block, takes the moments of
+        // ITS half of the row around its own shift, and the two halves are merged (equal counts) after a 64-thread barrier.
         float s1 = 0.f, s2 = 0.f, shift = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < P.N; c0 += 32) {
+        for (int c0 = 32 * cb0; c0 < P.N; c0 += 32 * cbstep) {
             float v[32];
             tmem_ld32(tbase + c0, v);
 #pragma unroll
@@ -350,7 +353,7 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
                     v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
                 }
             }
-            if (c0 == 0) shift = v[0];
+            if (c0 == 32 * cb0) shift = v[0];
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -362,13 +365,24 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
             s2 += (q0 + q1) + (q2 + q3);
             tmem_st32(tbase + c0, v);
         }
-        const float inv_n = 1.0f / (float)P.N;
-        const float dm = s1 * inv_n;
-        const float mean = shift + dm;
-        const float sq = fmaxf(s2 - s1 * dm, 0.f);               // sum (x - mean)^2 = sum d^2 - (sum d)^2 / N
+        float mean, sq;
+        if (stat) {
+            const float nw = 0.5f * (float)P.N;                  // columns per warp
+            const float dmw = s1 / nw;
+            stat[cb0 * 32 + lane] = make_float2(shift + dmw, fmaxf(s2 - s1 * dmw, 0.f));
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + warp) : "memory");       // the two warps of this quadrant
+            const float2 a = stat[lane], b = stat[32 + lane];    // same expression order in both warps: identical mean / rstd
+            const float d = a.x - b.x;
+            mean = 0.5f * (a.x + b.x);
+            sq = a.y + b.y + d * d * (0.5f * nw);
+        } else {
+            const float dm = s1 / (float)P.N;
+            mean = shift + dm;
+            sq = fmaxf(s2 - s1 * dm, 0.f);                       // sum (x - mean)^2 = sum d^2 - (sum d)^2 / N
+        }
         const float rstd = rsqrtf(sq / (float)P.N + 1e-5f);
 #pragma unroll 1
-        for (int c0 = 0; c0 < P.N; c0 += 32) {
+        for (int c0 = 32 * cb0; c0 < P.N; c0 += 32 * cbstep) {
             float v[32];
             tmem_ld32(tbase + c0, v);
 #pragma unroll
@@ -391,6 +405,9 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
     }
 }
 
+#ifndef LN_SPLIT
+#define LN_SPLIT 0
+#endif
 template <int BN, int OPS, int RAW, int LW, int MINB>
 __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MINB) linear_tc3_kernel(const Tc2Params P) {
     // EW epilogue warps: the deep configuration (one CTA per SM) runs EIGHT - the round-1 ablation (profiles/r01g_ablate_gemm.txt)
@@ -408,6 +425,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_pad[EW][32 * PAD_STRIDE];
     __shared__ __align__(16) float s_ln[3][BN];        // bias, gamma, beta of the fused LayerNorm epilogue
+    __shared__ float2 s_stat[EW == 8 ? 4 : 1][2][64];  // per quadrant, per tile parity: (mean, M2) of each warp's half row
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -533,9 +551,13 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
             const int acc = tcount & 1;
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             tc_fence_after();
-            if (!(P.ln && second))
+            // fused LayerNorm: split between the two warps of a quadrant when the row has an even number of 32-column blocks
+            const bool ln_split = LN_SPLIT && EW == 8 && P.ln && ((P.N >> 5) & 1) == 0;
+            const bool halves = EW == 8 && (!P.ln || ln_split);
+            if (!(P.ln && second && !ln_split))
                 tile_epilogue<BN>(P, pad, s_ln, quad, lane, tm, tn, (tile + (int)gridDim.x < total_tiles) ? (tile + (int)gridDim.x) / P.tiles_n : -1,
-                                  tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN), (EW == 8 && second) ? 1 : 0, EW == 8 ? 2 : 1);
+                                  tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN), (halves && second) ? 1 : 0, halves ? 2 : 1,
+                                  ln_split ? s_stat[EW == 8 ? quad : 0][tcount & 1] : nullptr);
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }

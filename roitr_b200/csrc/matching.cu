@@ -441,7 +441,10 @@ __device__ __forceinline__ float fast_ex2(float x) {
 
 constexpr int FT = 288, FW = FT / 32;      // 8 warps own rows/columns 0..63 (4 threads each), warp 8 owns the dustbin row/column
 
-__global__ void __launch_bounds__(FT, 3) fine_patch_kernel(FineParams P) {
+#ifndef FINE_MINB
+#define FINE_MINB 3
+#endif
+__global__ void __launch_bounds__(FT, FINE_MINB) fine_patch_kernel(FineParams P) {
     __shared__ float Z[FP1 * FP1];
     __shared__ __align__(16) float At[32][FP + 4];
     __shared__ __align__(16) float Bs[32][FP + 4];
