@@ -300,8 +300,8 @@ constexpr int RAW_BYTES = T2_BM * 128;
 // Epilogue of one finished accumulator tile (rows tm*128 .. +127, columns tn*BN .. ) held in TMEM at `tbase` (this warp's 32
 // lanes): plain bias / ReLU store, or the fused row epilogue. `next_tm` = the row tile this CTA processes next (-1: none),
 // whose residual rows are prefetched into L2. Shared by the streaming (linear_tc3) and weight-stationary (linear_ws) kernels.
-template <int BN>
-__device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, const float (*s_ln)[BN], int warp, int lane, int tm,
+template <int BN, int LNW>
+__device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, const float (*s_ln)[LNW], int warp, int lane, int tm,
                                               int tn, int next_tm, uint32_t tbase, int cb0 = 0, int cbstep = 1,
                                               float2* stat = nullptr) {
     // `warp` = the TMEM lane quadrant (rows 32 warp .. +31 of the tile); in the plain epilogue this warp stores the 32-column
@@ -309,7 +309,8 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
     const int row0 = tm * T2_BM + warp * 32;
     const int n0 = tn * BN;
     if (P.ln) {
-        // Fused row epilogue (host guarantees one n-tile, N % 32 == 0). After tcgen05.ld a thread holds 32 columns
+        // Fused row epilogue (host guarantees N % 32 == 0 and the whole row in TMEM at tbase: one n-tile, or two side by side
+        // in the 512-column layout of the deep configuration). After tcgen05.ld a thread holds 32 columns
         // of ITS row, so the LayerNorm statistics are thread-local: pass A adds bias and the (optionally gathered)
         // pre-norm residual and writes the row back to TMEM while summing it, pass B sums the squared deviations,
         // pass C normalises and hands 32x32 blocks to the transposed store (post-norm residual, ReLU, float4 rows).
@@ -406,7 +407,7 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
 }
 
 #ifndef LN_SPLIT
-#define LN_SPLIT 0
+#define LN_SPLIT 1
 #endif
 template <int BN, int OPS, int RAW, int LW, int MINB>
 __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MINB) linear_tc3_kernel(const Tc2Params P) {
@@ -424,7 +425,11 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
     __shared__ __align__(8) uint64_t full_bar[OPS], empty_bar[OPS], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_pad[EW][32 * PAD_STRIDE];
-    __shared__ __align__(16) float s_ln[3][BN];        // bias, gamma, beta of the fused LayerNorm epilogue
+    // Row groups: with the fused LayerNorm over TWO n-tiles (N <= 256 at BN = 128, deep configuration only) a CTA computes both
+    // n-tiles of a row tile back to back into the two halves of one 256-column accumulator slot (TMEM: 2 slots = 512 columns),
+    // and the epilogue sees the whole row. gshift = log2(tiles per row group); iteration i of this CTA is tile_of(i).
+    constexpr int LNW = (BN == 128 && MINB == 1) ? 256 : BN;
+    __shared__ __align__(16) float s_ln[3][LNW];       // bias, gamma, beta of the fused LayerNorm epilogue
     __shared__ float2 s_stat[EW == 8 ? 4 : 1][2][64];  // per quadrant, per tile parity: (mean, M2) of each warp's half row
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -433,9 +438,11 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW * 32); }
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&s_tmem, 2 * BN);
+    const int gshift = (LNW > BN && P.ln && P.tiles_n == 2) ? 1 : 0;
+    const uint32_t tmem_cols = (uint32_t)(2 * BN) << gshift;
+    if (warp == 0) tmem_alloc(&s_tmem, tmem_cols);
     if (P.ln && tid < 128) {
-        for (int i = tid; i < BN; i += 128) {
+        for (int i = tid; i < LNW; i += 128) {
             const bool in = i < P.N;
             s_ln[0][i] = (in && P.bias) ? __ldg(P.bias + i) : 0.f;
             s_ln[1][i] = in ? __ldg(P.ln_gamma + i) : 0.f;
@@ -449,6 +456,10 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
     const int total_tiles = P.tiles_m * P.tiles_n;
     const int nkc = P.nkc;
     constexpr int W_LOADER0 = 4, W_PRODUCER = 4 + T3_LOADERS / 32, W_MMA = W_PRODUCER + 1;
+    const int gmask = (1 << gshift) - 1;
+    auto tile_of = [&](uint32_t i) -> int {            // >= total_tiles: this CTA is done
+        return (int)(((blockIdx.x + (i >> gshift) * gridDim.x) << gshift) + (i & gmask));
+    };
 
     if (warp >= W_LOADER0 && warp < W_PRODUCER) {
         // ================================================= A loaders =================================================
@@ -457,7 +468,8 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
         const int c = t & 7, r0 = t >> 3;
         unsigned char* raw = smem + OPS * STAGE_BYTES;
         const uint32_t raw_u32 = smem_u32(raw);
-        int i_tile = blockIdx.x, i_kc = 0;
+        uint32_t i_i = 0;
+        int i_tile = tile_of(0), i_kc = 0;
         uint32_t i_it = 0;
         auto issue_one = [&]() {
             if (i_tile < total_tiles) {
@@ -471,14 +483,14 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
                     cp_async16(dst + j * RSTEP * 128, P.A + (ok ? (long long)am * P.lda + k : 0ll), ok ? 16u : 0u);
                 }
                 ++i_it;
-                if (++i_kc == nkc) { i_kc = 0; i_tile += gridDim.x; }
+                if (++i_kc == nkc) { i_kc = 0; i_tile = tile_of(++i_i); }
             }
             cp_async_commit();                                          // always commit: keeps the group count uniform
         };
 #pragma unroll
         for (int j = 0; j < RAW - 1; ++j) issue_one();
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (uint32_t i = 0; tile_of(i) < total_tiles; ++i) {
             for (int kc = 0; kc < nkc; ++kc, ++it) {
                 issue_one();                                            // refills the slot this thread drained last iteration
                 cp_async_wait<RAW - 1>();                               // this thread's pieces of chunk `it` have landed
@@ -500,8 +512,8 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
         // ================================================= W producer ================================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int tn = tile % P.tiles_n;
+            for (uint32_t i = 0; tile_of(i) < total_tiles; ++i) {
+                const int tn = tile_of(i) % P.tiles_n;
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const int st = it % OPS;
                     mbar_wait(&empty_bar[st], ((it / OPS) & 1) ^ 1);
@@ -515,12 +527,15 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
         // ================================================= MMA issuer ================================================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32(T2_BM, BN);
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                const int acc = tcount & 1;
-                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem + (uint32_t)(acc * BN);
+            uint32_t it = 0;
+            for (uint32_t i = 0; tile_of(i) < total_tiles; ++i) {
+                const uint32_t r = i >> gshift, sub = i & gmask;               // row group of this CTA, n-tile within it
+                const int acc = r & 1;
+                if (sub == 0) {
+                    mbar_wait(&tmem_empty[acc], ((r >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                }
+                const uint32_t d = tmem + (uint32_t)((acc * BN) << gshift) + sub * BN;
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const int st = it % OPS;
                     mbar_wait(&full_bar[st], (it / OPS) & 1);
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
                     }
                     umma_commit(&empty_bar[st]);
                 }
-                umma_commit(&tmem_full[acc]);
+                if (sub == (uint32_t)gmask) umma_commit(&tmem_full[acc]);
             }
         }
     } else if (warp < 4 || warp > W_MMA) {
@@ -545,8 +560,8 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
         const int quad = warp & 3;                                   // TMEM lanes 32 quad .. +31 are the ones this warp may read
         const bool second = ew >= 4;
         float* pad = s_pad[ew];
-        uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        for (uint32_t tcount = 0; tile_of(tcount << gshift) < total_tiles; ++tcount) {     // one row group per iteration
+            const int tile = tile_of(tcount << gshift), next_tile = tile_of((tcount + 1) << gshift);
             const int tm = tile / P.tiles_n, tn = tile % P.tiles_n;
             const int acc = tcount & 1;
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
@@ -555,8 +570,8 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
             const bool ln_split = LN_SPLIT && EW == 8 && P.ln && ((P.N >> 5) & 1) == 0;
             const bool halves = EW == 8 && (!P.ln || ln_split);
             if (!(P.ln && second && !ln_split))
-                tile_epilogue<BN>(P, pad, s_ln, quad, lane, tm, tn, (tile + (int)gridDim.x < total_tiles) ? (tile + (int)gridDim.x) / P.tiles_n : -1,
-                                  tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN), (halves && second) ? 1 : 0, halves ? 2 : 1,
+                tile_epilogue<BN, LNW>(P, pad, s_ln, quad, lane, tm, tn, next_tile < total_tiles ? next_tile / P.tiles_n : -1,
+                                       tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * BN) << gshift), (halves && second) ? 1 : 0, halves ? 2 : 1,
                                   ln_split ? s_stat[EW == 8 ? quad : 0][tcount & 1] : nullptr);
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 2 * BN);
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
 template <int BN, int OPS, int RAW, int LW, int MINB>
@@ -585,7 +600,7 @@ int launch_tc3(const Tc2Params& P, cudaStream_t st) {
         if (per_sm < 1) per_sm = 1;
         attr = true;
     }
-    const int total = P.tiles_m * P.tiles_n;
+    const int total = (P.ln && P.tiles_n == 2) ? P.tiles_m : P.tiles_m * P.tiles_n;      // row groups (see the kernel)
     const int grid = total < num_sms * per_sm ? total : num_sms * per_sm;
     linear_tc3_kernel<BN, OPS, RAW, LW, MINB><<<grid, T3_THREADS, smem, st>>>(P);
     ROITR_CHECK_LAUNCH("linear_tc3_kernel");
@@ -641,10 +656,12 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const bool stream_ok = !a_add && !a_index && lda % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0;
     if (P.ln)
-        ROITR_CHECK_ARG(stream_ok && P.tiles_n == 1 && N % 32 == 0 && ln_beta && ldr >= N && ldr % 4 == 0 &&
+        ROITR_CHECK_ARG(stream_ok && (P.tiles_n == 1 || (P.tiles_n == 2 && bn == 128)) && N % 32 == 0 && ln_beta && ldr >= N && ldr % 4 == 0 &&
                             ((uintptr_t)res_pre | (uintptr_t)res_post) % 16 == 0,
-                        "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile (N=%d, tile %d)", N, bn);
+                        "linear_ln_tc_packed: needs a plain 16-byte aligned input, N a multiple of 32 within one weight tile, or two "
+                        "128-row tiles (N=%d, tile %d)", N, bn);
     if (P.ln) {
+        if (P.tiles_n == 2) return launch_tc3<128, 2, 3, 8, 1>(P, st);          // the 512-column layout exists in the deep configuration only
         if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
         return bn == 64 ? launch_tc3<64, 2, 4, 8, 1>(P, st) : launch_tc3<128, 2, 3, 8, 1>(P, st);
     }

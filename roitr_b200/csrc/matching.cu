@@ -424,15 +424,6 @@ struct FineParams {
 
 constexpr int FP = 64, FP1 = 65;
 
-__device__ __forceinline__ float warp_lse3(float x0, float x1, float x2) {
-    // logsumexp over the values spread across the warp (x* = -inf for absent slots), torch.logsumexp semantics
-    float mx = warp_max(fmaxf(fmaxf(x0, x1), x2));
-    const float m0 = (mx == CUDART_INF_F || mx == -CUDART_INF_F) ? 0.f : mx;
-    float s = expf(x0 - m0) + expf(x1 - m0) + expf(x2 - m0);
-    s = warp_sum(s);
-    return logf(s) + m0;
-}
-
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -442,7 +433,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 constexpr int FT = 288, FW = FT / 32;      // 8 warps own rows/columns 0..63 (4 threads each), warp 8 owns the dustbin row/column
 
 #ifndef FINE_MINB
-#define FINE_MINB 3
+#define FINE_MINB 4
 #endif
 __global__ void __launch_bounds__(FT, FINE_MINB) fine_patch_kernel(FineParams P) {
     __shared__ float Z[FP1 * FP1];

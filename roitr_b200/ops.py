@@ -43,10 +43,11 @@ def linear(a, w, bias=None, relu=False, a_index=None, a_add=None, out=None, M=No
 
 def linear_ln(a, w, bias, wpack, gamma, beta, res_pre=None, res_pre_index=None, res_post=None, relu=False):
     """act(LN(a @ w^T + bias + res_pre[res_pre_index]) * gamma + beta + res_post) in ONE kernel when the layer fits the fused
-    epilogue (N a multiple of 32 within one weight tile, plain aligned input); otherwise linear + row_epilogue."""
+    epilogue (N a multiple of 32 within one weight tile - or two 128-row tiles, N <= 256 -, plain aligned input); otherwise
+    linear + row_epilogue."""
     M, K = a.shape
     N = w.shape[0]
-    fused = (wpack is not None and N % 32 == 0 and N <= wpack[1] and a.stride(0) % 4 == 0 and K % 4 == 0 and
+    fused = (wpack is not None and N % 32 == 0 and (N <= wpack[1] or (wpack[1] == 128 and N <= 256)) and a.stride(0) % 4 == 0 and K % 4 == 0 and
              a.data_ptr() % 16 == 0 and a.stride(1) == 1 and
              (res_pre is None or res_post is None or res_pre.stride(0) == res_post.stride(0)))      # one residual pitch
     if not fused:

@@ -175,7 +175,12 @@ def test_attention_matches_fp64(N, M, C):
 
 @pytest.mark.parametrize("M,N,K,pre,gather,post,relu", [(20000, 64, 64, True, False, False, False), (5000, 128, 128, True, True, False, False),
                                                        (4100, 64, 64, False, False, True, True), (1250, 128, 256, False, False, False, True),
-                                                       (777, 64, 128, True, True, True, True), (130, 128, 64, False, False, True, False)])
+                                                       (777, 64, 128, True, True, True, True), (130, 128, 64, False, False, True, False),
+                                                       # two weight tiles per row (N > 128): both halves of the row in TMEM, one LayerNorm
+                                                       (9984, 256, 256, True, False, False, False), (40000, 256, 512, False, False, True, True),
+                                                       (4992, 256, 1024, True, True, False, False), (1000, 192, 64, True, False, True, False),
+                                                       (300, 160, 96, False, False, False, True), (60000, 32, 64, True, False, False, False),
+                                                       (333, 96, 64, False, False, True, False)])
 def test_linear_ln_fused_matches_fp64(M, N, K, pre, gather, post, relu):
     """roitr_linear_ln_tc_packed (LayerNorm / residuals / ReLU in the dense layer's epilogue) against fp64."""
     from roitr_b200 import engine
