@@ -226,10 +226,6 @@ def _lin(W, p, x, **kw):
     return ops.linear(x, W[p + ".weight"], W[p + ".bias"], **_pk(W, p + ".weight"), **kw)
 
 
-def _ln(W, p, x, **kw):
-    return ops.row_epilogue(x, gamma=W[p + ".weight"], beta=W[p + ".bias"], **kw)
-
-
 def _lin_ln(W, p, n, x, **kw):
     """Linear p followed by LayerNorm n (+ residuals / ReLU), fused into the dense layer's epilogue where it fits."""
     return ops.linear_ln(x, W[p + ".weight"], W[p + ".bias"], W.get(p + ".weight#tc"),
@@ -471,8 +467,7 @@ def decode(W, L):
     l4 = L[3]
     p = "backbone.dec4.0"
     g = _lin(W, p + ".linear2.0", ops.segment_mean(l4["x"], l4["o"]), relu=True)
-    y = _ln(W, p + ".linear1.1", _lin(W, p + ".linear1.0", ops.concat_segment(l4["x"], g, l4["o"])),
-            mode=ops.MODE_LN | ops.MODE_RELU)
+    y = _lin_ln(W, p + ".linear1.0", p + ".linear1.1", ops.concat_segment(l4["x"], g, l4["o"]), relu=True)
     xs = [None, None, None, block(W, "backbone.dec4.1", y, l4["idx"], l4["ppf"], l4["order"])]
     for li in (2, 1, 0):
         p = "backbone.dec%d.0" % (li + 1)
@@ -488,7 +483,7 @@ def decode(W, L):
 # ------------------------------------------------------------------------------------------------ global transformer
 def _ffn(W, p, x):
     h = _lin(W, p + ".expand", x, relu=True)
-    return _ln(W, p + ".norm", _lin(W, p + ".squeeze", h), res_pre=x, mode=ops.MODE_LN)
+    return _lin_ln(W, p + ".squeeze", p + ".norm", h, res_pre=x)
 
 
 def _self_layer_batch(W, lp, x, E, nb, N):
@@ -500,9 +495,10 @@ def _self_layer_batch(W, lp, x, E, nb, N):
     qkvg = ops.linear(x, W[a + "#Wqkvg"], W[a + "#bqkvg"], **_pk(W, a + "#Wqkvg"))     # (R, 3C + H*C)
     qkv, gq = qkvg[:, :3 * C], qkvg[:, 3 * C:]
     hidden, G = ops.attention_tc(nb, N, N, C, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], E=E, gq=gq, bp=W[a + ".proj_p.bias"])
-    pos = ops.linear(G.view(R, HEADS * C), W[a + "#Wposf"], W[a + "#bposf"], **_pk(W, a + "#Wposf"))   # pos_linear already applied
-    y = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
-    pos = _ln(W, lp + ".attention.pos_norm", pos, mode=ops.MODE_LN)
+    n = lp + ".attention.pos_norm"
+    pos = ops.linear_ln(G.view(R, HEADS * C), W[a + "#Wposf"], W[a + "#bposf"], W.get(a + "#Wposf#tc"),    # pos_linear already applied
+                        W[n + ".weight"], W[n + ".bias"])
+    y = _lin_ln(W, lp + ".attention.linear", lp + ".attention.norm", hidden, res_pre=x)
     return _ffn(W, lp + ".output", y), _ffn(W, lp + ".pos_proj", pos)
 
 
@@ -513,7 +509,7 @@ def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, **_pk(W, a + ".proj_k.weight"))
     v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], **_pk(W, a + ".proj_v.weight"))
     hidden = ops.attention_tc(nb, N, M, C, q, k, v)
-    z = _ln(W, lp + ".attention.norm", _lin(W, lp + ".attention.linear", hidden), res_pre=x, mode=ops.MODE_LN)
+    z = _lin_ln(W, lp + ".attention.linear", lp + ".attention.norm", hidden, res_pre=x)
     return _ffn(W, lp + ".output", z)
 
 
