@@ -8,7 +8,7 @@
 // lo*lo term is dropped): relative error ~2^-21, i.e. fp32-grade, at 3 MMAs per K-step (measured against an fp64
 // reference in tests/test_gemm_gpu.py).
 //
-// Structure (one CTA = 128 threads = one 128 x BN output tile, BN in {64,128,256}):
+// Structure (one CTA = 128 threads = one 128 x BN output tile, BN in {64,128}):
 //   loader (all threads)   global fp32 -> registers -> split -> 128B-swizzled K-major smem tiles A_hi/A_lo/B_hi/B_lo
 //                          (K chunks of 32 floats = one 128-byte swizzle row), 2 stages
 //   MMA (thread 0)         per chunk: 4 K-steps x 3 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8), then
@@ -25,7 +25,6 @@ namespace {
 constexpr int TC_THREADS = 128;
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;            // floats per chunk = 128 bytes = one swizzle row
-constexpr int TC_STAGES = 2;
 
 struct TcParams {
     int M, N, K;
@@ -38,7 +37,7 @@ struct TcParams {
     int w_transposed;       // W is given as Wt (K, >=N) row-major with leading dimension ldw: W[n][k] = Wt[k * ldw + n]
 };
 
-template <int BN>
+template <int BN, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_) {
     TcParams P = P_;
     {
@@ -58,8 +57,7 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
 
     if (tid == 0) {
-        mbar_init(&mma_bar[0], 1);
-        mbar_init(&mma_bar[1], 1);
+        for (int i = 0; i < TC_STAGES; ++i) mbar_init(&mma_bar[i], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&s_tmem, BN);
@@ -116,7 +114,7 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_
     constexpr int BROWS = (BN + TC_THREADS - 1) / TC_THREADS;  // B rows per thread
 
     for (int kc = 0; kc < nk; ++kc) {
-        const int buf = kc & 1;
+        const int buf = kc % TC_STAGES;
         unsigned char* st = smem + buf * STAGE_BYTES;
         // global loads of this chunk are issued before waiting for the stage to drain
         float4 va[8], vb[BROWS][8];
@@ -128,8 +126,8 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_
             if (P.w_transposed) load_row_t(wrow, kc * TC_BK, vb[j]);
             else load_row(P.W, nullptr, wrow, P.ldw, kc * TC_BK, vecW, vb[j]);
         }
-        if (kc >= TC_STAGES) {  // the MMAs that read this stage (chunk kc-2) must have completed
-            mbar_wait(&mma_bar[buf], ((kc >> 1) - 1) & 1);
+        if (kc >= TC_STAGES) {  // the MMAs that read this stage (chunk kc - TC_STAGES) must have completed
+            mbar_wait(&mma_bar[buf], ((kc / TC_STAGES) - 1) & 1);
             tc_fence_after();
         }
 #pragma unroll
@@ -161,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_
     // drain: the last commit covers every earlier MMA (commits complete in order)
     {
         const int last = nk - 1;
-        mbar_wait(&mma_bar[last & 1], (last >> 1) & 1);
+        mbar_wait(&mma_bar[last % TC_STAGES], (last / TC_STAGES) & 1);
         tc_fence_after();
     }
     // ---- epilogue: warp w reads TMEM lanes 32w..32w+31 (= output rows), 32 columns at a time ----
@@ -198,17 +196,17 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_
     if (warp == 0) tmem_dealloc(tmem_d, BN);
 }
 
-template <int BN>
+template <int BN, int TC_STAGES>
 int launch_tc(const TcParams& P, cudaStream_t st, int batch = 1) {
     constexpr int smem = TC_STAGES * (2 * TC_BM * 128 + 2 * BN * 128) + 1024;
     static bool attr_dev[ROITR_MAX_DEVICES] = {};
     bool& attr = attr_dev[roitr_cur_device()];
     if (!attr) {
-        ROITR_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ROITR_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, TC_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     dim3 grid(ceil_div(P.M, TC_BM), ceil_div(P.N, BN), batch);
-    linear_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(P);
+    linear_tc_kernel<BN, TC_STAGES><<<grid, TC_THREADS, smem, st>>>(P);
     ROITR_CHECK_LAUNCH("linear_tc_kernel");
     return ROITR_OK;
 }
@@ -230,7 +228,9 @@ extern "C" int roitr_gemm_tc_batched(int batch_outer, int batch_inner, int M, in
     P.w_transposed = w_transposed;
     cudaStream_t st = (cudaStream_t)stream;
     const int batch = batch_outer * batch_inner;
-    if (N <= 64) return launch_tc<64>(P, st, batch);
-    if (N <= 128) return launch_tc<128>(P, st, batch);
-    return launch_tc<256>(P, st, batch);
+    // One operand stage and tiles of at most 128 columns: 49 / 65 KB of shared memory per CTA, so 4 / 3 CTAs share an SM and hide
+    // each other's load -> split -> MMA -> epilogue chain (the products here are short: K = 64 or 312). Two stages and
+    // 256-column tiles (one CTA per SM) measured 1.42 ms per step against 1.10 ms (profiles/r02f_gemm_batched_ab.txt).
+    if (N <= 64) return launch_tc<64, 1>(P, st, batch);
+    return launch_tc<128, 1>(P, st, batch);
 }
