@@ -101,6 +101,46 @@ __device__ __forceinline__ void store_block32(const Tc2Params& P, float* pad, co
     store_block32(P, pad, v, lane, row0, ncol0, P.bias, nullptr);
 }
 
+#ifndef EPI_FRAG
+#define EPI_FRAG 1
+#endif
+// The same 32x32 block straight from TMEM in the fragment layout (tc_common.cuh: tmem_ld_16x256b_x4): bias / ReLU and float2
+// stores, 8 rows x 32 bytes per instruction, no shared-memory transposition. `tq` = TMEM address of the quadrant's first lane
+// at the block's first column. Needs even N / ldc and 8-byte aligned C / bias (checked per launch by the caller).
+__device__ __forceinline__ bool frag_store_ok(const Tc2Params& P) {
+    return EPI_FRAG && (P.ldc % 2 == 0) && (P.N % 2 == 0) && ((uintptr_t)P.C % 8 == 0) && ((uintptr_t)P.bias % 8 == 0);
+}
+__device__ __forceinline__ void store_block32_frag(const Tc2Params& P, uint32_t tq, int lane, int row0, int ncol0) {
+    float v[2][16];
+    tmem_ld_16x256b_x4(tq, v[0]);
+    tmem_ld_16x256b_x4(tq + (16u << 16), v[1]);
+    const int cq = 2 * (lane & 3), rq = lane >> 2;
+    float2 b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = ncol0 + 8 * j + cq;
+        b[j] = (P.bias && n < P.N) ? __ldg(reinterpret_cast<const float2*>(P.bias + n)) : make_float2(0.f, 0.f);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = row0 + 16 * hl + 8 * h + rq;
+            if (row < P.M) {
+                float* dst = P.C + (long long)row * P.ldc + ncol0 + cq;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (ncol0 + 8 * j + cq < P.N) {
+                        float2 x = make_float2(v[hl][4 * j + 2 * h] + b[j].x, v[hl][4 * j + 2 * h + 1] + b[j].y);
+                        if (P.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
+                        *reinterpret_cast<float2*>(dst + 8 * j) = x;
+                    }
+                }
+            }
+        }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(T2_THREADS, 1) linear_tc2_kernel(const Tc2Params P) {
     extern __shared__ unsigned char smem_raw[];
@@ -300,7 +340,7 @@ constexpr int RAW_BYTES = T2_BM * 128;
 // Epilogue of one finished accumulator tile (rows tm*128 .. +127, columns tn*BN .. ) held in TMEM at `tbase` (this warp's 32
 // lanes): plain bias / ReLU store, or the fused row epilogue. `next_tm` = the row tile this CTA processes next (-1: none),
 // whose residual rows are prefetched into L2. Shared by the streaming (linear_tc3) and weight-stationary (linear_ws) kernels.
-template <int BN, int LNW>
+template <int BN, int LNW, bool FRAG>
 __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, const float (*s_ln)[LNW], int warp, int lane, int tm,
                                               int tn, int next_tm, uint32_t tbase, int cb0 = 0, int cbstep = 1,
                                               float2* stat = nullptr) {
@@ -394,6 +434,12 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
                 v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z; v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
             }
             store_block32(P, pad, v, lane, row0, c0, nullptr, P.res_post);
+        }
+    } else if (FRAG && frag_store_ok(P)) {
+#pragma unroll 1
+        for (int c0 = 32 * cb0; c0 < BN; c0 += 32 * cbstep) {
+            if (n0 + c0 >= P.N) break;
+            store_block32_frag(P, tbase + c0, lane, row0, n0 + c0);
         }
     } else {
 #pragma unroll 1
@@ -570,7 +616,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
             const bool ln_split = LN_SPLIT && EW == 8 && P.ln && ((P.N >> 5) & 1) == 0;
             const bool halves = EW == 8 && (!P.ln || ln_split);
             if (!(P.ln && second && !ln_split))
-                tile_epilogue<BN, LNW>(P, pad, s_ln, quad, lane, tm, tn, next_tile < total_tiles ? next_tile / P.tiles_n : -1,
+                tile_epilogue<BN, LNW, MINB == 1>(P, pad, s_ln, quad, lane, tm, tn, next_tile < total_tiles ? next_tile / P.tiles_n : -1,
                                        tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * BN) << gshift), (halves && second) ? 1 : 0, halves ? 2 : 1,
                                   ln_split ? s_stat[EW == 8 ? quad : 0][tcount & 1] : nullptr);
             tc_fence_before();
