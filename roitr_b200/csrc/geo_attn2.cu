@@ -258,13 +258,15 @@ __global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_v3_kernel(const
     const float* qk_row = P.qk + (((size_t)b * H) * N + n) * M;
     for (int i = tid; i < H * M; i += GA_THREADS) S[i] = __ldg(qk_row + (size_t)(i / M) * N * M + (i % M));
 
+    // Packed fp32 arithmetic (fma.rn.f32x2: two IEEE FMAs per instruction): channel pairs (2 j, 2 j + 1) of the lane's eight
+    // channels share a register pair, which halves the instruction count of the two 32-FMA blocks of the key loop.
     const int c0 = lane * CPL;
-    float gq[H][CPL];
+    float2 gq[H][CPL / 2];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(P.gq + rowid * (size_t)P.ldgq + h * C + c0));
         const float4 d = __ldg(reinterpret_cast<const float4*>(P.gq + rowid * (size_t)P.ldgq + h * C + c0) + 1);
-        gq[h][0] = a.x; gq[h][1] = a.y; gq[h][2] = a.z; gq[h][3] = a.w; gq[h][4] = d.x; gq[h][5] = d.y; gq[h][6] = d.z; gq[h][7] = d.w;
+        gq[h][0] = make_float2(a.x, a.y); gq[h][1] = make_float2(a.z, a.w); gq[h][2] = make_float2(d.x, d.y); gq[h][3] = make_float2(d.z, d.w);
     }
     float qb = 0.f;
     {
@@ -275,11 +277,12 @@ __global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_v3_kernel(const
     }
     const int myh = lane >> 3;                                      // the head whose total reduce4_to_head leaves in this lane
     const float qb_h = qb;                                          // lanes 8h .. 8h+7 hold channels of head h: qb IS q_h . b_p,h
-    float G[H][CPL];
+    float2 G[H][CPL / 2];
 #pragma unroll
     for (int h = 0; h < H; ++h)
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) G[h][i] = 0.f;
+        for (int i = 0; i < CPL / 2; ++i) G[h][i] = make_float2(0.f, 0.f);
+    const float inv_sqrt_c = 1.0f / P.sqrt_c;                       // sqrt(256 / 4) = 8: the product equals the reference's division bit for bit
     float mx = -CUDART_INF_F, den = 0.f;                            // running state of head myh (diagonal-free softmax)
     __syncthreads();                                                // S is in place
 
@@ -294,16 +297,17 @@ __global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_v3_kernel(const
             const int m = m0 + r;
             const float4 ea = *reinterpret_cast<const float4*>(Ec + (size_t)r * C + c0);
             const float4 eb = *reinterpret_cast<const float4*>(Ec + (size_t)r * C + c0 + 4);
-            const float e[CPL] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+            const float2 e[CPL / 2] = {make_float2(ea.x, ea.y), make_float2(ea.z, ea.w), make_float2(eb.x, eb.y), make_float2(eb.z, eb.w)};
             float a[H];
 #pragma unroll
             for (int h = 0; h < H; ++h) {
-                a[h] = gq[h][0] * e[0];
+                float2 t = __fmul2_rn(gq[h][0], e[0]);
 #pragma unroll
-                for (int i = 1; i < CPL; ++i) a[h] = fmaf(gq[h][i], e[i], a[h]);
+                for (int i = 1; i < CPL / 2; ++i) t = __ffma2_rn(gq[h][i], e[i], t);
+                a[h] = t.x + t.y;
             }
             const float sp = reduce4_to_head(a[0], a[1], a[2], a[3], lane);
-            const float sc = __fdiv_rn(S[myh * M + m] + (sp + qb_h), P.sqrt_c);
+            const float sc = (S[myh * M + m] + (sp + qb_h)) * inv_sqrt_c;
             if ((lane & 7) == 0) S[myh * M + m] = sc;
             if (m == n) continue;                                   // the position branch excludes the diagonal (warp-uniform)
             const float nm = fmaxf(mx, sc);
@@ -315,16 +319,20 @@ __global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_v3_kernel(const
                 const float f0 = __shfl_sync(FULL_MASK, f, 0), f1 = __shfl_sync(FULL_MASK, f, 8);
                 const float f2 = __shfl_sync(FULL_MASK, f, 16), f3 = __shfl_sync(FULL_MASK, f, 24);
 #pragma unroll
-                for (int i = 0; i < CPL; ++i) { G[0][i] *= f0; G[1][i] *= f1; G[2][i] *= f2; G[3][i] *= f3; }
+                for (int i = 0; i < CPL / 2; ++i) {
+                    G[0][i] = __fmul2_rn(G[0][i], make_float2(f0, f0)); G[1][i] = __fmul2_rn(G[1][i], make_float2(f1, f1));
+                    G[2][i] = __fmul2_rn(G[2][i], make_float2(f2, f2)); G[3][i] = __fmul2_rn(G[3][i], make_float2(f3, f3));
+                }
                 mx = nm;
             }
             den += w;
             const float w0 = __shfl_sync(FULL_MASK, w, 0), w1 = __shfl_sync(FULL_MASK, w, 8);
             const float w2 = __shfl_sync(FULL_MASK, w, 16), w3 = __shfl_sync(FULL_MASK, w, 24);
+            const float2 v0 = make_float2(w0, w0), v1 = make_float2(w1, w1), v2 = make_float2(w2, w2), v3 = make_float2(w3, w3);
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                G[0][i] = fmaf(w0, e[i], G[0][i]); G[1][i] = fmaf(w1, e[i], G[1][i]);
-                G[2][i] = fmaf(w2, e[i], G[2][i]); G[3][i] = fmaf(w3, e[i], G[3][i]);
+            for (int i = 0; i < CPL / 2; ++i) {
+                G[0][i] = __ffma2_rn(v0, e[i], G[0][i]); G[1][i] = __ffma2_rn(v1, e[i], G[1][i]);
+                G[2][i] = __ffma2_rn(v2, e[i], G[2][i]); G[3][i] = __ffma2_rn(v3, e[i], G[3][i]);
             }
         }
         __syncwarp();
@@ -348,11 +356,11 @@ __global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_v3_kernel(const
     const float f2 = __shfl_sync(FULL_MASK, fm, 16), f3 = __shfl_sync(FULL_MASK, fm, 24);
     float* mg = ring + (size_t)warp * H * C;                        // [warp][H][C]
 #pragma unroll
-    for (int i = 0; i < CPL; i += 4) {
-        *reinterpret_cast<float4*>(mg + 0 * C + c0 + i) = make_float4(G[0][i] * f0, G[0][i + 1] * f0, G[0][i + 2] * f0, G[0][i + 3] * f0);
-        *reinterpret_cast<float4*>(mg + 1 * C + c0 + i) = make_float4(G[1][i] * f1, G[1][i + 1] * f1, G[1][i + 2] * f1, G[1][i + 3] * f1);
-        *reinterpret_cast<float4*>(mg + 2 * C + c0 + i) = make_float4(G[2][i] * f2, G[2][i + 1] * f2, G[2][i + 2] * f2, G[2][i + 3] * f2);
-        *reinterpret_cast<float4*>(mg + 3 * C + c0 + i) = make_float4(G[3][i] * f3, G[3][i + 1] * f3, G[3][i + 2] * f3, G[3][i + 3] * f3);
+    for (int i = 0; i < CPL / 2; i += 2) {
+        *reinterpret_cast<float4*>(mg + 0 * C + c0 + 2 * i) = make_float4(G[0][i].x * f0, G[0][i].y * f0, G[0][i + 1].x * f0, G[0][i + 1].y * f0);
+        *reinterpret_cast<float4*>(mg + 1 * C + c0 + 2 * i) = make_float4(G[1][i].x * f1, G[1][i].y * f1, G[1][i + 1].x * f1, G[1][i + 1].y * f1);
+        *reinterpret_cast<float4*>(mg + 2 * C + c0 + 2 * i) = make_float4(G[2][i].x * f2, G[2][i].y * f2, G[2][i + 1].x * f2, G[2][i + 1].y * f2);
+        *reinterpret_cast<float4*>(mg + 3 * C + c0 + 2 * i) = make_float4(G[3][i].x * f3, G[3][i].y * f3, G[3][i + 1].x * f3, G[3][i + 1].y * f3);
     }
     if ((lane & 7) == 0 && warp == 0) s_den[0][myh] = gden;          // every warp computed the same gden; publish one copy
     __syncthreads();
