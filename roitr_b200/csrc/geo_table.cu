@@ -178,11 +178,14 @@ __global__ void __launch_bounds__(GTB_THREADS, 1) geo_embedding_table_kernel(con
                     const float4 v1 = *reinterpret_cast<const float4*>(tab + GTB_GROUP + 4 * l16);
                     const float4 v2 = *reinterpret_cast<const float4*>(tab + 2 * GTB_GROUP + 4 * l16);
                     const float4 v3 = *reinterpret_cast<const float4*>(tab + 3 * GTB_GROUP + 4 * l16);
-                    // inner nodes first (largest weights), outer corrections last
-                    acc[k].x = fmaf(w[3], v3.x, fmaf(w[0], v0.x, fmaf(w[2], v2.x, w[1] * v1.x)));
-                    acc[k].y = fmaf(w[3], v3.y, fmaf(w[0], v0.y, fmaf(w[2], v2.y, w[1] * v1.y)));
-                    acc[k].z = fmaf(w[3], v3.z, fmaf(w[0], v0.z, fmaf(w[2], v2.z, w[1] * v1.z)));
-                    acc[k].w = fmaf(w[3], v3.w, fmaf(w[0], v0.w, fmaf(w[2], v2.w, w[1] * v1.w)));
+                    // inner nodes first (largest weights), outer corrections last; packed fp32 (fma.rn.f32x2: the same IEEE
+                    // operations per component, half the instructions)
+                    const float2 w0 = make_float2(w[0], w[0]), w1 = make_float2(w[1], w[1]), w2 = make_float2(w[2], w[2]), w3 = make_float2(w[3], w[3]);
+                    const float2 lo = __ffma2_rn(w3, make_float2(v3.x, v3.y), __ffma2_rn(w0, make_float2(v0.x, v0.y),
+                                          __ffma2_rn(w2, make_float2(v2.x, v2.y), __fmul2_rn(w1, make_float2(v1.x, v1.y)))));
+                    const float2 hi = __ffma2_rn(w3, make_float2(v3.z, v3.w), __ffma2_rn(w0, make_float2(v0.z, v0.w),
+                                          __ffma2_rn(w2, make_float2(v2.z, v2.w), __fmul2_rn(w1, make_float2(v1.z, v1.w)))));
+                    acc[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
                 } else {   // beyond every table: evaluate from the weights
                     const float2 lo2 = (k == 0) ? direct_eval(P.Wd, P.bd, P.div_term, C, ch, tv) : direct_eval(P.Wa, P.ba, P.div_term, C, ch, tv);
                     const float2 hi2 = (k == 0) ? direct_eval(P.Wd, P.bd, P.div_term, C, ch + 2, tv)

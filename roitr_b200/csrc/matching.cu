@@ -572,36 +572,39 @@ __global__ void __launch_bounds__(FT, FINE_MINB) fine_patch_kernel(FineParams P)
     {
         constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
         const int ri = (tid >> 2) & 63, q = tid & 3;
-        float zr[17], zc[17];
+        // the 16 terms live in register PAIRS: the adds and FMAs of the sweep are packed (add / fma.rn.f32x2: the same IEEE
+        // operation per component, so the results are those of the scalar loop bit for bit, at half the instructions)
+        float2 zr[8], zc[8];
+        float zr16 = -CUDART_INF_F, zc16 = -CUDART_INF_F;      // the dustbin term (q = 3); warp 8: its third element
         if (warp < 8) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                zr[j] = Z[ri * FP1 + q * 16 + j];
-                zc[j] = Z[(q * 16 + j) * FP1 + ri];
+            for (int j = 0; j < 8; ++j) {
+                zr[j] = make_float2(Z[ri * FP1 + q * 16 + 2 * j], Z[ri * FP1 + q * 16 + 2 * j + 1]);
+                zc[j] = make_float2(Z[(q * 16 + 2 * j) * FP1 + ri], Z[(q * 16 + 2 * j + 1) * FP1 + ri]);
             }
-            zr[16] = q == 3 ? Z[ri * FP1 + 64] : -CUDART_INF_F;
-            zc[16] = q == 3 ? Z[64 * FP1 + ri] : -CUDART_INF_F;
+            if (q == 3) { zr16 = Z[ri * FP1 + 64]; zc16 = Z[64 * FP1 + ri]; }
         } else {
-            zr[0] = Z[64 * FP1 + lane]; zr[1] = Z[64 * FP1 + lane + 32]; zr[2] = lane == 0 ? Z[64 * FP1 + 64] : -CUDART_INF_F;
-            zc[0] = Z[lane * FP1 + 64]; zc[1] = Z[(lane + 32) * FP1 + 64]; zc[2] = lane == 0 ? Z[64 * FP1 + 64] : -CUDART_INF_F;
+            zr[0] = make_float2(Z[64 * FP1 + lane], Z[64 * FP1 + lane + 32]);
+            zc[0] = make_float2(Z[lane * FP1 + 64], Z[(lane + 32) * FP1 + 64]);
+            if (lane == 0) { zr16 = Z[64 * FP1 + 64]; zc16 = Z[64 * FP1 + 64]; }
         }
         // returns whether the value this thread wrote differs from the one it replaced (fixed-point detection below)
-        auto sweep = [&](const float (&z)[17], const float* __restrict__ add, const float* __restrict__ marg,
+        auto sweep = [&](const float2 (&z)[8], const float z16, const float* __restrict__ add, const float* __restrict__ marg,
                          float* __restrict__ dst) -> int {
             int changed = 0;
             if (warp < 8) {
-                float x[17];
+                float2 x[8];
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const float4 a = *reinterpret_cast<const float4*>(add + q * 16 + 4 * j4);
-                    x[4 * j4] = z[4 * j4] + a.x; x[4 * j4 + 1] = z[4 * j4 + 1] + a.y;
-                    x[4 * j4 + 2] = z[4 * j4 + 2] + a.z; x[4 * j4 + 3] = z[4 * j4 + 3] + a.w;
+                    x[2 * j4] = __fadd2_rn(z[2 * j4], make_float2(a.x, a.y));
+                    x[2 * j4 + 1] = __fadd2_rn(z[2 * j4 + 1], make_float2(a.z, a.w));
                 }
-                x[16] = z[16] + add[64];
-                float m0 = fmaxf(x[0], x[1]), m1 = fmaxf(x[2], x[3]), m2 = fmaxf(x[4], x[5]), m3 = fmaxf(x[6], x[7]);
-                m0 = fmaxf(m0, fmaxf(x[8], x[9])); m1 = fmaxf(m1, fmaxf(x[10], x[11]));
-                m2 = fmaxf(m2, fmaxf(x[12], x[13])); m3 = fmaxf(m3, fmaxf(x[14], x[15]));
-                float m = fmaxf(fmaxf(m0, m1), fmaxf(fmaxf(m2, m3), x[16]));
+                const float x16 = z16 + add[64];
+                float m0 = fmaxf(x[0].x, x[0].y), m1 = fmaxf(x[1].x, x[1].y), m2 = fmaxf(x[2].x, x[2].y), m3 = fmaxf(x[3].x, x[3].y);
+                m0 = fmaxf(m0, fmaxf(x[4].x, x[4].y)); m1 = fmaxf(m1, fmaxf(x[5].x, x[5].y));
+                m2 = fmaxf(m2, fmaxf(x[6].x, x[6].y)); m3 = fmaxf(m3, fmaxf(x[7].x, x[7].y));
+                float m = fmaxf(fmaxf(m0, m1), fmaxf(fmaxf(m2, m3), x16));
                 m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 1));
                 m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 2));
                 // nml = rn(-m log2 e) carries a rounding error eps = nml + m log2 e (up to 3e-5 for |m| ~ 500) that would scale
@@ -609,14 +612,16 @@ __global__ void __launch_bounds__(FT, FINE_MINB) fine_patch_kernel(FineParams P)
                 // after the log (one FMA per logsumexp instead of a subtraction per term)
                 const float nml = -m * L2E;
                 const float eps = fmaf(m, L2E, nml);
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                const float2 l2e2 = make_float2(L2E, L2E), nml2 = make_float2(nml, nml);
+                float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    s0 += fast_ex2(fmaf(x[j], L2E, nml)); s1 += fast_ex2(fmaf(x[j + 1], L2E, nml));
-                    s2 += fast_ex2(fmaf(x[j + 2], L2E, nml)); s3 += fast_ex2(fmaf(x[j + 3], L2E, nml));
+                for (int j = 0; j < 8; j += 2) {
+                    const float2 t01 = __ffma2_rn(x[j], l2e2, nml2), t23 = __ffma2_rn(x[j + 1], l2e2, nml2);
+                    s01 = __fadd2_rn(s01, make_float2(fast_ex2(t01.x), fast_ex2(t01.y)));
+                    s23 = __fadd2_rn(s23, make_float2(fast_ex2(t23.x), fast_ex2(t23.y)));
                 }
-                s0 += fast_ex2(fmaf(x[16], L2E, nml));
-                float sm = (s0 + s1) + (s2 + s3);
+                const float s0 = s01.x + fast_ex2(fmaf(x16, L2E, nml));
+                float sm = (s0 + s01.y) + (s23.x + s23.y);
                 sm += __shfl_xor_sync(FULL_MASK, sm, 1);
                 sm += __shfl_xor_sync(FULL_MASK, sm, 2);
                 if (q == 0) {
@@ -625,7 +630,7 @@ __global__ void __launch_bounds__(FT, FINE_MINB) fine_patch_kernel(FineParams P)
                     dst[ri] = nv;
                 }
             } else {
-                const float x0 = z[0] + add[lane], x1 = z[1] + add[lane + 32], x2 = z[2] + add[64];
+                const float x0 = z[0].x + add[lane], x1 = z[0].y + add[lane + 32], x2 = z16 + add[64];
                 const float m = warp_max(fmaxf(fmaxf(x0, x1), x2));
                 const float nml = -m * L2E;
                 const float eps = fmaf(m, L2E, nml);
@@ -643,9 +648,9 @@ __global__ void __launch_bounds__(FT, FINE_MINB) fine_patch_kernel(FineParams P)
         // num_iter iterations (the reference always runs 100, modules.py:21-26). The test is one compare per row folded into
         // the barrier the sweep needs anyway.
         for (int it = 0; it < P.num_iter; ++it) {
-            sweep(zr, v, log_mu, u);      // u = log_mu - LSE_j(Z + v)
+            sweep(zr, zr16, v, log_mu, u);      // u = log_mu - LSE_j(Z + v)
             __syncthreads();
-            const int changed = sweep(zc, u, log_nu, v);      // v = log_nu - LSE_i(Z + u)
+            const int changed = sweep(zc, zc16, u, log_nu, v);      // v = log_nu - LSE_i(Z + u)
             if (!__syncthreads_or(changed)) break;
         }
     }
