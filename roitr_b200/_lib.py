@@ -80,6 +80,7 @@ STATS = {"launches": 0, "calls": {}}
 TIMED = {}        # entry-point name -> list of (start_event, end_event); filled only for names present as keys
 RECORD_ARGS = False
 ARGS = {}         # entry-point name -> list of leading integer arguments per call (bench.py's work model)
+PTRS = {}         # entry-point name -> per call, which pointer arguments were non-NULL (optional operands: residuals, ...)
 
 
 def reset_stats():
@@ -88,6 +89,7 @@ def reset_stats():
     for k in TIMED:
         TIMED[k] = []
     ARGS.clear()
+    PTRS.clear()
 
 
 def call(name, *args):
@@ -117,5 +119,6 @@ def call(name, *args):
             else:
                 break
         ARGS.setdefault(name, []).append(ints)
+        PTRS.setdefault(name, []).append([bool(a.value) for a in args if isinstance(a, c_void_p)])
     STATS["launches"] += KERNELS_PER_CALL.get(name, 1)
     STATS["calls"][name] = STATS["calls"].get(name, 0) + 1
