@@ -455,7 +455,7 @@ __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, co
 #ifndef LN_SPLIT
 #define LN_SPLIT 1
 #endif
-template <int BN, int OPS, int RAW, int LW, int MINB>
+template <int BN, int OPS, int RAW, int LW, int MINB, bool GATHER>
 __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MINB) linear_tc3_kernel(const Tc2Params P) {
     // EW epilogue warps: the deep configuration (one CTA per SM) runs EIGHT - the round-1 ablation (profiles/r01g_ablate_gemm.txt)
     // shows the C stores and the main loop adding up instead of overlapping (0.247 ms = 0.117 + 0.130 at (640000, 192, 64)):
@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
                 for (int j = 0; j < NPIECE; ++j) {
                     const int am = am0 + RSTEP * j;
                     const bool ok = am < P.M && k < P.K;
-                    cp_async16(dst + j * RSTEP * 128, P.A + (ok ? (long long)am * P.lda + k : 0ll), ok ? 16u : 0u);
+                    const long long arow = (GATHER && ok) ? (long long)__ldg(P.a_index + am) : (long long)am;   // GATHER: rows through a_index
+                    cp_async16(dst + j * RSTEP * 128, P.A + (ok ? arow * P.lda + k : 0ll), ok ? 16u : 0u);
                 }
                 ++i_it;
                 if (++i_kc == nkc) { i_kc = 0; i_tile = tile_of(++i_i); }
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0), MI
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
-template <int BN, int OPS, int RAW, int LW, int MINB>
+template <int BN, int OPS, int RAW, int LW, int MINB, bool GATHER = false>
 int launch_tc3(const Tc2Params& P, cudaStream_t st) {
     constexpr int T3_THREADS = 128 + LW * 32 + 64 + (MINB == 1 ? 128 : 0);
     constexpr int smem = OPS * (2 * A_HALF + 2 * BN * 128) + RAW * RAW_BYTES + 1024;
@@ -638,17 +639,17 @@ int launch_tc3(const Tc2Params& P, cudaStream_t st) {
     bool& attr = attr_dev[dv];
     int &num_sms = num_sms_dev[dv], &per_sm = per_sm_dev[dv];
     if (!attr) {
-        ROITR_CUDA(cudaFuncSetAttribute(linear_tc3_kernel<BN, OPS, RAW, LW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ROITR_CUDA(cudaFuncSetAttribute(linear_tc3_kernel<BN, OPS, RAW, LW, MINB, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0;
         ROITR_CUDA(cudaGetDevice(&dev));
         ROITR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        ROITR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linear_tc3_kernel<BN, OPS, RAW, LW, MINB>, T3_THREADS, smem));
+        ROITR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linear_tc3_kernel<BN, OPS, RAW, LW, MINB, GATHER>, T3_THREADS, smem));
         if (per_sm < 1) per_sm = 1;
         attr = true;
     }
     const int total = (P.ln && P.tiles_n == 2) ? P.tiles_m : P.tiles_m * P.tiles_n;      // row groups (see the kernel)
     const int grid = total < num_sms * per_sm ? total : num_sms * per_sm;
-    linear_tc3_kernel<BN, OPS, RAW, LW, MINB><<<grid, T3_THREADS, smem, st>>>(P);
+    linear_tc3_kernel<BN, OPS, RAW, LW, MINB, GATHER><<<grid, T3_THREADS, smem, st>>>(P);
     ROITR_CHECK_LAUNCH("linear_tc3_kernel");
     return ROITR_OK;
 }
@@ -700,7 +701,9 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
     P.res_post = res_post; P.ldr = ldr;
     P.tiles_m = ceil_div(M, T2_BM); P.tiles_n = ceil_div(N, bn); P.nkc = ceil_div(K, T2_BK);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool stream_ok = !a_add && !a_index && lda % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0;
+    // the streaming kernel takes plain or GATHERED rows (a_index: 16-byte cp.async pieces of the indexed row); the sum of two
+    // inputs (a_add) needs the register-staged loaders of the coupled-ring kernel
+    const bool stream_ok = !a_add && lda % 4 == 0 && K % 4 == 0 && (uintptr_t)A % 16 == 0;
     if (P.ln)
         ROITR_CHECK_ARG(stream_ok && (P.tiles_n == 1 || (P.tiles_n == 2 && bn == 128)) && N % 32 == 0 && ln_beta && ldr >= N && ldr % 4 == 0 &&
                             ((uintptr_t)res_pre | (uintptr_t)res_post) % 16 == 0,
@@ -711,6 +714,7 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
         if (g_tc3_variant == 3) return bn == 64 ? launch_tc3<64, 1, 2, 4, 3>(P, st) : launch_tc3<128, 1, 2, 4, 3>(P, st);
         return bn == 64 ? launch_tc3<64, 2, 4, 8, 1>(P, st) : launch_tc3<128, 2, 3, 8, 1>(P, st);
     }
+    if (stream_ok && a_index) return bn == 128 ? launch_tc3<128, 2, 3, 8, 1, true>(P, st) : launch_tc3<64, 2, 4, 8, 1, true>(P, st);
     if (stream_ok) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
         return bn == 128 ? launch_tc3<128, 2, 3, 8, 1>(P, st) : launch_tc3<64, 2, 4, 8, 1>(P, st);

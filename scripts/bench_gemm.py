@@ -1,5 +1,5 @@
 """Dense-layer micro-benchmark at the bench step's shapes (B = 16 pairs): the streaming kernel (linear_tc3) and, with a row
-gather, the coupled-ring kernel (linear_tc2), with a 256 MiB L2 flush before every timed launch.
+gather (the same kernel, GATHER instantiation: 16-byte cp.async pieces of the indexed rows), with a 256 MiB L2 flush before every timed launch.
 usage: bench_gemm.py   (run on a GPU box; writes gpurun_out/bench_gemm.txt)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,7 +18,7 @@ def timeit(fn, iters=7):
 out = open(os.path.join(ROOT, "gpurun_out", "bench_gemm.txt"), "w")
 def log(s):
     print(s); out.write(s + "\n"); out.flush()
-log("M,N,K, streaming_ms (linear_tc3), gathered_rows_ms (linear_tc2), streaming GB/s(A+C+W), frac of measured HBM 6532 GB/s")
+log("M,N,K, streaming_ms (linear_tc3), gathered_rows_ms (linear_tc3, a_index), streaming GB/s(A+C+W), frac of measured HBM 6532 GB/s")
 SHAPES = [(640000, 64, 64), (640000, 192, 64), (640000, 128, 64), (640000, 256, 64), (640000, 384, 128), (160000, 128, 128),
           (160000, 384, 128), (160000, 256, 128), (160000, 768, 256), (40000, 256, 256), (40000, 768, 256), (9984, 256, 256),
           (9984, 768, 256), (4992, 256, 256), (4992, 512, 256), (4992, 256, 512), (4992, 768, 256), (4992, 1024, 256), (4992, 256, 1024)]
@@ -28,7 +28,7 @@ for (M, N, K) in SHAPES:
     wp = engine.pack_linear_tc(w)
     t3 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp))
     idx = torch.randperm(M, device=DEV).int()
-    t2 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp, a_index=idx))      # gathered rows: the coupled-ring kernel (linear_tc2)
+    t2 = timeit(lambda: ops.linear(a, w, b, out=o3, wpack=wp, a_index=idx))      # gathered rows
     gbs = (M * K + M * N + N * K) * 4 / t3 / 1e6
     log("%d,%d,%d, %.4f, %.4f, %.0f, %.3f" % (M, N, K, t3, t2, gbs, gbs / 6532.5))
 
