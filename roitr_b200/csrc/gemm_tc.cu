@@ -165,8 +165,42 @@ __global__ void __launch_bounds__(TC_THREADS) linear_tc_kernel(const TcParams P_
     // ---- epilogue: warp w reads TMEM lanes 32w..32w+31 (= output rows), 32 columns at a time ----
     const int row = m0 + warp * 32 + lane;
     const bool vecC = (P.ldc % 4 == 0) && ((uintptr_t)P.C % 16 == 0);
+    // fragment layout (tc_common.cuh: tmem_ld_16x256b_x4): a quad of lanes holds 32 contiguous bytes of one row, so float2
+    // stores fill whole sectors; the row layout below writes 16 bytes per lane into 32 different rows per instruction
+    const bool frag = (P.ldc % 2 == 0) && (P.N % 2 == 0) && ((uintptr_t)P.C % 8 == 0) && ((uintptr_t)P.bias % 8 == 0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < BN && frag; c0 += 32) {
+        if (n0 + c0 >= P.N) break;   // warp-uniform
+        float v[2][16];
+        const uint32_t tq = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        tmem_ld_16x256b_x4(tq, v[0]);
+        tmem_ld_16x256b_x4(tq + (16u << 16), v[1]);
+        const int cq = 2 * (lane & 3), rq = lane >> 2;
+        float2 b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + c0 + 8 * j + cq;
+            b[j] = (P.bias && n < P.N) ? __ldg(reinterpret_cast<const float2*>(P.bias + n)) : make_float2(0.f, 0.f);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                       // rows 8 i + rq of this warp's 32
+            const int r = m0 + warp * 32 + 8 * i + rq;
+            if (r < P.M) {
+                float* dst = P.C + (long long)r * P.ldc + n0 + c0 + cq;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (n0 + c0 + 8 * j + cq < P.N) {
+                        float2 x = make_float2(v[i >> 1][4 * j + 2 * (i & 1)] + b[j].x, v[i >> 1][4 * j + 2 * (i & 1) + 1] + b[j].y);
+                        if (P.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
+                        *reinterpret_cast<float2*>(dst + 8 * j) = x;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN && !frag; c0 += 32) {
         if (n0 + c0 >= P.N) break;   // warp-uniform
         float v[32];
         tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
