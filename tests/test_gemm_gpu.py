@@ -105,6 +105,26 @@ def test_linear_tc_packed_strided_gather_add():
     assert out[:, :512].abs().max().item() == 0 and out[:, 768:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("M,R,N,K", [(160000, 640000, 128, 64), (40000, 160000, 512, 128), (9984, 40000, 1024, 256), (333, 1000, 64, 64),
+                                     (5000, 5000, 192, 96)])
+def test_linear_tc_packed_gathered_rows(M, R, N, K):
+    """Rows gathered through a_index alone take the GATHER instantiation of the streaming kernel (the down-sampling [f|q]
+    layers): strided source, repeated and out-of-order indices, bias + ReLU, against fp64."""
+    from roitr_b200 import engine
+    g = torch.Generator().manual_seed(M + N + K)
+    big = torch.randn(R, K + 64, generator=g).to(DEV)
+    a = big[:, 32:32 + K]                                   # column slice of a wider buffer: lda = K + 64, 16-byte aligned
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    idx = torch.randint(0, R, (M,), generator=g).int().to(DEV)
+    y = ops.linear(a, w, b, relu=True, a_index=idx, wpack=engine.pack_linear_tc(w))
+    ref = torch.relu(a[idx.long()].double() @ w.double().t() + b.double())
+    assert (y.double() - ref).abs().max().item() <= 6e-6 * ref.abs().max().item() * max(1.0, (K / 256) ** 0.5)
+    # the same function as the plain path on pre-gathered rows, bit for bit
+    y2 = ops.linear(a[idx.long()].contiguous(), w, b, relu=True, wpack=engine.pack_linear_tc(w))
+    assert torch.equal(y, y2)
+
+
 @pytest.mark.parametrize("N,scale", [(16, 3.0), (64, 3.0), (312, 3.0), (97, 40.0), (64, 400.0)])
 def test_geo_embedding_table_matches_oracle_and_tensor_core(N, scale):
     """Tabulated embedding (csrc/geo_table.cu): shared-memory tables (scale 3 m), the global-table path (distances up to
