@@ -505,8 +505,10 @@ def _self_layer_batch(W, lp, x, E, nb, N):
 def _cross_layer_batch(W, lp, x, y, pos_x, pos_y, nb, N, M):
     a = lp + ".attention.attention"
     C = x.shape[1]
-    q = ops.linear(x, W[a + ".proj_q.weight"], W[a + ".proj_q.bias"], a_add=pos_x, **_pk(W, a + ".proj_q.weight"))
-    k = ops.linear(y, W[a + ".proj_k.weight"], W[a + ".proj_k.bias"], a_add=pos_y, **_pk(W, a + ".proj_k.weight"))
+    # x + pos / y + pos: a stand-alone add (3 us) and the STREAMING dense kernel beat the coupled-ring kernel's add-in-the-loader
+    # (32 vs 16 us per launch at these 5 k rows); the sum is the same fp32 add either way
+    q = _lin(W, a + ".proj_q", ops.row_epilogue(x, res_pre=pos_x))
+    k = _lin(W, a + ".proj_k", ops.row_epilogue(y, res_pre=pos_y))
     v = ops.linear(y, W[a + ".proj_v.weight"], W[a + ".proj_v.bias"], **_pk(W, a + ".proj_v.weight"))
     hidden = ops.attention_tc(nb, N, M, C, q, k, v)
     z = _lin_ln(W, lp + ".attention.linear", lp + ".attention.norm", hidden, res_pre=x)
