@@ -386,18 +386,40 @@ __global__ void __launch_bounds__(GA_THREADS, 2) geo_self_scores_v3_kernel(const
     }
 }
 
-// cross attention: P[row,:] = softmax(QK[row,:] / sqrt(c)); one warp per row of M scores, in place allowed
+// cross attention: P[row,:] = softmax(QK[row,:] / sqrt(c)); one warp per row of M scores, in place allowed. The scaled row
+// (IEEE division, like the reference's `/ sqrt(c)`) is read ONCE into registers for rows of up to 512 scores.
 __global__ void softmax_rows_kernel(long long rows, int M, const float* __restrict__ qk, float sqrt_c, float* __restrict__ out) {
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* s = qk + row * M;
+    float* o = out + row * M;
+    if (M <= 512) {
+        float v[16];
+        float mx = -CUDART_INF_F, den = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int m = lane + 32 * i;
+            v[i] = m < M ? __fdiv_rn(__ldg(s + m), sqrt_c) : -CUDART_INF_F;
+            mx = fmaxf(mx, v[i]);
+        }
+        mx = warp_max(mx);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            v[i] = (lane + 32 * i < M) ? expf(v[i] - mx) : 0.f;
+            den += v[i];
+        }
+        den = warp_sum(den);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (lane + 32 * i < M) o[lane + 32 * i] = v[i] / den;
+        return;
+    }
     float mx = -CUDART_INF_F, den = 0.f;
     for (int m = lane; m < M; m += 32) mx = fmaxf(mx, __fdiv_rn(s[m], sqrt_c));
     mx = warp_max(mx);
     for (int m = lane; m < M; m += 32) den += expf(__fdiv_rn(s[m], sqrt_c) - mx);
     den = warp_sum(den);
-    float* o = out + row * M;
     for (int m = lane; m < M; m += 32) o[m] = expf(__fdiv_rn(s[m], sqrt_c) - mx) / den;
 }
 

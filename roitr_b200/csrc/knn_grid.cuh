@@ -92,31 +92,55 @@ __global__ void grid_bin_kernel(int n, int b, const float* __restrict__ xyz, con
     }
 }
 
-// exclusive scan of the per-cell counts of each segment (cursor -> cell_start, cursor zeroed for the scatter pass)
-__global__ void grid_scan_kernel(const SegHeader* __restrict__ hdr, int* __restrict__ cursor, int* __restrict__ cell_start) {
+// exclusive scan of the per-cell counts of each segment (cursor -> cell_start, cursor zeroed for the scatter pass): one CTA
+// per segment, 8 consecutive cells per thread (serial), shuffle scan of the thread sums, one shared-memory pass over the 32
+// warp totals: 3 barriers per 8192 cells (the first version ran a 20-barrier Hillis-Steele pass per 1024 cells: 51 us for
+// the 40 000 cells of a 20 000-point cloud, on the search lane every kNN of the step waits for).
+__global__ void __launch_bounds__(1024) grid_scan_kernel(const SegHeader* __restrict__ hdr, int* __restrict__ cursor, int* __restrict__ cell_start) {
+    constexpr int IPT = 8;
     const SegHeader H = hdr[blockIdx.x];
     const int ncell = H.nx * H.ny * H.nz;
-    __shared__ int buf[1024];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < ncell; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < ncell ? cursor[H.cell_base + i] : 0;
-        buf[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
-            __syncthreads();
-            buf[threadIdx.x] += t;
-            __syncthreads();
+    __shared__ int wsum[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < ncell; base += 1024 * IPT) {
+        const int i0 = base + tid * IPT;
+        int v[IPT], sum = 0;
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            v[j] = (i0 + j < ncell) ? cursor[H.cell_base + i0 + j] : 0;
+            sum += v[j];
         }
-        if (i < ncell) { cell_start[H.cell_base + i] = carry + buf[threadIdx.x] - v; cursor[H.cell_base + i] = 0; }
+        int inc = sum;                                   // inclusive scan of the thread sums within the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
         __syncthreads();
-        if (threadIdx.x == 0) carry += buf[1023];
+        if (warp == 0) {
+            int w = wsum[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            wsum[lane] = winc - w;                       // exclusive offset of each warp
+            if (lane == 31) s_total = winc;
+        }
         __syncthreads();
+        int run = carry + wsum[warp] + inc - sum;        // exclusive prefix of this thread's first cell
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            if (i0 + j < ncell) { cell_start[H.cell_base + i0 + j] = run; cursor[H.cell_base + i0 + j] = 0; }
+            run += v[j];
+        }
+        carry += s_total;
+        __syncthreads();                                 // wsum / s_total are rewritten by the next pass
     }
-    if (threadIdx.x == 0) cell_start[H.cell_base + ncell] = carry;
+    if (tid == 0) cell_start[H.cell_base + ncell] = carry;
 }
 
 }  // namespace knngrid

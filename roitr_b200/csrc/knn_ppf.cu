@@ -923,7 +923,7 @@ extern "C" int roitr_knn_grid_build_target(int b, int n, const float* xyz, const
     int* cursor = (int*)(w + grid_hdr_bytes(b) + grid_cells_bytes(b));
     float4* sorted = (float4*)(w + grid_hdr_bytes(b) + 2 * grid_cells_bytes(b));
     ROITR_CUDA(cudaMemsetAsync(cursor, 0, grid_cells_bytes(b), st));
-    knngrid::grid_header_kernel<<<b, 256, 0, st>>>(b, xyz, offset, hdr, target_per_cell);
+    knngrid::grid_header_kernel<<<b, 1024, 0, st>>>(b, xyz, offset, hdr, target_per_cell);
     if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 0);
     knngrid::grid_scan_kernel<<<b, 1024, 0, st>>>(hdr, cursor, cell_start);
     if (n > 0) knngrid::grid_bin_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, b, xyz, offset, hdr, cell_start, cursor, sorted, 1);
