@@ -654,6 +654,193 @@ int launch_tc3(const Tc2Params& P, cudaStream_t st) {
     return ROITR_OK;
 }
 
+// ---- row-group variant ---------------------------------------------------------------------------------------------------
+// For N > 128 the streaming kernel above visits a row tile once per 128-column weight tile, so the activations are fetched
+// (from L2 the second time) and split into TF32 hi / lo once per weight tile - and the loader warps are what limits that
+// kernel. Here the unit of work is (row tile, PAIR of weight tiles): the operand rings are separate (SA activation stages,
+// SB weight stages), the k loop is outermost, and each split activation chunk feeds the MMAs of both weight tiles into the
+// two halves of a 256-column accumulator slot (2 slots = the whole TMEM). Plain epilogue only (bias / ReLU, fragment-layout
+// stores); the LayerNorm epilogue, gathered rows and the light configuration stay with the kernel above.
+constexpr int T4_LW = 8, T4_THREADS = 128 + T4_LW * 32 + 64 + 128;
+template <int SA, int SB, int RAW>
+__global__ void __launch_bounds__(T4_THREADS, 1) linear_tc4_kernel(const Tc2Params P) {
+    constexpr int BN = 128, EW = 8, T4_LOADERS = T4_LW * 32;
+    constexpr int B_HALF = BN * 128;
+    constexpr int A_STAGE = 2 * A_HALF, B_STAGE = 2 * B_HALF;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sA = smem;                              // SA x [hi | lo], 128 rows x 128 B each
+    unsigned char* sB = smem + SA * A_STAGE;               // SB x [hi | lo]
+    unsigned char* raw = sB + SB * B_STAGE;                // RAW x 16 KB of raw fp32 activations
+    __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], T4_LOADERS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW * 32); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int ngroups = (P.tiles_n + 1) >> 1;
+    const int units = P.tiles_m * ngroups;                 // unit u: row tile u / ngroups, weight tiles 2 g, 2 g + 1 (g = u % ngroups)
+    const int nkc = P.nkc;
+    constexpr int W_LOADER0 = 4, W_PRODUCER = 4 + T4_LW, W_MMA = W_PRODUCER + 1;
+
+    if (warp >= W_LOADER0 && warp < W_PRODUCER) {
+        // ================================================= A loaders =================================================
+        const int t = tid - 128;
+        constexpr int RSTEP = T4_LW * 4, NPIECE = T2_BM / RSTEP;
+        const int c = t & 7, r0 = t >> 3;
+        const uint32_t raw_u32 = smem_u32(raw);
+        int i_unit = blockIdx.x, i_kc = 0;
+        uint32_t i_it = 0;
+        auto issue_one = [&]() {
+            if (i_unit < units) {
+                const uint32_t dst = raw_u32 + (i_it % RAW) * RAW_BYTES + (uint32_t)(r0 * 128 + c * 16);
+                const int k = i_kc * T2_BK + 4 * c;
+                const int am0 = (i_unit / ngroups) * T2_BM + r0;
+#pragma unroll
+                for (int j = 0; j < NPIECE; ++j) {
+                    const int am = am0 + RSTEP * j;
+                    const bool ok = am < P.M && k < P.K;
+                    cp_async16(dst + j * RSTEP * 128, P.A + (ok ? (long long)am * P.lda + k : 0ll), ok ? 16u : 0u);
+                }
+                ++i_it;
+                if (++i_kc == nkc) { i_kc = 0; i_unit += gridDim.x; }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int j = 0; j < RAW - 1; ++j) issue_one();
+        uint32_t it = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            for (int kc = 0; kc < nkc; ++kc, ++it) {
+                issue_one();
+                cp_async_wait<RAW - 1>();
+                const unsigned char* src = raw + (it % RAW) * RAW_BYTES + r0 * 128 + c * 16;
+                float4 v[NPIECE];
+#pragma unroll
+                for (int j = 0; j < NPIECE; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * RSTEP * 128);
+                const int sa = it % SA;
+                mbar_wait(&a_empty[sa], ((it / SA) & 1) ^ 1);
+                unsigned char* a_hi = sA + sa * A_STAGE;
+#pragma unroll
+                for (int j = 0; j < NPIECE; ++j) split_store(a_hi, a_hi + A_HALF, r0 + RSTEP * j, c, v[j]);
+                fence_proxy_async_smem();
+                mbar_arrive(&a_full[sa]);
+            }
+        }
+        cp_async_wait<0>();
+    } else if (warp == W_PRODUCER) {
+        // ================================================= W producer ================================================
+        if (lane == 0) {
+            uint32_t ib = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int g = unit % ngroups;
+                const int nt = min(2, P.tiles_n - 2 * g);
+                for (int kc = 0; kc < nkc; ++kc) {
+                    for (int t = 0; t < nt; ++t, ++ib) {
+                        const int sb = ib % SB;
+                        mbar_wait(&b_empty[sb], ((ib / SB) & 1) ^ 1);
+                        mbar_expect_tx(&b_full[sb], 2 * B_HALF);
+                        tma_load_1d(sB + sb * B_STAGE, P.wpack + ((size_t)(2 * g + t) * nkc + kc) * (2 * B_HALF / 4), 2 * B_HALF, &b_full[sb]);
+                    }
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ================================================= MMA issuer ================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(T2_BM, BN);
+            uint32_t ia = 0, ib = 0, ucount = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++ucount) {
+                const int g = unit % ngroups;
+                const int nt = min(2, P.tiles_n - 2 * g);
+                const int slot = ucount & 1;
+                mbar_wait(&tmem_empty[slot], ((ucount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < nkc; ++kc, ++ia) {
+                    const int sa = ia % SA;
+                    mbar_wait(&a_full[sa], (ia / SA) & 1);
+                    tc_fence_after();
+                    const uint32_t ah = smem_u32(sA + sa * A_STAGE), al = ah + A_HALF;
+                    for (int t = 0; t < nt; ++t, ++ib) {
+                        const int sb = ib % SB;
+                        mbar_wait(&b_full[sb], (ib / SB) & 1);
+                        tc_fence_after();
+                        const uint32_t bh = smem_u32(sB + sb * B_STAGE), bl = bh + B_HALF;
+                        const uint32_t d = tmem + (uint32_t)(slot * 256 + t * BN);
+#pragma unroll
+                        for (int ks = 0; ks < T2_BK / 8; ++ks) {
+                            const uint64_t dah = make_desc_sw128(ah + ks * 32), dal = make_desc_sw128(al + ks * 32);
+                            const uint64_t dbh = make_desc_sw128(bh + ks * 32), dbl = make_desc_sw128(bl + ks * 32);
+                            umma_tf32(d, dal, dbh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                            umma_tf32(d, dah, dbl, idesc, 1u);
+                            umma_tf32(d, dah, dbh, idesc, 1u);
+                        }
+                        umma_commit(&b_empty[sb]);                             // weight stage reusable when these MMAs retire
+                    }
+                    umma_commit(&a_empty[sa]);                                 // activation stage: after BOTH weight tiles
+                }
+                umma_commit(&tmem_full[slot]);
+            }
+        }
+    } else {
+        // ================================================= epilogue (warps 0-3 and the last four) =====================
+        const int ew = warp < 4 ? warp : 4 + (warp - W_MMA - 1);
+        const int quad = warp & 3;
+        const int first = ew >= 4 ? 32 : 0;                  // the two warps of a quadrant take even / odd 32-column blocks
+        uint32_t ucount = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++ucount) {
+            const int tm = unit / ngroups, g = unit % ngroups;
+            const int nt = min(2, P.tiles_n - 2 * g);
+            const int slot = ucount & 1;
+            mbar_wait(&tmem_full[slot], (ucount >> 1) & 1);
+            tc_fence_after();
+            const int row0 = tm * T2_BM + quad * 32, ncol0 = g * 2 * BN;
+            const uint32_t tq = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * 256);
+#pragma unroll 1
+            for (int c0 = first; c0 < nt * BN; c0 += 64) {
+                if (ncol0 + c0 >= P.N) break;
+                store_block32_frag(P, tq + c0, lane, row0, ncol0 + c0);
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[slot]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int SA, int SB, int RAW>
+int launch_tc4(const Tc2Params& P, cudaStream_t st) {
+    constexpr int smem = SA * 2 * A_HALF + SB * 2 * 128 * 128 + RAW * RAW_BYTES + 1024;
+    static bool attr_dev[ROITR_MAX_DEVICES] = {};
+    static int num_sms_dev[ROITR_MAX_DEVICES] = {};
+    const int dv = roitr_cur_device();
+    bool& attr = attr_dev[dv];
+    int& num_sms = num_sms_dev[dv];
+    if (!attr) {
+        ROITR_CUDA(cudaFuncSetAttribute(linear_tc4_kernel<SA, SB, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int dev = 0;
+        ROITR_CUDA(cudaGetDevice(&dev));
+        ROITR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr = true;
+    }
+    const int units = P.tiles_m * ((P.tiles_n + 1) / 2);
+    const int grid = units < num_sms ? units : num_sms;
+    linear_tc4_kernel<SA, SB, RAW><<<grid, T4_THREADS, smem, st>>>(P);
+    ROITR_CHECK_LAUNCH("linear_tc4_kernel");
+    return ROITR_OK;
+}
+
 template <int BN, int STAGES>
 int launch_tc2(const Tc2Params& P, cudaStream_t st) {
     constexpr int smem = STAGES * (2 * A_HALF + 2 * BN * 128) + 1024;   // + ~21 KB static (transpose pads, bias)
@@ -682,6 +869,9 @@ int launch_tc2(const Tc2Params& P, cudaStream_t st) {
 // level-1 layers it issues while the FPS clusters hold most SMs): 0 = deep rings, one CTA per SM (215 KB, 57 K registers);
 // 3 = light footprint (one operand stage, two raw stages, 4 loader warps, <= 64 registers: ~115 KB, 20 K registers) that
 // shares an SM with the CTAs of other streams' kernels. Same arithmetic, same results.
+#ifndef TC4_ON
+#define TC4_ON 1
+#endif
 static int g_tc3_variant = 0;
 extern "C" int roitr_set_linear_config(int v) { g_tc3_variant = (v == 3) ? 3 : 0; return 0; }
 
@@ -717,6 +907,13 @@ static int linear_tc_packed_impl(int M, int N, int K, const float* A, const floa
     if (stream_ok && a_index) return bn == 128 ? launch_tc3<128, 2, 3, 8, 1, true>(P, st) : launch_tc3<64, 2, 4, 8, 1, true>(P, st);
     if (stream_ok) {
         if (g_tc3_variant == 3) return bn == 128 ? launch_tc3<128, 1, 2, 4, 3>(P, st) : launch_tc3<64, 1, 2, 4, 3>(P, st);
+        // more than one 128-column weight tile: activations loaded and split once per PAIR of weight tiles
+        // (measured, profiles/r02_bench_gemm.txt: 0.213 -> 0.148 ms at (640000, 192, 64), 0.201 -> 0.168 at N = 256; with fewer than
+        // ~74 row tiles the one-tile-per-CTA kernel spreads over more SMs and wins: 0.015 vs 0.023 ms at (4992, 256, 256); three
+        // weight tiles - one pair and a single - are no better than the kernel above)
+        if (TC4_ON && bn == 128 && P.tiles_n >= 2 && P.tiles_n != 3 && P.tiles_m >= 74 && ldc % 2 == 0 && N % 2 == 0 &&
+            (uintptr_t)C % 8 == 0 && (uintptr_t)bias % 8 == 0)
+            return launch_tc4<2, 3, 3>(P, st);
         return bn == 128 ? launch_tc3<128, 2, 3, 8, 1>(P, st) : launch_tc3<64, 2, 4, 8, 1>(P, st);
     }
     if (bn == 64) return launch_tc2<64, 4>(P, st);
