@@ -144,7 +144,10 @@ int roitr_linear(int M, int N, int K, const float* A, const float* a_add, int ld
  * accumulated in fp32 TMEM; relative error ~2^-21, fp32-grade); persistent, warp-specialised (A loader warps, bulk-TMA weight producer, single-
  * thread tcgen05 MMA issuer, epilogue warps; two TMEM accumulators so the epilogue of a tile overlaps the next tile).
  * wpack = the weight pre-split into TF32 hi/lo and pre-swizzled by roitr_b200.engine.pack_linear_tc:
- * [ceil(N/bn)][ceil(K/32)][hi|lo][bn*32] floats, zero padded, bn in {64,128}. Same contract as roitr_linear otherwise. */
+ * [ceil(N/bn)][ceil(K/32)][hi|lo][bn*32] floats, zero padded, bn in {64,128}. Same contract as roitr_linear otherwise.
+ * Kernel selection (same arithmetic, same results): plain or gathered (a_index) 16-byte aligned rows -> the streaming kernel
+ * (cp.async raw ring + split pass); N > 128 with >= 74 row tiles -> the row-group kernel (activations loaded and split once per
+ * pair of 128-column weight tiles); a_add or unaligned inputs -> the coupled-ring kernel with register-staged loaders. */
 int roitr_linear_tc_packed(int M, int N, int K, const float* A, const float* a_add, int lda, const int* a_index,
                            const float* wpack, int bn, const float* bias, float* C, int ldc, int relu, void* stream);
 
@@ -157,8 +160,9 @@ int roitr_set_linear_config(int config);
 /* Dense layer with the row epilogue fused (one kernel instead of roitr_linear_tc_packed + roitr_row_epilogue):
  *   C = act( LayerNorm_N( A W^T + bias + res_pre[res_pre_index] ) * gamma + beta + res_post ),  act = ReLU if relu
  * (LocalRPEAttentionLayer output: attention.py:317-319; RIPointTransformerBlock: model/model.py:139-141; TransitionUp:
- * model/model.py:103-105). N must be a multiple of 32 and fit one weight tile (N <= bn); res_pre / res_post rows have pitch
- * ldr; res_pre_index (int32, optional) gathers res_pre rows. eps = 1e-5. */
+ * model/model.py:103-105). N must be a multiple of 32 and fit one weight tile (N <= bn) or, with bn = 128, two (N <= 256: both
+ * halves of the row sit side by side in TMEM); res_pre / res_post rows have pitch ldr; res_pre_index (int32, optional) gathers
+ * res_pre rows. eps = 1e-5. */
 int roitr_linear_ln_tc_packed(int M, int N, int K, const float* A, int lda, const float* wpack, int bn, const float* bias,
                               const float* gamma, const float* beta, const float* res_pre, const int* res_pre_index,
                               const float* res_post, int ldr, int relu, float* C, int ldc, void* stream);
@@ -225,7 +229,7 @@ int roitr_geo_embedding_table(int batch, int N, int C, const float* pts, const i
                               const float* Wa, const float* ba, const float* div_term, float sigma_d, float sigma_a,
                               float* E, void* stream);
 
-/* Batched dense contraction on the tensor cores (tcgen05 3xTF32, one CTA per 128 x {64,128,256} tile, operands split on the fly) for
+/* Batched dense contraction on the tensor cores (tcgen05 3xTF32, one CTA per 128 x {64,128} tile, 3-4 CTAs per SM, operands split on the fly) for
  * operands that are activations: for every (o, i) in batch_outer x batch_inner
  *     C_oi[M,N] = A_oi[M,K] W_oi[N,K]^T,   X_oi = X + o * sX_o + i * sX_i  (element strides)
  * w_transposed != 0: W_oi is given as (K, >= N) row-major with leading dimension ldw (W_oi[n][k] = Wt[k * ldw + n]).
