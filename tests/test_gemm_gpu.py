@@ -74,7 +74,10 @@ def test_geo_embedding_tensor_core_matches_oracle(N):
     assert (b.cpu() - ref)[off].abs().max().item() < 2e-5
 
 
-PACKED_SHAPES = SHAPES + [(640000, 192, 64), (40000, 768, 256), (10000, 512, 512), (129, 65, 33), (4992, 1024, 64)]
+PACKED_SHAPES = SHAPES + [(640000, 192, 64), (40000, 768, 256), (10000, 512, 512), (129, 65, 33), (4992, 1024, 64),
+                          # row-group kernel (N > 128, >= 74 row tiles): odd number of weight tiles (last group holds ONE tile),
+                          # N not a multiple of 32 inside the second tile, a ragged last row tile
+                          (20000, 520, 96), (12000, 200, 64), (9473, 640, 32), (9472, 258, 128)]
 
 
 @pytest.mark.parametrize("M,N,K", PACKED_SHAPES)
