@@ -339,7 +339,7 @@ constexpr int RAW_BYTES = T2_BM * 128;
 
 // Epilogue of one finished accumulator tile (rows tm*128 .. +127, columns tn*BN .. ) held in TMEM at `tbase` (this warp's 32
 // lanes): plain bias / ReLU store, or the fused row epilogue. `next_tm` = the row tile this CTA processes next (-1: none),
-// whose residual rows are prefetched into L2. Shared by the streaming (linear_tc3) and weight-stationary (linear_ws) kernels.
+// whose residual rows are prefetched into L2. Used by the streaming kernel (linear_tc3).
 template <int BN, int LNW, bool FRAG>
 __device__ __forceinline__ void tile_epilogue(const Tc2Params& P, float* pad, const float (*s_ln)[LNW], int warp, int lane, int tm,
                                               int tn, int next_tm, uint32_t tbase, int cb0 = 0, int cbstep = 1,
